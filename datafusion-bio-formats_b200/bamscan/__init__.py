@@ -1,0 +1,297 @@
+"""bamscan -- python host mirror of the reference's BAM table provider over the C ABI (include/bamscan.h).
+
+Mirrors, name for name, the interface DataFusion drives in the reference
+(datafusion/bio-format-bam/src/table_provider.rs:314-335, 381-390, 928-1115; physical_exec.rs:84-173):
+
+    provider = BamTableProvider(file_path, None, coordinate_system_zero_based, tag_fields, binary_cigar,
+                                infer_tag_types, infer_tag_sample_size, tag_type_hints)
+    provider.schema()                                  -> pyarrow.Schema
+    provider.supports_filters_pushdown(filters)        -> ["Inexact" | "Unsupported", ...]
+    plan = provider.scan(projection, filters, limit, target_partitions=...)   -> BamExec
+    plan.output_partition_count()
+    for batch in plan.execute(partition): ...          -> pyarrow.RecordBatch
+
+Everything below the method signatures is libbamscan.so (CUDA, sm_100a).  There is no CPU path: importing works
+anywhere (so CPU-only CI can check symbols), but opening a file without a GPU raises BamScanError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import pyarrow as pa
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE.parent / "libbamscan.so"
+
+EXPORTED_SYMBOLS = [
+    "bamscan_open", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
+    "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_execute", "bamscan_next",
+    "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
+    "bamscan_last_error", "bamscan_version",
+]
+
+
+class BamScanError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class _Options(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("coordinate_system_zero_based", C.c_int32), ("binary_cigar", C.c_int32),
+                ("has_tag_fields", C.c_int32), ("n_tag_fields", C.c_int32), ("tag_fields", C.POINTER(C.c_char_p)),
+                ("infer_tag_types", C.c_int32), ("infer_tag_sample_size", C.c_int32),
+                ("n_tag_type_hints", C.c_int32), ("tag_type_hints", C.POINTER(C.c_char_p)),
+                ("device_id", C.c_int32), ("batch_rows", C.c_int32), ("chunk_inflated_bytes", C.c_uint64),
+                ("segment_bytes", C.c_uint32), ("skip_crc", C.c_int32), ("debug_flags", C.c_int32)]
+
+
+class _Filter(C.Structure):
+    _fields_ = [("column", C.c_int32), ("op", C.c_int32), ("n_values", C.c_int32),
+                ("num_values", C.POINTER(C.c_double)), ("str_values", C.POINTER(C.c_char_p))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("batches", C.c_uint64), ("chunks", C.c_uint64),
+                ("compressed_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64), ("arrow_bytes", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("blocks", C.c_uint64), ("kernel_launches", C.c_uint64), ("boundary_repairs", C.c_uint64),
+                ("ms_total", C.c_double), ("ms_inflate", C.c_double), ("ms_boundary", C.c_double), ("ms_decode", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_OPS = {"=": 0, "==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "between": 6, "not_between": 7, "in": 8, "not_in": 9,
+        "other": 100}
+CORE_COLUMNS = ["name", "chrom", "start", "end", "flags", "cigar", "mapping_quality", "mate_chrom", "mate_start",
+                "sequence", "quality_scores", "template_length"]
+
+_lib = None
+
+
+def load_library():
+    """Loads libbamscan.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise BamScanError(-4, f"{LIB_PATH} is missing: build it with `make -C {LIB_PATH.parent / 'csrc'}` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    L.bamscan_last_error.restype = C.c_char_p
+    L.bamscan_version.restype = C.c_char_p
+    L.bamscan_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(_Options), C.POINTER(C.c_void_p)]
+    L.bamscan_close.argtypes = [C.c_void_p]
+    L.bamscan_schema.argtypes = [C.c_void_p, C.c_void_p]
+    L.bamscan_classify_filters.argtypes = [C.c_void_p, C.POINTER(_Filter), C.c_int32, C.POINTER(C.c_uint8)]
+    L.bamscan_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(_Filter), C.c_int32, C.c_int64,
+                               C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.bamscan_plan_num_partitions.argtypes = [C.c_void_p]
+    L.bamscan_plan_schema.argtypes = [C.c_void_p, C.c_void_p]
+    L.bamscan_plan_free.argtypes = [C.c_void_p]
+    L.bamscan_execute.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.bamscan_next.argtypes = [C.c_void_p, C.c_void_p]
+    L.bamscan_stream_free.argtypes = [C.c_void_p]
+    L.bamscan_run_device_resident.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Stats)]
+    L.bamscan_stream_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.bamscan_bench_inflate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise BamScanError(rc, load_library().bamscan_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _strs(values):
+    if not values:
+        return None, []
+    enc = [v.encode() for v in values]
+    return (C.c_char_p * len(enc))(*enc), enc
+
+
+class _FilterPack:
+    """Converts [(column, op, values)] into BamScanFilter[]; column is a name or a schema index."""
+
+    def __init__(self, filters, schema_names):
+        self.keep = []
+        filters = filters or []
+        self.n = len(filters)
+        self.arr = (_Filter * max(1, self.n))()
+        for i, (col, op, vals) in enumerate(filters):
+            idx = schema_names.index(col) if isinstance(col, str) and col in schema_names else (col if isinstance(col, int) else -1)
+            self.arr[i].column = idx
+            self.arr[i].op = _OPS[op]
+            vals = list(vals) if isinstance(vals, (list, tuple)) else [vals]
+            self.arr[i].n_values = len(vals)
+            if vals and all(isinstance(v, str) for v in vals):
+                a, enc = _strs(vals)
+                self.keep += [a, enc]
+                self.arr[i].str_values = a
+            elif vals:
+                a = (C.c_double * len(vals))(*[float(v) for v in vals])
+                self.keep.append(a)
+                self.arr[i].num_values = a
+
+
+class BamExec:
+    """== BamExec : ExecutionPlan (physical_exec.rs:39-173)."""
+
+    def __init__(self, provider, handle):
+        self._provider = provider
+        self._h = handle
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().bamscan_plan_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def output_partition_count(self) -> int:
+        return load_library().bamscan_plan_num_partitions(self._h)
+
+    def schema(self) -> pa.Schema:
+        cs = _ArrowSchemaStruct()
+        _check(load_library().bamscan_plan_schema(self._h, C.byref(cs)))
+        return pa.Schema._import_from_c(C.addressof(cs))
+
+    def execute(self, partition: int):
+        """Generator of pyarrow.RecordBatch for one partition (== execute(partition) + poll_next)."""
+        L = load_library()
+        schema = self.schema()
+        st = C.c_void_p()
+        _check(L.bamscan_execute(self._h, partition, C.byref(st)))
+        try:
+            while True:
+                arr = _ArrowArrayStruct()
+                rc = _check(L.bamscan_next(st, C.byref(arr)))
+                if rc == 0:
+                    break
+                if len(schema) == 0:
+                    sa = pa.Array._import_from_c(C.addressof(arr), pa.struct([]))
+                    yield pa.RecordBatch.from_struct_array(sa)   # zero columns, row count kept (alignment_utils.rs:360-363)
+                else:
+                    yield pa.RecordBatch._import_from_c(C.addressof(arr), schema)
+            s = Stats()
+            L.bamscan_stream_stats(st, C.byref(s))
+            self.last_stats = s.as_dict()
+        finally:
+            L.bamscan_stream_free(st)
+
+    def collect(self) -> pa.Table:
+        """All partitions in partition order (CoalescePartitionsExec over the leaf)."""
+        schema = self.schema()
+        batches = []
+        for p in range(self.output_partition_count()):
+            batches += list(self.execute(p))
+        if len(schema) == 0:
+            return batches
+        return pa.Table.from_batches(batches, schema=schema)
+
+    def run_device_resident(self, partition=0, repeats=1) -> dict:
+        s = Stats()
+        _check(load_library().bamscan_run_device_resident(self._h, partition, repeats, C.byref(s)))
+        return s.as_dict()
+
+    def bench_inflate(self, partition=0, repeats=10) -> dict:
+        ms = C.c_double(); ib = C.c_uint64(); cb = C.c_uint64()
+        _check(load_library().bamscan_bench_inflate(self._h, partition, repeats, C.byref(ms), C.byref(ib), C.byref(cb)))
+        return {"ms_per_launch": ms.value, "inflated_bytes": ib.value, "compressed_bytes": cb.value}
+
+
+class _ArrowSchemaStruct(C.Structure):
+    _fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_void_p), ("flags", C.c_int64),
+                ("n_children", C.c_int64), ("children", C.c_void_p), ("dictionary", C.c_void_p), ("release", C.c_void_p),
+                ("private_data", C.c_void_p)]
+
+
+class _ArrowArrayStruct(C.Structure):
+    _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                ("n_children", C.c_int64), ("buffers", C.c_void_p), ("children", C.c_void_p), ("dictionary", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class BamTableProvider:
+    """== BamTableProvider (table_provider.rs:314-335); constructor arguments follow `new` (:381-390)."""
+
+    def __init__(self, file_path, object_storage_options=None, coordinate_system_zero_based=True, tag_fields=None,
+                 binary_cigar=False, infer_tag_types=True, infer_tag_sample_size=100, tag_type_hints=None, *,
+                 index_path=None, device_id=0, batch_rows=0, chunk_inflated_bytes=0, segment_bytes=0, skip_crc=False,
+                 debug_flags=0):
+        if object_storage_options is not None:
+            raise BamScanError(-5, "remote object storage is out of scope for this build (local files only)")
+        L = load_library()
+        o = _Options()
+        o.struct_size = C.sizeof(_Options)
+        o.coordinate_system_zero_based = int(coordinate_system_zero_based)
+        o.binary_cigar = int(binary_cigar)
+        o.has_tag_fields = int(tag_fields is not None)
+        self._tag_arr, self._tag_enc = _strs(list(tag_fields or []))
+        o.n_tag_fields = len(tag_fields or [])
+        if self._tag_arr is not None:
+            o.tag_fields = self._tag_arr
+        o.infer_tag_types = int(infer_tag_types)
+        o.infer_tag_sample_size = int(infer_tag_sample_size)
+        self._hint_arr, self._hint_enc = _strs(list(tag_type_hints or []))
+        o.n_tag_type_hints = len(tag_type_hints or [])
+        if self._hint_arr is not None:
+            o.tag_type_hints = self._hint_arr
+        o.device_id = device_id
+        o.batch_rows = batch_rows
+        o.chunk_inflated_bytes = chunk_inflated_bytes
+        o.segment_bytes = segment_bytes
+        o.skip_crc = int(skip_crc)
+        o.debug_flags = debug_flags
+        self._h = C.c_void_p()
+        _check(L.bamscan_open(str(file_path).encode(), index_path.encode() if index_path else None, C.byref(o), C.byref(self._h)))
+        self.file_path = str(file_path)
+        self._schema = None
+
+    def close(self):
+        if self._h:
+            load_library().bamscan_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def schema(self) -> pa.Schema:
+        if self._schema is None:
+            cs = _ArrowSchemaStruct()
+            _check(load_library().bamscan_schema(self._h, C.byref(cs)))
+            self._schema = pa.Schema._import_from_c(C.addressof(cs))
+        return self._schema
+
+    def table_type(self) -> str:
+        return "Base"
+
+    def supports_filters_pushdown(self, filters):
+        pack = _FilterPack(filters, self.schema().names)
+        out = (C.c_uint8 * max(1, pack.n))()
+        _check(load_library().bamscan_classify_filters(self._h, pack.arr, pack.n, out))
+        return ["Inexact" if out[i] else "Unsupported" for i in range(pack.n)]
+
+    def scan(self, projection=None, filters=None, limit=None, *, target_partitions=1, partition_mode="reference") -> BamExec:
+        L = load_library()
+        pack = _FilterPack(filters, self.schema().names)
+        if projection is None:
+            proj, n_proj = None, -1
+        else:
+            proj = (C.c_int32 * max(1, len(projection)))(*projection)
+            n_proj = len(projection)
+        ph = C.c_void_p()
+        mode = {"reference": 0, "block_range": 1}[partition_mode]
+        _check(L.bamscan_plan(self._h, proj, n_proj, pack.arr, pack.n, -1 if limit is None else int(limit),
+                              int(target_partitions), mode, C.byref(ph)))
+        return BamExec(self, ph)

@@ -1,0 +1,908 @@
+// engine.cu -- the device pipeline behind BamExec::execute, and the extern "C" entry points.
+//
+// Per partition (== one reference `execute(partition)` stream, physical_exec.rs:108-172) the engine walks the
+// partition's BGZF block ranges in CHUNKS (default 512 MiB inflated) and, per chunk, runs on one compute stream:
+//
+//   H2D (side stream, pinned source, double buffered)            BASELINE north_star (1)
+//   inflate_kernel              (kernels_inflate.cuh)            north_star (2)
+//   carry-in copy of the previous chunk's incomplete tail record
+//   seg_candidates / seg_walk / seg_check / seg_repair / seg_scan / seg_emit   north_star (3)
+//   decode_fixed_kernel -> multi_scan_* -> decode_var_kernel     north_star (4)
+//   D2H of the chunk's Arrow arena (side stream) while the next chunk computes
+//
+// Two host syncs per chunk (row count; var-len totals) size the arena exactly.  A batch is handed out one
+// chunk late so its D2H overlaps the next chunk's kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "bamscan_internal.h"
+#include "kernels_decode.cuh"
+#include "kernels_inflate.cuh"
+
+namespace bamscan {
+
+const char* last_error_cstr();
+bool filter_is_record_pushable(const BamFile& f, const BamScanFilter& flt);
+
+#define CU_TRY(expr)                                                                                         \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr);           \
+      return BAMSCAN_ERR_CUDA;                                                                               \
+    }                                                                                                        \
+  } while (0)
+
+constexpr uint32_t HEADROOM = 16u << 20;      // room in front of a chunk for the carried-over tail record
+constexpr uint32_t INFL_PAD = 4096;
+constexpr uint32_t MAX_BLOCK_SIZE = 256u << 20;
+
+void* pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed: %s (is a CUDA device present? this library has no CPU path)", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+void pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+struct DeviceBuf {
+  void* p = nullptr; size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return BAMSCAN_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return BAMSCAN_ERR_CUDA; }
+    cap = want;
+    return BAMSCAN_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- pinned host arenas: pooled, reference counted by the exported Arrow arrays ----
+struct HostArena { uint8_t* p = nullptr; size_t cap = 0; };
+static std::mutex g_pool_mu;
+static std::vector<HostArena> g_pool;
+static HostArena arena_acquire(size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_pool.size(); i++) if (g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = (int)i;
+    if (best >= 0) { HostArena a = g_pool[best]; g_pool.erase(g_pool.begin() + best); return a; }
+  }
+  HostArena a;
+  size_t cap = std::max<size_t>(bytes + bytes / 16, 1 << 16);
+  a.p = (uint8_t*)pinned_alloc(cap);
+  a.cap = a.p ? cap : 0;
+  return a;
+}
+static void arena_release(HostArena a) {
+  if (!a.p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool.size() < 4) { g_pool.push_back(a); return; }
+  // keep the largest ones
+  size_t smallest = 0;
+  for (size_t i = 1; i < g_pool.size(); i++) if (g_pool[i].cap < g_pool[smallest].cap) smallest = i;
+  if (g_pool[smallest].cap < a.cap) std::swap(g_pool[smallest], a);
+  cudaFreeHost(a.p);
+}
+
+struct BatchOwner {
+  HostArena arena;
+  std::atomic<int> refs{0};
+};
+static void owner_unref(BatchOwner* o) {
+  if (o->refs.fetch_sub(1) == 1) { arena_release(o->arena); delete o; }
+}
+
+// one output column of a chunk (offsets into the arena; same layout on device and host)
+struct ColLayout {
+  int32_t schema_idx = 0, kind = 0;
+  bool has_validity = false;
+  size_t validity_off = 0, offsets_off = 0, values_off = 0, data_off = 0;
+  uint64_t data_bytes = 0;      // var-len data bytes / list child bytes
+  uint64_t child_len = 0;       // list child element count
+};
+
+struct ChunkPlan { uint32_t b0 = 0, b1 = 0; uint64_t c0 = 0, c1 = 0, u0 = 0, ubytes = 0; bool extension = false; };
+
+struct PendingBatch {
+  BatchOwner* owner = nullptr;
+  std::vector<ColLayout> cols;
+  uint64_t rows = 0;
+  size_t arena_bytes = 0;
+  size_t err_off = 0;
+  cudaEvent_t done = nullptr;
+  bool valid = false;
+};
+
+struct ReadyBatch { BatchOwner* owner; std::vector<ColLayout> cols; uint64_t rows_total, row0, nrows; };
+
+}  // namespace bamscan
+
+using namespace bamscan;
+
+struct BamScanHandle { BamFile file; };
+struct BamScanPlan { Plan* plan = nullptr; BamScanHandle* handle = nullptr; };
+
+struct BamScanStream {
+  Plan* plan = nullptr; BamFile* f = nullptr; const Partition* part = nullptr;
+  bool device_resident = false;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute = nullptr, ev_flags = nullptr, ev_t[6] = {};
+  // iteration
+  size_t range_idx = 0;
+  std::vector<ChunkPlan> chunks; size_t chunk_idx = 0; bool range_open = false; bool finished = false;
+  uint32_t carry_len = 0; bool have_h2d_ahead = false; uint32_t ext_blocks = 8; bool need_spec = false;
+  // unique decoded columns
+  std::vector<int32_t> dec_cols;          // schema indices, unique
+  std::vector<int32_t> out_to_dec;        // projection position -> index into dec_cols
+  // device memory
+  DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_tiles, d_totals, d_scratch, d_arena[2], d_refs;
+  const uint8_t* d_comp_all = nullptr; DeviceBuf d_comp_all_buf; uint64_t comp_all_c0 = 0;
+  uint32_t* h_flags = nullptr;            // pinned mirror: [0..15] boundary flags / inflate err, [16..] totals (u64)
+  int arena_flip = 0;
+  PendingBatch pending;
+  std::vector<ReadyBatch> ready; size_t ready_pos = 0;
+  BamScanStats st{};
+  int error = 0;
+};
+
+namespace bamscan {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static bool g_crc_init[64] = {};
+static int init_device_constants(int dev) {
+  if (dev < 64 && g_crc_init[dev]) return BAMSCAN_OK;
+  // x^(8 * 2^j) mod P in the reflected domain
+  auto mulmod = [](uint32_t a, uint32_t b) { uint32_t p = 0; for (int i = 0; i < 32; i++) { if (b & 0x80000000u) p ^= a; a = (a >> 1) ^ ((a & 1u) ? 0xEDB88320u : 0u); b <<= 1; } return p; };
+  uint32_t tab[18];
+  tab[0] = 0x00800000u;   // x^8
+  for (int j = 1; j < 18; j++) tab[j] = mulmod(tab[j - 1], tab[j - 1]);
+  CU_TRY(cudaMemcpyToSymbol(c_crc_xpow8, tab, sizeof tab));
+  if (dev < 64) g_crc_init[dev] = true;
+  return BAMSCAN_OK;
+}
+
+static int stream_init(BamScanStream* s) {
+  BamFile* f = s->f;
+  CU_TRY(cudaSetDevice(f->device));
+  int rc = init_device_constants(f->device);
+  if (rc) return rc;
+  CU_TRY(cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) CU_TRY(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming));
+  for (auto& e : s->ev_t) CU_TRY(cudaEventCreate(&e));
+  s->h_flags = (uint32_t*)pinned_alloc(4096);
+  if (!s->h_flags) return BAMSCAN_ERR_CUDA;
+  CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+  // reference dictionary: lengths + names blob
+  size_t n_ref = f->ref_names.size();
+  std::vector<uint32_t> offs(n_ref + 1, 0);
+  std::string blob;
+  for (size_t i = 0; i < n_ref; i++) { offs[i] = (uint32_t)blob.size(); blob += f->ref_names[i]; }
+  offs[n_ref] = (uint32_t)blob.size();
+  size_t o_len = 0, o_off = align_up(4 * n_ref + 4, 16), o_blob = o_off + align_up(4 * (n_ref + 1), 16);
+  rc = s->d_refs.ensure(o_blob + blob.size() + 16);
+  if (rc) return rc;
+  if (n_ref) CU_TRY(cudaMemcpy(s->d_refs.as<uint8_t>() + o_len, f->ref_lens.data(), 4 * n_ref, cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(s->d_refs.as<uint8_t>() + o_off, offs.data(), 4 * (n_ref + 1), cudaMemcpyHostToDevice));
+  if (!blob.empty()) CU_TRY(cudaMemcpy(s->d_refs.as<uint8_t>() + o_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  // unique decode columns
+  const Plan* P = s->plan;
+  std::vector<int32_t> proj;
+  if (P->has_projection) proj = P->projection; else for (size_t i = 0; i < f->fields.size(); i++) proj.push_back((int32_t)i);
+  for (int32_t c : proj) {
+    auto it = std::find(s->dec_cols.begin(), s->dec_cols.end(), c);
+    if (it == s->dec_cols.end()) { s->out_to_dec.push_back((int32_t)s->dec_cols.size()); s->dec_cols.push_back(c); }
+    else s->out_to_dec.push_back((int32_t)(it - s->dec_cols.begin()));
+  }
+  int n_tag_cols = 0;
+  for (int32_t c : s->dec_cols) if (c >= 12) n_tag_cols++;
+  if (n_tag_cols > MAX_TAGS) { set_error("more than %d projected tag columns are not supported by this build", MAX_TAGS); return BAMSCAN_ERR_UNSUPPORTED; }
+  return BAMSCAN_OK;
+}
+
+static void stream_destroy(BamScanStream* s) {
+  if (!s) return;
+  cudaSetDevice(s->f->device);
+  if (s->s_compute) cudaStreamSynchronize(s->s_compute);
+  if (s->s_h2d) cudaStreamSynchronize(s->s_h2d);
+  if (s->s_d2h) cudaStreamSynchronize(s->s_d2h);
+  if (s->pending.valid) { owner_unref(s->pending.owner); if (s->pending.done) cudaEventDestroy(s->pending.done); }
+  for (size_t i = s->ready_pos; i < s->ready.size(); i++) owner_unref(s->ready[i].owner);
+  for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl, &s->d_carry, &s->d_status, &s->d_flags, &s->d_seg,
+                  &s->d_recoff, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf}) b->release();
+  if (s->h_flags) cudaFreeHost(s->h_flags);
+  for (auto& e : s->ev_h2d) if (e) cudaEventDestroy(e);
+  if (s->ev_compute) cudaEventDestroy(s->ev_compute);
+  if (s->ev_flags) cudaEventDestroy(s->ev_flags);
+  for (auto& e : s->ev_t) if (e) cudaEventDestroy(e);
+  if (s->s_compute) cudaStreamDestroy(s->s_compute);
+  if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
+  if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
+  delete s;
+}
+
+// cut blocks [b0, b1) into chunks of <= chunk_bytes inflated
+static void plan_chunks(const BamFile& f, uint32_t b0, uint32_t b1, bool extension, std::vector<ChunkPlan>* out) {
+  uint32_t b = b0;
+  while (b < b1) {
+    ChunkPlan c; c.b0 = b; c.u0 = f.blocks[b].uoff; c.c0 = f.blocks[b].coff; c.extension = extension;
+    uint64_t ub = 0;
+    while (b < b1 && (ub == 0 || ub + f.blocks[b].isize <= f.chunk_bytes)) { ub += f.blocks[b].isize; b++; }
+    c.b1 = b; c.ubytes = ub; c.c1 = f.blocks[b - 1].coff + f.blocks[b - 1].csize;
+    out->push_back(c);
+  }
+}
+
+static int issue_h2d(BamScanStream* s, const ChunkPlan& c, int slot) {
+  if (s->device_resident) return BAMSCAN_OK;
+  size_t bytes = (size_t)(c.c1 - c.c0);
+  int rc = s->d_comp[slot].ensure(bytes + 1024);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->f->data + c.c0, bytes + 512 /* pad is inside the pinned file buffer */, cudaMemcpyHostToDevice, s->s_h2d));
+  CU_TRY(cudaEventRecord(s->ev_h2d[slot], s->s_h2d));
+  s->st.h2d_bytes += bytes;
+  return BAMSCAN_OK;
+}
+
+struct ArenaBuilder {
+  size_t pos = 0;
+  size_t take(size_t bytes) { size_t o = pos; pos = align_up(pos + bytes, 256); return o; }
+};
+
+// Runs one chunk.  On success *produced tells whether a batch went into s->pending (previous pending must have been consumed).
+static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& range, int slot, bool first_of_range, bool* produced, uint32_t* new_carry, bool* owned_done) {
+  BamFile* f = s->f;
+  *produced = false;
+  const uint32_t nb_all = c.b1 - c.b0;
+  // ---- block descriptors
+  std::vector<BlockDesc> descs;
+  descs.reserve(nb_all);
+  uint32_t uoff = HEADROOM;
+  for (uint32_t b = c.b0; b < c.b1; b++) {
+    const BgzfBlock& B = f->blocks[b];
+    if (B.isize) { BlockDesc d; d.cdata_off = (uint32_t)(B.coff - c.c0) + B.cdata_off; d.cdata_len = B.csize - B.cdata_off - 8; d.isize = B.isize; d.crc = B.crc; d.uoff = uoff; descs.push_back(d); }
+    uoff += B.isize;
+  }
+  const uint32_t data_hi = uoff, seg0 = HEADROOM;
+  const uint32_t nb = (uint32_t)descs.size();
+  int rc;
+  if ((rc = s->d_infl.ensure((size_t)HEADROOM + c.ubytes + INFL_PAD))) return rc;
+  if ((rc = s->d_blk[slot].ensure(sizeof(BlockDesc) * std::max<uint32_t>(nb, 1)))) return rc;
+  if ((rc = s->d_status.ensure(4 * std::max<uint32_t>(nb, 1)))) return rc;
+  if ((rc = s->d_flags.ensure(256))) return rc;
+  if ((rc = s->d_carry.ensure(HEADROOM))) return rc;
+  const uint32_t seg_bytes = f->seg_bytes;
+  const uint32_t n_seg = std::max<uint32_t>(1, (uint32_t)((c.ubytes + seg_bytes - 1) / seg_bytes));
+  // seg arrays: start, exit, count, base (u32 each) + tail (u8)
+  if ((rc = s->d_seg.ensure((size_t)n_seg * 17 + 64))) return rc;
+  uint32_t* d_seg_start = s->d_seg.as<uint32_t>();
+  uint32_t* d_seg_exit = d_seg_start + n_seg;
+  uint32_t* d_seg_count = d_seg_exit + n_seg;
+  uint32_t* d_seg_base = d_seg_count + n_seg;
+  uint8_t* d_seg_tail = reinterpret_cast<uint8_t*>(d_seg_base + n_seg);
+  uint32_t* d_flags = s->d_flags.as<uint32_t>();   // [0..7] boundary flags, [8] inflate ticket, [9] inflate err, [10..11] decode err
+
+  cudaStream_t cs = s->s_compute;
+  const uint8_t* d_comp;
+  if (s->device_resident) d_comp = s->d_comp_all + (c.c0 - s->comp_all_c0);
+  else { d_comp = s->d_comp[slot].as<uint8_t>(); CU_TRY(cudaStreamWaitEvent(cs, s->ev_h2d[slot], 0)); }
+  CU_TRY(cudaMemcpyAsync(s->d_blk[slot].p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, cs));   // pageable source: staged synchronously by the driver
+  CU_TRY(cudaMemsetAsync(d_flags, 0, 64, cs));
+  uint32_t init2 = 0xffffffffu;
+  CU_TRY(cudaMemcpyAsync(d_flags + 2, &init2, 4, cudaMemcpyHostToDevice, cs));
+  CU_TRY(cudaEventRecord(s->ev_t[0], cs));
+  uint8_t* U = s->d_infl.as<uint8_t>();
+  if (nb) {
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * 6);
+    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, f->skip_crc ? 0 : 1);
+    s->st.kernel_launches++;
+  }
+  CU_TRY(cudaEventRecord(s->ev_t[1], cs));
+  // ---- carry-in
+  const uint32_t carry = s->carry_len;
+  if (carry) CU_TRY(cudaMemcpyAsync(U + HEADROOM - carry, s->d_carry.p, carry, cudaMemcpyDeviceToDevice, cs));
+  // ---- boundaries
+  BoundaryParams BP;
+  BP.U = U; BP.data_lo = HEADROOM - carry; BP.data_hi = data_hi; BP.seg0 = seg0; BP.seg_bytes = seg_bytes; BP.n_seg = n_seg;
+  BP.n_ref = (int32_t)f->ref_names.size(); BP.ref_len = s->d_refs.as<int32_t>(); BP.max_block_size = MAX_BLOCK_SIZE;
+  if (carry) BP.first_start = HEADROOM - carry;
+  else if (s->need_spec) BP.first_start = SEG_NONE;                 // shard without a known start: speculate
+  else if (!first_of_range) BP.first_start = HEADROOM;
+  else BP.first_start = HEADROOM + (uint32_t)(range.first_uoff - c.u0);
+  // ownership bound inside this chunk
+  uint64_t own = data_hi;
+  if (c.extension) own = seg0;
+  if (range.stop_uoff != ~0ull && range.stop_uoff < c.u0 + c.ubytes) own = std::min<uint64_t>(own, range.stop_uoff >= c.u0 ? HEADROOM + (range.stop_uoff - c.u0) : seg0);
+  BP.own_hi = (uint32_t)own;
+  WalkOut W{d_seg_start, d_seg_exit, d_seg_count, d_seg_tail, d_flags};
+  seg_candidates_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, cs>>>(BP, d_seg_start, (f->debug_flags & 1) ? 1 : 0);
+  seg_walk_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
+  seg_check_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
+  seg_repair_kernel<<<1, 1, 0, cs>>>(BP, W);
+  seg_scan_kernel<<<1, 1024, 0, cs>>>(d_seg_count, d_seg_start, d_seg_exit, d_seg_tail, d_seg_base, n_seg, d_flags);
+  s->st.kernel_launches += 5;
+  CU_TRY(cudaMemcpyAsync(s->h_flags, d_flags, 64, cudaMemcpyDeviceToHost, cs));
+  CU_TRY(cudaEventRecord(s->ev_flags, cs));
+  CU_TRY(cudaEventSynchronize(s->ev_flags));
+  CU_TRY(cudaGetLastError());
+  // ---- host: decisions
+  const uint32_t* hf = s->h_flags;
+  if (hf[9]) {
+    uint32_t bi = (hf[9] & 0x7fffffffu) >> 4, code = hf[9] & 15u;
+    static const char* names[] = {"ok", "reserved block type", "stored block LEN/NLEN", "Huffman table", "invalid literal/length code", "invalid distance", "output overrun", "ISIZE mismatch", "CRC32 mismatch", "input overrun"};
+    set_error("BAM read error: BGZF member %u (file offset %llu): inflate failed: %s", c.b0 + bi, (unsigned long long)0, code < 10 ? names[code] : "?");
+    return BAMSCAN_ERR_CRC;
+  }
+  if (hf[1]) { set_error("BAM read error: invalid record block_size at inflated offset %llu", (unsigned long long)(c.u0 + ((hf[1] & ~1u) - HEADROOM))); return BAMSCAN_ERR_FORMAT; }
+  s->st.boundary_repairs += hf[4];
+  const uint32_t n_rec = hf[3];
+  if (n_rec > 0 || hf[2] != 0xffffffffu) s->need_spec = false;
+  uint32_t tail_off = hf[2] == 0xffffffffu ? data_hi : hf[2];
+  if (tail_off > data_hi) tail_off = data_hi;
+  *owned_done = tail_off >= BP.own_hi;
+  *new_carry = *owned_done ? 0 : data_hi - tail_off;
+  if (*new_carry > HEADROOM) { set_error("BAM record larger than %u bytes is not supported", HEADROOM); return BAMSCAN_ERR_UNSUPPORTED; }
+  if (*new_carry) CU_TRY(cudaMemcpyAsync(s->d_carry.p, U + tail_off, *new_carry, cudaMemcpyDeviceToDevice, cs));
+  s->st.chunks++; s->st.blocks += nb; s->st.inflated_bytes += c.ubytes; s->st.compressed_bytes += c.c1 - c.c0;
+  CU_TRY(cudaEventRecord(s->ev_t[2], cs));
+  if (n_rec == 0) { CU_TRY(cudaEventRecord(s->ev_t[3], cs)); goto timing; }
+  {
+    // ---- record offsets
+    if ((rc = s->d_recoff.ensure(4ull * (n_rec + 1)))) return rc;
+    uint32_t* d_recoff = s->d_recoff.as<uint32_t>();
+    seg_emit_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, d_seg_start, d_seg_count, d_seg_base, d_recoff, n_rec, tail_off);
+    s->st.kernel_launches++;
+    const uint32_t n = n_rec;
+    // ---- arena region A
+    const size_t n_dec = s->dec_cols.size();
+    std::vector<ColLayout> cols(n_dec);
+    ArenaBuilder AB;
+    const size_t bm_bytes = 4ull * ((n + 31) / 32), off_bytes = 4ull * (n + 1), val_bytes = 4ull * n;
+    size_t err_off = AB.take(64);
+    std::vector<size_t> src_off(n_dec, 0);
+    size_t scratch = 0;
+    for (size_t i = 0; i < n_dec; i++) {
+      ColLayout& L = cols[i]; L.schema_idx = s->dec_cols[i]; L.kind = f->fields[L.schema_idx].kind;
+      const int c_id = L.schema_idx;
+      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+      L.has_validity = c_id >= 12 || c_id == 1 || c_id == 2 || c_id == 3 || c_id == 7 || c_id == 8;
+      if (L.has_validity) L.validity_off = AB.take(bm_bytes);
+      if (is_var) L.offsets_off = AB.take(off_bytes); else L.values_off = AB.take(val_bytes);
+      if (c_id >= 12 && is_var) { src_off[i] = scratch; scratch += align_up(val_bytes, 256); }
+    }
+    const size_t regionA = AB.pos;
+    if ((rc = s->d_scratch.ensure(scratch + 256))) return rc;
+    // a first arena sizing guess; grown after totals are known
+    DeviceBuf& arena = s->d_arena[s->arena_flip];
+    if (arena.cap < regionA) { if ((rc = arena.ensure(regionA + (size_t)c.ubytes * 2))) return rc; }
+    uint8_t* A = arena.as<uint8_t>();
+    DecodeParams DP;
+    memset(&DP, 0, sizeof DP);
+    DP.U = U; DP.rec_off = d_recoff; DP.n = n; DP.zero_based = f->zero_based; DP.binary_cigar = f->binary_cigar;
+    DP.n_ref = (int32_t)f->ref_names.size();
+    size_t n_ref = f->ref_names.size();
+    DP.ref_name_off = reinterpret_cast<const uint32_t*>(s->d_refs.as<uint8_t>() + align_up(4 * n_ref + 4, 16));
+    DP.ref_names = s->d_refs.as<uint8_t>() + align_up(4 * n_ref + 4, 16) + align_up(4 * (n_ref + 1), 16);
+    DP.err = reinterpret_cast<uint32_t*>(A + err_off);
+    ScanCols SC; memset(&SC, 0, sizeof SC); SC.n = n + 1;
+    std::vector<size_t> scan_owner;   // dec col index per scan column
+    int n_tags = 0;
+    std::vector<int> tag_slot(n_dec, -1);
+    for (size_t i = 0; i < n_dec; i++) {
+      ColLayout& L = cols[i];
+      uint32_t* v = L.has_validity ? reinterpret_cast<uint32_t*>(A + L.validity_off) : nullptr;
+      int32_t* offs = reinterpret_cast<int32_t*>(A + L.offsets_off);
+      uint32_t* vals = reinterpret_cast<uint32_t*>(A + L.values_off);
+      switch (L.schema_idx) {
+        case 0: DP.l_name = offs; break;
+        case 1: DP.l_chrom = offs; DP.v_chrom = v; break;
+        case 2: DP.start = vals; DP.v_start = v; break;
+        case 3: DP.end = vals; DP.v_end = v; break;
+        case 4: DP.flags = vals; break;
+        case 5: DP.l_cigar = offs; break;
+        case 6: DP.mapq = vals; break;
+        case 7: DP.l_mchrom = offs; DP.v_mchrom = v; break;
+        case 8: DP.mate_start = vals; DP.v_mstart = v; break;
+        case 9: DP.l_seq = offs; break;
+        case 10: DP.l_qual = offs; break;
+        case 11: DP.tlen = reinterpret_cast<int32_t*>(vals); break;
+        default: {
+          TagPlan& T = DP.tags[n_tags];
+          const std::string& tg = f->fields[L.schema_idx].name;
+          T.tag = tg.size() == 2 ? (uint16_t)((uint8_t)tg[0] | ((uint16_t)(uint8_t)tg[1] << 8)) : 0xffffu;   // names that are not 2 bytes never match (sam_tag_io.rs:58-68)
+          T.kind = L.kind; T.valid = v;
+          bool is_var = L.kind == HK_Utf8 || L.kind >= HK_ListInt8;
+          if (is_var) { T.lens = offs; T.src = reinterpret_cast<uint32_t*>(s->d_scratch.as<uint8_t>() + src_off[i]); }
+          else T.values = vals;
+          tag_slot[i] = n_tags++;
+        }
+      }
+      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+      if (is_var) { SC.col[SC.n_cols++] = offs; scan_owner.push_back(i); }
+    }
+    DP.n_tags = n_tags;
+    CU_TRY(cudaMemsetAsync(A + err_off, 0, 64, cs));
+    decode_fixed_kernel<<<(n + 255) / 256, 256, 0, cs>>>(DP);
+    s->st.kernel_launches++;
+    uint64_t* h_totals = reinterpret_cast<uint64_t*>(s->h_flags + 16);
+    if (SC.n_cols) {
+      uint32_t n_tiles = (SC.n + SCAN_TILE - 1) / SCAN_TILE;
+      if ((rc = s->d_tiles.ensure(8ull * n_tiles * SC.n_cols))) return rc;
+      if ((rc = s->d_totals.ensure(8ull * MAX_SCAN_COLS))) return rc;
+      multi_scan_reduce_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
+      multi_scan_tiles_kernel<<<SC.n_cols, 1024, 0, cs>>>(s->d_tiles.as<uint64_t>(), n_tiles, s->d_totals.as<uint64_t>());
+      multi_scan_apply_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
+      s->st.kernel_launches += 3;
+      CU_TRY(cudaMemcpyAsync(h_totals, s->d_totals.p, 8ull * SC.n_cols, cudaMemcpyDeviceToHost, cs));
+      CU_TRY(cudaEventRecord(s->ev_flags, cs));
+      CU_TRY(cudaEventSynchronize(s->ev_flags));
+      CU_TRY(cudaGetLastError());
+      // ---- arena region B
+      for (int k = 0; k < SC.n_cols; k++) {
+        ColLayout& L = cols[scan_owner[k]];
+        uint64_t tot = h_totals[k];
+        if (tot > 0x7fffffffull) { set_error("column '%s' exceeds 2^31-1 bytes in one batch; lower chunk_inflated_bytes", f->fields[L.schema_idx].name.c_str()); return BAMSCAN_ERR_UNSUPPORTED; }
+        uint64_t bytes = tot;
+        if (L.kind >= HK_ListInt8) { L.child_len = tot; bytes = tot * ((L.kind == HK_ListInt8 || L.kind == HK_ListUInt8) ? 1 : (L.kind == HK_ListInt16 || L.kind == HK_ListUInt16) ? 2 : 4); }
+        L.data_bytes = bytes;
+        L.data_off = AB.take((size_t)bytes + 16);
+      }
+      if (AB.pos > arena.cap) {
+        // grow, preserving region A
+        DeviceBuf bigger;
+        if ((rc = bigger.ensure(AB.pos))) return rc;
+        CU_TRY(cudaMemcpyAsync(bigger.p, arena.p, regionA, cudaMemcpyDeviceToDevice, cs));
+        CU_TRY(cudaStreamSynchronize(cs));
+        // rebase pointers
+        ptrdiff_t delta = (uint8_t*)bigger.p - A;
+        auto rb = [&](auto*& p) { if (p) p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<uint8_t*>(p) + delta); };
+        rb(DP.start); rb(DP.end); rb(DP.flags); rb(DP.mapq); rb(DP.mate_start); rb(DP.tlen);
+        rb(DP.v_chrom); rb(DP.v_start); rb(DP.v_end); rb(DP.v_mchrom); rb(DP.v_mstart);
+        rb(DP.l_name); rb(DP.l_chrom); rb(DP.l_cigar); rb(DP.l_mchrom); rb(DP.l_seq); rb(DP.l_qual); rb(DP.err);
+        for (int t = 0; t < n_tags; t++) { rb(DP.tags[t].valid); rb(DP.tags[t].values); rb(DP.tags[t].lens); }
+        arena.release(); arena = bigger; bigger.p = nullptr; bigger.cap = 0;
+        A = arena.as<uint8_t>();
+      }
+      for (size_t i = 0; i < n_dec; i++) {
+        ColLayout& L = cols[i];
+        bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+        if (!is_var) continue;
+        uint8_t* d = A + L.data_off;
+        switch (L.schema_idx) {
+          case 0: DP.d_name = d; break; case 1: DP.d_chrom = d; break; case 5: DP.d_cigar = d; break; case 7: DP.d_mchrom = d; break;
+          case 9: DP.d_seq = d; break; case 10: DP.d_qual = d; break;
+          default: DP.tags[tag_slot[i]].data = d;
+        }
+      }
+      decode_var_kernel<<<(n + VAR_WARPS - 1) / VAR_WARPS, VAR_WARPS * 32, 0, cs>>>(DP);
+      s->st.kernel_launches++;
+    }
+    CU_TRY(cudaEventRecord(s->ev_t[3], cs));
+    const size_t arena_bytes = AB.pos;
+    s->st.rows += n; s->st.batches++;
+    for (auto& L : cols) {
+      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+      s->st.arrow_bytes += (L.has_validity ? (n + 7) / 8 : 0) + (is_var ? off_bytes + L.data_bytes : val_bytes);
+    }
+    if (s->device_resident) {
+      // keep everything in HBM: only the decode error word travels
+      CU_TRY(cudaMemcpyAsync(s->h_flags + 64, A + err_off, 8, cudaMemcpyDeviceToHost, cs));
+      CU_TRY(cudaStreamSynchronize(cs));
+      if (s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
+    } else {
+      CU_TRY(cudaEventRecord(s->ev_compute, cs));
+      PendingBatch& P = s->pending;
+      P.owner = new BatchOwner();
+      P.owner->arena = arena_acquire(arena_bytes);
+      if (!P.owner->arena.p) { delete P.owner; P.owner = nullptr; return BAMSCAN_ERR_CUDA; }
+      P.owner->refs = 1;
+      P.cols = cols; P.rows = n; P.arena_bytes = arena_bytes; P.err_off = err_off; P.valid = true;
+      if (!P.done) CU_TRY(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+      CU_TRY(cudaStreamWaitEvent(s->s_d2h, s->ev_compute, 0));
+      CU_TRY(cudaMemcpyAsync(P.owner->arena.p, A, arena_bytes, cudaMemcpyDeviceToHost, s->s_d2h));
+      CU_TRY(cudaEventRecord(P.done, s->s_d2h));
+      s->st.d2h_bytes += arena_bytes;
+      s->arena_flip ^= 1;
+      // the next chunk must not overwrite this arena before the copy has read it: arenas are double buffered and the
+      // batch before this one has already been waited for (see bamscan_next)
+      *produced = true;
+    }
+  }
+timing:
+  CU_TRY(cudaEventRecord(s->ev_t[4], cs));
+  CU_TRY(cudaEventSynchronize(s->ev_t[4]));
+  {
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, s->ev_t[0], s->ev_t[1]);
+    cudaEventElapsedTime(&b, s->ev_t[1], s->ev_t[2]);
+    cudaEventElapsedTime(&d, s->ev_t[2], s->ev_t[3]);
+    s->st.ms_inflate += a; s->st.ms_boundary += b; s->st.ms_decode += d;
+  }
+  return BAMSCAN_OK;
+}
+
+// Advances the partition by one chunk.  Returns 1 when a chunk ran (a batch may be pending), 0 when the partition is exhausted.
+static int advance(BamScanStream* s, bool* produced) {
+  *produced = false;
+  BamFile* f = s->f;
+  for (;;) {
+    if (s->finished) return 0;
+    if (!s->range_open) {
+      if (s->range_idx >= s->part->ranges.size()) { s->finished = true; return 0; }
+      const ScanRange& r = s->part->ranges[s->range_idx];
+      s->chunks.clear(); s->chunk_idx = 0; s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = !r.exact_start;
+      plan_chunks(*f, r.block_begin, r.block_end, false, &s->chunks);
+      s->range_open = true;
+      if (s->chunks.empty()) { s->range_open = false; s->range_idx++; continue; }
+    }
+    const ScanRange& r = s->part->ranges[s->range_idx];
+    if (s->chunk_idx >= s->chunks.size()) {
+      // owned blocks exhausted: an incomplete tail record continues into the following blocks
+      uint32_t last = s->chunks.back().b1;
+      if (s->carry_len == 0 || last >= f->blocks.size()) {
+        if (s->carry_len) {
+          bool only_empty = true;
+          (void)only_empty;
+          set_error("BAM read error: unexpected EOF inside a record (%u trailing bytes)", s->carry_len);
+          return BAMSCAN_ERR_FORMAT;
+        }
+        s->range_open = false; s->range_idx++;
+        continue;
+      }
+      uint32_t e = std::min<uint32_t>((uint32_t)f->blocks.size(), last + s->ext_blocks);
+      s->ext_blocks = std::min<uint32_t>(s->ext_blocks * 2, 4096);
+      plan_chunks(*f, last, e, true, &s->chunks);
+      s->have_h2d_ahead = false;
+    }
+    const size_t k = s->chunk_idx;
+    const int slot = (int)(k & 1);
+    int rc;
+    if (!s->have_h2d_ahead) { if ((rc = issue_h2d(s, s->chunks[k], slot))) return rc; }
+    s->have_h2d_ahead = false;
+    if (k + 1 < s->chunks.size()) { if ((rc = issue_h2d(s, s->chunks[k + 1], slot ^ 1))) return rc; s->have_h2d_ahead = true; }
+    uint32_t new_carry = 0; bool owned_done = false;
+    rc = run_chunk(s, s->chunks[k], r, slot, k == 0, produced, &new_carry, &owned_done);
+    if (rc) return rc;
+    s->carry_len = new_carry;
+    s->chunk_idx++;
+    if (owned_done && s->chunks[k].extension) { s->carry_len = 0; s->range_open = false; s->range_idx++; }   // the tail record is complete
+    return 1;
+  }
+}
+
+// ---- Arrow export ---------------------------------------------------------------------------
+struct NodePriv { BatchOwner* owner; std::vector<const void*> buffers; std::vector<ArrowArray> child_storage; std::vector<ArrowArray*> child_ptrs; };
+
+static void release_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  NodePriv* p = static_cast<NodePriv*>(a->private_data);
+  for (int64_t i = 0; i < a->n_children; i++) if (a->children[i] && a->children[i]->release) a->children[i]->release(a->children[i]);
+  owner_unref(p->owner);
+  delete p;
+  a->release = nullptr;
+}
+
+static NodePriv* new_node(ArrowArray* a, BatchOwner* owner, int64_t length, int64_t null_count, int64_t offset, size_t n_buffers, size_t n_children) {
+  NodePriv* p = new NodePriv();
+  p->owner = owner; owner->refs.fetch_add(1);
+  p->buffers.assign(n_buffers, nullptr);
+  p->child_storage.resize(n_children); p->child_ptrs.resize(n_children);
+  for (size_t i = 0; i < n_children; i++) { memset(&p->child_storage[i], 0, sizeof(ArrowArray)); p->child_ptrs[i] = &p->child_storage[i]; }
+  a->length = length; a->null_count = null_count; a->offset = offset;
+  a->n_buffers = (int64_t)n_buffers; a->n_children = (int64_t)n_children;
+  a->buffers = p->buffers.data(); a->children = n_children ? p->child_ptrs.data() : nullptr;
+  a->dictionary = nullptr; a->release = release_array; a->private_data = p;
+  return p;
+}
+
+static int64_t count_nulls(const uint8_t* bm, uint64_t row0, uint64_t n) {
+  int64_t set = 0;
+  for (uint64_t i = row0; i < row0 + n;) {
+    if ((i & 63) == 0 && i + 64 <= row0 + n) { uint64_t w; memcpy(&w, bm + i / 8, 8); set += __builtin_popcountll(w); i += 64; }
+    else { set += (bm[i >> 3] >> (i & 7)) & 1; i++; }
+  }
+  return (int64_t)n - set;
+}
+
+static void export_batch(const BamScanStream* s, const ReadyBatch& rb, ArrowArray* out) {
+  const uint8_t* H = rb.owner->arena.p;
+  const size_t n_out = s->out_to_dec.size();
+  new_node(out, rb.owner, (int64_t)rb.nrows, 0, 0, 1, n_out);
+  for (size_t i = 0; i < n_out; i++) {
+    const ColLayout& L = rb.cols[s->out_to_dec[i]];
+    ArrowArray* ch = out->children[i];
+    const bool is_list = L.kind >= HK_ListInt8, is_var = L.kind == HK_Utf8 || L.kind == HK_Binary;
+    int64_t nulls = L.has_validity ? count_nulls(H + L.validity_off, rb.row0, rb.nrows) : 0;
+    const void* validity = (L.has_validity && nulls) ? H + L.validity_off : nullptr;
+    if (is_list) {
+      NodePriv* p = new_node(ch, rb.owner, (int64_t)rb.nrows, nulls, (int64_t)rb.row0, 2, 1);
+      p->buffers[0] = validity; p->buffers[1] = H + L.offsets_off;
+      NodePriv* cp = new_node(ch->children[0], rb.owner, (int64_t)L.child_len, 0, 0, 2, 0);
+      cp->buffers[0] = nullptr; cp->buffers[1] = H + L.data_off;
+    } else if (is_var) {
+      NodePriv* p = new_node(ch, rb.owner, (int64_t)rb.nrows, nulls, (int64_t)rb.row0, 3, 0);
+      p->buffers[0] = validity; p->buffers[1] = H + L.offsets_off; p->buffers[2] = H + L.data_off;
+    } else {
+      NodePriv* p = new_node(ch, rb.owner, (int64_t)rb.nrows, nulls, (int64_t)rb.row0, 2, 0);
+      p->buffers[0] = validity; p->buffers[1] = H + L.values_off;
+    }
+  }
+}
+
+static int decode_error_to_rc(uint32_t code, uint32_t row) {
+  switch (code) {
+    case DEC_ERR_FIELDS: set_error("BAM read error: record %u: fields exceed block_size", row); return BAMSCAN_ERR_FORMAT;
+    case DEC_ERR_REF: set_error("BAM read error: record %u: reference sequence id out of range", row); return BAMSCAN_ERR_FORMAT;
+    case DEC_ERR_CIGAR_OP: set_error("BAM read error: record %u: invalid CIGAR op", row); return BAMSCAN_ERR_FORMAT;
+    case DEC_ERR_TAG_RANGE: set_error("tag value in record %u does not fit the column type", row); return BAMSCAN_ERR_SCHEMA;
+    case DEC_ERR_TAG_TYPE: set_error("tag value type mismatch in record %u", row); return BAMSCAN_ERR_SCHEMA;
+    case DEC_ERR_UNSUPPORTED_F2S: set_error("record %u: float tag into a Utf8 column is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
+    case DEC_ERR_QUAL: set_error("record %u: quality score >= 95 (multi-byte char) is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
+    case DEC_ERR_NAME: set_error("record %u: non-ASCII read name is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
+  }
+  set_error("decode error %u at record %u", code, row);
+  return BAMSCAN_ERR_FORMAT;
+}
+
+// waits for the pending batch's D2H and queues it (sliced to batch_rows) for hand-out
+static int finalize_pending(BamScanStream* s) {
+  PendingBatch& P = s->pending;
+  if (!P.valid) return BAMSCAN_OK;
+  CU_TRY(cudaEventSynchronize(P.done));
+  P.valid = false;
+  const uint32_t* err = reinterpret_cast<const uint32_t*>(P.owner->arena.p + P.err_off);
+  if (err[0]) { int rc = decode_error_to_rc(err[0], err[1]); owner_unref(P.owner); P.owner = nullptr; return rc; }
+  s->ready.clear(); s->ready_pos = 0;
+  uint64_t step = s->f->batch_rows > 0 ? (uint64_t)s->f->batch_rows : P.rows;
+  for (uint64_t r0 = 0; r0 < P.rows; r0 += step) {
+    ReadyBatch rb{P.owner, P.cols, P.rows, r0, std::min<uint64_t>(step, P.rows - r0)};
+    P.owner->refs.fetch_add(1);
+    s->ready.push_back(std::move(rb));
+  }
+  owner_unref(P.owner);   // the pending's own reference
+  P.owner = nullptr;
+  return BAMSCAN_OK;
+}
+
+}  // namespace bamscan
+
+// =============================================================================================
+extern "C" {
+
+const char* bamscan_last_error(void) { return last_error_cstr(); }
+const char* bamscan_version(void) { return "bamscan-b200 0.1 (sm_100a)"; }
+
+int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out) {
+  if (!path || !out) { set_error("bamscan_open: null argument"); return BAMSCAN_ERR_INVALID; }
+  BamScanOptions opt;
+  memset(&opt, 0, sizeof opt);
+  opt.coordinate_system_zero_based = 1; opt.infer_tag_types = 1; opt.infer_tag_sample_size = 100;
+  if (options) memcpy(&opt, options, std::min<size_t>(sizeof opt, options->struct_size ? options->struct_size : sizeof opt));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available: libbamscan has no CPU path"); return BAMSCAN_ERR_CUDA; }
+  if (opt.device_id < 0 || opt.device_id >= ndev) { set_error("device_id %d out of range (%d devices)", opt.device_id, ndev); return BAMSCAN_ERR_INVALID; }
+  if (cudaSetDevice(opt.device_id) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", opt.device_id); return BAMSCAN_ERR_CUDA; }
+  std::unique_ptr<BamScanHandle> h(new BamScanHandle());
+  BamFile& f = h->file;
+  f.path = path; f.device = opt.device_id;
+  f.zero_based = opt.coordinate_system_zero_based != 0; f.binary_cigar = opt.binary_cigar != 0;
+  f.has_tag_fields = opt.has_tag_fields != 0;
+  for (int i = 0; i < opt.n_tag_fields && opt.tag_fields; i++) f.tag_fields.push_back(opt.tag_fields[i]);
+  f.batch_rows = opt.batch_rows;
+  if (opt.chunk_inflated_bytes) f.chunk_bytes = std::min<uint64_t>(opt.chunk_inflated_bytes, 768ull << 20);
+  if (opt.segment_bytes) f.seg_bytes = std::max<uint32_t>(256, opt.segment_bytes);
+  f.skip_crc = opt.skip_crc != 0; f.debug_flags = opt.debug_flags;
+  int rc = load_file(&f);
+  if (rc == BAMSCAN_ERR_IO || rc == BAMSCAN_ERR_CUDA) { if (f.data) pinned_free(f.data); return rc; }
+  // a file whose header cannot be read still yields a provider with empty metadata (table_provider.rs:423-426);
+  // scans on it fail later
+  if ((rc = build_schema(&f, &opt))) { if (f.data) pinned_free(f.data); return rc; }
+  if (index_path_or_null) f.index_path = index_path_or_null; else f.index_path = discover_index(f.path);
+  if (!f.index_path.empty()) {
+    f.bai.reset(new BaiIndex());
+    if (load_bai(f.index_path, f.bai.get()) != BAMSCAN_OK) { f.bai.reset(); if (index_path_or_null) { pinned_free(f.data); return BAMSCAN_ERR_IO; } f.index_path.clear(); }
+  }
+  *out = h.release();
+  return BAMSCAN_OK;
+}
+
+void bamscan_close(BamScanHandle* h) {
+  if (!h) return;
+  if (h->file.data) { cudaSetDevice(h->file.device); pinned_free(h->file.data); }
+  delete h;
+}
+
+int bamscan_schema(BamScanHandle* h, struct ArrowSchema* out) {
+  if (!h || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  return export_schema(h->file.fields, h->file.schema_metadata, out);
+}
+
+int bamscan_classify_filters(BamScanHandle* h, const BamScanFilter* filters, int32_t n_filters, uint8_t* out_pushdown) {
+  if (!h || (n_filters && (!filters || !out_pushdown))) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  return classify_filters(h->file, filters, n_filters, out_pushdown);
+}
+
+int bamscan_plan(BamScanHandle* h, const int32_t* projection, int32_t n_projection, const BamScanFilter* filters, int32_t n_filters,
+                 int64_t limit_or_neg, int32_t target_partitions, int32_t partition_mode, BamScanPlan** out) {
+  (void)limit_or_neg;   // stored and never used by the reference either (physical_exec.rs:38,44)
+  if (!h || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  Plan* p = nullptr;
+  int rc = make_plan(&h->file, projection, n_projection, filters, n_filters, target_partitions, partition_mode, &p);
+  if (rc) return rc;
+  BamScanPlan* bp = new BamScanPlan();
+  bp->plan = p; bp->handle = h;
+  *out = bp;
+  return BAMSCAN_OK;
+}
+
+int32_t bamscan_plan_num_partitions(const BamScanPlan* plan) { return plan && !plan->plan->empty_exec ? (int32_t)plan->plan->partitions.size() : 0; }
+
+int bamscan_plan_schema(const BamScanPlan* plan, struct ArrowSchema* out) {
+  if (!plan || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  return export_schema(plan->plan->out_fields, plan->plan->file->schema_metadata, out);
+}
+
+void bamscan_plan_free(BamScanPlan* plan) { if (plan) { delete plan->plan; delete plan; } }
+
+static int make_stream(BamScanPlan* plan, int32_t partition, bool device_resident, BamScanStream** out) {
+  if (!plan || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  if (partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) { set_error("partition %d out of range", partition); return BAMSCAN_ERR_INVALID; }
+  BamScanStream* s = new BamScanStream();
+  s->plan = plan->plan; s->f = plan->plan->file; s->part = &plan->plan->partitions[partition];
+  s->device_resident = device_resident;
+  int rc = stream_init(s);
+  if (rc) { stream_destroy(s); return rc; }
+  *out = s;
+  return BAMSCAN_OK;
+}
+
+int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out) { return make_stream(plan, partition, false, out); }
+
+int bamscan_next(BamScanStream* s, struct ArrowArray* out) {
+  if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  if (s->error) { set_error("stream is in an error state"); return s->error; }
+  if (cudaSetDevice(s->f->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return BAMSCAN_ERR_CUDA; }
+  for (;;) {
+    if (s->ready_pos < s->ready.size()) {
+      export_batch(s, s->ready[s->ready_pos], out);
+      owner_unref(s->ready[s->ready_pos].owner);   // the queue's reference; the exported nodes hold their own
+      s->ready_pos++;
+      return 1;
+    }
+    if (!s->finished) {
+      // the batch produced by the previous chunk has had its D2H overlapped with nothing yet: keep it pending while
+      // the next chunk is launched, then hand it out
+      PendingBatch prev = s->pending;
+      s->pending = PendingBatch();
+      bool produced = false;
+      int rc = advance(s, &produced);
+      if (rc < 0) { s->error = rc; if (prev.valid) { cudaEventSynchronize(prev.done); owner_unref(prev.owner); cudaEventDestroy(prev.done); } return rc; }
+      PendingBatch fresh = s->pending;
+      s->pending = prev;
+      if (prev.valid) {
+        rc = finalize_pending(s);
+        if (prev.done) cudaEventDestroy(prev.done);
+        s->pending = PendingBatch();
+        if (rc) { s->error = rc; if (fresh.valid) { cudaEventSynchronize(fresh.done); owner_unref(fresh.owner); cudaEventDestroy(fresh.done); } return rc; }
+      }
+      s->pending = fresh;
+      continue;
+    }
+    if (s->pending.valid) {
+      cudaEvent_t ev = s->pending.done;
+      int rc = finalize_pending(s);
+      if (ev) cudaEventDestroy(ev);
+      s->pending = PendingBatch();
+      if (rc) { s->error = rc; return rc; }
+      continue;
+    }
+    return 0;
+  }
+}
+
+void bamscan_stream_free(BamScanStream* s) { stream_destroy(s); }
+
+int bamscan_stream_stats(const BamScanStream* s, BamScanStats* out) {
+  if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  *out = s->st;
+  return BAMSCAN_OK;
+}
+
+int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t repeats, BamScanStats* stats) {
+  if (!stats) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  BamScanStream* s = nullptr;
+  int rc = make_stream(plan, partition, true, &s);
+  if (rc) return rc;
+  BamFile* f = s->f;
+  // stage the partition's compressed bytes in HBM (untimed)
+  uint32_t bmin = 0xffffffffu, bmax = 0;
+  for (auto& r : s->part->ranges) { bmin = std::min(bmin, r.block_begin); bmax = std::max(bmax, r.block_end); }
+  if (bmin >= bmax) { memset(stats, 0, sizeof *stats); stream_destroy(s); return BAMSCAN_OK; }
+  uint32_t bext = std::min<uint32_t>((uint32_t)f->blocks.size(), bmax + 8192);   // room for tail-record extension chunks
+  uint64_t c0 = f->blocks[bmin].coff, c1 = f->blocks[bext - 1].coff + f->blocks[bext - 1].csize;
+  if ((rc = s->d_comp_all_buf.ensure((size_t)(c1 - c0) + 1024))) { stream_destroy(s); return rc; }
+  if (cudaMemcpy(s->d_comp_all_buf.p, f->data + c0, (size_t)(c1 - c0) + 512, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("staging copy failed"); stream_destroy(s); return BAMSCAN_ERR_CUDA; }
+  s->d_comp_all = s->d_comp_all_buf.as<uint8_t>(); s->comp_all_c0 = c0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best_total = 0;
+  BamScanStats acc{};
+  for (int rep = 0; rep < std::max(1, repeats); rep++) {
+    s->st = BamScanStats{}; s->range_idx = 0; s->range_open = false; s->finished = false; s->carry_len = 0;
+    cudaEventRecord(e0, s->s_compute);
+    bool produced;
+    while ((rc = advance(s, &produced)) == 1) {}
+    if (rc < 0) break;
+    cudaEventRecord(e1, s->s_compute);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    s->st.ms_total = ms;
+    best_total += ms;
+    acc = s->st;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc >= 0) { acc.ms_total = best_total / std::max(1, repeats); *stats = acc; rc = BAMSCAN_OK; }
+  stream_destroy(s);
+  return rc;
+}
+
+int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats, double* ms_per_launch, uint64_t* inflated_bytes, uint64_t* compressed_bytes) {
+  BamScanStream* s = nullptr;
+  int rc = make_stream(plan, partition, true, &s);
+  if (rc) return rc;
+  BamFile* f = s->f;
+  if (s->part->ranges.empty()) { stream_destroy(s); set_error("empty partition"); return BAMSCAN_ERR_INVALID; }
+  const ScanRange& r = s->part->ranges[0];
+  std::vector<ChunkPlan> chunks;
+  plan_chunks(*f, r.block_begin, r.block_end, false, &chunks);
+  const ChunkPlan& c = chunks[0];
+  std::vector<BlockDesc> descs;
+  uint32_t uoff = 0;
+  for (uint32_t b = c.b0; b < c.b1; b++) {
+    const BgzfBlock& B = f->blocks[b];
+    if (B.isize) { BlockDesc d; d.cdata_off = (uint32_t)(B.coff - c.c0) + B.cdata_off; d.cdata_len = B.csize - B.cdata_off - 8; d.isize = B.isize; d.crc = B.crc; d.uoff = uoff; descs.push_back(d); }
+    uoff += B.isize;
+  }
+  uint32_t nb = (uint32_t)descs.size();
+  DeviceBuf comp, blk, infl, status, flags;
+  auto fail = [&](int code) { comp.release(); blk.release(); infl.release(); status.release(); flags.release(); stream_destroy(s); return code; };
+  if (comp.ensure((size_t)(c.c1 - c.c0) + 1024) || blk.ensure(sizeof(BlockDesc) * nb) || infl.ensure((size_t)c.ubytes + INFL_PAD) || status.ensure(4ull * nb) || flags.ensure(256)) return fail(BAMSCAN_ERR_CUDA);
+  cudaMemcpy(comp.p, f->data + c.c0, (size_t)(c.c1 - c.c0) + 512, cudaMemcpyHostToDevice);
+  cudaMemcpy(blk.p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice);
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+  uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * 6);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float total = 0;
+  for (int rep = 0; rep < repeats + 1; rep++) {
+    cudaMemsetAsync(flags.p, 0, 64, s->s_compute);
+    cudaEventRecord(e0, s->s_compute);
+    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), s->s_compute>>>(comp.as<uint8_t>(), blk.as<BlockDesc>(), nb, infl.as<uint8_t>(), status.as<uint32_t>(), flags.as<uint32_t>() + 8, flags.as<uint32_t>() + 9, f->skip_crc ? 0 : 1);
+    cudaEventRecord(e1, s->s_compute);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) total += ms;   // first launch is warm-up
+  }
+  uint32_t hflags[16];
+  cudaMemcpy(hflags, flags.p, 64, cudaMemcpyDeviceToHost);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess || hflags[9]) { set_error("inflate benchmark failed (flag %u)", hflags[9]); return fail(BAMSCAN_ERR_CRC); }
+  *ms_per_launch = total / std::max(1, repeats); *inflated_bytes = c.ubytes; *compressed_bytes = c.c1 - c.c0;
+  return fail(BAMSCAN_OK);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+/*
+ * bamscan.h -- C ABI of the B200-native BAM table scan (libbamscan.so).
+ *
+ * This is the drop-in boundary for ONE path of biodatageeks/datafusion-bio-formats: the local-file
+ * `SELECT ... FROM bam` scan, `BamTableProvider::scan -> BamExec::execute`.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repository root).  Everything that
+ * crosses is POD or the Arrow C Data Interface (struct ArrowSchema / struct ArrowArray); there are no
+ * CUDA, torch or C++ types in any signature.  Batches come back in host memory, ready for
+ * `arrow::ffi::from_ffi` (Rust) / `pyarrow.RecordBatch._import_from_c` (Python).
+ *
+ * There is no CPU fallback inside the library: a call that needs the GPU fails with BAMSCAN_ERR_CUDA
+ * when no sm_100 device is present.
+ *
+ * Threading: handles are not thread-safe individually; distinct streams may be driven from distinct
+ * host threads (the reference's "one thread per partition", bio-format-core/src/sync_stream.rs:7-33).
+ */
+#ifndef BAMSCAN_H
+#define BAMSCAN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct ArrowSchema;
+struct ArrowArray;
+
+typedef struct BamScanHandle BamScanHandle;   /* an opened BAM  == BamTableProvider          */
+typedef struct BamScanPlan BamScanPlan;       /* a planned scan == Arc<dyn ExecutionPlan> (BamExec | EmptyExec) */
+typedef struct BamScanStream BamScanStream;   /* one partition  == SendableRecordBatchStream */
+
+/* return codes: 0 ok, negative error class; message via bamscan_last_error() */
+enum {
+  BAMSCAN_OK = 0,
+  BAMSCAN_ERR_IO = -1,           /* open/read failure                                   */
+  BAMSCAN_ERR_FORMAT = -2,       /* not BGZF/BAM, corrupt record chain, bad aux         */
+  BAMSCAN_ERR_CRC = -3,          /* BGZF CRC32 / ISIZE / DEFLATE stream error           */
+  BAMSCAN_ERR_CUDA = -4,         /* no device, allocation or launch failure             */
+  BAMSCAN_ERR_UNSUPPORTED = -5,  /* an unpinned edge this build refuses     */
+  BAMSCAN_ERR_INVALID = -6,      /* bad argument / configuration                        */
+  BAMSCAN_ERR_SCHEMA = -7        /* tag value does not fit the column type (ArrowError::SchemaError in the reference) */
+};
+
+/*
+ * Options == the constructor arguments of the reference provider
+ *   BamTableProvider::new(file_path, object_storage_options, coordinate_system_zero_based, tag_fields,
+ *                         binary_cigar, infer_tag_types, infer_tag_sample_size, tag_type_hints)
+ *   (datafusion/bio-format-bam/src/table_provider.rs:381-390)
+ * plus the DataFusion SessionConfig knobs the scan reads (batch_size: physical_exec.rs:129) and device
+ * placement.  Zero-initialise, set struct_size = sizeof(BamScanOptions).
+ */
+typedef struct BamScanOptions {
+  uint32_t struct_size;
+  int32_t coordinate_system_zero_based;   /* table_provider.rs:384 */
+  int32_t binary_cigar;                   /* table_provider.rs:386 */
+  int32_t has_tag_fields;                 /* 0 => tag_fields = None */
+  int32_t n_tag_fields;
+  const char* const* tag_fields;          /* table_provider.rs:385 */
+  int32_t infer_tag_types;                /* table_provider.rs:387 */
+  int32_t infer_tag_sample_size;          /* table_provider.rs:388 */
+  int32_t n_tag_type_hints;
+  const char* const* tag_type_hints;      /* "TAG:TYPE" | "TAG:B:SUBTYPE", tag_registry.rs:698-752 */
+  int32_t device_id;                      /* CUDA device ordinal for this handle */
+  int32_t batch_rows;                     /* rows per emitted batch; 0 = one batch per device chunk (reference default 8192) */
+  uint64_t chunk_inflated_bytes;          /* device chunk size (inflated bytes); 0 = default 512 MiB */
+  uint32_t segment_bytes;                 /* record-boundary segment size; 0 = default 16 KiB */
+  int32_t skip_crc;                       /* 0 (default): verify CRC32 of every BGZF member on the device; 1: skip */
+  int32_t debug_flags;                    /* bit0: poison boundary candidates (exercises the repair path in tests) */
+} BamScanOptions;
+
+/* ---- pushed-down predicates (reference: `filters: &[Expr]` of TableProvider::scan, restricted to the
+ * shapes the reference can push: genomic_filter.rs:151-329 and record_filter.rs:285-355) ---- */
+enum { BAMSCAN_COL_NAME = 0, BAMSCAN_COL_CHROM = 1, BAMSCAN_COL_START = 2, BAMSCAN_COL_END = 3, BAMSCAN_COL_FLAGS = 4,
+       BAMSCAN_COL_CIGAR = 5, BAMSCAN_COL_MAPQ = 6, BAMSCAN_COL_MATE_CHROM = 7, BAMSCAN_COL_MATE_START = 8,
+       BAMSCAN_COL_SEQUENCE = 9, BAMSCAN_COL_QUALITY = 10, BAMSCAN_COL_TLEN = 11 };
+enum { BAMSCAN_OP_EQ = 0, BAMSCAN_OP_NE = 1, BAMSCAN_OP_LT = 2, BAMSCAN_OP_LE = 3, BAMSCAN_OP_GT = 4, BAMSCAN_OP_GE = 5,
+       BAMSCAN_OP_BETWEEN = 6, BAMSCAN_OP_NOT_BETWEEN = 7, BAMSCAN_OP_IN = 8, BAMSCAN_OP_NOT_IN = 9,
+       BAMSCAN_OP_OTHER = 100 /* any expression shape the reference cannot push (OR, functions, ...) */ };
+typedef struct BamScanFilter {
+  int32_t column;                 /* schema index (BAMSCAN_COL_* or >= 12 for a tag column) */
+  int32_t op;
+  int32_t n_values;
+  const double* num_values;       /* numeric literals (EQ..GE: 1, BETWEEN: 2, IN: n) or NULL */
+  const char* const* str_values;  /* string literals for Utf8 columns or NULL */
+} BamScanFilter;
+enum { BAMSCAN_PUSHDOWN_UNSUPPORTED = 0, BAMSCAN_PUSHDOWN_INEXACT = 1 };
+
+/* ---- partitioning ---- */
+enum {
+  BAMSCAN_PARTITION_REFERENCE = 0,   /* the reference's rule: no index -> 1 partition; index -> <= target_partitions
+                                        balanced region partitions (table_provider.rs:1036-1114) */
+  BAMSCAN_PARTITION_BLOCK_RANGE = 1  /* target_partitions contiguous BGZF block ranges (multi-GPU full scans);
+                                        concatenated in partition order the rows equal the 1-partition scan */
+};
+
+typedef struct BamScanStats {
+  uint64_t rows, batches, chunks;
+  uint64_t compressed_bytes, inflated_bytes, arrow_bytes;   /* B_comp, B_inflated, B_arrow */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t blocks, kernel_launches, boundary_repairs;
+  double ms_total, ms_inflate, ms_boundary, ms_decode;      /* CUDA-event device times */
+} BamScanStats;
+
+/* == BamTableProvider::new (table_provider.rs:381-529): header read, tag-type inference, schema, index discovery.
+ * index_path_or_null: NULL => discover `<path>.bai`, `<stem>.bai`, `<path>.csi` (index_utils.rs:43-76). */
+int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
+void bamscan_close(BamScanHandle* h);
+
+/* == TableProvider::schema (table_provider.rs:933-935): the full, unprojected schema with all metadata. */
+int bamscan_schema(BamScanHandle* h, struct ArrowSchema* out);
+
+/* == TableProvider::supports_filters_pushdown (table_provider.rs:941-962). */
+int bamscan_classify_filters(BamScanHandle* h, const BamScanFilter* filters, int32_t n_filters, uint8_t* out_pushdown);
+
+/* == TableProvider::scan (table_provider.rs:964-1115).  n_projection < 0 => projection None (all columns);
+ * 0 => empty projection (row counts only).  `limit` is accepted and ignored like the reference (physical_exec.rs:44). */
+int bamscan_plan(BamScanHandle* h, const int32_t* projection, int32_t n_projection, const BamScanFilter* filters,
+                 int32_t n_filters, int64_t limit_or_neg, int32_t target_partitions, int32_t partition_mode, BamScanPlan** out);
+int32_t bamscan_plan_num_partitions(const BamScanPlan* plan);   /* == output_partitioning().partition_count(); 0 => EmptyExec */
+int bamscan_plan_schema(const BamScanPlan* plan, struct ArrowSchema* out);   /* == ExecutionPlan::schema (projected) */
+void bamscan_plan_free(BamScanPlan* plan);
+
+/* == ExecutionPlan::execute(partition, ctx) (physical_exec.rs:108-172). */
+int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out);
+/* == Stream::poll_next: 1 = a batch was written to *out (struct array, children in projection order),
+ * 0 = end of stream, < 0 = error (DataFusionError::Execution in the reference, physical_exec.rs:567-571). */
+int bamscan_next(BamScanStream* s, struct ArrowArray* out);
+void bamscan_stream_free(BamScanStream* s);
+
+/* ---- measurement hooks (bench.py only) ---- */
+/* Stages the partition's compressed bytes in HBM before the clock starts and keeps every Arrow buffer in HBM
+ * (no H2D / D2H inside the scan); runs the whole partition and fills *stats.  Used for the device-resident
+ * `value` of bench.py; the product path is bamscan_execute/bamscan_next. */
+int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t repeats, BamScanStats* stats);
+int bamscan_stream_stats(const BamScanStream* s, BamScanStats* out);
+/* Inflate-only microbenchmark on the partition's blocks (roofline of the dominant kernel): device ms per launch. */
+int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats, double* ms_per_launch, uint64_t* inflated_bytes,
+                          uint64_t* compressed_bytes);
+
+const char* bamscan_last_error(void);   /* thread-local message of the last failing call on this thread */
+const char* bamscan_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAMSCAN_H */
