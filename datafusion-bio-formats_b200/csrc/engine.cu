@@ -39,7 +39,7 @@ bool filter_is_record_pushable(const BamFile& f, const BamScanFilter& flt);
   } while (0)
 
 constexpr uint32_t HEADROOM = 16u << 20;      // room in front of a chunk for the carried-over tail record
-constexpr uint32_t INFL_PAD = 4096;
+constexpr uint32_t INFL_PAD = 1u << 20;   // slack behind a chunk: literal runs of a corrupt member may overshoot before the check
 constexpr uint32_t MAX_BLOCK_SIZE = 256u << 20;
 
 void* pinned_alloc(size_t bytes) {
@@ -308,7 +308,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   uint8_t* U = s->d_infl.as<uint8_t>();
   if (nb) {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * 6);
+    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * INF_CTAS_PER_SM);
     inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, f->skip_crc ? 0 : 1);
     s->st.kernel_launches++;
   }
@@ -885,7 +885,7 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   cudaMemcpy(comp.p, f->data + c.c0, (size_t)(c.c1 - c.c0) + 512, cudaMemcpyHostToDevice);
   cudaMemcpy(blk.p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice);
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-  uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * 6);
+  uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * INF_CTAS_PER_SM);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float total = 0;
   for (int rep = 0; rep < repeats + 1; rep++) {

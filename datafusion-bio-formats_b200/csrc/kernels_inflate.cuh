@@ -37,16 +37,20 @@ enum InflateStatus : uint32_t {
 };
 
 constexpr int INF_WARPS = 8;                 // warps per CTA
+constexpr int INF_CTAS_PER_SM = 4;
 constexpr int INF_LL_BITS = 10, INF_D_BITS = 8;
 constexpr uint32_t FULL = 0xffffffffu;
 
-// 16-bit LUT entry: [15:14] kind, [13:10] code length, [9:0] value
-//   kind 0 literal (value = byte) | 1 length symbol (value = sym-257) / distance symbol | 2 end of block | 3 long code / invalid (len 0 = invalid)
-constexpr uint32_t E_LIT = 0u << 14, E_SYM = 1u << 14, E_EOB = 2u << 14, E_LONG = 3u << 14;
+// 32-bit LUT entry, decoded without table look-ups or branches:
+//   [3:0]  code length (0 = invalid code)      [7:4] number of extra bits
+//   [9:8]  kind: 1 length / distance, 2 end of block, 3 code longer than the LUT index (canonical walk)
+//   [30:16] literal byte | base length | base distance        [31] literal flag (sign test on the hot path)
+// value = base + ((bits >> code_len) & mask(extra)) ; bits consumed = code_len + extra
+constexpr uint32_t E_LIT = 0x80000000u, E_SYM = 1u << 8, E_EOB = 2u << 8, E_LONG = 3u << 8, E_KIND = 3u << 8;
 
 struct WarpTables {
-  uint16_t lut_ll[1 << INF_LL_BITS];
-  uint16_t lut_d[1 << INF_D_BITS];
+  uint32_t lut_ll[1 << INF_LL_BITS];
+  uint32_t lut_d[1 << INF_D_BITS];
   uint16_t sorted_ll[288];
   uint16_t sorted_d[32];
   uint16_t first_ll[16], offs_ll[16], cnt_ll[16];
@@ -60,72 +64,75 @@ struct InflateShared {
   WarpTables wt[INF_WARPS];
 };
 
-__constant__ uint16_t c_len_base[32] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258, 0, 0, 0};
-__constant__ uint8_t c_len_extra[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0, 0, 0, 0};
-__constant__ uint16_t c_dist_base[32] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577, 0, 0};
-__constant__ uint8_t c_dist_extra[32] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 0, 0};
 __constant__ uint8_t c_clc_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 // x^(8 * 2^j) mod P (reflected CRC-32 domain), j = 0..17 ; filled by the host at init
 __constant__ uint32_t c_crc_xpow8[18];
 
+enum TableKind { TK_LITLEN = 0, TK_DIST = 1, TK_PRECODE = 2 };
+
+// LUT entry of symbol `sym` with code length `len` (RFC 1951 3.2.5 base/extra tables, computed arithmetically)
+template <int TK>
+__device__ __forceinline__ uint32_t make_entry(uint32_t sym, uint32_t len) {
+  if (TK == TK_PRECODE) return E_SYM | len | (sym << 16);
+  if (TK == TK_LITLEN) {
+    if (sym < 256u) return E_LIT | len | (sym << 16);
+    if (sym == 256u) return E_EOB | len;
+    uint32_t s = sym - 257u;
+    if (s > 28u) return E_LONG;                                   // 286, 287: invalid
+    uint32_t extra = (s < 8u || s == 28u) ? 0u : (s - 4u) >> 2;
+    uint32_t base = s == 28u ? 258u : (s < 8u ? 3u + s : 3u + ((4u + (s & 3u)) << extra));
+    return E_SYM | len | (extra << 4) | (base << 16);
+  }
+  if (sym > 29u) return E_LONG;
+  uint32_t extra = sym < 4u ? 0u : (sym - 2u) >> 1;
+  uint32_t base = sym < 4u ? 1u + sym : 1u + ((2u + (sym & 1u)) << extra);
+  return E_SYM | len | (extra << 4) | (base << 16);
+}
+
 // ---------------------------------------------------------------------------------------------
-// warp-uniform bit reader over a double-buffered 128-byte register window
+// warp-uniform bit reader: every lane holds the same 64-bit window (lo:hi) plus one prefetched word.  Refills are
+// plain warp-uniform loads (one 32-byte sector, L1-resident after the first touch of a line), issued one word ahead
+// so their latency is off the critical path.  Invariant after init()/consume(): bp < 32 => peek() returns 32 valid bits.
 struct BitReader {
   const uint32_t* base;   // 4-byte aligned start
-  uint32_t win, winnext;  // lane's word of the current / next 32-word window
-  uint32_t lo, hi;        // 64 valid bits starting at bit `bp` of lo
-  uint32_t bp;            // 0..31
-  uint32_t wi;            // index of the next word to fetch
-  uint32_t limit_words;   // words that may legitimately be consumed (+ slack)
-  bool overrun;
+  uint32_t lo, hi, nxt;   // words wi-3, wi-2, wi-1
+  uint32_t bp;            // 0..31: position of the next unread bit inside lo
+  uint32_t wi;            // index of the next word to load
+  uint32_t limit_words;   // words that may legitimately be touched (+ slack)
 
-  __device__ __forceinline__ void init(const uint8_t* p, uint32_t nbytes, int lane) {
+  __device__ __forceinline__ void init(const uint8_t* p, uint32_t nbytes) {
     uintptr_t a = reinterpret_cast<uintptr_t>(p);
     base = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
     bp = uint32_t(a & 3) * 8;
-    limit_words = (uint32_t(a & 3) + nbytes + 3) / 4 + 2;
-    win = __ldg(base + lane);
-    winnext = __ldg(base + 32 + lane);
-    lo = __shfl_sync(FULL, win, 0);
-    hi = __shfl_sync(FULL, win, 1);
-    wi = 2;
-    overrun = false;
+    limit_words = (uint32_t(a & 3) + nbytes + 3) / 4 + 6;
+    lo = __ldg(base); hi = __ldg(base + 1); nxt = __ldg(base + 2);
+    wi = 3;
   }
   __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bp); }
-  __device__ __forceinline__ void consume(uint32_t n, int lane) {
+  __device__ __forceinline__ void consume(uint32_t n) {   // n <= 32
     bp += n;
-    if (bp >= 32) {
-      bp -= 32;
-      lo = hi;
-      hi = __shfl_sync(FULL, win, wi & 31);
-      wi++;
-      if ((wi & 31) == 0) {
-        win = winnext;
-        if (wi > limit_words) overrun = true;
-        winnext = __ldg(base + wi + 32 + lane);
-      }
-    }
+    if (bp >= 32u) { lo = hi; hi = nxt; nxt = __ldg(base + wi); wi++; bp -= 32u; }
   }
-  __device__ __forceinline__ uint32_t take(uint32_t n, int lane) {   // n <= 24... (any n < 32)
+  __device__ __forceinline__ uint32_t take(uint32_t n) {   // n < 32
     uint32_t v = peek() & ((1u << n) - 1u);
-    consume(n, lane);
+    consume(n);
     return v;
   }
+  __device__ __forceinline__ bool exhausted() const { return wi > limit_words; }
   // byte address of the next unread bit (must be byte aligned)
   __device__ __forceinline__ const uint8_t* byte_ptr() const {
-    return reinterpret_cast<const uint8_t*>(base + (wi - 2)) + (bp >> 3);
+    return reinterpret_cast<const uint8_t*>(base + (wi - 3)) + (bp >> 3);
   }
 };
 
 // ---------------------------------------------------------------------------------------------
 // Canonical Huffman table build, warp-cooperative.  cl[0..n) code lengths (0 = unused).
 // Returns false when the code is over-subscribed.
-template <int PBITS, bool IS_LITLEN>
-__device__ __forceinline__ bool build_table(const uint8_t* cl, int n, uint16_t* lut, uint16_t* sorted,
+template <int PBITS, int TK>
+__device__ __forceinline__ bool build_table(const uint8_t* cl, int n, uint32_t* lut, uint16_t* sorted,
                                             uint16_t* first, uint16_t* offs, uint16_t* cnt, uint16_t* nxt, int lane) {
   if (lane < 16) { cnt[lane] = 0; nxt[lane] = 0; }
-  // invalidate LUT (kind LONG with len 0 = invalid)
-  for (int i = lane; i < (1 << PBITS) / 2; i += 32) reinterpret_cast<uint32_t*>(lut)[i] = (E_LONG << 16) | E_LONG;
+  for (int i = lane; i < (1 << PBITS); i += 32) lut[i] = E_LONG;          // kind LONG with length 0 = invalid code
   __syncwarp();
   for (int s = lane; s < n; s += 32) {
     uint32_t L = cl[s];
@@ -137,7 +144,7 @@ __device__ __forceinline__ bool build_table(const uint8_t* cl, int n, uint16_t* 
   bool over = false;
   for (int len = 1; len <= 15; len++) {
     uint32_t c = cnt[len];
-    code = (code + (len > 1 ? cnt[len - 1] : 0u)) << 1;
+    code = (code + cnt[len - 1]) << 1;
     left <<= 1;
     if (c > left) over = true;
     left -= c;
@@ -160,13 +167,10 @@ __device__ __forceinline__ bool build_table(const uint8_t* cl, int n, uint16_t* 
       uint32_t cd = first[L] + r;
       uint32_t rev = __brev(cd) >> (32 - L);
       if (L <= (uint32_t)PBITS) {
-        uint32_t e;
-        if (IS_LITLEN) e = s < 256 ? (E_LIT | (uint32_t)s) : (s == 256 ? E_EOB : (E_SYM | (uint32_t)(s - 257)));
-        else e = E_SYM | (uint32_t)s;
-        e |= L << 10;
-        for (uint32_t idx = rev; idx < (1u << PBITS); idx += (1u << L)) lut[idx] = (uint16_t)e;
+        uint32_t e = make_entry<TK>((uint32_t)s, L);
+        for (uint32_t idx = rev; idx < (1u << PBITS); idx += (1u << L)) lut[idx] = e;
       } else {
-        lut[rev & ((1u << PBITS) - 1u)] = (uint16_t)(E_LONG | (1u << 10));   // long-code marker (len field != 0)
+        lut[rev & ((1u << PBITS) - 1u)] = E_LONG | 1u;   // long-code marker (length field != 0)
       }
     }
   }
@@ -174,28 +178,15 @@ __device__ __forceinline__ bool build_table(const uint8_t* cl, int n, uint16_t* 
   return true;
 }
 
-// Decodes one symbol with the LUT, falling back to the canonical walk for codes longer than PBITS.
-// Returns the 16-bit entry (kind | len | value); kind LONG with len 0 means invalid code.
-template <int PBITS, bool IS_LITLEN>
-__device__ __forceinline__ uint32_t decode_sym(uint32_t bits, const uint16_t* lut, const uint16_t* sorted,
-                                               const uint16_t* first, const uint16_t* offs, const uint16_t* cnt) {
-  uint32_t e = lut[bits & ((1u << PBITS) - 1u)];
-  if (e >= E_LONG) {
-    if ((e & (15u << 10)) == 0) return E_LONG;          // invalid
-    uint32_t rb = __brev(bits);
-    e = E_LONG;
-    for (uint32_t len = PBITS + 1; len <= 15; len++) {
-      uint32_t d = (rb >> (32 - len)) - first[len];
-      if (d < cnt[len]) {
-        uint32_t s = sorted[offs[len] + d];
-        if (IS_LITLEN) e = s < 256 ? (E_LIT | s) : (s == 256 ? E_EOB : (E_SYM | (s - 257)));
-        else e = E_SYM | s;
-        e |= len << 10;
-        break;
-      }
-    }
+// Canonical walk for codes longer than the LUT index.  Returns E_LONG (length 0) for an invalid code.
+template <int PBITS, int TK>
+__device__ __noinline__ uint32_t decode_long(uint32_t bits, const uint16_t* sorted, const uint16_t* first, const uint16_t* offs, const uint16_t* cnt) {
+  uint32_t rb = __brev(bits);
+  for (uint32_t len = PBITS + 1; len <= 15; len++) {
+    uint32_t d = (rb >> (32 - len)) - first[len];
+    if (d < cnt[len]) return make_entry<TK>(sorted[offs[len] + d], len);
   }
-  return e;
+  return E_LONG;
 }
 
 __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {   // a*b mod P, reflected domain
@@ -215,7 +206,7 @@ __device__ __forceinline__ uint32_t crc_shift(uint32_t crc, uint32_t nbytes) {  
 }
 
 // CRC-32 (IEEE, reflected, init/final 0xffffffff) of out[0..n) by one warp.
-__device__ __forceinline__ uint32_t warp_crc32(const uint8_t* out, uint32_t n, const uint32_t (*tab)[256], int lane) {
+__device__ __noinline__ uint32_t warp_crc32(const uint8_t* out, uint32_t n, const uint32_t (*tab)[256], int lane) {
   uint32_t chunk = ((n + 31) / 32 + 3) & ~3u;
   uint32_t b = min(n, chunk * lane), e = min(n, b + chunk);
   uint32_t st = (lane == 0) ? 0xffffffffu : 0u;
@@ -235,8 +226,46 @@ __device__ __forceinline__ uint32_t warp_crc32(const uint8_t* out, uint32_t n, c
   return ~st;
 }
 
+// Reads the dynamic-block header (HLIT/HDIST/HCLEN + code lengths) into T.cl.  Returns an InflateStatus.
+__device__ __forceinline__ uint32_t read_dynamic_header(BitReader& br, WarpTables& T, int lane, int* n_ll_out, int* n_d_out) {
+  uint32_t h = br.take(14);
+  int n_ll = (int)(h & 31u) + 257, n_d = (int)((h >> 5) & 31u) + 1;
+  int n_clc = (int)(h >> 10) + 4;
+  if (n_ll > 286 || n_d > 30) return INF_ERR_TABLE;
+  if (lane < 19) T.cl[lane] = 0;
+  __syncwarp();
+  for (int i = 0; i < n_clc; i++) {
+    uint32_t v = br.take(3);
+    if (lane == 0) T.cl[c_clc_order[i]] = (uint8_t)v;
+  }
+  __syncwarp();
+  // pre-code (max length 7) goes into lut_d; the decoded lengths then overwrite cl[]
+  if (!build_table<7, TK_PRECODE>(T.cl, 19, T.lut_d, T.sorted_d, T.first_d, T.offs_d, T.cnt_d, T.nxt, lane)) return INF_ERR_TABLE;
+  int total = n_ll + n_d, i = 0;
+  uint32_t prev = 0;
+  while (i < total) {
+    uint32_t bits = br.peek();
+    uint32_t e = T.lut_d[bits & 127u];
+    uint32_t L = e & 15u, s = e >> 16;
+    if (L == 0) return INF_ERR_TABLE;
+    uint32_t rep, val, xb;
+    if (s < 16) { rep = 1; val = s; prev = s; xb = 0; }
+    else if (s == 16) { if (i == 0) return INF_ERR_TABLE; xb = 2; rep = 3 + ((bits >> L) & 3u); val = prev; }
+    else if (s == 17) { xb = 3; rep = 3 + ((bits >> L) & 7u); val = 0; prev = 0; }
+    else { xb = 7; rep = 11 + ((bits >> L) & 127u); val = 0; prev = 0; }
+    br.consume(L + xb);
+    if (i + (int)rep > total) return INF_ERR_TABLE;
+    for (uint32_t k = lane; k < rep; k += 32) T.cl[i + k] = (uint8_t)val;
+    i += (int)rep;
+  }
+  __syncwarp();
+  if (T.cl[256] == 0) return INF_ERR_TABLE;
+  *n_ll_out = n_ll; *n_d_out = n_d;
+  return INF_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(INF_WARPS * 32, 6)
+__global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM)
 inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
                uint8_t* __restrict__ infl, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
                uint32_t* __restrict__ err_flag, int check_crc) {
@@ -256,150 +285,105 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
   }
   __syncthreads();
   WarpTables& T = sh.wt[warp];
+  const bool lane0 = lane == 0;
 
   for (;;) {
     uint32_t bi = 0;
-    if (lane == 0) bi = atomicAdd(ticket, 1u);
+    if (lane0) bi = atomicAdd(ticket, 1u);
     bi = __shfl_sync(FULL, bi, 0);
     if (bi >= n_blocks) break;
     const BlockDesc bd = blocks[bi];
-    uint8_t* out = infl + bd.uoff;
+    uint8_t* const out = infl + bd.uoff;
     const uint32_t isize = bd.isize;
     uint32_t outpos = 0, err = INF_OK;
     BitReader br;
-    br.init(comp + bd.cdata_off, bd.cdata_len, lane);
-    uint32_t mylit = 0, npend = 0, pend_base = 0;   // parked literals: lane i holds out[pend_base + i]
+    br.init(comp + bd.cdata_off, bd.cdata_len);
+    const uint32_t obase = bd.uoff;                 // infl[obase + k]: uniform base + 32-bit offset addressing
     bool final_block = false;
 
     while (!final_block && err == INF_OK) {
-      uint32_t hdr = br.take(3, lane);
+      uint32_t hdr = br.take(3);
       final_block = hdr & 1u;
       uint32_t btype = hdr >> 1;
       if (btype == 0) {
         // stored: skip to byte boundary, LEN / NLEN, raw copy
-        br.consume((8 - (br.bp & 7)) & 7, lane);
-        uint32_t len = br.take(16, lane), nlen = br.take(16, lane);
+        br.consume((8 - (br.bp & 7)) & 7);
+        uint32_t len = br.take(16), nlen = br.take(16);
         if ((len ^ nlen) != 0xffffu || outpos + len > isize) { err = INF_ERR_STORED; break; }
-        if ((uint32_t)lane < npend) out[pend_base + lane] = (uint8_t)mylit;   // flush parked literals
-        npend = 0;
         const uint8_t* src = br.byte_ptr();
-        for (uint32_t i = lane; i < len; i += 32) out[outpos + i] = src[i];
-        outpos += len;
         uint32_t used = (uint32_t)(src + len - (comp + bd.cdata_off));
         if (used > bd.cdata_len) { err = INF_ERR_INPUT; break; }
-        br.init(src + len, bd.cdata_len - used, lane);
+        for (uint32_t i = lane; i < len; i += 32) out[outpos + i] = src[i];
+        outpos += len;
+        br.init(src + len, bd.cdata_len - used);
         continue;
       }
       if (btype == 3) { err = INF_ERR_BTYPE; break; }
-      int n_ll, n_d;
+      int n_ll = 288, n_d = 30;
       if (btype == 1) {
         for (int i = lane; i < 288; i += 32) T.cl[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
         if (lane < 30) T.cl[288 + lane] = 5;
-        n_ll = 288; n_d = 30;
         __syncwarp();
       } else {
-        uint32_t h = br.take(14, lane);
-        n_ll = (int)(h & 31u) + 257; n_d = (int)((h >> 5) & 31u) + 1;
-        int n_clc = (int)(h >> 10) + 4;
-        if (n_ll > 286 || n_d > 30) { err = INF_ERR_TABLE; break; }
-        // code-length code: 19 3-bit lengths, staged in cl[] then built into lut_d (7-bit index)
-        if (lane < 19) T.cl[lane] = 0;
-        __syncwarp();
-        for (int i = 0; i < n_clc; i++) {
-          uint32_t v = br.take(3, lane);
-          if (lane == 0) T.cl[c_clc_order[i]] = (uint8_t)v;
-        }
-        __syncwarp();
-        if (!build_table<7, false>(T.cl, 19, T.lut_d, T.sorted_d, T.first_d, T.offs_d, T.cnt_d, T.nxt, lane)) { err = INF_ERR_TABLE; break; }
-        int total = n_ll + n_d, i = 0;
-        uint32_t prev = 0;
-        uint8_t* cl2 = T.cl + 0;   // decoded lengths overwrite the (no longer needed) pre-code lengths
-        while (i < total) {
-          uint32_t e = T.lut_d[br.peek() & 127u];
-          uint32_t L = (e >> 10) & 15u, s = e & 1023u;
-          if (e >= E_LONG || L == 0) { err = INF_ERR_TABLE; break; }
-          br.consume(L, lane);
-          uint32_t rep, val;
-          if (s < 16) { rep = 1; val = s; prev = s; }
-          else if (s == 16) { if (i == 0) { err = INF_ERR_TABLE; break; } rep = 3 + br.take(2, lane); val = prev; }
-          else if (s == 17) { rep = 3 + br.take(3, lane); val = 0; prev = 0; }
-          else { rep = 11 + br.take(7, lane); val = 0; prev = 0; }
-          if (i + (int)rep > total) { err = INF_ERR_TABLE; break; }
-          for (uint32_t k = lane; k < rep; k += 32) cl2[i + k] = (uint8_t)val;
-          i += (int)rep;
-        }
+        err = read_dynamic_header(br, T, lane, &n_ll, &n_d);
         if (err) break;
-        __syncwarp();
-        if (T.cl[256] == 0) { err = INF_ERR_TABLE; break; }
       }
-      if (!build_table<INF_LL_BITS, true>(T.cl, n_ll, T.lut_ll, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll, T.nxt, lane)) { err = INF_ERR_TABLE; break; }
-      if (!build_table<INF_D_BITS, false>(T.cl + n_ll, n_d, T.lut_d, T.sorted_d, T.first_d, T.offs_d, T.cnt_d, T.nxt, lane)) { err = INF_ERR_TABLE; break; }
+      if (!build_table<INF_LL_BITS, TK_LITLEN>(T.cl, n_ll, T.lut_ll, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll, T.nxt, lane)) { err = INF_ERR_TABLE; break; }
+      if (!build_table<INF_D_BITS, TK_DIST>(T.cl + n_ll, n_d, T.lut_d, T.sorted_d, T.first_d, T.offs_d, T.cnt_d, T.nxt, lane)) { err = INF_ERR_TABLE; break; }
 
-      // ---------------- symbol loop (warp-uniform) ----------------
-      for (;;) {
+      // ---------------- symbol loop (warp-uniform; one look-up decodes code + extra bits) ----------------
+      // Output overrun is checked at every match and at the end of the member (the inflated buffer carries slack for
+      // literal runs); the loop is bounded by the input: past the member's last word the reader reports exhaustion.
+      while (!br.exhausted()) {
         uint32_t bits = br.peek();
-        uint32_t e = decode_sym<INF_LL_BITS, true>(bits, T.lut_ll, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll);
-        uint32_t L = (e >> 10) & 15u;
-        if (e < E_SYM) {                       // literal
-          br.consume(L, lane);
-          if (npend == 0) pend_base = outpos;
-          if ((uint32_t)lane == npend) mylit = e;
-          npend++; outpos++;
-          if (npend == 32) {
-            if (outpos > isize) { err = INF_ERR_OVERRUN; break; }
-            out[pend_base + lane] = (uint8_t)mylit;
-            npend = 0;
-          }
+        uint32_t e = T.lut_ll[bits & ((1u << INF_LL_BITS) - 1u)];
+        if ((int32_t)e < 0) {                              // literal
+          br.consume(e & 15u);
+          if (lane0) infl[obase + outpos] = (uint8_t)(e >> 16);
+          outpos++;
           continue;
         }
-        if (e >= E_LONG) { err = INF_ERR_SYMBOL; break; }
-        br.consume(L, lane);
-        if (e >= E_EOB) break;                  // end of block
-        // length symbol
-        uint32_t ls = e & 31u;
-        if (ls > 28) { err = INF_ERR_SYMBOL; break; }
-        uint32_t len = c_len_base[ls];
-        uint32_t xb = c_len_extra[ls];
-        if (xb) len += br.take(xb, lane);
-        uint32_t de = decode_sym<INF_D_BITS, false>(br.peek(), T.lut_d, T.sorted_d, T.first_d, T.offs_d, T.cnt_d);
-        if (de >= E_LONG) { err = INF_ERR_DIST; break; }
-        br.consume((de >> 10) & 15u, lane);
-        uint32_t ds = de & 31u;
-        if (ds > 29) { err = INF_ERR_DIST; break; }
-        uint32_t dist = c_dist_base[ds];
-        uint32_t dxb = c_dist_extra[ds];
-        if (dxb) dist += br.take(dxb, lane);
-        if (dist > outpos || outpos + len > isize) { err = dist > outpos ? INF_ERR_DIST : INF_ERR_OVERRUN; break; }
-        // flush parked literals, then fence so earlier stores are visible to the copy's loads
-        if ((uint32_t)lane < npend) out[pend_base + lane] = (uint8_t)mylit;
-        npend = 0;
-        __syncwarp();
-        uint8_t* dst = out + outpos;
-        const uint8_t* src = dst - dist;
-        if (dist >= 32) {
-          for (uint32_t b0 = 0; b0 < len; b0 += 32) {      // uniform trip count; stripes may feed each other
-            uint32_t i = b0 + lane;
-            if (i < len) dst[i] = src[i];
-            __syncwarp();
-          }
+        if ((e & E_KIND) == E_LONG) {
+          e = decode_long<INF_LL_BITS, TK_LITLEN>(bits, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll);
+          if ((int32_t)e < 0) { br.consume(e & 15u); if (lane0) infl[obase + outpos] = (uint8_t)(e >> 16); outpos++; continue; }
+        }
+        const uint32_t nb = e & 15u, xb = (e >> 4) & 15u;
+        if ((e & E_KIND) != E_SYM) {                       // end of block, or an invalid code
+          br.consume(nb);
+          if (nb == 0) err = INF_ERR_SYMBOL;
+          break;
+        }
+        const uint32_t len = ((e >> 16) & 0x7fffu) + ((bits >> nb) & ((1u << xb) - 1u));
+        br.consume(nb + xb);
+        bits = br.peek();
+        uint32_t de = T.lut_d[bits & ((1u << INF_D_BITS) - 1u)];
+        if ((de & E_KIND) == E_LONG) de = decode_long<INF_D_BITS, TK_DIST>(bits, T.sorted_d, T.first_d, T.offs_d, T.cnt_d);
+        const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
+        const uint32_t dist = (de >> 16) + ((bits >> dnb) & ((1u << dxb) - 1u));
+        br.consume(dnb + dxb);
+        if (dnb == 0 || dist > outpos || outpos + len > isize) { err = (dnb == 0 || dist > outpos) ? INF_ERR_DIST : INF_ERR_OVERRUN; break; }
+        __syncwarp();                                     // earlier stores (other lanes) become visible to the loads below
+        // byte i of the match is src[i mod dist]: only bytes that already exist are read, for every dist/len combination
+        const uint32_t d0 = obase + outpos, s0 = d0 - dist;
+        if (dist >= len) {
+          for (uint32_t i = lane; i < len; i += 32) infl[d0 + i] = infl[s0 + i];
         } else if (dist == 1) {
-          uint8_t v = src[0];
-          for (uint32_t i = lane; i < len; i += 32) dst[i] = v;
+          const uint8_t v = infl[s0];
+          for (uint32_t i = lane; i < len; i += 32) infl[d0 + i] = v;
         } else {
-          for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i % dist];
+          for (uint32_t i = lane; i < len; i += 32) infl[d0 + i] = infl[s0 + i % dist];
         }
         outpos += len;
       }
-      if (br.overrun && err == INF_OK) err = INF_ERR_INPUT;
+      if (br.exhausted() && err == INF_OK) err = INF_ERR_INPUT;
     }
-    if (err == INF_OK && outpos != isize) err = outpos > isize ? INF_ERR_OVERRUN : INF_ERR_ISIZE;
-    if ((uint32_t)lane < npend && err == INF_OK) out[pend_base + lane] = (uint8_t)mylit;
     __syncwarp();
+    if (err == INF_OK && outpos != isize) err = outpos > isize ? INF_ERR_OVERRUN : INF_ERR_ISIZE;
     if (err == INF_OK && check_crc) {
       uint32_t crc = warp_crc32(out, isize, sh.crc_tab, lane);
       if (crc != bd.crc) err = INF_ERR_CRC;
     }
-    if (lane == 0) {
+    if (lane0) {
       status[bi] = err;
       if (err) atomicCAS(err_flag, 0u, (bi << 4) | err | 0x80000000u);
     }

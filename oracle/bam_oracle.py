@@ -420,10 +420,15 @@ class OracleBam:
                 raise RuntimeError(err.decode())
             n = L.orc_result_rows(r)
             arrays = []
-            for i in range(L.orc_result_ncols(r)):
-                arrays.append(self._col_to_arrow(r, i, n))
             schema = self.projected_schema(projection)
-            if arrays:
+            if batch_rows > 0:
+                batch = None      # timing mode: batches were built and dropped inside the C loop
+            else:
+                for i in range(L.orc_result_ncols(r)):
+                    arrays.append(self._col_to_arrow(r, i, n))
+            if batch_rows > 0:
+                pass
+            elif arrays:
                 batch = pa.RecordBatch.from_arrays(arrays, schema=schema)
             else:
                 batch = pa.RecordBatch.from_struct_array(pa.array([{}] * n, type=pa.struct([]))) if n else \
