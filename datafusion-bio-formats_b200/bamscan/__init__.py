@@ -27,7 +27,8 @@ LIB_PATH = _HERE.parent / "libbamscan.so"
 
 EXPORTED_SYMBOLS = [
     "bamscan_open", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
-    "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_execute", "bamscan_next",
+    "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_plan_num_ranges",
+    "bamscan_plan_range_info", "bamscan_execute", "bamscan_next",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
     "bamscan_last_error", "bamscan_version",
 ]
@@ -92,6 +93,8 @@ def load_library():
     L.bamscan_plan_num_partitions.argtypes = [C.c_void_p]
     L.bamscan_plan_schema.argtypes = [C.c_void_p, C.c_void_p]
     L.bamscan_plan_free.argtypes = [C.c_void_p]
+    L.bamscan_plan_num_ranges.argtypes = [C.c_void_p, C.c_int32]
+    L.bamscan_plan_range_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
     L.bamscan_execute.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.bamscan_next.argtypes = [C.c_void_p, C.c_void_p]
     L.bamscan_stream_free.argtypes = [C.c_void_p]
@@ -157,6 +160,20 @@ class BamExec:
 
     def output_partition_count(self) -> int:
         return load_library().bamscan_plan_num_partitions(self._h)
+
+    def partition_ranges(self, partition: int):
+        """Block ranges (+ row rule) a partition scans: list of dicts (bamscan_plan_range_info)."""
+        L = load_library()
+        keys = ["block_begin", "block_end", "coff_begin", "coff_end", "exact_start", "first_uoff", "stop_uoff",
+                "region_mode", "region_ref", "region_start", "region_end", "estimated_bytes"]
+        out = []
+        for r in range(L.bamscan_plan_num_ranges(self._h, partition)):
+            buf = (C.c_uint64 * 12)()
+            _check(L.bamscan_plan_range_info(self._h, partition, r, buf))
+            d = dict(zip(keys, list(buf)))
+            d["region_ref"] = C.c_int64(d["region_ref"]).value
+            out.append(d)
+        return out
 
     def schema(self) -> pa.Schema:
         cs = _ArrowSchemaStruct()

@@ -42,13 +42,17 @@ constexpr uint32_t HEADROOM = 16u << 20;      // room in front of a chunk for th
 constexpr uint32_t INFL_PAD = 1u << 20;   // slack behind a chunk: literal runs of a corrupt member may overshoot before the check
 constexpr uint32_t MAX_BLOCK_SIZE = 256u << 20;
 
+static bool g_have_device = false;
+// Page-locked host memory.  Without a device (planning-only use: open / schema / classify / plan) plain memory is
+// handed out instead; bamscan_execute refuses to run in that case -- there is no CPU scan path.
 void* pinned_alloc(size_t bytes) {
   void* p = nullptr;
+  if (!g_have_device) { if (posix_memalign(&p, 4096, bytes ? bytes : 1) != 0) { set_error("out of host memory (%zu bytes)", bytes); return nullptr; } return p; }
   cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
-  if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed: %s (is a CUDA device present? this library has no CPU path)", bytes, cudaGetErrorString(e)); return nullptr; }
+  if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
   return p;
 }
-void pinned_free(void* p) { if (p) cudaFreeHost(p); }
+void pinned_free(void* p) { if (!p) return; if (g_have_device) cudaFreeHost(p); else free(p); }
 
 struct DeviceBuf {
   void* p = nullptr; size_t cap = 0;
@@ -694,9 +698,12 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
   opt.coordinate_system_zero_based = 1; opt.infer_tag_types = 1; opt.infer_tag_sample_size = 100;
   if (options) memcpy(&opt, options, std::min<size_t>(sizeof opt, options->struct_size ? options->struct_size : sizeof opt));
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available: libbamscan has no CPU path"); return BAMSCAN_ERR_CUDA; }
-  if (opt.device_id < 0 || opt.device_id >= ndev) { set_error("device_id %d out of range (%d devices)", opt.device_id, ndev); return BAMSCAN_ERR_INVALID; }
-  if (cudaSetDevice(opt.device_id) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", opt.device_id); return BAMSCAN_ERR_CUDA; }
+  g_have_device = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+  if (!g_have_device) cudaGetLastError();   // planning-only mode: header, schema, filter classification and plans work; execute() does not
+  else {
+    if (opt.device_id < 0 || opt.device_id >= ndev) { set_error("device_id %d out of range (%d devices)", opt.device_id, ndev); return BAMSCAN_ERR_INVALID; }
+    if (cudaSetDevice(opt.device_id) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", opt.device_id); return BAMSCAN_ERR_CUDA; }
+  }
   std::unique_ptr<BamScanHandle> h(new BamScanHandle());
   BamFile& f = h->file;
   f.path = path; f.device = opt.device_id;
@@ -723,7 +730,7 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
 
 void bamscan_close(BamScanHandle* h) {
   if (!h) return;
-  if (h->file.data) { cudaSetDevice(h->file.device); pinned_free(h->file.data); }
+  if (h->file.data) { if (g_have_device) cudaSetDevice(h->file.device); pinned_free(h->file.data); }
   delete h;
 }
 
@@ -759,9 +766,30 @@ int bamscan_plan_schema(const BamScanPlan* plan, struct ArrowSchema* out) {
 
 void bamscan_plan_free(BamScanPlan* plan) { if (plan) { delete plan->plan; delete plan; } }
 
+int32_t bamscan_plan_num_ranges(const BamScanPlan* plan, int32_t partition) {
+  if (!plan || partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) return -1;
+  return (int32_t)plan->plan->partitions[partition].ranges.size();
+}
+
+int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t range, uint64_t out[12]) {
+  if (!plan || !out || partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) { set_error("bad partition"); return BAMSCAN_ERR_INVALID; }
+  const Partition& P = plan->plan->partitions[partition];
+  if (range < 0 || range >= (int32_t)P.ranges.size()) { set_error("bad range"); return BAMSCAN_ERR_INVALID; }
+  const ScanRange& r = P.ranges[range];
+  const BamFile& f = *plan->plan->file;
+  out[0] = r.block_begin; out[1] = r.block_end;
+  out[2] = r.block_begin < f.blocks.size() ? f.blocks[r.block_begin].coff : f.size;
+  out[3] = r.block_end < f.blocks.size() ? f.blocks[r.block_end].coff : f.size;
+  out[4] = r.exact_start; out[5] = r.first_uoff; out[6] = r.stop_uoff;
+  out[7] = (uint64_t)r.region_mode; out[8] = (uint64_t)(int64_t)r.region_ref; out[9] = r.region_start; out[10] = r.region_end;
+  out[11] = P.estimated_bytes;
+  return BAMSCAN_OK;
+}
+
 static int make_stream(BamScanPlan* plan, int32_t partition, bool device_resident, BamScanStream** out) {
   if (!plan || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
   if (partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) { set_error("partition %d out of range", partition); return BAMSCAN_ERR_INVALID; }
+  if (!g_have_device) { set_error("no CUDA device available: the BAM scan runs on the GPU only (libbamscan has no CPU path)"); return BAMSCAN_ERR_CUDA; }
   BamScanStream* s = new BamScanStream();
   s->plan = plan->plan; s->f = plan->plan->file; s->part = &plan->plan->partitions[partition];
   s->device_resident = device_resident;

@@ -8,8 +8,9 @@
  * CUDA, torch or C++ types in any signature.  Batches come back in host memory, ready for
  * `arrow::ffi::from_ffi` (Rust) / `pyarrow.RecordBatch._import_from_c` (Python).
  *
- * There is no CPU fallback inside the library: a call that needs the GPU fails with BAMSCAN_ERR_CUDA
- * when no sm_100 device is present.
+ * There is no CPU fallback inside the library: bamscan_execute / bamscan_run_device_resident fail with
+ * BAMSCAN_ERR_CUDA when no device is present.  Planning calls (open, schema, classify_filters, plan) are host-only,
+ * like the reference's provider construction and `scan()`, and work anywhere.
  *
  * Threading: handles are not thread-safe individually; distinct streams may be driven from distinct
  * host threads (the reference's "one thread per partition", bio-format-core/src/sync_stream.rs:7-33).
@@ -120,6 +121,12 @@ int bamscan_plan(BamScanHandle* h, const int32_t* projection, int32_t n_projecti
 int32_t bamscan_plan_num_partitions(const BamScanPlan* plan);   /* == output_partitioning().partition_count(); 0 => EmptyExec */
 int bamscan_plan_schema(const BamScanPlan* plan, struct ArrowSchema* out);   /* == ExecutionPlan::schema (projected) */
 void bamscan_plan_free(BamScanPlan* plan);
+/* Introspection of a partition's device work (== BamExec::partition_assignments, physical_exec.rs:52): number of block
+ * ranges and, per range, out[12] = { block_begin, block_end, compressed offset of block_begin, compressed offset of
+ * block_end, exact_start, first inflated offset, stop inflated offset (~0 = none), region_mode, region_ref,
+ * region_start, region_end (1-based closed, 0 = open), partition estimated bytes }. */
+int32_t bamscan_plan_num_ranges(const BamScanPlan* plan, int32_t partition);
+int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t range, uint64_t out[12]);
 
 /* == ExecutionPlan::execute(partition, ctx) (physical_exec.rs:108-172). */
 int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out);

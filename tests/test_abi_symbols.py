@@ -1,0 +1,47 @@
+"""CPU: the C-ABI library loads and exports every symbol include/bamscan.h declares; planning calls work without a GPU;
+the scan itself refuses to run without one (no CPU fallback)."""
+import ctypes
+import re
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def test_every_declared_symbol_is_exported():
+    import bamscan
+    header = (ROOT / "include" / "bamscan.h").read_text()
+    declared = sorted(set(re.findall(r"\b(bamscan_[a-z_]+)\s*\(", header)))
+    assert len(declared) >= 16
+    lib = bamscan.load_library()
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/bamscan.h but not exported by libbamscan.so"
+    assert set(bamscan.EXPORTED_SYMBOLS) == set(declared)
+    assert b"sm_100a" in lib.bamscan_version()
+
+
+def test_header_cites_reference_interfaces():
+    header = (ROOT / "include" / "bamscan.h").read_text()
+    for cite in ("table_provider.rs:381-390", "table_provider.rs:941-962", "table_provider.rs:964-1115", "physical_exec.rs:108-172"):
+        assert cite in header
+
+
+def test_library_links_no_torch_and_oracle():
+    import subprocess, bamscan
+    out = subprocess.check_output(["ldd", str(bamscan.LIB_PATH)]).decode()
+    assert "torch" not in out and "oracle" not in out
+
+
+def test_scan_refuses_without_gpu():
+    import bamscan
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    p = bamscan.BamTableProvider(str(GOLDEN / "multi_chrom.bam"))
+    plan = p.scan(None, [], None)
+    with pytest.raises(bamscan.BamScanError) as e:
+        list(plan.execute(0))
+    assert e.value.code == -4 and "no CPU path" in str(e.value)

@@ -1,0 +1,116 @@
+"""CPU: host-side planning of the product (schema, tag typing, filter classification, partitions) against the oracle's
+restatement and the reference's pins.  No kernels run here."""
+import json
+
+import pyarrow as pa
+import pytest
+
+from conftest import GOLDEN, gen_bam
+
+
+def _provider(path, **kw):
+    import bamscan
+    return bamscan.BamTableProvider(str(path), None, kw.pop("zero_based", True), kw.pop("tag_fields", None), kw.pop("binary_cigar", False),
+                                    kw.pop("infer_tag_types", True), kw.pop("infer_tag_sample_size", 100), kw.pop("tag_type_hints", None), **kw)
+
+
+CASES = [
+    ("multi_chrom.bam", dict()),
+    ("multi_chrom.bam", dict(zero_based=False, binary_cigar=True)),
+    ("multi_chrom_large.bam", dict(tag_fields=["NM", "MD", "RG", "OQ", "XT", "OP"])),
+    ("nanopore_custom_tags.bam", dict(tag_fields=["pa", "ns", "ts", "de", "NM", "ML", "zz"])),
+    ("nanopore_custom_tags.bam", dict(tag_fields=["pa", "ns"], infer_tag_types=False)),
+    ("nanopore_custom_tags.bam", dict(tag_fields=["pa", "ns", "qq"], infer_tag_types=False, tag_type_hints=["pa:B:i", "ns:I", "qq:f"])),
+    ("bam_with_tags.bam", dict(tag_fields=["XT", "X0", "X1", "NM"], infer_tag_sample_size=1)),
+    ("10x_pbmc_tags.bam", dict(tag_fields=["CB", "CR", "RE", "xf", "ts", "pa", "GX"])),
+    ("no_coor_only.bam", dict(tag_fields=["CB", "CR"])),
+]
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_schema_equals_oracle(name, kw):
+    from oracle.bam_oracle import OracleBam, schema_equal
+    okw = dict(kw)
+    o = OracleBam(str(GOLDEN / name), **okw)
+    p = _provider(GOLDEN / name, **dict(kw))
+    assert schema_equal(p.schema(), o.schema), f"\n{p.schema().to_string(show_schema_metadata=True)}\nvs\n{o.schema.to_string(show_schema_metadata=True)}"
+
+
+def test_schema_shape_pins():
+    # table_provider.rs:57-70: names, types, nullability of the 12 core columns
+    s = _provider(GOLDEN / "multi_chrom.bam").schema()
+    assert s.names == ["name", "chrom", "start", "end", "flags", "cigar", "mapping_quality", "mate_chrom", "mate_start", "sequence", "quality_scores", "template_length"]
+    assert [str(t) for t in s.types] == ["string", "string", "uint32", "uint32", "uint32", "string", "uint32", "string", "uint32", "string", "string", "int32"]
+    assert [f.nullable for f in s] == [True, True, True, True, False, False, False, True, True, False, False, False]
+    assert s.metadata[b"bio.coordinate_system_zero_based"] == b"true" and b"bio.bam.binary_cigar" not in s.metadata
+
+
+def test_bad_hint_is_rejected():
+    import bamscan
+    with pytest.raises(bamscan.BamScanError) as e:
+        _provider(GOLDEN / "multi_chrom.bam", tag_fields=["NM"], tag_type_hints=["NM:B"])
+    assert "requires a subtype" in str(e.value)
+
+
+def test_projected_plan_schema_follows_projection():
+    # projection_pushdown_test.rs:33-61,115-126
+    p = _provider(GOLDEN / "multi_chrom.bam", tag_fields=["NM"])
+    plan = p.scan([6, 0, 12], [], None)
+    s = plan.schema()
+    assert s.names == ["mapping_quality", "name", "NM"] and s.metadata == p.schema().metadata
+    assert p.scan([], [], None).schema().names == []
+    import bamscan
+    with pytest.raises(bamscan.BamScanError):
+        p.scan([13], [], None)
+
+
+def test_filter_classification(tmp_path):
+    # table_provider.rs:941-962, genomic_filter.rs:120-148, record_filter.rs:285-355
+    import shutil
+    idx = _provider(GOLDEN / "multi_chrom.bam", tag_fields=["NM", "MD"])
+    f = tmp_path / "noindex.bam"
+    shutil.copy(GOLDEN / "multi_chrom.bam", f)
+    noidx = _provider(f, tag_fields=["NM", "MD"])
+    filters = [("chrom", "=", ["chr1"]), ("chrom", "in", ["chr1", "chr2"]), ("start", "between", [1, 2]), ("end", "<=", [5]),
+               ("mapping_quality", ">=", [30]), ("flags", "not_in", [4, 8]), ("name", "=", ["x"]), ("name", "<", ["x"]),
+               ("NM", ">", [2]), ("MD", "=", ["10"]), ("sequence", "other", []), ("chrom", "other", []), ("cigar", "!=", ["*"])]
+    want_common = ["Inexact"] * 7 + ["Unsupported", "Inexact", "Inexact", "Unsupported", "Unsupported", "Inexact"]
+    assert noidx.supports_filters_pushdown(filters) == want_common
+    assert idx.supports_filters_pushdown(filters) == want_common      # genomic filters are also record-pushable here
+    # a shape only the index makes pushable: start NOT BETWEEN is "genomic" by column name (genomic_filter.rs:130-137) and also record-pushable
+    assert idx.supports_filters_pushdown([("start", "not_between", [1, 2])]) == ["Inexact"]
+
+
+@pytest.mark.parametrize("nparts", [1, 2, 3, 5, 8, 64])
+def test_block_range_partitions_tile_the_file(syn_dir, nparts):
+    path = gen_bam(syn_dir, "short", 20000, seed=11)
+    p = _provider(path)
+    plan = p.scan(None, [], None, target_partitions=nparts, partition_mode="block_range")
+    assert plan.output_partition_count() == nparts
+    ranges = [r for i in range(nparts) for r in plan.partition_ranges(i)]
+    assert ranges[0]["exact_start"] == 1 and all(r["exact_start"] == 0 for r in ranges[1:])
+    for a, b in zip(ranges, ranges[1:]):
+        assert a["block_end"] == b["block_begin"] and a["stop_uoff"] == b["first_uoff"]
+    assert ranges[-1]["stop_uoff"] == 2 ** 64 - 1
+    sizes = [r["coff_end"] - r["coff_begin"] for r in ranges]
+    if nparts <= 8:
+        assert max(sizes) - min(sizes) <= 2 * 65536 + 28        # balanced by compressed bytes to within a block or two
+
+
+def test_reference_partition_rule_without_index(syn_dir):
+    # table_provider.rs:1097-1114: no index => UnknownPartitioning(1) whatever target_partitions says
+    path = gen_bam(syn_dir, "short", 20000, seed=11)
+    p = _provider(path)
+    assert p.scan(None, [], None, target_partitions=8).output_partition_count() == 1
+
+
+def test_not_bgzf_and_missing_file(tmp_path):
+    import bamscan
+    f = tmp_path / "html.bam"
+    f.write_bytes(b"\n\n<!DOCTYPE html><html></html>" * 20)
+    prov = _provider(f)                       # provider construction tolerates an unreadable header (table_provider.rs:423-426)
+    assert len(prov.schema()) == 12
+    with pytest.raises(bamscan.BamScanError):
+        prov.scan(None, [], None)
+    with pytest.raises(bamscan.BamScanError):
+        _provider(tmp_path / "nope.bam")
