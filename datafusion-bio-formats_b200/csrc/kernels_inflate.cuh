@@ -37,8 +37,8 @@ enum InflateStatus : uint32_t {
 };
 
 constexpr int INF_WARPS = 8;                 // warps per CTA
-constexpr int INF_CTAS_PER_SM = 4;
-constexpr int INF_LL_BITS = 10, INF_D_BITS = 8;
+constexpr int INF_CTAS_PER_SM = 5;
+constexpr int INF_LL_BITS = 10, INF_D_BITS = 7;
 constexpr uint32_t FULL = 0xffffffffu;
 
 // 32-bit LUT entry, decoded without table look-ups or branches:
@@ -332,48 +332,74 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
       if (!build_table<INF_D_BITS, TK_DIST>(T.cl + n_ll, n_d, T.lut_d, T.sorted_d, T.first_d, T.offs_d, T.cnt_d, T.nxt, lane)) { err = INF_ERR_TABLE; break; }
 
       // ---------------- symbol loop (warp-uniform; one look-up decodes code + extra bits) ----------------
+      // The reader state lives in plain registers here; refills are real (rare) branches so the common path stays short.
       // Output overrun is checked at every match and at the end of the member (the inflated buffer carries slack for
-      // literal runs); the loop is bounded by the input: past the member's last word the reader reports exhaustion.
-      while (!br.exhausted()) {
-        uint32_t bits = br.peek();
-        uint32_t e = T.lut_ll[bits & ((1u << INF_LL_BITS) - 1u)];
-        if ((int32_t)e < 0) {                              // literal
-          br.consume(e & 15u);
-          if (lane0) infl[obase + outpos] = (uint8_t)(e >> 16);
-          outpos++;
-          continue;
+      // literal runs); the loop is bounded by the input: the refill path stops at the member's last word (+ slack).
+      {
+        uint32_t lo = br.lo, hi = br.hi, nxt = br.nxt, bp = br.bp, wi = br.wi;
+        const uint32_t* const wbase = br.base;
+        const uint32_t wlimit = br.limit_words;
+        const uint32_t* const lut_ll = T.lut_ll;
+        const uint32_t* const lut_d = T.lut_d;
+        uint8_t* outl = infl + obase + outpos + lane;        // this lane's byte of the next output stripe
+        uint8_t* pend_p = outl; uint8_t pend_v = 0; uint32_t pend_n = 0;   // deferred single-stripe match store
+#define INF_REFILL()                                                                         \
+        if (bp >= 32u) {                                                                     \
+          lo = hi; hi = nxt; nxt = __ldg(wbase + wi); wi++; bp -= 32u;                        \
+          if (wi > wlimit) { err = INF_ERR_INPUT; break; }                                    \
         }
-        if ((e & E_KIND) == E_LONG) {
-          e = decode_long<INF_LL_BITS, TK_LITLEN>(bits, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll);
-          if ((int32_t)e < 0) { br.consume(e & 15u); if (lane0) infl[obase + outpos] = (uint8_t)(e >> 16); outpos++; continue; }
+        for (;;) {
+          uint32_t bits = __funnelshift_r(lo, hi, bp);
+          uint32_t e = lut_ll[bits & ((1u << INF_LL_BITS) - 1u)];
+          if ((int32_t)e >= 0) {
+            if ((e & E_KIND) == E_LONG) e = decode_long<INF_LL_BITS, TK_LITLEN>(bits, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll);
+            if ((int32_t)e >= 0) {
+              const uint32_t nb = e & 15u, xb = (e >> 4) & 15u;
+              if ((e & E_KIND) != E_SYM) {                     // end of block, or an invalid code
+                bp += nb;
+                if (nb == 0) err = INF_ERR_SYMBOL;
+                break;
+              }
+              const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << xb) - 1u));
+              bp += nb + xb;
+              INF_REFILL();
+              bits = __funnelshift_r(lo, hi, bp);
+              uint32_t de = lut_d[bits & ((1u << INF_D_BITS) - 1u)];
+              if ((de & E_KIND) == E_LONG) de = decode_long<INF_D_BITS, TK_DIST>(bits, T.sorted_d, T.first_d, T.offs_d, T.cnt_d);
+              const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
+              const uint32_t dist = (de >> 16) + ((bits >> dnb) & ((1u << dxb) - 1u));
+              bp += dnb + dxb;
+              if (dnb == 0 || dist > outpos || outpos + len > isize) { err = (dnb == 0 || dist > outpos) ? INF_ERR_DIST : INF_ERR_OVERRUN; break; }
+              // The copy's store is DEFERRED: the load is issued now, the store happens right before the next match's
+              // fence (or at the end of the block), so the L2 round trip overlaps the decoding of the symbols in between.
+              if (pend_n) { if ((uint32_t)lane < pend_n) *pend_p = pend_v; pend_n = 0; }
+              __syncwarp();                                   // earlier stores (other lanes) become visible to the loads below
+              // byte i of the match is src[i mod dist]: only bytes that already exist are read, whatever dist/len are
+              if (dist >= len && len <= 32u) {                // the common case: one stripe, no overlap
+                pend_v = *(outl - dist); pend_p = outl; pend_n = len;
+              } else {
+                uint8_t* const d0 = outl - lane;
+                const uint8_t* const s0 = d0 - dist;
+                if (dist >= len) { for (uint32_t i = lane; i < len; i += 32) d0[i] = s0[i]; }
+                else if (dist == 1) { const uint8_t v = s0[0]; for (uint32_t i = lane; i < len; i += 32) d0[i] = v; }
+                else { for (uint32_t i = lane; i < len; i += 32) d0[i] = s0[i % dist]; }
+              }
+              outl += len; outpos += len;
+              INF_REFILL();
+              continue;
+            }
+          }
+          // literal
+          if (lane0) *outl = (uint8_t)(e >> 16);
+          outl++; outpos++;
+          bp += e & 15u;
+          INF_REFILL();
         }
-        const uint32_t nb = e & 15u, xb = (e >> 4) & 15u;
-        if ((e & E_KIND) != E_SYM) {                       // end of block, or an invalid code
-          br.consume(nb);
-          if (nb == 0) err = INF_ERR_SYMBOL;
-          break;
-        }
-        const uint32_t len = ((e >> 16) & 0x7fffu) + ((bits >> nb) & ((1u << xb) - 1u));
-        br.consume(nb + xb);
-        bits = br.peek();
-        uint32_t de = T.lut_d[bits & ((1u << INF_D_BITS) - 1u)];
-        if ((de & E_KIND) == E_LONG) de = decode_long<INF_D_BITS, TK_DIST>(bits, T.sorted_d, T.first_d, T.offs_d, T.cnt_d);
-        const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
-        const uint32_t dist = (de >> 16) + ((bits >> dnb) & ((1u << dxb) - 1u));
-        br.consume(dnb + dxb);
-        if (dnb == 0 || dist > outpos || outpos + len > isize) { err = (dnb == 0 || dist > outpos) ? INF_ERR_DIST : INF_ERR_OVERRUN; break; }
-        __syncwarp();                                     // earlier stores (other lanes) become visible to the loads below
-        // byte i of the match is src[i mod dist]: only bytes that already exist are read, for every dist/len combination
-        const uint32_t d0 = obase + outpos, s0 = d0 - dist;
-        if (dist >= len) {
-          for (uint32_t i = lane; i < len; i += 32) infl[d0 + i] = infl[s0 + i];
-        } else if (dist == 1) {
-          const uint8_t v = infl[s0];
-          for (uint32_t i = lane; i < len; i += 32) infl[d0 + i] = v;
-        } else {
-          for (uint32_t i = lane; i < len; i += 32) infl[d0 + i] = infl[s0 + i % dist];
-        }
-        outpos += len;
+#undef INF_REFILL
+        if (pend_n && (uint32_t)lane < pend_n) *pend_p = pend_v;
+        br.lo = lo; br.hi = hi; br.nxt = nxt; br.bp = bp; br.wi = wi;
+        // normalise (a block may end with bp in [32, 47))
+        if (br.bp >= 32u) { br.lo = br.hi; br.hi = br.nxt; br.nxt = __ldg(br.base + br.wi); br.wi++; br.bp -= 32u; }
       }
       if (br.exhausted() && err == INF_OK) err = INF_ERR_INPUT;
     }
