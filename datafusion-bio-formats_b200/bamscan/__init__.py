@@ -28,7 +28,8 @@ LIB_PATH = _HERE.parent / "libbamscan.so"
 EXPORTED_SYMBOLS = [
     "bamscan_open", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
     "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_plan_num_ranges",
-    "bamscan_plan_range_info", "bamscan_execute", "bamscan_next",
+    "bamscan_plan_range_info", "bamscan_plan_partition_regions", "bamscan_extract_regions", "bamscan_balance_partitions",
+    "bamscan_execute", "bamscan_next",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
     "bamscan_last_error", "bamscan_version",
 ]
@@ -52,6 +53,22 @@ class _Options(C.Structure):
 class _Filter(C.Structure):
     _fields_ = [("column", C.c_int32), ("op", C.c_int32), ("n_values", C.c_int32),
                 ("num_values", C.POINTER(C.c_double)), ("str_values", C.POINTER(C.c_char_p))]
+
+
+class RegionAnalysis(C.Structure):
+    _fields_ = [("unsatisfiable", C.c_int32), ("has_start", C.c_int32), ("has_end", C.c_int32), ("n_chroms", C.c_int32),
+                ("start", C.c_uint64), ("end", C.c_uint64), ("residual_mask", C.c_uint64), ("chroms", C.c_ubyte * 4096)]
+
+
+class RegionEstimate(C.Structure):
+    _fields_ = [("chrom", C.c_char_p), ("has_start", C.c_int32), ("has_end", C.c_int32), ("start", C.c_uint64), ("end", C.c_uint64),
+                ("estimated_bytes", C.c_uint64), ("contig_length", C.c_uint64), ("unmapped_count", C.c_uint64),
+                ("nonempty_bin_positions", C.POINTER(C.c_uint64)), ("n_bin_positions", C.c_int32), ("leaf_bin_span", C.c_uint64)]
+
+
+class AssignedRegion(C.Structure):
+    _fields_ = [("partition", C.c_int32), ("estimate_index", C.c_int32), ("has_start", C.c_int32), ("has_end", C.c_int32),
+                ("start", C.c_uint64), ("end", C.c_uint64), ("unmapped_tail", C.c_int32), ("partition_total_estimated_bytes", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -95,6 +112,10 @@ def load_library():
     L.bamscan_plan_free.argtypes = [C.c_void_p]
     L.bamscan_plan_num_ranges.argtypes = [C.c_void_p, C.c_int32]
     L.bamscan_plan_range_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
+    L.bamscan_plan_partition_regions.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AssignedRegion), C.c_int32]
+    L.bamscan_extract_regions.argtypes = [C.POINTER(_Filter), C.c_int32, C.c_int32, C.POINTER(RegionAnalysis)]
+    L.bamscan_balance_partitions.argtypes = [C.POINTER(RegionEstimate), C.c_int32, C.c_int32, C.POINTER(AssignedRegion), C.c_int32,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.bamscan_execute.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.bamscan_next.argtypes = [C.c_void_p, C.c_void_p]
     L.bamscan_stream_free.argtypes = [C.c_void_p]
@@ -165,15 +186,24 @@ class BamExec:
         """Block ranges (+ row rule) a partition scans: list of dicts (bamscan_plan_range_info)."""
         L = load_library()
         keys = ["block_begin", "block_end", "coff_begin", "coff_end", "exact_start", "first_uoff", "stop_uoff",
-                "region_mode", "region_ref", "region_start", "region_end", "estimated_bytes"]
+                "region_mode", "region_ref", "region_start", "region_end", "estimated_bytes", "start_voffset", "stop_voffset"]
         out = []
         for r in range(L.bamscan_plan_num_ranges(self._h, partition)):
-            buf = (C.c_uint64 * 12)()
+            buf = (C.c_uint64 * 14)()
             _check(L.bamscan_plan_range_info(self._h, partition, r, buf))
             d = dict(zip(keys, list(buf)))
             d["region_ref"] = C.c_int64(d["region_ref"]).value
             out.append(d)
         return out
+
+    def partition_regions(self, partition: int):
+        """GenomicRegions assigned to a partition (PartitionAssignment::regions): list of dicts."""
+        L = load_library()
+        n = L.bamscan_plan_partition_regions(self._h, partition, None, 0)
+        arr = (AssignedRegion * max(1, n))()
+        L.bamscan_plan_partition_regions(self._h, partition, arr, n)
+        return [dict(ref=a.estimate_index, start=a.start if a.has_start else None, end=a.end if a.has_end else None,
+                     unmapped_tail=bool(a.unmapped_tail), estimated_bytes=a.partition_total_estimated_bytes) for a in arr[:n]]
 
     def schema(self) -> pa.Schema:
         cs = _ArrowSchemaStruct()
@@ -268,7 +298,7 @@ class BamTableProvider:
         o.skip_crc = int(skip_crc)
         o.debug_flags = debug_flags
         self._h = C.c_void_p()
-        _check(L.bamscan_open(str(file_path).encode(), index_path.encode() if index_path else None, C.byref(o), C.byref(self._h)))
+        _check(L.bamscan_open(str(file_path).encode(), index_path.encode() if index_path is not None else None, C.byref(o), C.byref(self._h)))
         self.file_path = str(file_path)
         self._schema = None
 
@@ -312,3 +342,49 @@ class BamTableProvider:
         _check(L.bamscan_plan(self._h, proj, n_proj, pack.arr, pack.n, -1 if limit is None else int(limit),
                               int(target_partitions), mode, C.byref(ph)))
         return BamExec(self, ph)
+
+
+def extract_genomic_regions(filters, coordinate_system_zero_based: bool) -> dict:
+    """== extract_genomic_regions (genomic_filter.rs:51-100) over [(column, op, values)]."""
+    pack = _FilterPack(filters, CORE_COLUMNS)
+    out = RegionAnalysis()
+    _check(load_library().bamscan_extract_regions(pack.arr, pack.n, int(coordinate_system_zero_based), C.byref(out)))
+    raw = bytes(out.chroms)
+    chroms = [c.decode() for c in raw.split(b"\0")[:out.n_chroms]]
+    start = out.start if out.has_start else None
+    end = out.end if out.has_end else None
+    regions = [] if out.unsatisfiable else [dict(chrom=c, start=start, end=end, unmapped_tail=False) for c in chroms]
+    return dict(regions=regions, unsatisfiable=bool(out.unsatisfiable), start=start, end=end,
+                residual=[i for i in range(pack.n) if (out.residual_mask >> i) & 1])
+
+
+def balance_partitions(estimates, target_partitions: int):
+    """== balance_partitions (partition_balancer.rs:61-295).  estimates: list of dicts with keys chrom, bytes and optionally
+    start, end, contig_length, unmapped_count, bins, leaf_bin_span.  Returns a list of partitions:
+    dict(regions=[dict(chrom, start, end, unmapped_tail)], total_estimated_bytes)."""
+    n = len(estimates)
+    arr = (RegionEstimate * max(1, n))()
+    keep = []
+    for i, e in enumerate(estimates):
+        name = e["chrom"].encode(); keep.append(name)
+        arr[i].chrom = name
+        arr[i].has_start = int(e.get("start") is not None); arr[i].start = e.get("start") or 0
+        arr[i].has_end = int(e.get("end") is not None); arr[i].end = e.get("end") or 0
+        arr[i].estimated_bytes = e["bytes"]; arr[i].contig_length = e.get("contig_length") or 0
+        arr[i].unmapped_count = e.get("unmapped_count", 0)
+        bins = e.get("bins") or []
+        if bins:
+            b = (C.c_uint64 * len(bins))(*bins); keep.append(b)
+            arr[i].nonempty_bin_positions = b
+        arr[i].n_bin_positions = len(bins); arr[i].leaf_bin_span = e.get("leaf_bin_span", 0)
+    cap = 64 * max(1, n) + 4 * max(1, target_partitions) + 64
+    out = (AssignedRegion * cap)()
+    n_out, n_parts = C.c_int32(), C.c_int32()
+    _check(load_library().bamscan_balance_partitions(arr, n, target_partitions, out, cap, C.byref(n_out), C.byref(n_parts)))
+    parts = [dict(regions=[], total_estimated_bytes=0) for _ in range(n_parts.value)]
+    for a in out[:n_out.value]:
+        p = parts[a.partition]
+        p["total_estimated_bytes"] = a.partition_total_estimated_bytes
+        p["regions"].append(dict(chrom=estimates[a.estimate_index]["chrom"], start=a.start if a.has_start else None,
+                                 end=a.end if a.has_end else None, unmapped_tail=bool(a.unmapped_tail)))
+    return parts

@@ -22,6 +22,7 @@
 
 #include "bamscan_internal.h"
 #include "kernels_decode.cuh"
+#include "kernels_filter.cuh"
 #include "kernels_inflate.cuh"
 
 namespace bamscan {
@@ -149,7 +150,8 @@ struct BamScanStream {
   std::vector<int32_t> dec_cols;          // schema indices, unique
   std::vector<int32_t> out_to_dec;        // projection position -> index into dec_cols
   // device memory
-  DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_tiles, d_totals, d_scratch, d_arena[2], d_refs;
+  DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_recoff2, d_keep, d_tiles, d_totals, d_scratch, d_arena[2], d_refs;
+  bool tail_seen = false, range_stop = false;   // per-reference unmapped tail state (physical_exec.rs:1203-1215)
   const uint8_t* d_comp_all = nullptr; DeviceBuf d_comp_all_buf; uint64_t comp_all_c0 = 0;
   uint32_t* h_flags = nullptr;            // pinned mirror: [0..15] boundary flags / inflate err, [16..] totals (u64)
   int arena_flip = 0;
@@ -227,7 +229,7 @@ static void stream_destroy(BamScanStream* s) {
   if (s->pending.valid) { owner_unref(s->pending.owner); if (s->pending.done) cudaEventDestroy(s->pending.done); }
   for (size_t i = s->ready_pos; i < s->ready.size(); i++) owner_unref(s->ready[i].owner);
   for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl, &s->d_carry, &s->d_status, &s->d_flags, &s->d_seg,
-                  &s->d_recoff, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf}) b->release();
+                  &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf}) b->release();
   if (s->h_flags) cudaFreeHost(s->h_flags);
   for (auto& e : s->ev_h2d) if (e) cudaEventDestroy(e);
   if (s->ev_compute) cudaEventDestroy(s->ev_compute);
@@ -306,8 +308,8 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   else { d_comp = s->d_comp[slot].as<uint8_t>(); CU_TRY(cudaStreamWaitEvent(cs, s->ev_h2d[slot], 0)); }
   CU_TRY(cudaMemcpyAsync(s->d_blk[slot].p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, cs));   // pageable source: staged synchronously by the driver
   CU_TRY(cudaMemsetAsync(d_flags, 0, 64, cs));
-  uint32_t init2 = 0xffffffffu;
-  CU_TRY(cudaMemcpyAsync(d_flags + 2, &init2, 4, cudaMemcpyHostToDevice, cs));
+  CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
+  CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
   CU_TRY(cudaEventRecord(s->ev_t[0], cs));
   uint8_t* U = s->d_infl.as<uint8_t>();
   if (nb) {
@@ -371,7 +373,38 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     uint32_t* d_recoff = s->d_recoff.as<uint32_t>();
     seg_emit_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, d_seg_start, d_seg_count, d_seg_base, d_recoff, n_rec, tail_off);
     s->st.kernel_launches++;
-    const uint32_t n = n_rec;
+    uint32_t n = n_rec;
+    if (range.region_mode > 0) {
+      // ---- row rule of the indexed scan + residual filters -> compacted record list
+      RowRule RR;
+      memset(&RR, 0, sizeof RR);
+      RR.mode = range.region_mode; RR.ref = range.region_ref; RR.start1 = (uint32_t)range.region_start; RR.end1 = (uint32_t)range.region_end;
+      RR.zero_based = f->zero_based; RR.seen_before = s->tail_seen;
+      for (const RecordFilter& rf : s->plan->residual) {
+        if (RR.n_filters >= MAX_DEV_FILTERS || rf.nums.size() > (size_t)MAX_FILTER_VALUES || rf.strs.size() > (size_t)MAX_FILTER_VALUES) continue;   // not pushed: DataFusion re-applies it (Inexact)
+        DevFilter& D = RR.f[RR.n_filters++];
+        D.column = rf.column; D.op = rf.op; D.is_str = !rf.strs.empty(); D.n = (int32_t)(D.is_str ? rf.strs.size() : rf.nums.size());
+        for (size_t k = 0; k < rf.nums.size(); k++) D.nums[k] = rf.nums[k];
+        for (size_t k = 0; k < rf.strs.size(); k++) { D.refs[k] = -2; for (size_t r = 0; r < f->ref_names.size(); r++) if (f->ref_names[r] == rf.strs[k]) { D.refs[k] = (int32_t)r; break; } }
+        if (rf.column == BAMSCAN_COL_END) RR.needs_end = 1;
+      }
+      if ((rc = s->d_keep.ensure(8ull * n_rec + 64))) return rc;
+      if ((rc = s->d_recoff2.ensure(4ull * (n_rec + 1)))) return rc;
+      uint32_t* d_keep = s->d_keep.as<uint32_t>(); uint32_t* d_pos = d_keep + n_rec;
+      if (RR.mode == 2) { rule_first_target_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(U, d_recoff, n_rec, RR.ref, d_flags); s->st.kernel_launches++; }
+      rule_keep_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(U, d_recoff, n_rec, RR, d_keep, d_flags);
+      rule_scan_kernel<<<1, 1024, 0, cs>>>(d_keep, d_pos, n_rec, d_flags);
+      rule_compact_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(d_recoff, d_pos, n_rec, s->d_recoff2.as<uint32_t>());
+      s->st.kernel_launches += 3;
+      CU_TRY(cudaMemcpyAsync(s->h_flags, d_flags, 64, cudaMemcpyDeviceToHost, cs));
+      CU_TRY(cudaEventRecord(s->ev_flags, cs));
+      CU_TRY(cudaEventSynchronize(s->ev_flags));
+      CU_TRY(cudaGetLastError());
+      n = s->h_flags[7];
+      if (RR.mode == 2) { if (s->h_flags[5] != 0xffffffffu) s->tail_seen = true; if (s->h_flags[6] != 0xffffffffu) s->range_stop = true; }
+      d_recoff = s->d_recoff2.as<uint32_t>();
+      if (n == 0) { CU_TRY(cudaEventRecord(s->ev_t[3], cs)); goto timing; }
+    }
     // ---- arena region A
     const size_t n_dec = s->dec_cols.size();
     std::vector<ColLayout> cols(n_dec);
@@ -549,6 +582,8 @@ static int advance(BamScanStream* s, bool* produced) {
     if (!s->range_open) {
       if (s->range_idx >= s->part->ranges.size()) { s->finished = true; return 0; }
       const ScanRange& r = s->part->ranges[s->range_idx];
+      if (r.region_mode < 0) { set_error("BAM region query failed: a region names a reference sequence that is not in the BAM header"); return BAMSCAN_ERR_INVALID; }
+      s->tail_seen = false; s->range_stop = false;
       s->chunks.clear(); s->chunk_idx = 0; s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = !r.exact_start;
       plan_chunks(*f, r.block_begin, r.block_end, false, &s->chunks);
       s->range_open = true;
@@ -585,6 +620,7 @@ static int advance(BamScanStream* s, bool* produced) {
     s->carry_len = new_carry;
     s->chunk_idx++;
     if (owned_done && s->chunks[k].extension) { s->carry_len = 0; s->range_open = false; s->range_idx++; }   // the tail record is complete
+    else if (s->range_stop) { s->carry_len = 0; s->range_open = false; s->range_idx++; }                      // unmapped tail: another reference began
     return 1;
   }
 }
@@ -719,7 +755,7 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
   // a file whose header cannot be read still yields a provider with empty metadata (table_provider.rs:423-426);
   // scans on it fail later
   if ((rc = build_schema(&f, &opt))) { if (f.data) pinned_free(f.data); return rc; }
-  if (index_path_or_null) f.index_path = index_path_or_null; else f.index_path = discover_index(f.path);
+  if (index_path_or_null) f.index_path = index_path_or_null; else f.index_path = discover_index(f.path);   // "" = no index
   if (!f.index_path.empty()) {
     f.bai.reset(new BaiIndex());
     if (load_bai(f.index_path, f.bai.get()) != BAMSCAN_OK) { f.bai.reset(); if (index_path_or_null) { pinned_free(f.data); return BAMSCAN_ERR_IO; } f.index_path.clear(); }
@@ -771,7 +807,25 @@ int32_t bamscan_plan_num_ranges(const BamScanPlan* plan, int32_t partition) {
   return (int32_t)plan->plan->partitions[partition].ranges.size();
 }
 
-int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t range, uint64_t out[12]) {
+int32_t bamscan_plan_partition_regions(const BamScanPlan* plan, int32_t partition, struct BamScanAssignedRegion* out, int32_t cap) {
+  if (!plan || partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) return -1;
+  const Partition& P = plan->plan->partitions[partition];
+  const BamFile& f = *plan->plan->file;
+  int32_t k = 0;
+  for (const GenomicRegion& g : P.regions) {
+    if (k < cap && out) {
+      int ref = -1;
+      for (size_t r = 0; r < f.ref_names.size(); r++) if (f.ref_names[r] == g.chrom) { ref = (int)r; break; }
+      out[k].partition = partition; out[k].estimate_index = ref;
+      out[k].has_start = g.has_start; out[k].start = g.start; out[k].has_end = g.has_end; out[k].end = g.end;
+      out[k].unmapped_tail = g.unmapped_tail; out[k].partition_total_estimated_bytes = P.estimated_bytes;
+    }
+    k++;
+  }
+  return k;
+}
+
+int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t range, uint64_t out[14]) {
   if (!plan || !out || partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) { set_error("bad partition"); return BAMSCAN_ERR_INVALID; }
   const Partition& P = plan->plan->partitions[partition];
   if (range < 0 || range >= (int32_t)P.ranges.size()) { set_error("bad range"); return BAMSCAN_ERR_INVALID; }
@@ -783,6 +837,13 @@ int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t 
   out[4] = r.exact_start; out[5] = r.first_uoff; out[6] = r.stop_uoff;
   out[7] = (uint64_t)r.region_mode; out[8] = (uint64_t)(int64_t)r.region_ref; out[9] = r.region_start; out[10] = r.region_end;
   out[11] = P.estimated_bytes;
+  auto to_voffset = [&](uint64_t uoff) -> uint64_t {
+    if (uoff == ~0ull || uoff >= f.total_inflated) return uoff == ~0ull ? 0 : (uint64_t)f.size << 16;
+    size_t lo = 0, hi = f.blocks.size();
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (f.blocks[mid].uoff + f.blocks[mid].isize <= uoff) lo = mid + 1; else hi = mid; }
+    return (f.blocks[lo].coff << 16) | (uoff - f.blocks[lo].uoff);
+  };
+  out[12] = to_voffset(r.first_uoff); out[13] = to_voffset(r.stop_uoff);   // virtual offsets (stop 0 = none)
   return BAMSCAN_OK;
 }
 

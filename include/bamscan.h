@@ -95,6 +95,7 @@ enum {
                                         concatenated in partition order the rows equal the 1-partition scan */
 };
 
+struct BamScanAssignedRegion;
 typedef struct BamScanStats {
   uint64_t rows, batches, chunks;
   uint64_t compressed_bytes, inflated_bytes, arrow_bytes;   /* B_comp, B_inflated, B_arrow */
@@ -104,7 +105,8 @@ typedef struct BamScanStats {
 } BamScanStats;
 
 /* == BamTableProvider::new (table_provider.rs:381-529): header read, tag-type inference, schema, index discovery.
- * index_path_or_null: NULL => discover `<path>.bai`, `<stem>.bai`, `<path>.csi` (index_utils.rs:43-76). */
+ * index_path_or_null: NULL => discover `<path>.bai`, `<stem>.bai` (index_utils.rs:43-76; CSI is not read by this build);
+ * "" => behave as if no index existed (sequential single-partition scans). */
 int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
 void bamscan_close(BamScanHandle* h);
 
@@ -122,11 +124,50 @@ int32_t bamscan_plan_num_partitions(const BamScanPlan* plan);   /* == output_par
 int bamscan_plan_schema(const BamScanPlan* plan, struct ArrowSchema* out);   /* == ExecutionPlan::schema (projected) */
 void bamscan_plan_free(BamScanPlan* plan);
 /* Introspection of a partition's device work (== BamExec::partition_assignments, physical_exec.rs:52): number of block
- * ranges and, per range, out[12] = { block_begin, block_end, compressed offset of block_begin, compressed offset of
- * block_end, exact_start, first inflated offset, stop inflated offset (~0 = none), region_mode, region_ref,
- * region_start, region_end (1-based closed, 0 = open), partition estimated bytes }. */
+ * ranges and, per range, out[14] = { block_begin, block_end, compressed offset of block_begin, compressed offset of
+ * block_end, exact_start, first inflated offset, stop inflated offset (~0 = none), region_mode (0 none, 1 mapped region,
+ * 2 per-reference unmapped tail, 3 "*" unplaced), region_ref, region_start, region_end (1-based closed, 0 = open),
+ * partition estimated bytes, start virtual offset, stop virtual offset (0 = none) }. */
 int32_t bamscan_plan_num_ranges(const BamScanPlan* plan, int32_t partition);
-int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t range, uint64_t out[12]);
+int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t range, uint64_t out[14]);
+/* The GenomicRegions assigned to a partition (== PartitionAssignment::regions): returns the count; fills up to `cap`
+ * entries (estimate_index = reference id of the region's chromosome, -1 for "*" / unknown names). */
+int32_t bamscan_plan_partition_regions(const BamScanPlan* plan, int32_t partition, struct BamScanAssignedRegion* out, int32_t cap);
+
+/* == extract_genomic_regions (bio-format-core/src/genomic_filter.rs:51-100): the conjunction of `filters` reduced to
+ * chromosomes + one [start, end] window in 1-based closed coordinates.  `chroms` holds n_chroms NUL-terminated names,
+ * sorted and de-duplicated; bit i of residual_mask is set when filter i was NOT consumed as a genomic constraint. */
+typedef struct BamScanRegionAnalysis {
+  int32_t unsatisfiable, has_start, has_end, n_chroms;
+  uint64_t start, end, residual_mask;
+  char chroms[4096];
+} BamScanRegionAnalysis;
+int bamscan_extract_regions(const BamScanFilter* filters, int32_t n_filters, int32_t coordinate_system_zero_based,
+                            BamScanRegionAnalysis* out);
+
+/* == balance_partitions (bio-format-core/src/partition_balancer.rs:15-41, 61-295).  Input = RegionSizeEstimate[],
+ * output = the regions of every PartitionAssignment, flattened in partition order (estimate_index says which input
+ * estimate a (sub-)region came from). */
+typedef struct BamScanRegionEstimate {
+  const char* chrom;
+  int32_t has_start, has_end;
+  uint64_t start, end;                 /* 1-based closed */
+  uint64_t estimated_bytes;
+  uint64_t contig_length;              /* 0 = None */
+  uint64_t unmapped_count;
+  const uint64_t* nonempty_bin_positions;
+  int32_t n_bin_positions;
+  uint64_t leaf_bin_span;
+} BamScanRegionEstimate;
+typedef struct BamScanAssignedRegion {
+  int32_t partition, estimate_index;
+  int32_t has_start, has_end;
+  uint64_t start, end;
+  int32_t unmapped_tail;
+  uint64_t partition_total_estimated_bytes;
+} BamScanAssignedRegion;
+int bamscan_balance_partitions(const BamScanRegionEstimate* estimates, int32_t n, int32_t target_partitions,
+                               BamScanAssignedRegion* out, int32_t cap, int32_t* n_out, int32_t* n_partitions);
 
 /* == ExecutionPlan::execute(partition, ctx) (physical_exec.rs:108-172). */
 int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out);

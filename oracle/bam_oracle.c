@@ -581,7 +581,7 @@ ORC_API OrcResult *orc_scan(const OrcFile *f, const OrcArgs *a) {
   size_t rec_cap = 1 << 16; uint8_t *rec = (uint8_t *)malloc(rec_cap);
   Buf tmp = {0};
   int64_t rows = 0, batch_rows = 0;
-  int rc_err = 0;
+  int rc_err = 0, seen_target = 0;
 
   if (skip) { if (bgzf_settle(z) <= 0 || z->buf_len < skip) { snprintf(r->err, sizeof r->err, "bad start voffset"); rc_err = 1; } else z->buf_pos = skip; }
 
@@ -628,11 +628,14 @@ ORC_API OrcResult *orc_scan(const OrcFile *f, const OrcArgs *a) {
       if (a->region_start && start1 < (uint64_t)a->region_start) continue;
       if (a->region_end && start1 > (uint64_t)a->region_end) continue;
       if (!eval_filters(a, ref_id >= 0 ? f->ref_names[ref_id] : NULL, has_start, a->zero_based ? start1 - 1 : start1, has_end, end1, mapq, flag)) continue;
-    } else if (a->region_mode == 2) {    /* :1131-1258 per-reference unmapped tail */
-      if (ref_id != a->region_ref) break;
+    } else if (a->region_mode == 2) {    /* :1131-1258 per-reference unmapped tail: skip until the reference is seen, stop after it */
+      if (ref_id != a->region_ref) { if (seen_target) break; continue; }
+      seen_target = 1;
       if (has_start) continue;
+      if (!eval_filters(a, f->ref_names[ref_id], 0, 0, 0, 0, mapq, flag)) continue;
     } else if (a->region_mode == 3) {    /* :1038-1129 "*" partition */
       if (ref_id != -1 || has_start) continue;
+      if (!eval_filters(a, NULL, 0, 0, 0, 0, mapq, flag)) continue;
     }
 
     if (need[0]) { /* name: physical_exec.rs:413-418 */

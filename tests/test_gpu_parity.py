@@ -23,6 +23,7 @@ def _oracle(path, **kw):
 def _provider(path, **kw):
     import bamscan
     zero_based = kw.pop("zero_based", True)
+    kw.setdefault("index_path", "")      # these tests pin the sequential path (physical_exec.rs:371-598); indexed scans: test_gpu_indexed.py
     return bamscan.BamTableProvider(str(path), None, zero_based, kw.pop("tag_fields", None), kw.pop("binary_cigar", False),
                                     kw.pop("infer_tag_types", True), kw.pop("infer_tag_sample_size", 100),
                                     kw.pop("tag_type_hints", None), **kw)
@@ -70,7 +71,7 @@ def test_fixture_full_projection(name, tags, rows, zero_based):
 
 def test_multi_chrom_counts_and_pins():
     # indexed_read_test.rs:76-77,108,121 ; SURVEY App. C first/last record
-    p = _provider(GOLDEN / "multi_chrom.bam", index_path=None)
+    p = _provider(GOLDEN / "multi_chrom.bam")
     t = p.scan(None, [], None).collect()
     c = collections.Counter(t["chrom"].to_pylist())
     assert (c["chr1"], c["chr2"], c["chrX"]) == (160, 159, 102)

@@ -1,0 +1,251 @@
+"""CPU: the indexed-scan planning functions of the product, replaying the reference's own unit tests
+(bio-format-core/src/genomic_filter.rs:350-557 and partition_balancer.rs:297-1005) through the C ABI mirrors
+bamscan_extract_regions / bamscan_balance_partitions, plus plan-level pins of table_provider.rs:1001-1093."""
+import pytest
+
+from conftest import GOLDEN, gen_bam
+
+
+def eg(filters, zero_based):
+    import bamscan
+    return bamscan.extract_genomic_regions(filters, zero_based)
+
+
+def bp(estimates, target):
+    import bamscan
+    return bamscan.balance_partitions(estimates, target)
+
+
+def est(chrom, b, contig_len=None, unmapped=0, bins=None, span=0):
+    return dict(chrom=chrom, bytes=b, contig_length=contig_len, unmapped_count=unmapped, bins=bins, leaf_bin_span=span)
+
+
+# ---------------------------------------------------------------- genomic_filter.rs tests
+def test_extract_chrom_eq():
+    a = eg([("chrom", "=", ["chr1"])], True)
+    assert a["regions"] == [dict(chrom="chr1", start=None, end=None, unmapped_tail=False)] and a["residual"] == []
+
+
+def test_extract_chrom_in_list():
+    a = eg([("chrom", "in", ["chr2", "chr1", "chr1"])], True)
+    assert [r["chrom"] for r in a["regions"]] == ["chr1", "chr2"]        # sorted + de-duplicated (:72-73)
+
+
+@pytest.mark.parametrize("zero_based,lo,want_start", [(True, 999, 1000), (False, 1000, 1000)])
+def test_extract_chrom_with_range(zero_based, lo, want_start):
+    a = eg([("chrom", "=", ["chr1"]), ("start", ">=", [lo]), ("end", "<=", [2000])], zero_based)
+    assert (a["regions"][0]["start"], a["regions"][0]["end"]) == (want_start, 2000) and a["residual"] == []
+
+
+@pytest.mark.parametrize("zero_based,v", [(True, 999), (False, 1000)])
+def test_exact_start_bounds_region(zero_based, v):
+    a = eg([("chrom", "=", ["chr1"]), ("start", "=", [v])], zero_based)
+    assert (a["regions"][0]["start"], a["regions"][0]["end"]) == (1000, 1000)
+
+
+def test_contradictory_start_bounds_unsatisfiable():
+    a = eg([("chrom", "=", ["chr1"]), ("start", "=", [1000]), ("start", ">", [1000])], False)
+    assert a["unsatisfiable"] and a["regions"] == [] and a["residual"] == []
+
+
+@pytest.mark.parametrize("zero_based,lo,hi", [(False, 1000, 2000), (True, 999, 1999)])
+def test_start_upper_bound(zero_based, lo, hi):
+    a = eg([("chrom", "=", ["chr1"]), ("start", ">=", [lo]), ("start", "<=", [hi])], zero_based)
+    assert (a["regions"][0]["start"], a["regions"][0]["end"]) == (1000, 2000)
+
+
+def test_start_exclusive_upper_bound_one_based():
+    a = eg([("chrom", "=", ["chr1"]), ("start", ">=", [1000]), ("start", "<", [2000])], False)
+    assert (a["regions"][0]["start"], a["regions"][0]["end"]) == (1000, 1999)
+
+
+def test_non_genomic_filter_becomes_residual():
+    a = eg([("chrom", "=", ["chr1"]), ("mapping_quality", ">=", [30])], True)
+    assert len(a["regions"]) == 1 and a["residual"] == [1]
+    b = eg([("mapping_quality", ">=", [30])], True)
+    assert b["regions"] == [] and not b["unsatisfiable"] and b["residual"] == [0]
+
+
+def test_between_start_with_and_without_chrom():
+    assert eg([("start", "between", [999, 1999])], True)["regions"] == []
+    a = eg([("chrom", "=", ["chr1"]), ("start", "between", [999, 1999])], True)
+    assert (a["regions"][0]["start"], a["regions"][0]["end"]) == (1000, 2000)
+
+
+def test_shapes_that_stay_residual():
+    # chrom != , start != , end > , NOT BETWEEN, NOT IN: genomic_filter.rs:188-189,225-227,259-261,299,324-327
+    a = eg([("chrom", "=", ["chr1"]), ("chrom", "!=", ["chr2"]), ("start", "!=", [5]), ("end", ">", [7]), ("start", "not_between", [1, 2]),
+            ("chrom", "not_in", ["chrX"]), ("end", "<", [100]), ("start", ">=", [2.5])], False)
+    assert a["residual"] == [1, 2, 3, 4, 5, 7] and a["end"] == 99 and a["start"] is None
+
+
+# ---------------------------------------------------------------- partition_balancer.rs tests
+def test_empty_and_single_partition():
+    assert bp([], 4) == []
+    r = bp([est("chr1", 100), est("chr2", 50), est("chrX", 30)], 1)
+    assert len(r) == 1 and len(r[0]["regions"]) == 3 and r[0]["total_estimated_bytes"] == 180
+
+
+def test_uniform_and_skewed():
+    r = bp([est(c, 100) for c in ("chr1", "chr2", "chr3", "chr4")], 2)
+    assert [p["total_estimated_bytes"] for p in r] == [200, 200]
+    r = bp([est("chr1", 100), est("chr2", 50), est("chr3", 10)], 2)                      # unsplittable
+    assert [p["total_estimated_bytes"] for p in r] == [100, 60]
+    r = bp([est("chr1", 100, 249_000_000), est("chr2", 50), est("chr3", 10)], 2)        # splittable at the byte budget
+    assert [p["total_estimated_bytes"] for p in r] == [80, 80]
+    assert r[0]["regions"] == [dict(chrom="chr1", start=1, end=199_200_000, unmapped_tail=False)]
+    assert r[1]["regions"][0] == dict(chrom="chr1", start=199_200_001, end=None, unmapped_tail=False)
+
+
+def test_region_splitting_and_counts():
+    r = bp([est("chr1", 200, 249_000_000), est("chr2", 10)], 4)
+    assert sum(len(p["regions"]) for p in r) > 2 and len(r) <= 4
+    r = bp([est(f"chr{i}", 0) for i in range(1, 5)], 2)                                   # all-zero: round robin
+    assert [len(p["regions"]) for p in r] == [2, 2]
+    assert len(bp([est("chr1", 100), est("chr2", 50)], 8)) == 2
+    r = bp([est("chr1", 100, 249_000_000), est("chr2", 50, 243_000_000)], 8)
+    assert 2 < len(r) <= 8
+    r = bp([est("chr1", 100)], 4)
+    assert len(r) == 1 and len(r[0]["regions"]) == 1
+
+
+HUMAN = [("chr1", 249), ("chr2", 243), ("chr3", 198), ("chr4", 191), ("chr5", 181), ("chr6", 171), ("chr7", 159), ("chr8", 146),
+         ("chr9", 141), ("chr10", 136), ("chr11", 135), ("chr12", 134), ("chr13", 115), ("chr14", 107), ("chr15", 102), ("chr16", 90),
+         ("chr17", 84), ("chr18", 80), ("chr19", 59), ("chr20", 64), ("chr21", 47), ("chr22", 51), ("chrX", 155), ("chrY", 57)]
+
+
+def test_never_exceeds_target_and_keeps_all_regions():
+    r = bp([est(c, b, l) for c, b, l in [("chr1", 100, 249_000_000), ("chr2", 90, 243_000_000), ("chr3", 80, 198_000_000),
+                                        ("chr4", 70, 191_000_000), ("chr5", 60, 181_000_000), ("chrX", 50, 155_000_000)]], 4)
+    assert len(r) <= 4
+    r = bp([est("chr1", 100), est("chr2", 50), est("chr3", 30), est("chrX", 20)], 3)
+    assert sorted({g["chrom"] for p in r for g in p["regions"]}) == ["chr1", "chr2", "chr3", "chrX"]
+
+
+@pytest.mark.parametrize("target", [2, 4, 8])
+def test_single_contig_splits_to_target_partitions(target):
+    r = bp([est("chr1", 1000, 249_000_000)], target)
+    assert len(r) == target
+    regs = [g for p in r for g in p["regions"]]
+    assert all(g["chrom"] == "chr1" and g["start"] is not None for g in regs)
+    assert all(g["end"] is not None for g in regs[:-1]) and regs[-1]["end"] is None      # last piece open-ended
+
+
+def test_realistic_human_genome_distribution():
+    r = bp([est(c, b, b * 1_000_000) for c, b in HUMAN], 8)
+    assert 0 < len(r) <= 8
+    tot = [p["total_estimated_bytes"] for p in r]
+    assert sum(tot) == sum(b for _, b in HUMAN) and max(tot) <= 2 * min(tot)
+
+
+def test_unmapped_tail_emission():
+    r = bp([est("chr1", 200, 249_000_000, unmapped=1000), est("chr2", 10)], 4)
+    tails = [g for p in r for g in p["regions"] if g["unmapped_tail"]]
+    assert tails == [dict(chrom="chr1", start=None, end=None, unmapped_tail=True)]
+    r = bp([est("chr1", 100, 249_000_000, 500), est("chr2", 95, 243_000_000, 300), est("chrM", 5, 16_569, 100)], 4)
+    assert len([g for p in r for g in p["regions"] if g["chrom"] == "chrM" and g["unmapped_tail"]]) == 1
+
+
+def test_linear_scan_perfect_balance():
+    r = bp([est("chr1", 249, 249_000_000), est("chr2", 243, 243_000_000), est("chr3", 198, 198_000_000), est("chrX", 60, 155_000_000)], 4)
+    assert len(r) == 4 and sum(p["total_estimated_bytes"] for p in r) == 750
+    assert all(187 <= p["total_estimated_bytes"] <= 189 for p in r)
+
+
+def test_zero_byte_regions_not_dropped():
+    r = bp([est("chr1", 0), est("chr2", 100), est("chrX", 0)], 4)
+    assert sorted(g["chrom"] for p in r for g in p["regions"]) == ["chr1", "chr2", "chrX"]
+
+
+@pytest.mark.parametrize("target", [2, 3, 4, 8, 16])
+def test_total_bytes_preserved(target):
+    r = bp([est("chr1", 249, 249_000_000), est("chr2", 243, 243_000_000), est("chr3", 198, 198_000_000)], target)
+    assert sum(p["total_estimated_bytes"] for p in r) == 690
+
+
+def test_bin_aware_split_concentrates_on_data():
+    span = 16384
+    r = bp([est("chr1", 1000, 249_000_000, bins=[i * span + 1 for i in range(100)], span=span)], 4)
+    assert len(r) == 4
+    regs = [g for p in r for g in p["regions"]]
+    assert all(g["end"] < 2_000_000 for g in regs[:-1] if g["end"] is not None)
+
+
+@pytest.mark.parametrize("target", [2, 4, 8])
+def test_bin_aware_preserves_total(target):
+    span = 16384
+    r = bp([est("chr1", 500, 249_000_000, bins=[i * span + 1 for i in range(200)], span=span)], target)
+    assert sum(p["total_estimated_bytes"] for p in r) == 500
+
+
+def test_bin_aware_fallback_when_no_bins():
+    a = bp([est("chr1", 200, 249_000_000, bins=[], span=0)], 4)
+    b = bp([est("chr1", 200, 249_000_000)], 4)
+    assert a == b
+
+
+def test_bin_aware_sparse_wes_pattern():
+    span = 16384
+    bins = sorted([10_000_000 + i * span for i in range(40)] + [50_000_000 + i * span for i in range(30)] + [200_000_000 + i * span for i in range(30)])
+    r = bp([est("chr1", 600, 249_000_000, bins=bins, span=span)], 4)
+    assert len(r) == 4 and sum(p["total_estimated_bytes"] for p in r) == 600
+    for e in [g["end"] for p in r for g in p["regions"] if g["end"] is not None]:
+        assert 10_000_000 <= e <= 11_000_000 or 50_000_000 <= e <= 51_000_000 or 200_000_000 <= e <= 201_000_000
+
+
+def test_zero_estimate_regions_distributed_evenly():
+    ests = [est(c, b, b * 1_000_000) for c, b in HUMAN] + [est(f"alt_contig_{i}", 0) for i in range(60)]
+    r = bp(ests, 8)
+    assert sum(len(p["regions"]) for p in r) >= 84 and sum(p["total_estimated_bytes"] for p in r) == 3095
+    z = [sum(1 for g in p["regions"] if g["chrom"].startswith("alt_contig_")) for p in r]
+    assert max(z) <= 15 and min(z) >= 1
+    ests = [est("chr1", 100, 249_000_000), est("chr2", 80, 243_000_000), est("chr3", 60, 198_000_000)] + [est(f"scaffold_{i}", 0) for i in range(20)]
+    r = bp(ests, 4)
+    s = [sum(1 for g in p["regions"] if g["chrom"].startswith("scaffold_")) for p in r]
+    assert sum(p["total_estimated_bytes"] for p in r) == 240 and max(s) <= 8
+
+
+# ---------------------------------------------------------------- plan-level pins (table_provider.rs:1001-1093)
+def _provider(path, **kw):
+    import bamscan
+    return bamscan.BamTableProvider(str(path), None, True, kw.pop("tag_fields", None), False, True, 100, None, **kw)
+
+
+@pytest.mark.parametrize("tp", [1, 2, 3, 4, 8])
+def test_indexed_full_scan_partition_count_never_exceeds_target(tp):
+    p = _provider(GOLDEN / "multi_chrom.bam")
+    plan = p.scan(None, [], None, target_partitions=tp)
+    n = plan.output_partition_count()
+    assert 1 <= n <= tp
+    regs = [g for i in range(n) for g in plan.partition_regions(i)]
+    assert {g["ref"] for g in regs} == {0, 1, 2}                       # one (possibly split) region per reference
+    # BAI metadata (mapped, unmapped) = (159,1) (157,2) (100,2) => a tail per reference; the target == 1 fast path emits none
+    # (partition_balancer.rs:71-79)
+    assert sum(1 for g in regs if g["unmapped_tail"]) == (3 if tp > 1 else 0)
+
+
+def test_unsatisfiable_filters_give_empty_exec():
+    p = _provider(GOLDEN / "multi_chrom.bam")
+    plan = p.scan(None, [("chrom", "=", ["chr1"]), ("start", ">", [1000]), ("start", "<", [500])], None, target_partitions=4)
+    assert plan.output_partition_count() == 0                          # EmptyExec (table_provider.rs:1005-1010)
+
+
+def test_no_coor_file_gets_star_partition():
+    # table_provider.rs:1048-1056, :1180-1206 ; tests/no_coor_only.bam(.bai): n_no_coor = 2, one reference without bins
+    p = _provider(GOLDEN / "no_coor_only.bam")
+    plan = p.scan(None, [], None, target_partitions=4)
+    n = plan.output_partition_count()
+    last = plan.partition_regions(n - 1)
+    assert last == [dict(ref=-1, start=None, end=None, unmapped_tail=True, estimated_bytes=2)]
+    assert [r["region_mode"] for r in plan.partition_ranges(n - 1)] == [3]
+
+
+def test_region_query_ranges_cover_only_needed_blocks(syn_dir):
+    path = gen_bam(syn_dir, "short", 20000, seed=4, bai=True)
+    p = _provider(path)
+    total_blocks = p.scan(None, [], None, partition_mode="block_range").partition_ranges(0)[0]["block_end"]
+    plan = p.scan(None, [("chrom", "=", ["chr2"]), ("start", "between", [100_000_000, 120_000_000])], None, target_partitions=2)
+    ranges = [r for i in range(plan.output_partition_count()) for r in plan.partition_ranges(i)]
+    assert ranges and all(r["region_mode"] in (1, 2) and r["region_ref"] == 1 for r in ranges)
+    touched = sum(r["block_end"] - r["block_begin"] for r in ranges if r["region_mode"] == 1)
+    assert touched < total_blocks // 4                                   # the index pruned most of the file
