@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "bamscan_plan_range_info", "bamscan_plan_partition_regions", "bamscan_extract_regions", "bamscan_balance_partitions",
     "bamscan_execute", "bamscan_next",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
-    "bamscan_last_error", "bamscan_version",
+    "bamscan_probe_pcie", "bamscan_last_error", "bamscan_version",
 ]
 
 
@@ -123,6 +123,7 @@ def load_library():
     L.bamscan_stream_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.bamscan_bench_inflate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64)]
+    L.bamscan_probe_pcie.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -388,3 +389,9 @@ def balance_partitions(estimates, target_partitions: int):
         p["regions"].append(dict(chrom=estimates[a.estimate_index]["chrom"], start=a.start if a.has_start else None,
                                  end=a.end if a.has_end else None, unmapped_tail=bool(a.unmapped_tail)))
     return parts
+
+
+def probe_pcie(device_id=0, nbytes=1 << 30) -> dict:
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    _check(load_library().bamscan_probe_pcie(device_id, nbytes, C.byref(a), C.byref(b), C.byref(c)))
+    return {"h2d_gbps": a.value, "d2h_gbps": b.value, "bidir_gbps": c.value, "bytes": nbytes}

@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 
 #include "bamscan_internal.h"
@@ -134,11 +135,13 @@ struct ReadyBatch { BatchOwner* owner; std::vector<ColLayout> cols; uint64_t row
 
 using namespace bamscan;
 
-struct BamScanHandle { BamFile file; };
+struct BamScanStream;
+struct BamScanHandle { BamFile file; std::mutex mu; std::vector<BamScanStream*> idle_streams; };   // idle_streams: device buffers, CUDA streams and events kept for the next execute()
 struct BamScanPlan { Plan* plan = nullptr; BamScanHandle* handle = nullptr; };
 
 struct BamScanStream {
-  Plan* plan = nullptr; BamFile* f = nullptr; const Partition* part = nullptr;
+  Plan* plan = nullptr; BamFile* f = nullptr; const Partition* part = nullptr; BamScanHandle* handle = nullptr;
+  bool resources_ready = false;
   bool device_resident = false;
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute = nullptr, ev_flags = nullptr, ev_t[6] = {};
@@ -164,6 +167,7 @@ struct BamScanStream {
 namespace bamscan {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static double wall_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 static bool g_crc_init[64] = {};
 static int init_device_constants(int dev) {
@@ -181,7 +185,14 @@ static int init_device_constants(int dev) {
 static int stream_init(BamScanStream* s) {
   BamFile* f = s->f;
   CU_TRY(cudaSetDevice(f->device));
-  int rc = init_device_constants(f->device);
+  int rc = BAMSCAN_OK;
+  // per-scan state
+  s->range_idx = 0; s->chunks.clear(); s->chunk_idx = 0; s->range_open = false; s->finished = false;
+  s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = false; s->tail_seen = false; s->range_stop = false;
+  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
+  s->st = BamScanStats{}; s->error = 0; s->d_comp_all = nullptr; s->comp_all_c0 = 0;
+  if (!s->resources_ready) {
+  rc = init_device_constants(f->device);
   if (rc) return rc;
   CU_TRY(cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
@@ -205,6 +216,8 @@ static int stream_init(BamScanStream* s) {
   if (n_ref) CU_TRY(cudaMemcpy(s->d_refs.as<uint8_t>() + o_len, f->ref_lens.data(), 4 * n_ref, cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(s->d_refs.as<uint8_t>() + o_off, offs.data(), 4 * (n_ref + 1), cudaMemcpyHostToDevice));
   if (!blob.empty()) CU_TRY(cudaMemcpy(s->d_refs.as<uint8_t>() + o_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  s->resources_ready = true;
+  }
   // unique decode columns
   const Plan* P = s->plan;
   std::vector<int32_t> proj;
@@ -220,7 +233,7 @@ static int stream_init(BamScanStream* s) {
   return BAMSCAN_OK;
 }
 
-static void stream_destroy(BamScanStream* s) {
+static void stream_destroy(BamScanStream* s, bool recycle = true) {
   if (!s) return;
   cudaSetDevice(s->f->device);
   if (s->s_compute) cudaStreamSynchronize(s->s_compute);
@@ -228,6 +241,12 @@ static void stream_destroy(BamScanStream* s) {
   if (s->s_d2h) cudaStreamSynchronize(s->s_d2h);
   if (s->pending.valid) { owner_unref(s->pending.owner); if (s->pending.done) cudaEventDestroy(s->pending.done); }
   for (size_t i = s->ready_pos; i < s->ready.size(); i++) owner_unref(s->ready[i].owner);
+  s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
+  s->d_comp_all_buf.release();     // the staged copy of a whole partition is never kept
+  if (recycle && s->resources_ready && s->handle && cudaGetLastError() == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(s->handle->mu);
+    if (s->handle->idle_streams.size() < 2) { s->handle->idle_streams.push_back(s); return; }
+  }
   for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl, &s->d_carry, &s->d_status, &s->d_flags, &s->d_seg,
                   &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf}) b->release();
   if (s->h_flags) cudaFreeHost(s->h_flags);
@@ -273,6 +292,8 @@ struct ArenaBuilder {
 static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& range, int slot, bool first_of_range, bool* produced, uint32_t* new_carry, bool* owned_done) {
   BamFile* f = s->f;
   *produced = false;
+  static const bool trace2 = getenv("BAMSCAN_TRACE") && atoi(getenv("BAMSCAN_TRACE")) >= 2;
+  const double tw0 = wall_ms(); double tw1 = 0, tw2 = 0, tw3 = 0;
   const uint32_t nb_all = c.b1 - c.b0;
   // ---- block descriptors
   std::vector<BlockDesc> descs;
@@ -311,6 +332,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
   CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
   CU_TRY(cudaEventRecord(s->ev_t[0], cs));
+  tw1 = wall_ms();
   uint8_t* U = s->d_infl.as<uint8_t>();
   if (nb) {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
@@ -347,6 +369,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaEventSynchronize(s->ev_flags));
   CU_TRY(cudaGetLastError());
   // ---- host: decisions
+  tw2 = wall_ms();
   const uint32_t* hf = s->h_flags;
   if (hf[9]) {
     uint32_t bi = (hf[9] & 0x7fffffffu) >> 4, code = hf[9] & 15u;
@@ -490,6 +513,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
       CU_TRY(cudaEventSynchronize(s->ev_flags));
       CU_TRY(cudaGetLastError());
       // ---- arena region B
+      tw3 = wall_ms();
       for (int k = 0; k < SC.n_cols; k++) {
         ColLayout& L = cols[scan_owner[k]];
         uint64_t tot = h_totals[k];
@@ -569,6 +593,8 @@ timing:
     cudaEventElapsedTime(&b, s->ev_t[1], s->ev_t[2]);
     cudaEventElapsedTime(&d, s->ev_t[2], s->ev_t[3]);
     s->st.ms_inflate += a; s->st.ms_boundary += b; s->st.ms_decode += d;
+    if (trace2) fprintf(stderr, "[bamscan chunk] prep %.2f | inflate+boundary(sync) %.2f | fixed+scan(sync) %.2f | var+end %.2f ms wall ; gpu inflate %.2f boundary %.2f decode %.2f\n",
+                        tw1 - tw0, tw2 - tw1, tw3 - tw2, wall_ms() - tw3, a, b, d);
   }
   return BAMSCAN_OK;
 }
@@ -766,6 +792,8 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
 
 void bamscan_close(BamScanHandle* h) {
   if (!h) return;
+  for (BamScanStream* s : h->idle_streams) stream_destroy(s, false);
+  h->idle_streams.clear();
   if (h->file.data) { if (g_have_device) cudaSetDevice(h->file.device); pinned_free(h->file.data); }
   delete h;
 }
@@ -851,11 +879,16 @@ static int make_stream(BamScanPlan* plan, int32_t partition, bool device_residen
   if (!plan || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
   if (partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) { set_error("partition %d out of range", partition); return BAMSCAN_ERR_INVALID; }
   if (!g_have_device) { set_error("no CUDA device available: the BAM scan runs on the GPU only (libbamscan has no CPU path)"); return BAMSCAN_ERR_CUDA; }
-  BamScanStream* s = new BamScanStream();
-  s->plan = plan->plan; s->f = plan->plan->file; s->part = &plan->plan->partitions[partition];
+  BamScanStream* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(plan->handle->mu);
+    if (!plan->handle->idle_streams.empty()) { s = plan->handle->idle_streams.back(); plan->handle->idle_streams.pop_back(); }
+  }
+  if (!s) s = new BamScanStream();
+  s->plan = plan->plan; s->f = plan->plan->file; s->part = &plan->plan->partitions[partition]; s->handle = plan->handle;
   s->device_resident = device_resident;
   int rc = stream_init(s);
-  if (rc) { stream_destroy(s); return rc; }
+  if (rc) { stream_destroy(s, false); return rc; }
   *out = s;
   return BAMSCAN_OK;
 }
@@ -864,6 +897,9 @@ int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out) {
 
 int bamscan_next(BamScanStream* s, struct ArrowArray* out) {
   if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  static const bool trace = getenv("BAMSCAN_TRACE") != nullptr;
+  static thread_local double t_last_return = 0;
+  const double t_enter = wall_ms();
   if (s->error) { set_error("stream is in an error state"); return s->error; }
   if (cudaSetDevice(s->f->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return BAMSCAN_ERR_CUDA; }
   for (;;) {
@@ -871,6 +907,7 @@ int bamscan_next(BamScanStream* s, struct ArrowArray* out) {
       export_batch(s, s->ready[s->ready_pos], out);
       owner_unref(s->ready[s->ready_pos].owner);   // the queue's reference; the exported nodes hold their own
       s->ready_pos++;
+      t_last_return = wall_ms();
       return 1;
     }
     if (!s->finished) {
@@ -879,12 +916,15 @@ int bamscan_next(BamScanStream* s, struct ArrowArray* out) {
       PendingBatch prev = s->pending;
       s->pending = PendingBatch();
       bool produced = false;
+      const double t0 = wall_ms();
       int rc = advance(s, &produced);
+      const double t1 = wall_ms();
       if (rc < 0) { s->error = rc; if (prev.valid) { cudaEventSynchronize(prev.done); owner_unref(prev.owner); cudaEventDestroy(prev.done); } return rc; }
       PendingBatch fresh = s->pending;
       s->pending = prev;
       if (prev.valid) {
         rc = finalize_pending(s);
+        if (trace) fprintf(stderr, "[bamscan] outside %.2f ms | advance %.2f ms | wait+finalize d2h %.2f ms\n", t_last_return ? t_enter - t_last_return : 0.0, t1 - t0, wall_ms() - t1);
         if (prev.done) cudaEventDestroy(prev.done);
         s->pending = PendingBatch();
         if (rc) { s->error = rc; if (fresh.valid) { cudaEventSynchronize(fresh.done); owner_unref(fresh.owner); cudaEventDestroy(fresh.done); } return rc; }
@@ -948,6 +988,31 @@ int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t re
   if (rc >= 0) { acc.ms_total = best_total / std::max(1, repeats); *stats = acc; rc = BAMSCAN_OK; }
   stream_destroy(s);
   return rc;
+}
+
+int bamscan_probe_pcie(int32_t device_id, uint64_t bytes, double* h2d_gbps, double* d2h_gbps, double* bidir_gbps) {
+  if (cudaSetDevice(device_id) != cudaSuccess) { set_error("cudaSetDevice failed"); return BAMSCAN_ERR_CUDA; }
+  void *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+  cudaStream_t s0, s1; cudaEvent_t e0, e1, e2;
+  if (cudaHostAlloc(&h0, bytes, cudaHostAllocPortable) != cudaSuccess || cudaHostAlloc(&h1, bytes, cudaHostAllocPortable) != cudaSuccess ||
+      cudaMalloc(&d0, bytes) != cudaSuccess || cudaMalloc(&d1, bytes) != cudaSuccess) { set_error("probe allocation failed"); return BAMSCAN_ERR_CUDA; }
+  memset(h0, 1, bytes); memset(h1, 2, bytes);
+  cudaStreamCreate(&s0); cudaStreamCreate(&s1); cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  float best_h2d = 1e30f, best_d2h = 1e30f, best_bi = 1e30f, ms;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, s0); cudaMemcpyAsync(d0, h0, bytes, cudaMemcpyHostToDevice, s0); cudaEventRecord(e1, s0); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1); best_h2d = std::min(best_h2d, ms);
+    cudaEventRecord(e0, s0); cudaMemcpyAsync(h1, d1, bytes, cudaMemcpyDeviceToHost, s0); cudaEventRecord(e1, s0); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1); best_d2h = std::min(best_d2h, ms);
+    cudaEventRecord(e0, s0); cudaStreamWaitEvent(s1, e0, 0);
+    cudaMemcpyAsync(d0, h0, bytes, cudaMemcpyHostToDevice, s0); cudaMemcpyAsync(h1, d1, bytes, cudaMemcpyDeviceToHost, s1);
+    cudaEventRecord(e2, s1); cudaStreamWaitEvent(s0, e2, 0); cudaEventRecord(e1, s0); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1); best_bi = std::min(best_bi, ms);
+  }
+  *h2d_gbps = bytes / 1e6 / best_h2d; *d2h_gbps = bytes / 1e6 / best_d2h; *bidir_gbps = 2.0 * bytes / 1e6 / best_bi;
+  cudaFreeHost(h0); cudaFreeHost(h1); cudaFree(d0); cudaFree(d1); cudaStreamDestroy(s0); cudaStreamDestroy(s1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  return BAMSCAN_OK;
 }
 
 int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats, double* ms_per_launch, uint64_t* inflated_bytes, uint64_t* compressed_bytes) {

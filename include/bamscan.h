@@ -186,6 +186,9 @@ int bamscan_stream_stats(const BamScanStream* s, BamScanStats* out);
 int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats, double* ms_per_launch, uint64_t* inflated_bytes,
                           uint64_t* compressed_bytes);
 
+/* Pinned-memory PCIe probe (the end-to-end ceiling): best of 3 for H2D, D2H and both at once, GB/s. */
+int bamscan_probe_pcie(int32_t device_id, uint64_t bytes, double* h2d_gbps, double* d2h_gbps, double* bidir_gbps);
+
 const char* bamscan_last_error(void);   /* thread-local message of the last failing call on this thread */
 const char* bamscan_version(void);
 
