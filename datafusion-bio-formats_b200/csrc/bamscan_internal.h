@@ -52,9 +52,9 @@ struct BaiIndex { std::vector<BaiRef> refs; bool has_no_coor = false; uint64_t n
 // == BamTableProvider (table_provider.rs:314-335)
 struct BamFile {
   std::string path, index_path;
-  uint8_t* data = nullptr;   // whole file in page-locked host memory (cudaHostAlloc), padded
+  uint8_t* data = nullptr;   // whole file: read-only mapping page-locked in place (cudaHostRegister), or a pinned copy
   uint64_t size = 0;
-  bool pinned = false;
+  bool pinned = false, mapped = false, registered = false;
   int device = 0;
   std::vector<BgzfBlock> blocks;
   uint64_t total_inflated = 0;
@@ -133,5 +133,8 @@ int make_plan(BamFile* f, const int32_t* projection, int32_t n_projection, const
 // pinned memory helpers implemented in engine.cu (so that host .cpp files need no CUDA headers)
 void* pinned_alloc(size_t bytes);
 void pinned_free(void* p);
+void* map_file_pinned(const char* path, uint64_t size, bool* registered);
+void unmap_file_pinned(void* p, uint64_t size, bool registered);
+void release_file(BamFile* f);
 
 }  // namespace bamscan

@@ -13,6 +13,9 @@
 // Two host syncs per chunk (row count; var-len totals) size the arena exactly.  A batch is handed out one
 // chunk late so its D2H overlaps the next chunk's kernels.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -55,6 +58,35 @@ void* pinned_alloc(size_t bytes) {
   return p;
 }
 void pinned_free(void* p) { if (!p) return; if (g_have_device) cudaFreeHost(p); else free(p); }
+
+// Maps the file and page-locks the mapping in place (cudaHostRegister): no private copy is made, and the N processes
+// of one node that scan the same file (one per GPU) share its page-cache pages.  The driver only accepts writable shared
+// mappings (measured on this stack: PROT_READ mappings are refused even with cudaHostRegisterReadOnly), so the file is
+// opened O_RDWR; nothing is ever written through the mapping.  Returns nullptr when this is not possible (read-only
+// file, no device): the caller then falls back to a page-locked copy.
+void* map_file_pinned(const char* path, uint64_t size, bool* registered) {
+  *registered = false;
+  if (!g_have_device) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return nullptr;
+    void* p = mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
+    close(fd);
+    return p == MAP_FAILED ? nullptr : p;
+  }
+  int fd = open(path, O_RDWR);
+  if (fd < 0) return nullptr;
+  void* p = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return nullptr;
+  if (cudaHostRegister(p, size, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); munmap(p, size); return nullptr; }
+  *registered = true;
+  return p;
+}
+void unmap_file_pinned(void* p, uint64_t size, bool registered) {
+  if (!p) return;
+  if (registered) cudaHostUnregister(p);
+  munmap(p, size);
+}
 
 struct DeviceBuf {
   void* p = nullptr; size_t cap = 0;
@@ -277,7 +309,8 @@ static int issue_h2d(BamScanStream* s, const ChunkPlan& c, int slot) {
   size_t bytes = (size_t)(c.c1 - c.c0);
   int rc = s->d_comp[slot].ensure(bytes + 1024);
   if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->f->data + c.c0, bytes + 512 /* pad is inside the pinned file buffer */, cudaMemcpyHostToDevice, s->s_h2d));
+  CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->f->data + c.c0, bytes, cudaMemcpyHostToDevice, s->s_h2d));
+  CU_TRY(cudaMemsetAsync(s->d_comp[slot].as<uint8_t>() + bytes, 0, 1024, s->s_h2d));   // the bit reader may look a few words past the last member
   CU_TRY(cudaEventRecord(s->ev_h2d[slot], s->s_h2d));
   s->st.h2d_bytes += bytes;
   return BAMSCAN_OK;
@@ -777,14 +810,14 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
   if (opt.segment_bytes) f.seg_bytes = std::max<uint32_t>(256, opt.segment_bytes);
   f.skip_crc = opt.skip_crc != 0; f.debug_flags = opt.debug_flags;
   int rc = load_file(&f);
-  if (rc == BAMSCAN_ERR_IO || rc == BAMSCAN_ERR_CUDA) { if (f.data) pinned_free(f.data); return rc; }
+  if (rc == BAMSCAN_ERR_IO || rc == BAMSCAN_ERR_CUDA) { release_file(&f); return rc; }
   // a file whose header cannot be read still yields a provider with empty metadata (table_provider.rs:423-426);
   // scans on it fail later
-  if ((rc = build_schema(&f, &opt))) { if (f.data) pinned_free(f.data); return rc; }
+  if ((rc = build_schema(&f, &opt))) { release_file(&f); return rc; }
   if (index_path_or_null) f.index_path = index_path_or_null; else f.index_path = discover_index(f.path);   // "" = no index
   if (!f.index_path.empty()) {
     f.bai.reset(new BaiIndex());
-    if (load_bai(f.index_path, f.bai.get()) != BAMSCAN_OK) { f.bai.reset(); if (index_path_or_null) { pinned_free(f.data); return BAMSCAN_ERR_IO; } f.index_path.clear(); }
+    if (load_bai(f.index_path, f.bai.get()) != BAMSCAN_OK) { f.bai.reset(); if (index_path_or_null) { release_file(&f); return BAMSCAN_ERR_IO; } f.index_path.clear(); }
   }
   *out = h.release();
   return BAMSCAN_OK;
@@ -794,7 +827,7 @@ void bamscan_close(BamScanHandle* h) {
   if (!h) return;
   for (BamScanStream* s : h->idle_streams) stream_destroy(s, false);
   h->idle_streams.clear();
-  if (h->file.data) { if (g_have_device) cudaSetDevice(h->file.device); pinned_free(h->file.data); }
+  if (h->file.data) { if (g_have_device) cudaSetDevice(h->file.device); release_file(&h->file); }
   delete h;
 }
 
@@ -965,7 +998,8 @@ int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t re
   uint32_t bext = std::min<uint32_t>((uint32_t)f->blocks.size(), bmax + 8192);   // room for tail-record extension chunks
   uint64_t c0 = f->blocks[bmin].coff, c1 = f->blocks[bext - 1].coff + f->blocks[bext - 1].csize;
   if ((rc = s->d_comp_all_buf.ensure((size_t)(c1 - c0) + 1024))) { stream_destroy(s); return rc; }
-  if (cudaMemcpy(s->d_comp_all_buf.p, f->data + c0, (size_t)(c1 - c0) + 512, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("staging copy failed"); stream_destroy(s); return BAMSCAN_ERR_CUDA; }
+  if (cudaMemcpy(s->d_comp_all_buf.p, f->data + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemset(s->d_comp_all_buf.as<uint8_t>() + (c1 - c0), 0, 1024) != cudaSuccess) { set_error("staging copy failed"); stream_destroy(s); return BAMSCAN_ERR_CUDA; }
   s->d_comp_all = s->d_comp_all_buf.as<uint8_t>(); s->comp_all_c0 = c0;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1036,7 +1070,8 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   DeviceBuf comp, blk, infl, status, flags;
   auto fail = [&](int code) { comp.release(); blk.release(); infl.release(); status.release(); flags.release(); stream_destroy(s); return code; };
   if (comp.ensure((size_t)(c.c1 - c.c0) + 1024) || blk.ensure(sizeof(BlockDesc) * nb) || infl.ensure((size_t)c.ubytes + INFL_PAD) || status.ensure(4ull * nb) || flags.ensure(256)) return fail(BAMSCAN_ERR_CUDA);
-  cudaMemcpy(comp.p, f->data + c.c0, (size_t)(c.c1 - c.c0) + 512, cudaMemcpyHostToDevice);
+  cudaMemcpy(comp.p, f->data + c.c0, (size_t)(c.c1 - c.c0), cudaMemcpyHostToDevice);
+  cudaMemset(comp.as<uint8_t>() + (c.c1 - c.c0), 0, 1024);
   cudaMemcpy(blk.p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice);
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
   uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * INF_CTAS_PER_SM);

@@ -87,24 +87,36 @@ static int walk_blocks(BamFile* f) {
   return BAMSCAN_OK;
 }
 
+void release_file(BamFile* f) {
+  if (!f->data) return;
+  if (f->mapped) unmap_file_pinned(f->data, f->size, f->registered); else pinned_free(f->data);
+  f->data = nullptr;
+}
+
 int load_file(BamFile* f) {
   FILE* fp = fopen(f->path.c_str(), "rb");
   if (!fp) { set_error("cannot open %s", f->path.c_str()); return BAMSCAN_ERR_IO; }
   struct stat st;
   if (fstat(fileno(fp), &st) != 0) { fclose(fp); set_error("cannot stat %s", f->path.c_str()); return BAMSCAN_ERR_IO; }
   f->size = (uint64_t)st.st_size;
-  f->data = (uint8_t*)pinned_alloc(f->size + 4096);    // padded: the inflate kernel's window loads may over-read
-  if (!f->data) { fclose(fp); return BAMSCAN_ERR_CUDA; }
-  f->pinned = true;
-  uint64_t got = 0;
-  while (got < f->size) {
-    size_t n = fread(f->data + got, 1, (size_t)std::min<uint64_t>(f->size - got, 1ull << 30), fp);
-    if (n == 0) break;
-    got += n;
+  if (f->size >= (1u << 20)) {   // large files: map + page-lock in place (shared between the per-GPU processes of one node)
+    f->data = (uint8_t*)map_file_pinned(f->path.c_str(), f->size, &f->registered);
+    f->mapped = f->data != nullptr;
+  }
+  if (!f->data) {
+    f->data = (uint8_t*)pinned_alloc(f->size + 4096);
+    if (!f->data) { fclose(fp); return BAMSCAN_ERR_CUDA; }
+    f->pinned = true;
+    uint64_t got = 0;
+    while (got < f->size) {
+      size_t n = fread(f->data + got, 1, (size_t)std::min<uint64_t>(f->size - got, 1ull << 30), fp);
+      if (n == 0) break;
+      got += n;
+    }
+    if (got != f->size) { fclose(fp); set_error("short read on %s", f->path.c_str()); return BAMSCAN_ERR_IO; }
+    memset(f->data + f->size, 0, 4096);
   }
   fclose(fp);
-  if (got != f->size) { set_error("short read on %s", f->path.c_str()); return BAMSCAN_ERR_IO; }
-  memset(f->data + f->size, 0, 4096);
   int rc = walk_blocks(f);
   if (rc) return rc;
 
