@@ -292,13 +292,28 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
   delete s;
 }
 
-// cut blocks [b0, b1) into chunks of <= chunk_bytes inflated
+// Members the inflate kernel keeps in flight: one per resident warp.  A member takes milliseconds, so a chunk whose member
+// count is not a whole number of such waves leaves most of the GPU idle in its last wave.
+static uint32_t g_inflate_wave = 0;
+static uint32_t inflate_wave_members(int device) {
+  if (g_inflate_wave) return g_inflate_wave;
+  int sms = 148, ctas = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, inflate_kernel, INF_WARPS * 32, sizeof(InflateShared)) != cudaSuccess || ctas < 1) { cudaGetLastError(); ctas = INF_CTAS_PER_SM; }
+  g_inflate_wave = (uint32_t)sms * (uint32_t)ctas * INF_WARPS;
+  return g_inflate_wave;
+}
+
+// cut blocks [b0, b1) into chunks of <= chunk_bytes inflated, a whole number of inflate waves each when the cap allows it
 static void plan_chunks(const BamFile& f, uint32_t b0, uint32_t b1, bool extension, std::vector<ChunkPlan>* out) {
+  const uint32_t wave = inflate_wave_members(f.device);
+  const uint64_t waves = f.chunk_bytes / ((uint64_t)wave * 65280ull);
+  const uint32_t member_cap = waves >= 1 ? (uint32_t)waves * wave : 0xffffffffu;   // small (test) chunk sizes: bytes only
   uint32_t b = b0;
   while (b < b1) {
     ChunkPlan c; c.b0 = b; c.u0 = f.blocks[b].uoff; c.c0 = f.blocks[b].coff; c.extension = extension;
-    uint64_t ub = 0;
-    while (b < b1 && (ub == 0 || ub + f.blocks[b].isize <= f.chunk_bytes)) { ub += f.blocks[b].isize; b++; }
+    uint64_t ub = 0; uint32_t members = 0;
+    while (b < b1 && (ub == 0 || (ub + f.blocks[b].isize <= f.chunk_bytes && members < member_cap))) { ub += f.blocks[b].isize; members += f.blocks[b].isize ? 1u : 0u; b++; }
     c.b1 = b; c.ubytes = ub; c.c1 = f.blocks[b - 1].coff + f.blocks[b - 1].csize;
     out->push_back(c);
   }
@@ -368,8 +383,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   tw1 = wall_ms();
   uint8_t* U = s->d_infl.as<uint8_t>();
   if (nb) {
-    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * INF_CTAS_PER_SM);
+    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, inflate_wave_members(f->device) / INF_WARPS);
     inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, f->skip_crc ? 0 : 1);
     s->st.kernel_launches++;
   }
@@ -1073,8 +1087,7 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   cudaMemcpy(comp.p, f->data + c.c0, (size_t)(c.c1 - c.c0), cudaMemcpyHostToDevice);
   cudaMemset(comp.as<uint8_t>() + (c.c1 - c.c0), 0, 1024);
   cudaMemcpy(blk.p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice);
-  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-  uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)sms * INF_CTAS_PER_SM);
+  uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, inflate_wave_members(f->device) / INF_WARPS);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float total = 0;
   for (int rep = 0; rep < repeats + 1; rep++) {

@@ -37,16 +37,16 @@ enum InflateStatus : uint32_t {
 };
 
 constexpr int INF_WARPS = 8;                 // warps per CTA
-constexpr int INF_CTAS_PER_SM = 5;
-constexpr int INF_LL_BITS = 10, INF_D_BITS = 7;
+constexpr int INF_CTAS_PER_SM = 6;
+constexpr int INF_LL_BITS = 9, INF_D_BITS = 7;
 constexpr uint32_t FULL = 0xffffffffu;
 
 // 32-bit LUT entry, decoded without table look-ups or branches:
 //   [3:0]  code length (0 = invalid code)      [7:4] number of extra bits
-//   [9:8]  kind: 1 length / distance, 2 end of block, 3 code longer than the LUT index (canonical walk)
+//   [10:8] kind bits: 0x100 length / distance, 0x200 end of block, 0x400 code longer than the LUT index (canonical walk) or invalid
 //   [30:16] literal byte | base length | base distance        [31] literal flag (sign test on the hot path)
 // value = base + ((bits >> code_len) & mask(extra)) ; bits consumed = code_len + extra
-constexpr uint32_t E_LIT = 0x80000000u, E_SYM = 1u << 8, E_EOB = 2u << 8, E_LONG = 3u << 8, E_KIND = 3u << 8;
+constexpr uint32_t E_LIT = 0x80000000u, E_SYM = 1u << 8, E_EOB = 2u << 8, E_LONG = 4u << 8;   // one bit each: single-instruction tests
 
 struct WarpTables {
   uint32_t lut_ll[1 << INF_LL_BITS];
@@ -342,7 +342,6 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
         const uint32_t* const lut_ll = T.lut_ll;
         const uint32_t* const lut_d = T.lut_d;
         uint8_t* outl = infl + obase + outpos + lane;        // this lane's byte of the next output stripe
-        uint8_t* pend_p = outl; uint8_t pend_v = 0; uint32_t pend_n = 0;   // deferred single-stripe match store
 #define INF_REFILL()                                                                         \
         if (bp >= 32u) {                                                                     \
           lo = hi; hi = nxt; nxt = __ldg(wbase + wi); wi++; bp -= 32u;                        \
@@ -351,52 +350,59 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
         for (;;) {
           uint32_t bits = __funnelshift_r(lo, hi, bp);
           uint32_t e = lut_ll[bits & ((1u << INF_LL_BITS) - 1u)];
-          if ((int32_t)e >= 0) {
-            if ((e & E_KIND) == E_LONG) e = decode_long<INF_LL_BITS, TK_LITLEN>(bits, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll);
-            if ((int32_t)e >= 0) {
-              const uint32_t nb = e & 15u, xb = (e >> 4) & 15u;
-              if ((e & E_KIND) != E_SYM) {                     // end of block, or an invalid code
-                bp += nb;
-                if (nb == 0) err = INF_ERR_SYMBOL;
-                break;
+          if ((int32_t)e < 0) {                                // literal
+            if (lane0) *outl = (uint8_t)(e >> 16);
+            outl++; outpos++;
+            bp += e & 15u;
+            INF_REFILL();
+            continue;
+          }
+          if (!(e & E_SYM)) {                                  // rare: code longer than the LUT index, end of block, invalid code
+            if (e & E_LONG) {
+              e = decode_long<INF_LL_BITS, TK_LITLEN>(bits, T.sorted_ll, T.first_ll, T.offs_ll, T.cnt_ll);
+              if ((int32_t)e < 0) {
+                if (lane0) *outl = (uint8_t)(e >> 16);
+                outl++; outpos++;
+                bp += e & 15u;
+                INF_REFILL();
+                continue;
               }
-              const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << xb) - 1u));
-              bp += nb + xb;
-              INF_REFILL();
-              bits = __funnelshift_r(lo, hi, bp);
-              uint32_t de = lut_d[bits & ((1u << INF_D_BITS) - 1u)];
-              if ((de & E_KIND) == E_LONG) de = decode_long<INF_D_BITS, TK_DIST>(bits, T.sorted_d, T.first_d, T.offs_d, T.cnt_d);
-              const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
-              const uint32_t dist = (de >> 16) + ((bits >> dnb) & ((1u << dxb) - 1u));
-              bp += dnb + dxb;
-              if (dnb == 0 || dist > outpos || outpos + len > isize) { err = (dnb == 0 || dist > outpos) ? INF_ERR_DIST : INF_ERR_OVERRUN; break; }
-              // The copy's store is DEFERRED: the load is issued now, the store happens right before the next match's
-              // fence (or at the end of the block), so the L2 round trip overlaps the decoding of the symbols in between.
-              if (pend_n) { if ((uint32_t)lane < pend_n) *pend_p = pend_v; pend_n = 0; }
-              __syncwarp();                                   // earlier stores (other lanes) become visible to the loads below
-              // byte i of the match is src[i mod dist]: only bytes that already exist are read, whatever dist/len are
-              if (dist >= len && len <= 32u) {                // the common case: one stripe, no overlap
-                pend_v = *(outl - dist); pend_p = outl; pend_n = len;
-              } else {
-                uint8_t* const d0 = outl - lane;
-                const uint8_t* const s0 = d0 - dist;
-                if (dist >= len) { for (uint32_t i = lane; i < len; i += 32) d0[i] = s0[i]; }
-                else if (dist == 1) { const uint8_t v = s0[0]; for (uint32_t i = lane; i < len; i += 32) d0[i] = v; }
-                else { for (uint32_t i = lane; i < len; i += 32) d0[i] = s0[i % dist]; }
-              }
-              outl += len; outpos += len;
-              INF_REFILL();
-              continue;
+            }
+            if (!(e & E_SYM)) {
+              bp += e & 15u;
+              if ((e & 15u) == 0) err = INF_ERR_SYMBOL;
+              break;
             }
           }
-          // literal
-          if (lane0) *outl = (uint8_t)(e >> 16);
-          outl++; outpos++;
-          bp += e & 15u;
-          INF_REFILL();
+          {
+            const uint32_t nb = e & 15u, xb = (e >> 4) & 15u;
+            const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << xb) - 1u));
+            bp += nb + xb;
+            INF_REFILL();
+            bits = __funnelshift_r(lo, hi, bp);
+            uint32_t de = lut_d[bits & ((1u << INF_D_BITS) - 1u)];
+            if (de & E_LONG) de = decode_long<INF_D_BITS, TK_DIST>(bits, T.sorted_d, T.first_d, T.offs_d, T.cnt_d);
+            const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
+            const uint32_t dist = (de >> 16) + ((bits >> dnb) & ((1u << dxb) - 1u));
+            bp += dnb + dxb;
+            if (dnb == 0 || dist > outpos || outpos + len > isize) { err = (dnb == 0 || dist > outpos) ? INF_ERR_DIST : INF_ERR_OVERRUN; break; }
+            __syncwarp();                                   // earlier stores (other lanes) become visible to the loads below
+            // byte i of the match is src[i mod dist]: only bytes that already exist are read, whatever dist/len are
+            if (dist >= len && len <= 32u) {                // the common case: one stripe, no overlap
+              const uint8_t v = *(outl - dist);
+              if ((uint32_t)lane < len) *outl = v;
+            } else {
+              uint8_t* const d0 = outl - lane;
+              const uint8_t* const s0 = d0 - dist;
+              if (dist >= len) { for (uint32_t i = lane; i < len; i += 32) d0[i] = s0[i]; }
+              else if (dist == 1) { const uint8_t v = s0[0]; for (uint32_t i = lane; i < len; i += 32) d0[i] = v; }
+              else { for (uint32_t i = lane; i < len; i += 32) d0[i] = s0[i % dist]; }
+            }
+            outl += len; outpos += len;
+            INF_REFILL();
+          }
         }
 #undef INF_REFILL
-        if (pend_n && (uint32_t)lane < pend_n) *pend_p = pend_v;
         br.lo = lo; br.hi = hi; br.nxt = nxt; br.bp = bp; br.wi = wi;
         // normalise (a block may end with bp in [32, 47))
         if (br.bp >= 32u) { br.lo = br.hi; br.hi = br.nxt; br.nxt = __ldg(br.base + br.wi); br.wi++; br.bp -= 32u; }

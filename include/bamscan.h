@@ -64,7 +64,7 @@ typedef struct BamScanOptions {
   const char* const* tag_type_hints;      /* "TAG:TYPE" | "TAG:B:SUBTYPE", tag_registry.rs:698-752 */
   int32_t device_id;                      /* CUDA device ordinal for this handle */
   int32_t batch_rows;                     /* rows per emitted batch; 0 = one batch per device chunk (reference default 8192) */
-  uint64_t chunk_inflated_bytes;          /* device chunk size (inflated bytes); 0 = default 512 MiB */
+  uint64_t chunk_inflated_bytes;          /* device chunk size cap (inflated bytes); 0 = default 640 MiB, max 768 MiB */
   uint32_t segment_bytes;                 /* record-boundary segment size; 0 = default 16 KiB */
   int32_t skip_crc;                       /* 0 (default): verify CRC32 of every BGZF member on the device; 1: skip */
   int32_t debug_flags;                    /* bit0: poison boundary candidates (exercises the repair path in tests) */
