@@ -88,6 +88,13 @@ void unmap_file_pinned(void* p, uint64_t size, bool registered) {
   munmap(p, size);
 }
 
+// Tiny results (row counts, totals, error words) reach the host through mapped pinned memory written by a kernel:
+// a cudaMemcpyAsync D2H would queue on the copy engine behind the previous chunk's multi-hundred-MB Arrow transfer.
+__global__ void publish_kernel(const uint32_t* __restrict__ src, volatile uint32_t* __restrict__ dst, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
 struct DeviceBuf {
   void* p = nullptr; size_t cap = 0;
   int ensure(size_t n) {
@@ -188,7 +195,9 @@ struct BamScanStream {
   DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_recoff2, d_keep, d_tiles, d_totals, d_scratch, d_arena[2], d_refs;
   bool tail_seen = false, range_stop = false;   // per-reference unmapped tail state (physical_exec.rs:1203-1215)
   const uint8_t* d_comp_all = nullptr; DeviceBuf d_comp_all_buf; uint64_t comp_all_c0 = 0;
+  uint32_t* d_hflags = nullptr;           // device alias of h_flags (mapped)
   uint32_t* h_flags = nullptr;            // pinned mirror: [0..15] boundary flags / inflate err, [16..] totals (u64)
+  BlockDesc* h_descs[2] = {nullptr, nullptr}; size_t h_descs_cap[2] = {0, 0}; uint32_t n_descs[2] = {0, 0}; uint32_t chunk_data_hi[2] = {0, 0};
   int arena_flip = 0;
   PendingBatch pending;
   std::vector<ReadyBatch> ready; size_t ready_pos = 0;
@@ -233,8 +242,8 @@ static int stream_init(BamScanStream* s) {
   CU_TRY(cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming));
   for (auto& e : s->ev_t) CU_TRY(cudaEventCreate(&e));
-  s->h_flags = (uint32_t*)pinned_alloc(4096);
-  if (!s->h_flags) return BAMSCAN_ERR_CUDA;
+  CU_TRY(cudaHostAlloc((void**)&s->h_flags, 4096, cudaHostAllocPortable | cudaHostAllocMapped));
+  CU_TRY(cudaHostGetDevicePointer((void**)&s->d_hflags, s->h_flags, 0));
   CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
   // reference dictionary: lengths + names blob
   size_t n_ref = f->ref_names.size();
@@ -282,6 +291,7 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
   for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl, &s->d_carry, &s->d_status, &s->d_flags, &s->d_seg,
                   &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf}) b->release();
   if (s->h_flags) cudaFreeHost(s->h_flags);
+  for (auto& hd : s->h_descs) if (hd) cudaFreeHost(hd);
   for (auto& e : s->ev_h2d) if (e) cudaEventDestroy(e);
   if (s->ev_compute) cudaEventDestroy(s->ev_compute);
   if (s->ev_flags) cudaEventDestroy(s->ev_flags);
@@ -319,15 +329,38 @@ static void plan_chunks(const BamFile& f, uint32_t b0, uint32_t b1, bool extensi
   }
 }
 
+// Builds the chunk's member descriptors in pinned memory and queues them, with the compressed bytes, on the H2D stream.
+// Everything the compute stream needs from the host for this chunk travels here, so the copy engine never makes the
+// kernels of the previous chunk wait (a pageable copy issued on the compute stream would queue behind the big transfer).
 static int issue_h2d(BamScanStream* s, const ChunkPlan& c, int slot) {
-  if (s->device_resident) return BAMSCAN_OK;
-  size_t bytes = (size_t)(c.c1 - c.c0);
-  int rc = s->d_comp[slot].ensure(bytes + 1024);
+  const BamFile* f = s->f;
+  const uint32_t nb_all = c.b1 - c.b0;
+  if (s->h_descs_cap[slot] < nb_all) {
+    if (s->h_descs[slot]) cudaFreeHost(s->h_descs[slot]);
+    size_t cap = std::max<size_t>(nb_all + nb_all / 4, 1024);
+    s->h_descs[slot] = (BlockDesc*)pinned_alloc(cap * sizeof(BlockDesc));
+    if (!s->h_descs[slot]) { s->h_descs_cap[slot] = 0; return BAMSCAN_ERR_CUDA; }
+    s->h_descs_cap[slot] = cap;
+  }
+  BlockDesc* descs = s->h_descs[slot];
+  uint32_t uoff = HEADROOM, nb = 0;
+  for (uint32_t b = c.b0; b < c.b1; b++) {
+    const BgzfBlock& B = f->blocks[b];
+    if (B.isize) { BlockDesc d; d.cdata_off = (uint32_t)(B.coff - c.c0) + B.cdata_off; d.cdata_len = B.csize - B.cdata_off - 8; d.isize = B.isize; d.crc = B.crc; d.uoff = uoff; descs[nb++] = d; }
+    uoff += B.isize;
+  }
+  s->n_descs[slot] = nb; s->chunk_data_hi[slot] = uoff;
+  int rc = s->d_blk[slot].ensure(sizeof(BlockDesc) * std::max<uint32_t>(nb, 1));
   if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->f->data + c.c0, bytes, cudaMemcpyHostToDevice, s->s_h2d));
-  CU_TRY(cudaMemsetAsync(s->d_comp[slot].as<uint8_t>() + bytes, 0, 1024, s->s_h2d));   // the bit reader may look a few words past the last member
+  if (nb) CU_TRY(cudaMemcpyAsync(s->d_blk[slot].p, descs, sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, s->s_h2d));
+  if (!s->device_resident) {
+    size_t bytes = (size_t)(c.c1 - c.c0);
+    if ((rc = s->d_comp[slot].ensure(bytes + 1024))) return rc;
+    CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->f->data + c.c0, bytes, cudaMemcpyHostToDevice, s->s_h2d));
+    CU_TRY(cudaMemsetAsync(s->d_comp[slot].as<uint8_t>() + bytes, 0, 1024, s->s_h2d));   // the bit reader may look a few words past the last member
+    s->st.h2d_bytes += bytes;
+  }
   CU_TRY(cudaEventRecord(s->ev_h2d[slot], s->s_h2d));
-  s->st.h2d_bytes += bytes;
   return BAMSCAN_OK;
 }
 
@@ -343,20 +376,11 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   static const bool trace2 = getenv("BAMSCAN_TRACE") && atoi(getenv("BAMSCAN_TRACE")) >= 2;
   const double tw0 = wall_ms(); double tw1 = 0, tw2 = 0, tw3 = 0;
   const uint32_t nb_all = c.b1 - c.b0;
-  // ---- block descriptors
-  std::vector<BlockDesc> descs;
-  descs.reserve(nb_all);
-  uint32_t uoff = HEADROOM;
-  for (uint32_t b = c.b0; b < c.b1; b++) {
-    const BgzfBlock& B = f->blocks[b];
-    if (B.isize) { BlockDesc d; d.cdata_off = (uint32_t)(B.coff - c.c0) + B.cdata_off; d.cdata_len = B.csize - B.cdata_off - 8; d.isize = B.isize; d.crc = B.crc; d.uoff = uoff; descs.push_back(d); }
-    uoff += B.isize;
-  }
-  const uint32_t data_hi = uoff, seg0 = HEADROOM;
-  const uint32_t nb = (uint32_t)descs.size();
+  (void)nb_all;
+  const uint32_t data_hi = s->chunk_data_hi[slot], seg0 = HEADROOM;
+  const uint32_t nb = s->n_descs[slot];
   int rc;
   if ((rc = s->d_infl.ensure((size_t)HEADROOM + c.ubytes + INFL_PAD))) return rc;
-  if ((rc = s->d_blk[slot].ensure(sizeof(BlockDesc) * std::max<uint32_t>(nb, 1)))) return rc;
   if ((rc = s->d_status.ensure(4 * std::max<uint32_t>(nb, 1)))) return rc;
   if ((rc = s->d_flags.ensure(256))) return rc;
   if ((rc = s->d_carry.ensure(HEADROOM))) return rc;
@@ -374,8 +398,8 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   cudaStream_t cs = s->s_compute;
   const uint8_t* d_comp;
   if (s->device_resident) d_comp = s->d_comp_all + (c.c0 - s->comp_all_c0);
-  else { d_comp = s->d_comp[slot].as<uint8_t>(); CU_TRY(cudaStreamWaitEvent(cs, s->ev_h2d[slot], 0)); }
-  CU_TRY(cudaMemcpyAsync(s->d_blk[slot].p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice, cs));   // pageable source: staged synchronously by the driver
+  else d_comp = s->d_comp[slot].as<uint8_t>();
+  CU_TRY(cudaStreamWaitEvent(cs, s->ev_h2d[slot], 0));   // descriptors (+ compressed bytes) of this chunk have landed
   CU_TRY(cudaMemsetAsync(d_flags, 0, 64, cs));
   CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
   CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
@@ -411,7 +435,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   seg_repair_kernel<<<1, 1, 0, cs>>>(BP, W);
   seg_scan_kernel<<<1, 1024, 0, cs>>>(d_seg_count, d_seg_start, d_seg_exit, d_seg_tail, d_seg_base, n_seg, d_flags);
   s->st.kernel_launches += 5;
-  CU_TRY(cudaMemcpyAsync(s->h_flags, d_flags, 64, cudaMemcpyDeviceToHost, cs));
+  publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
   CU_TRY(cudaEventRecord(s->ev_flags, cs));
   CU_TRY(cudaEventSynchronize(s->ev_flags));
   CU_TRY(cudaGetLastError());
@@ -466,7 +490,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
       rule_scan_kernel<<<1, 1024, 0, cs>>>(d_keep, d_pos, n_rec, d_flags);
       rule_compact_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(d_recoff, d_pos, n_rec, s->d_recoff2.as<uint32_t>());
       s->st.kernel_launches += 3;
-      CU_TRY(cudaMemcpyAsync(s->h_flags, d_flags, 64, cudaMemcpyDeviceToHost, cs));
+      publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
       CU_TRY(cudaEventRecord(s->ev_flags, cs));
       CU_TRY(cudaEventSynchronize(s->ev_flags));
       CU_TRY(cudaGetLastError());
@@ -555,7 +579,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
       multi_scan_tiles_kernel<<<SC.n_cols, 1024, 0, cs>>>(s->d_tiles.as<uint64_t>(), n_tiles, s->d_totals.as<uint64_t>());
       multi_scan_apply_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
       s->st.kernel_launches += 3;
-      CU_TRY(cudaMemcpyAsync(h_totals, s->d_totals.p, 8ull * SC.n_cols, cudaMemcpyDeviceToHost, cs));
+      publish_kernel<<<1, 64, 0, cs>>>(s->d_totals.as<uint32_t>(), s->d_hflags + 16, 2 * SC.n_cols);
       CU_TRY(cudaEventRecord(s->ev_flags, cs));
       CU_TRY(cudaEventSynchronize(s->ev_flags));
       CU_TRY(cudaGetLastError());
@@ -609,7 +633,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     }
     if (s->device_resident) {
       // keep everything in HBM: only the decode error word travels
-      CU_TRY(cudaMemcpyAsync(s->h_flags + 64, A + err_off, 8, cudaMemcpyDeviceToHost, cs));
+      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);
       CU_TRY(cudaStreamSynchronize(cs));
       if (s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
     } else {
