@@ -302,6 +302,7 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
     bool final_block = false;
 
     while (!final_block && err == INF_OK) {
+      if (br.exhausted()) { err = INF_ERR_INPUT; break; }   // every path below consumes input, so this bounds the loop
       uint32_t hdr = br.take(3);
       final_block = hdr & 1u;
       uint32_t btype = hdr >> 1;
