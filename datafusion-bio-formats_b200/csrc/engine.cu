@@ -621,7 +621,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
           default: DP.tags[tag_slot[i]].data = d;
         }
       }
-      decode_var_kernel<<<(n + VAR_WARPS - 1) / VAR_WARPS, VAR_WARPS * 32, 0, cs>>>(DP);
+      decode_var_kernel<<<std::min<uint32_t>((n + VAR_WARPS - 1) / VAR_WARPS, 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
       s->st.kernel_launches++;
     }
     CU_TRY(cudaEventRecord(s->ev_t[3], cs));

@@ -320,6 +320,7 @@ multi_scan_apply_kernel(ScanCols C, const uint64_t* __restrict__ tile_sums, uint
 // ---------------------------------------------------------------------------------------------
 // phase 3: one warp per record
 __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+  if (n <= 32u) { if ((uint32_t)lane < n) dst[lane] = src[lane]; return; }      // names, short tags: one predicated load/store
   for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
@@ -347,9 +348,9 @@ decode_var_kernel(const DecodeParams P) {
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t r = blockIdx.x * VAR_WARPS + (threadIdx.x >> 5);
-  if (r >= P.n || P.err[0] != 0u) return;
   const uint8_t* U = P.U;
+  // grid-stride over records: a resident warp handles many records, so the LUT set-up and launch cost are amortised
+  for (uint32_t r = blockIdx.x * VAR_WARPS + (threadIdx.x >> 5); r < P.n; r += gridDim.x * VAR_WARPS) {
   const uint32_t o = P.rec_off[r];
   const uint32_t bs = ld_u32(U, o);
   const int32_t ref = (int32_t)ld_u32(U, o + 4);
@@ -464,6 +465,7 @@ decode_var_kernel(const DecodeParams P) {
       }
       if (bad) set_err(P.err, DEC_ERR_TAG_RANGE, r);
     }
+  }
   }
 }
 
