@@ -236,8 +236,18 @@ static std::vector<BaiChunk> bai_query(const BaiRef& R, uint64_t start1, bool ha
   uint64_t min_off = 0;
   size_t win = (size_t)(beg0 >> 14);
   if (!R.intervals.empty()) min_off = win < R.intervals.size() ? R.intervals[win] : R.intervals.back();
+  // Upper bound (this build; noodles reads every chunk of the overlapping bins): a BAI indexes a coordinate-sorted file, so
+  // every record that starts at or before the region end precedes the first record held by a LEAF bin (16 kb window,
+  // records lying entirely inside it) of a later window.  Chunks of the coarse bins beyond that offset only hold records
+  // that start after the region and would be dropped by the row rule (physical_exec.rs:1295-1314) anyway.
+  uint64_t max_off = ~0ull;
+  if (has_end) {
+    const uint32_t last_leaf = 4681u + (uint32_t)std::min<uint64_t>((end1 ? end1 - 1 : 0) >> 14, 32767);
+    for (auto it = R.bins.upper_bound(last_leaf); it != R.bins.end() && it->first <= 37448u; ++it)
+      for (auto& c : it->second) max_off = std::min(max_off, c.beg);
+  }
   std::vector<BaiChunk> kept;
-  for (auto& c : chunks) if (c.end > min_off) kept.push_back(BaiChunk{std::max(c.beg, min_off), c.end});
+  for (auto& c : chunks) if (c.end > min_off && c.beg < max_off) kept.push_back(BaiChunk{std::max(c.beg, min_off), std::min(c.end, max_off)});
   std::sort(kept.begin(), kept.end(), [](const BaiChunk& a, const BaiChunk& b) { return a.beg < b.beg; });
   std::vector<BaiChunk> merged;
   for (auto& c : kept) {
@@ -273,6 +283,9 @@ static int add_range(const BamFile& f, uint64_t beg_v, uint64_t end_v_or_0, cons
     r.stop_uoff = u1;
     r.block_end = (b1 < f.blocks.size() && u1 > f.blocks[b1].uoff) ? b1 + 1 : b1;
     if (r.block_end <= r.block_begin) r.block_end = std::min<uint32_t>((uint32_t)f.blocks.size(), r.block_begin + 1);
+    // one look-ahead member: the last owned record usually ends in the next block; inflating it in the same launch costs
+    // nothing, a separate extension chunk costs a full single-member latency (records past stop_uoff are not owned)
+    r.block_end = std::min<uint32_t>((uint32_t)f.blocks.size(), r.block_end + 1);
   } else { r.stop_uoff = ~0ull; r.block_end = (uint32_t)f.blocks.size(); }
   if (u0 >= f.total_inflated || r.block_begin >= f.blocks.size()) return BAMSCAN_OK;   // nothing to read
   if (r.stop_uoff != ~0ull && r.stop_uoff <= r.first_uoff) return BAMSCAN_OK;
