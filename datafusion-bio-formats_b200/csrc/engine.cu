@@ -403,6 +403,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaMemsetAsync(d_flags, 0, 64, cs));
   CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
   CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
+  CU_TRY(cudaMemsetAsync(d_flags + 11, 0xff, 4, cs));    // [11] first disagreeing seam
   CU_TRY(cudaEventRecord(s->ev_t[0], cs));
   tw1 = wall_ms();
   uint8_t* U = s->d_infl.as<uint8_t>();
@@ -449,7 +450,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     return BAMSCAN_ERR_CRC;
   }
   if (hf[1]) { set_error("BAM read error: invalid record block_size at inflated offset %llu", (unsigned long long)(c.u0 + ((hf[1] & ~1u) - HEADROOM))); return BAMSCAN_ERR_FORMAT; }
-  s->st.boundary_repairs += hf[4];
+  s->st.boundary_repairs += hf[4]; s->st.boundary_seam_mismatches += hf[10];
   const uint32_t n_rec = hf[3];
   if (n_rec > 0 || hf[2] != 0xffffffffu) s->need_spec = false;
   uint32_t tail_off = hf[2] == 0xffffffffu ? data_hi : hf[2];

@@ -124,7 +124,8 @@ struct WalkOut {
   uint32_t* seg_exit;    // chain position after the segment's last record
   uint32_t* seg_count;   // records starting in the segment
   uint8_t* seg_tail;     // 1: the walk stopped at an incomplete record / end of data
-  uint32_t* flags;       // [0] seams that disagree, [1] corrupt block_size (offset|1), [2] tail offset, [3] total records, [4] repairs
+  uint32_t* flags;       // [0] seams that disagree, [1] corrupt block_size (offset|1), [2] tail offset, [3] total records, [4] repairs,
+                         // [10] copy of [0] for the stats, [11] first disagreeing segment
 };
 
 struct WalkResult { uint32_t n, exit; uint8_t tail; };   // tail: 0 ran past the segment, 1 incomplete record / end of data, 2 corrupt block_size
@@ -172,14 +173,16 @@ seg_check_kernel(BoundaryParams P, WalkOut W) {
     for (uint32_t u = s + 1; u < t; u++) if (W.seg_start[u] != SEG_NONE) { bad = true; break; }
     if (W.seg_start[t] != e) bad = true;
   }
-  if (bad) atomicAdd(&W.flags[0], 1u);
+  if (bad) { atomicAdd(&W.flags[0], 1u); atomicMin(&W.flags[11], s); }   // [11] = first segment whose seam disagrees
 }
 
 // Sequential repair (rare): follows the chain from the first start, reusing per-segment walks whose start
 // agrees and re-walking those that do not.  Launched with one thread; returns at once when every seam agreed.
 __global__ void seg_repair_kernel(BoundaryParams P, WalkOut W) {
   if (W.flags[0] == 0) return;
-  uint32_t s = 0;
+  W.flags[10] = W.flags[0];   // reported in the stats
+  // every seam before the first disagreeing one was verified, so that segment's own start is on the true chain
+  uint32_t s = W.flags[11] < P.n_seg ? W.flags[11] : 0;
   while (s < P.n_seg && W.seg_start[s] == SEG_NONE) s++;
   uint32_t tail_off = P.data_hi;
   while (s < P.n_seg) {

@@ -102,6 +102,7 @@ typedef struct BamScanStats {
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t blocks, kernel_launches, boundary_repairs;
   double ms_total, ms_inflate, ms_boundary, ms_decode;      /* CUDA-event device times */
+  uint64_t boundary_seam_mismatches;                        /* seams the parallel check rejected (each triggers the repair walk) */
 } BamScanStats;
 
 /* == BamTableProvider::new (table_provider.rs:381-529): header read, tag-type inference, schema, index discovery.
