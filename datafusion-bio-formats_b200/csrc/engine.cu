@@ -569,7 +569,12 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     }
     DP.n_tags = n_tags;
     CU_TRY(cudaMemsetAsync(A + err_off, 0, 64, cs));
-    decode_fixed_kernel<<<(n + 255) / 256, 256, 0, cs>>>(DP);
+    if ((f->debug_flags & 2) || (uint64_t)(data_hi - HEADROOM) / std::max<uint32_t>(n_rec, 1) > 2048) {
+      CU_TRY(cudaMemsetAsync(A, 0, regionA, cs));                                        // validity words are OR-ed in
+      decode_fixed_warp_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, cs>>>(DP);     // long records: a warp per row, lanes co-operate inside the record
+    }
+    else
+      decode_fixed_kernel<<<(n + 255) / 256, 256, 0, cs>>>(DP);
     s->st.kernel_launches++;
     uint64_t* h_totals = reinterpret_cast<uint64_t*>(s->h_flags + 16);
     if (SC.n_cols) {

@@ -98,6 +98,48 @@ __device__ __forceinline__ bool utf8_valid(const uint8_t* U, uint32_t o, uint32_
   return true;
 }
 
+// One aux field -> the requested column's representation (sam_tag_io.rs:658-741 scalars, :761-1036 arrays are sized here and
+// converted in decode_var_kernel).  `a` = offset of the field's tag bytes, `v` = offset of its value, vlen = value bytes.
+struct TagConv { bool ok; uint32_t val; int32_t len; uint32_t src; };
+__device__ __forceinline__ TagConv convert_tag(const DecodeParams& P, const TagPlan& T, const uint8_t* U, uint32_t a, uint8_t ty, uint32_t v,
+                                               uint32_t vlen, bool utf8_ok, uint32_t r) {
+  const int32_t kind = T.kind;
+  bool ok = true; uint32_t val = 0; int32_t len = 0; uint32_t src = 0;
+  int64_t iv = 0; bool is_int = true;
+  switch (ty) {
+    case 'c': iv = (int8_t)U[v]; break;
+    case 'C': iv = U[v]; break;
+    case 's': iv = (int16_t)ld_u16(U, v); break;
+    case 'S': iv = ld_u16(U, v); break;
+    case 'i': iv = (int32_t)ld_u32(U, v); break;
+    case 'I': iv = ld_u32(U, v); break;
+    default: is_int = false; break;
+  }
+  if (is_int) {
+    if (kind == K_Int32) { if (iv < -2147483648ll || iv > 2147483647ll) { set_err(P.err, DEC_ERR_TAG_RANGE, r); ok = false; } val = (uint32_t)(int32_t)iv; }
+    else if (kind == K_UInt32) { if (iv < 0) { set_err(P.err, DEC_ERR_TAG_RANGE, r); ok = false; } val = (uint32_t)iv; }
+    else if (kind == K_Utf8) { len = is_scalar_value(iv) ? (int32_t)utf8_len((uint32_t)iv) : (int32_t)(ndigits_u32((uint32_t)(iv < 0 ? -iv : iv)) + (iv < 0 ? 1u : 0u)); src = a + 2u; }
+    else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
+  } else if (ty == 'f') {
+    if (kind == K_Float32) val = ld_u32(U, v);
+    else if (kind == K_Utf8) { set_err(P.err, DEC_ERR_UNSUPPORTED_F2S, r); ok = false; }
+    else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
+  } else if (ty == 'A') {
+    if (kind == K_Int32 || kind == K_UInt32) val = U[v];
+    else if (kind == K_Utf8) { len = U[v] < 0x80 ? 1 : 2; src = a + 2u; }
+    else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
+  } else if (ty == 'Z' || ty == 'H') {
+    if (kind == K_Utf8) { if (utf8_ok) { len = (int32_t)(vlen - 1u); src = a + 2u; } else ok = false; /* invalid UTF-8 -> NULL */ }
+    else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
+  } else {   // 'B'
+    uint8_t st = U[v];
+    if (kind >= K_ListInt8 && !(st == 'f' && kind != K_ListFloat32)) { len = (int32_t)ld_u32(U, v + 1); src = a + 2u; }
+    else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
+  }
+  TagConv c; c.ok = ok; c.val = ok ? val : 0u; c.len = ok ? len : 0; c.src = ok ? src : 0u;
+  return c;
+}
+
 // ---------------------------------------------------------------------------------------------
 // phase 1: one thread per record
 __global__ void __launch_bounds__(256)
@@ -181,44 +223,13 @@ decode_fixed_kernel(const DecodeParams P) {
       for (int k = 0; k < P.n_tags; k++) if (P.tags[k].tag == tag) t = k;   // HashMap<Tag, idx>: the last duplicate name wins
       if (t >= 0) {
         const TagPlan& T = P.tags[t];
-        const int32_t kind = T.kind;
-        bool ok = true; uint32_t val = 0; int32_t len = 0; uint32_t src = 0;
-        int64_t iv = 0; bool is_int = true;
-        switch (ty) {
-          case 'c': iv = (int8_t)U[v]; break;
-          case 'C': iv = U[v]; break;
-          case 's': iv = (int16_t)ld_u16(U, v); break;
-          case 'S': iv = ld_u16(U, v); break;
-          case 'i': iv = (int32_t)ld_u32(U, v); break;
-          case 'I': iv = ld_u32(U, v); break;
-          default: is_int = false; break;
-        }
-        if (is_int) {
-          if (kind == K_Int32) { if (iv < -2147483648ll || iv > 2147483647ll) { set_err(P.err, DEC_ERR_TAG_RANGE, r); ok = false; } val = (uint32_t)(int32_t)iv; }
-          else if (kind == K_UInt32) { if (iv < 0) { set_err(P.err, DEC_ERR_TAG_RANGE, r); ok = false; } val = (uint32_t)iv; }
-          else if (kind == K_Utf8) { len = is_scalar_value(iv) ? (int32_t)utf8_len((uint32_t)iv) : (int32_t)(ndigits_u32((uint32_t)(iv < 0 ? -iv : iv)) + (iv < 0 ? 1u : 0u)); src = a + 2u; }
-          else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
-        } else if (ty == 'f') {
-          if (kind == K_Float32) val = ld_u32(U, v);
-          else if (kind == K_Utf8) { set_err(P.err, DEC_ERR_UNSUPPORTED_F2S, r); ok = false; }
-          else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
-        } else if (ty == 'A') {
-          if (kind == K_Int32 || kind == K_UInt32) val = U[v];
-          else if (kind == K_Utf8) { len = U[v] < 0x80 ? 1 : 2; src = a + 2u; }
-          else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
-        } else if (ty == 'Z' || ty == 'H') {
-          if (kind == K_Utf8) { if (utf8_valid(U, v, vlen - 1u)) { len = (int32_t)(vlen - 1u); src = a + 2u; } else ok = false; /* invalid UTF-8 -> NULL */ }
-          else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
-        } else {   // 'B'
-          uint8_t st = U[v];
-          if (kind >= K_ListInt8 && !(st == 'f' && kind != K_ListFloat32)) { len = (int32_t)ld_u32(U, v + 1); src = a + 2u; }
-          else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
-        }
+        const bool utf8_ok = (T.kind == K_Utf8 && (ty == 'Z' || ty == 'H')) ? utf8_valid(U, v, vlen - 1u) : true;
+        const TagConv c = convert_tag(P, T, U, a, ty, v, vlen, utf8_ok, r);
         seen |= 1u << t;
-        if (ok) valid_mask |= 1u << t; else valid_mask &= ~(1u << t);
-        if (T.values) T.values[r] = ok ? val : 0u;
-        if (T.lens) T.lens[r] = ok ? len : 0;
-        if (T.src) T.src[r] = ok ? src : 0u;
+        if (c.ok) valid_mask |= 1u << t; else valid_mask &= ~(1u << t);
+        if (T.values) T.values[r] = c.val;
+        if (T.lens) T.lens[r] = c.len;
+        if (T.src) T.src[r] = c.src;
       }
       a = v + vlen;
     }
@@ -231,6 +242,124 @@ decode_fixed_kernel(const DecodeParams P) {
       if (T.lens) T.lens[r] = 0;
       if (T.src) T.src[r] = 0u;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1 for LONG records (mean record > 2 KiB: long-read BAMs): one warp per row, the lanes co-operate inside the
+// record -- CIGAR ops are strided over the lanes, Z/H strings are measured and ASCII-checked 32 bytes at a time.  Same
+// results as decode_fixed_kernel; validity bits are OR-ed into the (pre-zeroed) bitmap words.
+__global__ void __launch_bounds__(256)
+decode_fixed_warp_kernel(const DecodeParams P) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= P.n) return;
+  const uint8_t* U = P.U;
+  {
+    const uint32_t o = P.rec_off[r];
+    const uint32_t bs = ld_u32(U, o);
+    const int32_t ref = (int32_t)ld_u32(U, o + 4), pos = (int32_t)ld_u32(U, o + 8);
+    uint32_t x = ld_u32(U, o + 12); const uint32_t l_name = x & 0xffu, mapq = (x >> 8) & 0xffu;
+    x = ld_u32(U, o + 16); const uint32_t n_cig = x & 0xffffu, flag = x >> 16;
+    const int32_t l_seq = (int32_t)ld_u32(U, o + 20);
+    const int32_t nref = (int32_t)ld_u32(U, o + 24), npos = (int32_t)ld_u32(U, o + 28), tlen = (int32_t)ld_u32(U, o + 32);
+    const uint32_t o_name = o + 36, o_cig = o_name + l_name, o_seq = o_cig + 4u * n_cig;
+    const uint32_t o_qual = o_seq + ((uint32_t)l_seq + 1u) / 2u, o_aux = o_qual + (uint32_t)l_seq, o_end = o + 4u + bs;
+    const uint64_t need = 32ull + l_name + 4ull * n_cig + ((uint64_t)(uint32_t)l_seq + 1) / 2 + (uint64_t)(uint32_t)l_seq;
+    if (lane == 0) {
+      if (l_seq < 0 || need > bs) set_err(P.err, DEC_ERR_FIELDS, r);
+      if (ref < -1 || ref >= P.n_ref || nref < -1 || nref >= P.n_ref) set_err(P.err, DEC_ERR_REF, r);
+    }
+    const bool sane = l_seq >= 0 && need <= bs && ref >= -1 && ref < P.n_ref && nref >= -1 && nref < P.n_ref;
+    uint32_t span = 0, cig_txt = 0;
+    if (sane && (P.end || (P.l_cigar && !P.binary_cigar))) {
+      bool bad_op = false;
+      for (uint32_t k = lane; k < n_cig; k += 32) {
+        uint32_t cw = ld_u32(U, o_cig + 4u * k), op = cw & 15u, len = cw >> 4;
+        bad_op |= op > 8u;
+        if ((0x18Du >> op) & 1u) span += len;
+        cig_txt += ndigits_u32(len) + 1u;
+      }
+      #pragma unroll
+      for (int s2 = 16; s2; s2 >>= 1) { span += __shfl_xor_sync(0xffffffffu, span, s2); cig_txt += __shfl_xor_sync(0xffffffffu, cig_txt, s2); }
+      if (__any_sync(0xffffffffu, bad_op) && lane == 0) set_err(P.err, DEC_ERR_CIGAR_OP, r);
+    }
+    const bool has_start = sane && pos >= 0, has_end = has_start && span > 0, has_mstart = sane && npos >= 0;
+    if (lane == 0) {
+      if (P.start) P.start[r] = has_start ? (uint32_t)pos + (P.zero_based ? 0u : 1u) : 0u;
+      if (P.end) P.end[r] = has_end ? (uint32_t)pos + span : 0u;
+      if (P.flags) P.flags[r] = flag;
+      if (P.mapq) P.mapq[r] = mapq;
+      if (P.mate_start) P.mate_start[r] = has_mstart ? (uint32_t)npos + (P.zero_based ? 0u : 1u) : 0u;
+      if (P.tlen) P.tlen[r] = tlen;
+      if (P.l_name) P.l_name[r] = sane ? (int32_t)(l_name ? l_name - 1u : 0u) : 0;
+      if (P.l_chrom) P.l_chrom[r] = (sane && ref >= 0) ? (int32_t)(P.ref_name_off[ref + 1] - P.ref_name_off[ref]) : 0;
+      if (P.l_mchrom) P.l_mchrom[r] = (sane && nref >= 0) ? (int32_t)(P.ref_name_off[nref + 1] - P.ref_name_off[nref]) : 0;
+      if (P.l_cigar) P.l_cigar[r] = sane ? (int32_t)(P.binary_cigar ? 4u * n_cig : cig_txt) : 0;
+      if (P.l_seq) P.l_seq[r] = sane ? l_seq : 0;
+      if (P.l_qual) P.l_qual[r] = sane ? l_seq : 0;
+    }
+    const uint32_t bit = 1u << (r & 31u), word = r >> 5;
+    if (lane == 0) {
+      if (P.v_chrom && sane && ref >= 0) atomicOr(&P.v_chrom[word], bit);
+      if (P.v_start && has_start) atomicOr(&P.v_start[word], bit);
+      if (P.v_end && has_end) atomicOr(&P.v_end[word], bit);
+      if (P.v_mchrom && sane && nref >= 0) atomicOr(&P.v_mchrom[word], bit);
+      if (P.v_mstart && has_mstart) atomicOr(&P.v_mstart[word], bit);
+    }
+    if (P.n_tags == 0) return;
+    uint32_t valid_mask = 0, seen = 0;
+    if (sane) {
+      uint32_t a = o_aux;
+      while (a + 3u <= o_end) {
+        const uint32_t tag = ld_u16(U, a); const uint8_t ty = U[a + 2];
+        const uint32_t v = a + 3u, rem = o_end - v;
+        uint32_t vlen; bool ascii = true;
+        if (ty == 'A' || ty == 'c' || ty == 'C') vlen = 1;
+        else if (ty == 's' || ty == 'S') vlen = 2;
+        else if (ty == 'i' || ty == 'I' || ty == 'f') vlen = 4;
+        else if (ty == 'Z' || ty == 'H') {
+          uint32_t found = 0xffffffffu;
+          for (uint32_t b0 = 0; b0 < rem && found == 0xffffffffu; b0 += 32) {    // uniform trip count
+            const uint32_t k = b0 + lane;
+            const uint8_t c = k < rem ? U[v + k] : (uint8_t)1;
+            const uint32_t z = __ballot_sync(0xffffffffu, k < rem && c == 0);
+            const uint32_t hi = __ballot_sync(0xffffffffu, k < rem && c >= 0x80);
+            if (z) { found = b0 + (uint32_t)__ffs(z) - 1u; ascii &= (hi & ((1u << (__ffs(z) - 1)) - 1u)) == 0u; }
+            else ascii &= hi == 0u;
+          }
+          if (found == 0xffffffffu) break;
+          vlen = found + 1u;
+        }
+        else if (ty == 'B') { if (rem < 5u) break; uint32_t es = sub_size(U[v]); if (!es) break; uint64_t nb2 = 5ull + (uint64_t)ld_u32(U, v + 1) * es; if (nb2 > rem) break; vlen = (uint32_t)nb2; }
+        else break;
+        if (vlen > rem) break;
+        int t = -1;
+        for (int k = 0; k < P.n_tags; k++) if (P.tags[k].tag == tag) t = k;
+        if (t >= 0) {
+          const TagPlan& T = P.tags[t];
+          const bool utf8_ok = (T.kind == K_Utf8 && (ty == 'Z' || ty == 'H') && !ascii) ? utf8_valid(U, v, vlen - 1u) : true;
+          const TagConv c = convert_tag(P, T, U, a, ty, v, vlen, utf8_ok, r);
+          seen |= 1u << t;
+          if (c.ok) valid_mask |= 1u << t; else valid_mask &= ~(1u << t);
+          if (lane == 0) {
+            if (T.values) T.values[r] = c.val;
+            if (T.lens) T.lens[r] = c.len;
+            if (T.src) T.src[r] = c.src;
+          }
+        }
+        a = v + vlen;
+      }
+    }
+    if (lane == 0)
+      for (int t = 0; t < P.n_tags; t++) {
+        const TagPlan& T = P.tags[t];
+        if (T.valid && ((valid_mask >> t) & 1u)) atomicOr(&T.valid[word], bit);
+        if ((seen >> t) & 1u) continue;
+        if (T.values) T.values[r] = 0u;
+        if (T.lens) T.lens[r] = 0;
+        if (T.src) T.src[r] = 0u;
+      }
   }
 }
 

@@ -67,7 +67,7 @@ typedef struct BamScanOptions {
   uint64_t chunk_inflated_bytes;          /* device chunk size cap (inflated bytes); 0 = default 640 MiB, max 768 MiB */
   uint32_t segment_bytes;                 /* record-boundary segment size; 0 = default 16 KiB */
   int32_t skip_crc;                       /* 0 (default): verify CRC32 of every BGZF member on the device; 1: skip */
-  int32_t debug_flags;                    /* bit0: poison boundary candidates (exercises the repair path in tests) */
+  int32_t debug_flags;                    /* bit0: poison boundary candidates (exercises the repair path in tests); bit1: force the long-record decode kernel */
 } BamScanOptions;
 
 /* ---- pushed-down predicates (reference: `filters: &[Expr]` of TableProvider::scan, restricted to the

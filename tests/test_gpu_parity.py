@@ -220,3 +220,13 @@ def test_corrupt_payload_bytes_never_pass_silently(tmp_path, seed):
             continue
         # only a flip inside a BGZF header field the scan does not use (MTIME, XFL, OS) may leave the result intact
         assert t.num_rows == o_rows
+
+
+@pytest.mark.parametrize("name,tags", [("multi_chrom_large.bam", ["NM", "MD", "RG", "OQ", "XT"]), ("nanopore_custom_tags.bam", ["pa", "ns", "NM", "ts", "de", "MD", "tp"]),
+                                       ("10x_pbmc_tags.bam", ["RE", "ts", "CB", "NH", "xf"]), ("no_coor_only.bam", ["CB", "CR"])])
+def test_long_record_decode_kernel_matches_on_short_records(name, tags):
+    """decode_fixed_warp_kernel (a warp per 32 rows, chosen automatically for long-read files) forced on ordinary fixtures."""
+    path = GOLDEN / name
+    o = _oracle(path, tag_fields=tags)
+    p = _provider(path, tag_fields=tags, debug_flags=2)
+    _assert_tables_equal(p.scan(None, [], None).collect(), o.scan(), f"warp decode {name}")
