@@ -448,10 +448,35 @@ multi_scan_apply_kernel(ScanCols C, const uint64_t* __restrict__ tile_sums, uint
 
 // ---------------------------------------------------------------------------------------------
 // phase 3: one warp per record
-__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
-  if (n <= 32u) { if ((uint32_t)lane < n) dst[lane] = src[lane]; return; }      // names, short tags: one predicated load/store
-  for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+// out[i] = in[i] + add (byte-wise), 4 bytes per lane and step on destination-aligned words; the source word is assembled from
+// two aligned loads.  Returns (per lane) the OR of the "bad byte" masks: a byte >= 0x80 on input, or on output when add != 0.
+// Reads up to 3 bytes past src + n (the inflated buffer carries slack).
+__device__ __forceinline__ uint32_t warp_map4(uint8_t* dst, const uint8_t* src, uint32_t n, int lane, uint32_t add4) {
+  uint32_t bad = 0;
+  const uint32_t add1 = add4 & 0xffu;
+  if (n <= 32u) {                                              // names, short tags: one predicated byte load / store
+    if ((uint32_t)lane < n) { uint32_t c = src[lane]; bad = (c | ((c & 0x7fu) + add1)) & 0x80u; dst[lane] = (uint8_t)(c + add1); }
+    return bad;
+  }
+  const uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+  if ((uint32_t)lane < head) { uint32_t c = src[lane]; bad |= (c | ((c & 0x7fu) + add1)) & 0x80u; dst[lane] = (uint8_t)(c + add1); }
+  dst += head; src += head; n -= head;
+  const uint32_t nw = n >> 2;
+  const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(sa & 3u) * 8u;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+  for (uint32_t j = lane; j < nw; j += 32) {
+    const uint32_t lo = sw[j];
+    const uint32_t v = sh ? __funnelshift_r(lo, sw[j + 1], sh) : lo;
+    bad |= (v | ((v & 0x7f7f7f7fu) + add4)) & 0x80808080u;
+    dw[j] = v + add4;                                          // no inter-byte carry unless a byte is "bad" (then the scan fails anyway)
+  }
+  const uint32_t t0 = nw << 2;
+  if (t0 + (uint32_t)lane < n) { uint32_t c = src[t0 + lane]; bad |= (c | ((c & 0x7fu) + add1)) & 0x80u; dst[t0 + lane] = (uint8_t)(c + add1); }
+  return bad;
 }
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) { (void)warp_map4(dst, src, n, lane, 0u); }
 
 __device__ __forceinline__ uint32_t render_u32(uint8_t* dst, uint32_t v) {   // decimal, returns digits written
   uint32_t d = ndigits_u32(v);
@@ -495,9 +520,7 @@ decode_var_kernel(const DecodeParams P) {
   if (P.d_name) {
     uint8_t* dst = P.d_name + P.l_name[r];
     uint32_t n = l_name ? l_name - 1u : 0u;
-    bool bad = false;
-    for (uint32_t i = lane; i < n; i += 32) { uint8_t c = U[o_name + i]; dst[i] = c; bad |= c >= 0x80; }
-    if (bad) set_err(P.err, DEC_ERR_NAME, r);
+    if (warp_map4(dst, U + o_name, n, lane, 0u)) set_err(P.err, DEC_ERR_NAME, r);
   }
   if (P.d_chrom && ref >= 0) warp_copy(P.d_chrom + P.l_chrom[r], P.ref_names + P.ref_name_off[ref], P.ref_name_off[ref + 1] - P.ref_name_off[ref], lane);
   if (P.d_mchrom && nref >= 0) warp_copy(P.d_mchrom + P.l_mchrom[r], P.ref_names + P.ref_name_off[nref], P.ref_name_off[nref + 1] - P.ref_name_off[nref], lane);
@@ -523,18 +546,28 @@ decode_var_kernel(const DecodeParams P) {
   }
   if (P.d_seq) {
     uint8_t* dst = P.d_seq + P.l_seq[r];
-    uint32_t nb = (l_seq + 1u) / 2u;
-    for (uint32_t k = lane; k < nb; k += 32) {
-      uint16_t two = seq_lut[U[o_seq + k]];
-      dst[2u * k] = (uint8_t)two;
-      if (2u * k + 1u < l_seq) dst[2u * k + 1u] = (uint8_t)(two >> 8);
+    // 4 output characters (one aligned word) per lane and step: 2 or 3 input bytes through the two-base LUT
+    const uint32_t head = min(l_seq, (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+    const uint8_t* ps = U + o_seq;
+    if ((uint32_t)lane < head) { uint16_t two = seq_lut[ps[lane >> 1]]; dst[lane] = (uint8_t)((lane & 1) ? (two >> 8) : two); }
+    const uint32_t nw = (l_seq - head) >> 2;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    if ((head & 1u) == 0u) {
+      const uint8_t* p2 = ps + (head >> 1);
+      for (uint32_t j = lane; j < nw; j += 32) dw[j] = (uint32_t)seq_lut[p2[2u * j]] | ((uint32_t)seq_lut[p2[2u * j + 1u]] << 16);
+    } else {
+      const uint8_t* p2 = ps + (head >> 1);                    // char `head` is the LOW nibble of p2[0]
+      for (uint32_t j = lane; j < nw; j += 32) {
+        const uint32_t t0 = seq_lut[p2[2u * j]], t1 = seq_lut[p2[2u * j + 1u]], t2 = seq_lut[p2[2u * j + 2u]];
+        dw[j] = (t0 >> 8) | (t1 << 8) | ((t2 & 0xffu) << 24);
+      }
     }
+    const uint32_t c0 = head + (nw << 2);
+    if (c0 + (uint32_t)lane < l_seq) { const uint32_t c = c0 + lane; uint16_t two = seq_lut[ps[c >> 1]]; dst[c] = (uint8_t)((c & 1u) ? (two >> 8) : two); }
   }
   if (P.d_qual) {
     uint8_t* dst = P.d_qual + P.l_qual[r];
-    bool bad = false;
-    for (uint32_t i = lane; i < l_seq; i += 32) { uint8_t q = (uint8_t)(U[o_qual + i] + 33u); dst[i] = q; bad |= q >= 0x80; }
-    if (bad) set_err(P.err, DEC_ERR_QUAL, r);
+    if (warp_map4(dst, U + o_qual, l_seq, lane, 0x21212121u)) set_err(P.err, DEC_ERR_QUAL, r);
   }
   for (int t = 0; t < P.n_tags; t++) {
     const TagPlan& T = P.tags[t];
