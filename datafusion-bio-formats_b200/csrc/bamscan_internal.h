@@ -72,7 +72,7 @@ struct BamFile {
   std::vector<std::string> meta_ref_names;   // from the bio.bam.reference_sequences JSON (table_provider.rs:439-444)
   std::vector<uint64_t> meta_ref_lens;
   int32_t batch_rows = 0;
-  uint64_t chunk_bytes = 640ull << 20;   // two inflate waves of 4736 members on a B200 (engine.cu::plan_chunks)
+  uint64_t chunk_bytes = 0;              // 0 = one inflate wave per chunk (engine.cu::plan_chunks); else the caller's cap (<= 768 MiB)
   uint32_t seg_bytes = 16384;
   bool skip_crc = false;
   int32_t debug_flags = 0;

@@ -192,13 +192,15 @@ struct BamScanStream {
   std::vector<int32_t> dec_cols;          // schema indices, unique
   std::vector<int32_t> out_to_dec;        // projection position -> index into dec_cols
   // device memory
-  DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_recoff2, d_keep, d_tiles, d_totals, d_scratch, d_arena[2], d_refs;
+  DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_recoff2, d_keep, d_tiles, d_totals, d_scratch, d_arena[2], d_refs, d_sorted;
   bool tail_seen = false, range_stop = false;   // per-reference unmapped tail state (physical_exec.rs:1203-1215)
   const uint8_t* d_comp_all = nullptr; DeviceBuf d_comp_all_buf; uint64_t comp_all_c0 = 0;
   uint32_t* d_hflags = nullptr;           // device alias of h_flags (mapped)
   uint32_t* h_flags = nullptr;            // pinned mirror: [0..15] boundary flags / inflate err, [16..] totals (u64)
   BlockDesc* h_descs[2] = {nullptr, nullptr}; size_t h_descs_cap[2] = {0, 0}; uint32_t n_descs[2] = {0, 0}; uint32_t chunk_data_hi[2] = {0, 0};
   int arena_flip = 0;
+  // rows of the current chunk that are not decoded yet: a chunk is one inflate wave, a batch is one slice of its rows
+  struct { const uint8_t* U = nullptr; const uint32_t* recoff = nullptr; uint32_t n = 0, pos = 0, rows_per_slice = 0; bool long_records = false; uint64_t ubytes = 0; } cur;
   PendingBatch pending;
   std::vector<ReadyBatch> ready; size_t ready_pos = 0;
   BamScanStats st{};
@@ -223,6 +225,50 @@ static int init_device_constants(int dev) {
   return BAMSCAN_OK;
 }
 
+// ---- inflate kernel selection (BAMSCAN_INFLATE_VARIANT: experiment switch; 0 = warp-per-member kernel) ----
+typedef void (*InflateLgFn)(const uint8_t*, const BlockDesc*, uint32_t, uint8_t*, uint32_t*, uint32_t*, uint32_t*, uint8_t*);
+struct InflateVariant { int groups, warps, ctas; size_t smem; InflateLgFn fn; };
+template <int G, int W, int NLIT, int CTAS> static InflateVariant lg_variant() { return {32 / G, W, CTAS, LgConfig<G, W>::SMEM, inflate_lg_kernel<G, W, NLIT, CTAS>}; }
+static const InflateVariant& inflate_variant() {
+  static InflateVariant v = [] {
+    const char* e = getenv("BAMSCAN_INFLATE_VARIANT");
+    int k = e ? atoi(e) : 1;
+    switch (k) {
+      case 0: return InflateVariant{0, 0, 0, 0, nullptr};
+      case 2: return lg_variant<4, 20, 1, 1>();
+      case 3: return lg_variant<4, 16, 2, 1>();
+      case 4: return lg_variant<8, 32, 2, 1>();
+      default: return lg_variant<4, 20, 2, 1>();
+    }
+  }();
+  return v;
+}
+static int device_sms(int device) { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); return sms; }
+
+// Inflates the nb members described by d_blk (and verifies their CRC-32 unless skip_crc) on stream cs.
+static int launch_inflate(const BamFile* f, cudaStream_t cs, const uint8_t* d_comp, const BlockDesc* d_blk, uint32_t nb, uint8_t* U,
+                          uint32_t* d_status, uint32_t* d_ticket, uint32_t* d_err, DeviceBuf* slots, int* launches) {
+  const InflateVariant& v = inflate_variant();
+  if (!v.fn) {
+    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)device_sms(f->device) * INF_CTAS_PER_SM);
+    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, f->skip_crc ? 0 : 1);
+    *launches += 1;
+    return BAMSCAN_OK;
+  }
+  const uint32_t per_cta = (uint32_t)(v.groups * v.warps);
+  const uint32_t max_grid = (uint32_t)(device_sms(f->device) * v.ctas);
+  const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, max_grid);
+  int rc = slots->ensure((size_t)max_grid * per_cta * LG_SLOT_BYTES);
+  if (rc) return rc;
+  v.fn<<<grid, v.warps * 32, v.smem, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, slots->as<uint8_t>());
+  *launches += 1;
+  if (!f->skip_crc) {
+    crc_kernel<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)device_sms(f->device) * 8), 256, 0, cs>>>(d_blk, nb, U, d_status, d_err);
+    *launches += 1;
+  }
+  return BAMSCAN_OK;
+}
+
 static int stream_init(BamScanStream* s) {
   BamFile* f = s->f;
   CU_TRY(cudaSetDevice(f->device));
@@ -230,7 +276,7 @@ static int stream_init(BamScanStream* s) {
   // per-scan state
   s->range_idx = 0; s->chunks.clear(); s->chunk_idx = 0; s->range_open = false; s->finished = false;
   s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = false; s->tail_seen = false; s->range_stop = false;
-  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
+  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->cur.n = s->cur.pos = 0; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
   s->st = BamScanStats{}; s->error = 0; s->d_comp_all = nullptr; s->comp_all_c0 = 0;
   if (!s->resources_ready) {
   rc = init_device_constants(f->device);
@@ -245,6 +291,7 @@ static int stream_init(BamScanStream* s) {
   CU_TRY(cudaHostAlloc((void**)&s->h_flags, 4096, cudaHostAllocPortable | cudaHostAllocMapped));
   CU_TRY(cudaHostGetDevicePointer((void**)&s->d_hflags, s->h_flags, 0));
   CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+  if (inflate_variant().fn) CU_TRY(cudaFuncSetAttribute(inflate_variant().fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inflate_variant().smem));
   // reference dictionary: lengths + names blob
   size_t n_ref = f->ref_names.size();
   std::vector<uint32_t> offs(n_ref + 1, 0);
@@ -289,7 +336,7 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
     if (s->handle->idle_streams.size() < 2) { s->handle->idle_streams.push_back(s); return; }
   }
   for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl, &s->d_carry, &s->d_status, &s->d_flags, &s->d_seg,
-                  &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf}) b->release();
+                  &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf, &s->d_sorted}) b->release();
   if (s->h_flags) cudaFreeHost(s->h_flags);
   for (auto& hd : s->h_descs) if (hd) cudaFreeHost(hd);
   for (auto& e : s->ev_h2d) if (e) cudaEventDestroy(e);
@@ -307,23 +354,31 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
 static uint32_t g_inflate_wave = 0;
 static uint32_t inflate_wave_members(int device) {
   if (g_inflate_wave) return g_inflate_wave;
-  int sms = 148, ctas = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int sms = device_sms(device), ctas = 0;
+  if (inflate_variant().fn) { g_inflate_wave = (uint32_t)sms * inflate_variant().ctas * inflate_variant().groups * inflate_variant().warps; return g_inflate_wave; }
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, inflate_kernel, INF_WARPS * 32, sizeof(InflateShared)) != cudaSuccess || ctas < 1) { cudaGetLastError(); ctas = INF_CTAS_PER_SM; }
   g_inflate_wave = (uint32_t)sms * (uint32_t)ctas * INF_WARPS;
   return g_inflate_wave;
 }
 
-// cut blocks [b0, b1) into chunks of <= chunk_bytes inflated, a whole number of inflate waves each when the cap allows it
+// A chunk is the unit of H2D, inflate and record-boundary resolution; its rows are decoded in slices of <= SLICE_BYTES
+// inflated (Arrow offsets are i32).  Default: one whole inflate wave per chunk (a member takes milliseconds, so a chunk
+// that is not a whole number of waves leaves most of the GPU idle in its last wave); chunk_inflated_bytes overrides it.
+static const uint64_t SLICE_BYTES = 768ull << 20;
+static uint64_t chunk_cap_bytes(const BamFile& f) {
+  if (f.chunk_bytes) return f.chunk_bytes;
+  return std::min<uint64_t>((uint64_t)inflate_wave_members(f.device) * 65280ull + 65536ull, 3ull << 30);
+}
 static void plan_chunks(const BamFile& f, uint32_t b0, uint32_t b1, bool extension, std::vector<ChunkPlan>* out) {
   const uint32_t wave = inflate_wave_members(f.device);
-  const uint64_t waves = f.chunk_bytes / ((uint64_t)wave * 65280ull);
+  const uint64_t cap = chunk_cap_bytes(f);
+  const uint64_t waves = cap / ((uint64_t)wave * 65280ull);
   const uint32_t member_cap = waves >= 1 ? (uint32_t)waves * wave : 0xffffffffu;   // small (test) chunk sizes: bytes only
   uint32_t b = b0;
   while (b < b1) {
     ChunkPlan c; c.b0 = b; c.u0 = f.blocks[b].uoff; c.c0 = f.blocks[b].coff; c.extension = extension;
     uint64_t ub = 0; uint32_t members = 0;
-    while (b < b1 && (ub == 0 || (ub + f.blocks[b].isize <= f.chunk_bytes && members < member_cap))) { ub += f.blocks[b].isize; members += f.blocks[b].isize ? 1u : 0u; b++; }
+    while (b < b1 && (ub == 0 || (ub + f.blocks[b].isize <= cap && members < member_cap))) { ub += f.blocks[b].isize; members += f.blocks[b].isize ? 1u : 0u; b++; }
     c.b1 = b; c.ubytes = ub; c.c1 = f.blocks[b - 1].coff + f.blocks[b - 1].csize;
     out->push_back(c);
   }
@@ -369,6 +424,186 @@ struct ArenaBuilder {
   size_t take(size_t bytes) { size_t o = pos; pos = align_up(pos + bytes, 256); return o; }
 };
 
+// Decodes the next slice of the current chunk's rows into a fresh arena and queues its D2H (one batch).
+static int decode_slice(BamScanStream* s, bool* produced) {
+  BamFile* f = s->f;
+  cudaStream_t cs = s->s_compute;
+  int rc;
+  const uint8_t* U = s->cur.U;
+  const uint32_t n = std::min<uint32_t>(s->cur.rows_per_slice, s->cur.n - s->cur.pos);
+  const uint32_t* d_recoff = s->cur.recoff + s->cur.pos;
+  s->cur.pos += n;
+  uint32_t* d_flags = s->d_flags.as<uint32_t>();
+  (void)d_flags;
+  double tw3 = 0; (void)tw3;
+  CU_TRY(cudaEventRecord(s->ev_t[5], cs));
+  {
+    // ---- arena region A
+    const size_t n_dec = s->dec_cols.size();
+    std::vector<ColLayout> cols(n_dec);
+    ArenaBuilder AB;
+    const size_t bm_bytes = 4ull * ((n + 31) / 32), off_bytes = 4ull * (n + 1), val_bytes = 4ull * n;
+    size_t err_off = AB.take(64);
+    std::vector<size_t> src_off(n_dec, 0);
+    size_t scratch = 0;
+    for (size_t i = 0; i < n_dec; i++) {
+      ColLayout& L = cols[i]; L.schema_idx = s->dec_cols[i]; L.kind = f->fields[L.schema_idx].kind;
+      const int c_id = L.schema_idx;
+      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+      L.has_validity = c_id >= 12 || c_id == 1 || c_id == 2 || c_id == 3 || c_id == 7 || c_id == 8;
+      if (L.has_validity) L.validity_off = AB.take(bm_bytes);
+      if (is_var) L.offsets_off = AB.take(off_bytes); else L.values_off = AB.take(val_bytes);
+      if (c_id >= 12 && is_var) { src_off[i] = scratch; scratch += align_up(val_bytes, 256); }
+    }
+    const size_t regionA = AB.pos;
+    if ((rc = s->d_scratch.ensure(scratch + 256))) return rc;
+    // a first arena sizing guess; grown after totals are known
+    DeviceBuf& arena = s->d_arena[s->arena_flip];
+    if (arena.cap < regionA) { if ((rc = arena.ensure(regionA + (size_t)s->cur.ubytes * 2))) return rc; }
+    uint8_t* A = arena.as<uint8_t>();
+    DecodeParams DP;
+    memset(&DP, 0, sizeof DP);
+    DP.U = U; DP.rec_off = d_recoff; DP.n = n; DP.zero_based = f->zero_based; DP.binary_cigar = f->binary_cigar;
+    DP.n_ref = (int32_t)f->ref_names.size();
+    size_t n_ref = f->ref_names.size();
+    DP.ref_name_off = reinterpret_cast<const uint32_t*>(s->d_refs.as<uint8_t>() + align_up(4 * n_ref + 4, 16));
+    DP.ref_names = s->d_refs.as<uint8_t>() + align_up(4 * n_ref + 4, 16) + align_up(4 * (n_ref + 1), 16);
+    DP.err = reinterpret_cast<uint32_t*>(A + err_off);
+    ScanCols SC; memset(&SC, 0, sizeof SC); SC.n = n + 1;
+    std::vector<size_t> scan_owner;   // dec col index per scan column
+    int n_tags = 0;
+    std::vector<int> tag_slot(n_dec, -1);
+    for (size_t i = 0; i < n_dec; i++) {
+      ColLayout& L = cols[i];
+      uint32_t* v = L.has_validity ? reinterpret_cast<uint32_t*>(A + L.validity_off) : nullptr;
+      int32_t* offs = reinterpret_cast<int32_t*>(A + L.offsets_off);
+      uint32_t* vals = reinterpret_cast<uint32_t*>(A + L.values_off);
+      switch (L.schema_idx) {
+        case 0: DP.l_name = offs; break;
+        case 1: DP.l_chrom = offs; DP.v_chrom = v; break;
+        case 2: DP.start = vals; DP.v_start = v; break;
+        case 3: DP.end = vals; DP.v_end = v; break;
+        case 4: DP.flags = vals; break;
+        case 5: DP.l_cigar = offs; break;
+        case 6: DP.mapq = vals; break;
+        case 7: DP.l_mchrom = offs; DP.v_mchrom = v; break;
+        case 8: DP.mate_start = vals; DP.v_mstart = v; break;
+        case 9: DP.l_seq = offs; break;
+        case 10: DP.l_qual = offs; break;
+        case 11: DP.tlen = reinterpret_cast<int32_t*>(vals); break;
+        default: {
+          TagPlan& T = DP.tags[n_tags];
+          const std::string& tg = f->fields[L.schema_idx].name;
+          T.tag = tg.size() == 2 ? (uint16_t)((uint8_t)tg[0] | ((uint16_t)(uint8_t)tg[1] << 8)) : 0xffffu;   // names that are not 2 bytes never match (sam_tag_io.rs:58-68)
+          T.kind = L.kind; T.valid = v;
+          bool is_var = L.kind == HK_Utf8 || L.kind >= HK_ListInt8;
+          if (is_var) { T.lens = offs; T.src = reinterpret_cast<uint32_t*>(s->d_scratch.as<uint8_t>() + src_off[i]); }
+          else T.values = vals;
+          tag_slot[i] = n_tags++;
+        }
+      }
+      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+      if (is_var) { SC.col[SC.n_cols++] = offs; scan_owner.push_back(i); }
+    }
+    DP.n_tags = n_tags;
+    CU_TRY(cudaMemsetAsync(A + err_off, 0, 64, cs));
+    if (s->cur.long_records) {
+      CU_TRY(cudaMemsetAsync(A, 0, regionA, cs));                                        // validity words are OR-ed in
+      decode_fixed_warp_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, cs>>>(DP);     // long records: a warp per row, lanes co-operate inside the record
+    }
+    else
+      decode_fixed_kernel<<<(n + 255) / 256, 256, 0, cs>>>(DP);
+    s->st.kernel_launches++;
+    uint64_t* h_totals = reinterpret_cast<uint64_t*>(s->h_flags + 16);
+    if (SC.n_cols) {
+      uint32_t n_tiles = (SC.n + SCAN_TILE - 1) / SCAN_TILE;
+      if ((rc = s->d_tiles.ensure(8ull * n_tiles * SC.n_cols))) return rc;
+      if ((rc = s->d_totals.ensure(8ull * MAX_SCAN_COLS))) return rc;
+      multi_scan_reduce_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
+      multi_scan_tiles_kernel<<<SC.n_cols, 1024, 0, cs>>>(s->d_tiles.as<uint64_t>(), n_tiles, s->d_totals.as<uint64_t>());
+      multi_scan_apply_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
+      s->st.kernel_launches += 3;
+      publish_kernel<<<1, 64, 0, cs>>>(s->d_totals.as<uint32_t>(), s->d_hflags + 16, 2 * SC.n_cols);
+      CU_TRY(cudaEventRecord(s->ev_flags, cs));
+      CU_TRY(cudaEventSynchronize(s->ev_flags));
+      CU_TRY(cudaGetLastError());
+      // ---- arena region B
+      tw3 = wall_ms();
+      for (int k = 0; k < SC.n_cols; k++) {
+        ColLayout& L = cols[scan_owner[k]];
+        uint64_t tot = h_totals[k];
+        if (tot > 0x7fffffffull) { set_error("column '%s' exceeds 2^31-1 bytes in one batch; lower chunk_inflated_bytes", f->fields[L.schema_idx].name.c_str()); return BAMSCAN_ERR_UNSUPPORTED; }
+        uint64_t bytes = tot;
+        if (L.kind >= HK_ListInt8) { L.child_len = tot; bytes = tot * ((L.kind == HK_ListInt8 || L.kind == HK_ListUInt8) ? 1 : (L.kind == HK_ListInt16 || L.kind == HK_ListUInt16) ? 2 : 4); }
+        L.data_bytes = bytes;
+        L.data_off = AB.take((size_t)bytes + 16);
+      }
+      if (AB.pos > arena.cap) {
+        // grow, preserving region A
+        DeviceBuf bigger;
+        if ((rc = bigger.ensure(AB.pos))) return rc;
+        CU_TRY(cudaMemcpyAsync(bigger.p, arena.p, regionA, cudaMemcpyDeviceToDevice, cs));
+        CU_TRY(cudaStreamSynchronize(cs));
+        // rebase pointers
+        ptrdiff_t delta = (uint8_t*)bigger.p - A;
+        auto rb = [&](auto*& p) { if (p) p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<uint8_t*>(p) + delta); };
+        rb(DP.start); rb(DP.end); rb(DP.flags); rb(DP.mapq); rb(DP.mate_start); rb(DP.tlen);
+        rb(DP.v_chrom); rb(DP.v_start); rb(DP.v_end); rb(DP.v_mchrom); rb(DP.v_mstart);
+        rb(DP.l_name); rb(DP.l_chrom); rb(DP.l_cigar); rb(DP.l_mchrom); rb(DP.l_seq); rb(DP.l_qual); rb(DP.err);
+        for (int t = 0; t < n_tags; t++) { rb(DP.tags[t].valid); rb(DP.tags[t].values); rb(DP.tags[t].lens); }
+        arena.release(); arena = bigger; bigger.p = nullptr; bigger.cap = 0;
+        A = arena.as<uint8_t>();
+      }
+      for (size_t i = 0; i < n_dec; i++) {
+        ColLayout& L = cols[i];
+        bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+        if (!is_var) continue;
+        uint8_t* d = A + L.data_off;
+        switch (L.schema_idx) {
+          case 0: DP.d_name = d; break; case 1: DP.d_chrom = d; break; case 5: DP.d_cigar = d; break; case 7: DP.d_mchrom = d; break;
+          case 9: DP.d_seq = d; break; case 10: DP.d_qual = d; break;
+          default: DP.tags[tag_slot[i]].data = d;
+        }
+      }
+      decode_var_kernel<<<std::min<uint32_t>((n + VAR_WARPS - 1) / VAR_WARPS, 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
+      s->st.kernel_launches++;
+    }
+    const size_t arena_bytes = AB.pos;
+    s->st.rows += n; s->st.batches++;
+    for (auto& L : cols) {
+      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
+      s->st.arrow_bytes += (L.has_validity ? (n + 7) / 8 : 0) + (is_var ? off_bytes + L.data_bytes : val_bytes);
+    }
+    if (s->device_resident) {
+      // keep everything in HBM: only the decode error word travels
+      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);
+      CU_TRY(cudaStreamSynchronize(cs));
+      if (s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
+    } else {
+      CU_TRY(cudaEventRecord(s->ev_compute, cs));
+      PendingBatch& P = s->pending;
+      P.owner = new BatchOwner();
+      P.owner->arena = arena_acquire(arena_bytes);
+      if (!P.owner->arena.p) { delete P.owner; P.owner = nullptr; return BAMSCAN_ERR_CUDA; }
+      P.owner->refs = 1;
+      P.cols = cols; P.rows = n; P.arena_bytes = arena_bytes; P.err_off = err_off; P.valid = true;
+      if (!P.done) CU_TRY(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+      CU_TRY(cudaStreamWaitEvent(s->s_d2h, s->ev_compute, 0));
+      CU_TRY(cudaMemcpyAsync(P.owner->arena.p, A, arena_bytes, cudaMemcpyDeviceToHost, s->s_d2h));
+      CU_TRY(cudaEventRecord(P.done, s->s_d2h));
+      s->st.d2h_bytes += arena_bytes;
+      s->arena_flip ^= 1;
+      // the next chunk must not overwrite this arena before the copy has read it: arenas are double buffered and the
+      // batch before this one has already been waited for (see bamscan_next)
+      *produced = true;
+    }
+    }
+  CU_TRY(cudaEventRecord(s->ev_t[4], cs));
+  CU_TRY(cudaEventSynchronize(s->ev_t[4]));
+  { float d = 0; cudaEventElapsedTime(&d, s->ev_t[5], s->ev_t[4]); s->st.ms_decode += d; }
+  return BAMSCAN_OK;
+}
+
 // Runs one chunk.  On success *produced tells whether a batch went into s->pending (previous pending must have been consumed).
 static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& range, int slot, bool first_of_range, bool* produced, uint32_t* new_carry, bool* owned_done) {
   BamFile* f = s->f;
@@ -408,9 +643,9 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   tw1 = wall_ms();
   uint8_t* U = s->d_infl.as<uint8_t>();
   if (nb) {
-    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, inflate_wave_members(f->device) / INF_WARPS);
-    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, f->skip_crc ? 0 : 1);
-    s->st.kernel_launches++;
+    int nl = 0;
+    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, &s->d_sorted, &nl))) return rc;
+    s->st.kernel_launches += nl;
   }
   CU_TRY(cudaEventRecord(s->ev_t[1], cs));
   // ---- carry-in
@@ -500,166 +735,13 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
       d_recoff = s->d_recoff2.as<uint32_t>();
       if (n == 0) { CU_TRY(cudaEventRecord(s->ev_t[3], cs)); goto timing; }
     }
-    // ---- arena region A
-    const size_t n_dec = s->dec_cols.size();
-    std::vector<ColLayout> cols(n_dec);
-    ArenaBuilder AB;
-    const size_t bm_bytes = 4ull * ((n + 31) / 32), off_bytes = 4ull * (n + 1), val_bytes = 4ull * n;
-    size_t err_off = AB.take(64);
-    std::vector<size_t> src_off(n_dec, 0);
-    size_t scratch = 0;
-    for (size_t i = 0; i < n_dec; i++) {
-      ColLayout& L = cols[i]; L.schema_idx = s->dec_cols[i]; L.kind = f->fields[L.schema_idx].kind;
-      const int c_id = L.schema_idx;
-      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
-      L.has_validity = c_id >= 12 || c_id == 1 || c_id == 2 || c_id == 3 || c_id == 7 || c_id == 8;
-      if (L.has_validity) L.validity_off = AB.take(bm_bytes);
-      if (is_var) L.offsets_off = AB.take(off_bytes); else L.values_off = AB.take(val_bytes);
-      if (c_id >= 12 && is_var) { src_off[i] = scratch; scratch += align_up(val_bytes, 256); }
-    }
-    const size_t regionA = AB.pos;
-    if ((rc = s->d_scratch.ensure(scratch + 256))) return rc;
-    // a first arena sizing guess; grown after totals are known
-    DeviceBuf& arena = s->d_arena[s->arena_flip];
-    if (arena.cap < regionA) { if ((rc = arena.ensure(regionA + (size_t)c.ubytes * 2))) return rc; }
-    uint8_t* A = arena.as<uint8_t>();
-    DecodeParams DP;
-    memset(&DP, 0, sizeof DP);
-    DP.U = U; DP.rec_off = d_recoff; DP.n = n; DP.zero_based = f->zero_based; DP.binary_cigar = f->binary_cigar;
-    DP.n_ref = (int32_t)f->ref_names.size();
-    size_t n_ref = f->ref_names.size();
-    DP.ref_name_off = reinterpret_cast<const uint32_t*>(s->d_refs.as<uint8_t>() + align_up(4 * n_ref + 4, 16));
-    DP.ref_names = s->d_refs.as<uint8_t>() + align_up(4 * n_ref + 4, 16) + align_up(4 * (n_ref + 1), 16);
-    DP.err = reinterpret_cast<uint32_t*>(A + err_off);
-    ScanCols SC; memset(&SC, 0, sizeof SC); SC.n = n + 1;
-    std::vector<size_t> scan_owner;   // dec col index per scan column
-    int n_tags = 0;
-    std::vector<int> tag_slot(n_dec, -1);
-    for (size_t i = 0; i < n_dec; i++) {
-      ColLayout& L = cols[i];
-      uint32_t* v = L.has_validity ? reinterpret_cast<uint32_t*>(A + L.validity_off) : nullptr;
-      int32_t* offs = reinterpret_cast<int32_t*>(A + L.offsets_off);
-      uint32_t* vals = reinterpret_cast<uint32_t*>(A + L.values_off);
-      switch (L.schema_idx) {
-        case 0: DP.l_name = offs; break;
-        case 1: DP.l_chrom = offs; DP.v_chrom = v; break;
-        case 2: DP.start = vals; DP.v_start = v; break;
-        case 3: DP.end = vals; DP.v_end = v; break;
-        case 4: DP.flags = vals; break;
-        case 5: DP.l_cigar = offs; break;
-        case 6: DP.mapq = vals; break;
-        case 7: DP.l_mchrom = offs; DP.v_mchrom = v; break;
-        case 8: DP.mate_start = vals; DP.v_mstart = v; break;
-        case 9: DP.l_seq = offs; break;
-        case 10: DP.l_qual = offs; break;
-        case 11: DP.tlen = reinterpret_cast<int32_t*>(vals); break;
-        default: {
-          TagPlan& T = DP.tags[n_tags];
-          const std::string& tg = f->fields[L.schema_idx].name;
-          T.tag = tg.size() == 2 ? (uint16_t)((uint8_t)tg[0] | ((uint16_t)(uint8_t)tg[1] << 8)) : 0xffffu;   // names that are not 2 bytes never match (sam_tag_io.rs:58-68)
-          T.kind = L.kind; T.valid = v;
-          bool is_var = L.kind == HK_Utf8 || L.kind >= HK_ListInt8;
-          if (is_var) { T.lens = offs; T.src = reinterpret_cast<uint32_t*>(s->d_scratch.as<uint8_t>() + src_off[i]); }
-          else T.values = vals;
-          tag_slot[i] = n_tags++;
-        }
-      }
-      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
-      if (is_var) { SC.col[SC.n_cols++] = offs; scan_owner.push_back(i); }
-    }
-    DP.n_tags = n_tags;
-    CU_TRY(cudaMemsetAsync(A + err_off, 0, 64, cs));
-    if ((f->debug_flags & 2) || (uint64_t)(data_hi - HEADROOM) / std::max<uint32_t>(n_rec, 1) > 2048) {
-      CU_TRY(cudaMemsetAsync(A, 0, regionA, cs));                                        // validity words are OR-ed in
-      decode_fixed_warp_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, cs>>>(DP);     // long records: a warp per row, lanes co-operate inside the record
-    }
-    else
-      decode_fixed_kernel<<<(n + 255) / 256, 256, 0, cs>>>(DP);
-    s->st.kernel_launches++;
-    uint64_t* h_totals = reinterpret_cast<uint64_t*>(s->h_flags + 16);
-    if (SC.n_cols) {
-      uint32_t n_tiles = (SC.n + SCAN_TILE - 1) / SCAN_TILE;
-      if ((rc = s->d_tiles.ensure(8ull * n_tiles * SC.n_cols))) return rc;
-      if ((rc = s->d_totals.ensure(8ull * MAX_SCAN_COLS))) return rc;
-      multi_scan_reduce_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
-      multi_scan_tiles_kernel<<<SC.n_cols, 1024, 0, cs>>>(s->d_tiles.as<uint64_t>(), n_tiles, s->d_totals.as<uint64_t>());
-      multi_scan_apply_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
-      s->st.kernel_launches += 3;
-      publish_kernel<<<1, 64, 0, cs>>>(s->d_totals.as<uint32_t>(), s->d_hflags + 16, 2 * SC.n_cols);
-      CU_TRY(cudaEventRecord(s->ev_flags, cs));
-      CU_TRY(cudaEventSynchronize(s->ev_flags));
-      CU_TRY(cudaGetLastError());
-      // ---- arena region B
-      tw3 = wall_ms();
-      for (int k = 0; k < SC.n_cols; k++) {
-        ColLayout& L = cols[scan_owner[k]];
-        uint64_t tot = h_totals[k];
-        if (tot > 0x7fffffffull) { set_error("column '%s' exceeds 2^31-1 bytes in one batch; lower chunk_inflated_bytes", f->fields[L.schema_idx].name.c_str()); return BAMSCAN_ERR_UNSUPPORTED; }
-        uint64_t bytes = tot;
-        if (L.kind >= HK_ListInt8) { L.child_len = tot; bytes = tot * ((L.kind == HK_ListInt8 || L.kind == HK_ListUInt8) ? 1 : (L.kind == HK_ListInt16 || L.kind == HK_ListUInt16) ? 2 : 4); }
-        L.data_bytes = bytes;
-        L.data_off = AB.take((size_t)bytes + 16);
-      }
-      if (AB.pos > arena.cap) {
-        // grow, preserving region A
-        DeviceBuf bigger;
-        if ((rc = bigger.ensure(AB.pos))) return rc;
-        CU_TRY(cudaMemcpyAsync(bigger.p, arena.p, regionA, cudaMemcpyDeviceToDevice, cs));
-        CU_TRY(cudaStreamSynchronize(cs));
-        // rebase pointers
-        ptrdiff_t delta = (uint8_t*)bigger.p - A;
-        auto rb = [&](auto*& p) { if (p) p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<uint8_t*>(p) + delta); };
-        rb(DP.start); rb(DP.end); rb(DP.flags); rb(DP.mapq); rb(DP.mate_start); rb(DP.tlen);
-        rb(DP.v_chrom); rb(DP.v_start); rb(DP.v_end); rb(DP.v_mchrom); rb(DP.v_mstart);
-        rb(DP.l_name); rb(DP.l_chrom); rb(DP.l_cigar); rb(DP.l_mchrom); rb(DP.l_seq); rb(DP.l_qual); rb(DP.err);
-        for (int t = 0; t < n_tags; t++) { rb(DP.tags[t].valid); rb(DP.tags[t].values); rb(DP.tags[t].lens); }
-        arena.release(); arena = bigger; bigger.p = nullptr; bigger.cap = 0;
-        A = arena.as<uint8_t>();
-      }
-      for (size_t i = 0; i < n_dec; i++) {
-        ColLayout& L = cols[i];
-        bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
-        if (!is_var) continue;
-        uint8_t* d = A + L.data_off;
-        switch (L.schema_idx) {
-          case 0: DP.d_name = d; break; case 1: DP.d_chrom = d; break; case 5: DP.d_cigar = d; break; case 7: DP.d_mchrom = d; break;
-          case 9: DP.d_seq = d; break; case 10: DP.d_qual = d; break;
-          default: DP.tags[tag_slot[i]].data = d;
-        }
-      }
-      decode_var_kernel<<<std::min<uint32_t>((n + VAR_WARPS - 1) / VAR_WARPS, 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
-      s->st.kernel_launches++;
-    }
+    // ---- hand the rows to decode_slice(): one batch per slice of <= SLICE_BYTES inflated
+    const uint32_t n_slices = (uint32_t)std::max<uint64_t>(1, (c.ubytes + SLICE_BYTES - 1) / SLICE_BYTES);
+    s->cur.U = U; s->cur.recoff = d_recoff; s->cur.n = n; s->cur.pos = 0;
+    s->cur.rows_per_slice = (n + n_slices - 1) / n_slices;
+    s->cur.long_records = (f->debug_flags & 2) || (uint64_t)(data_hi - HEADROOM) / std::max<uint32_t>(n_rec, 1) > 2048;
+    s->cur.ubytes = c.ubytes / n_slices + (HEADROOM / 4);
     CU_TRY(cudaEventRecord(s->ev_t[3], cs));
-    const size_t arena_bytes = AB.pos;
-    s->st.rows += n; s->st.batches++;
-    for (auto& L : cols) {
-      bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
-      s->st.arrow_bytes += (L.has_validity ? (n + 7) / 8 : 0) + (is_var ? off_bytes + L.data_bytes : val_bytes);
-    }
-    if (s->device_resident) {
-      // keep everything in HBM: only the decode error word travels
-      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);
-      CU_TRY(cudaStreamSynchronize(cs));
-      if (s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
-    } else {
-      CU_TRY(cudaEventRecord(s->ev_compute, cs));
-      PendingBatch& P = s->pending;
-      P.owner = new BatchOwner();
-      P.owner->arena = arena_acquire(arena_bytes);
-      if (!P.owner->arena.p) { delete P.owner; P.owner = nullptr; return BAMSCAN_ERR_CUDA; }
-      P.owner->refs = 1;
-      P.cols = cols; P.rows = n; P.arena_bytes = arena_bytes; P.err_off = err_off; P.valid = true;
-      if (!P.done) CU_TRY(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
-      CU_TRY(cudaStreamWaitEvent(s->s_d2h, s->ev_compute, 0));
-      CU_TRY(cudaMemcpyAsync(P.owner->arena.p, A, arena_bytes, cudaMemcpyDeviceToHost, s->s_d2h));
-      CU_TRY(cudaEventRecord(P.done, s->s_d2h));
-      s->st.d2h_bytes += arena_bytes;
-      s->arena_flip ^= 1;
-      // the next chunk must not overwrite this arena before the copy has read it: arenas are double buffered and the
-      // batch before this one has already been waited for (see bamscan_next)
-      *produced = true;
-    }
   }
 timing:
   CU_TRY(cudaEventRecord(s->ev_t[4], cs));
@@ -681,6 +763,7 @@ static int advance(BamScanStream* s, bool* produced) {
   *produced = false;
   BamFile* f = s->f;
   for (;;) {
+    if (s->cur.pos < s->cur.n) { int rc = decode_slice(s, produced); return rc ? rc : 1; }   // rows of the current chunk still to decode
     if (s->finished) return 0;
     if (!s->range_open) {
       if (s->range_idx >= s->part->ranges.size()) { s->finished = true; return 0; }
@@ -718,8 +801,10 @@ static int advance(BamScanStream* s, bool* produced) {
     s->have_h2d_ahead = false;
     if (k + 1 < s->chunks.size()) { if ((rc = issue_h2d(s, s->chunks[k + 1], slot ^ 1))) return rc; s->have_h2d_ahead = true; }
     uint32_t new_carry = 0; bool owned_done = false;
+    s->cur.n = s->cur.pos = 0;
     rc = run_chunk(s, s->chunks[k], r, slot, k == 0, produced, &new_carry, &owned_done);
     if (rc) return rc;
+    if (s->cur.pos < s->cur.n && (rc = decode_slice(s, produced))) return rc;   // first slice now, the others on the next calls
     s->carry_len = new_carry;
     s->chunk_idx++;
     if (owned_done && s->chunks[k].extension) { s->carry_len = 0; s->range_open = false; s->range_idx++; }   // the tail record is complete
@@ -850,7 +935,7 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
   f.has_tag_fields = opt.has_tag_fields != 0;
   for (int i = 0; i < opt.n_tag_fields && opt.tag_fields; i++) f.tag_fields.push_back(opt.tag_fields[i]);
   f.batch_rows = opt.batch_rows;
-  if (opt.chunk_inflated_bytes) f.chunk_bytes = std::min<uint64_t>(opt.chunk_inflated_bytes, 768ull << 20);
+  if (opt.chunk_inflated_bytes) f.chunk_bytes = std::min<uint64_t>(opt.chunk_inflated_bytes, 768ull << 20);   // an explicit size is also the slice size
   if (opt.segment_bytes) f.seg_bytes = std::max<uint32_t>(256, opt.segment_bytes);
   f.skip_crc = opt.skip_crc != 0; f.debug_flags = opt.debug_flags;
   int rc = load_file(&f);
@@ -1101,7 +1186,12 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   if (s->part->ranges.empty()) { stream_destroy(s); set_error("empty partition"); return BAMSCAN_ERR_INVALID; }
   const ScanRange& r = s->part->ranges[0];
   std::vector<ChunkPlan> chunks;
-  plan_chunks(*f, r.block_begin, r.block_end, false, &chunks);
+  {   // kernel-only benchmark: one full inflate wave, whatever the scan's chunk cap is (nothing is decoded here)
+    const uint64_t saved = f->chunk_bytes;
+    f->chunk_bytes = 0;
+    plan_chunks(*f, r.block_begin, r.block_end, false, &chunks);
+    f->chunk_bytes = saved;
+  }
   const ChunkPlan& c = chunks[0];
   std::vector<BlockDesc> descs;
   uint32_t uoff = 0;
@@ -1117,13 +1207,13 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   cudaMemcpy(comp.p, f->data + c.c0, (size_t)(c.c1 - c.c0), cudaMemcpyHostToDevice);
   cudaMemset(comp.as<uint8_t>() + (c.c1 - c.c0), 0, 1024);
   cudaMemcpy(blk.p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice);
-  uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, inflate_wave_members(f->device) / INF_WARPS);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float total = 0;
   for (int rep = 0; rep < repeats + 1; rep++) {
     cudaMemsetAsync(flags.p, 0, 64, s->s_compute);
     cudaEventRecord(e0, s->s_compute);
-    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), s->s_compute>>>(comp.as<uint8_t>(), blk.as<BlockDesc>(), nb, infl.as<uint8_t>(), status.as<uint32_t>(), flags.as<uint32_t>() + 8, flags.as<uint32_t>() + 9, f->skip_crc ? 0 : 1);
+    int nl = 0;
+    launch_inflate(f, s->s_compute, comp.as<uint8_t>(), blk.as<BlockDesc>(), nb, infl.as<uint8_t>(), status.as<uint32_t>(), flags.as<uint32_t>() + 8, flags.as<uint32_t>() + 9, &s->d_sorted, &nl);
     cudaEventRecord(e1, s->s_compute);
     cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

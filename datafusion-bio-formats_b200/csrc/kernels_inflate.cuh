@@ -227,7 +227,8 @@ __device__ __noinline__ uint32_t warp_crc32(const uint8_t* out, uint32_t n, cons
 }
 
 // Reads the dynamic-block header (HLIT/HDIST/HCLEN + code lengths) into T.cl.  Returns an InflateStatus.
-__device__ __forceinline__ uint32_t read_dynamic_header(BitReader& br, WarpTables& T, int lane, int* n_ll_out, int* n_d_out) {
+template <class TT>
+__device__ __forceinline__ uint32_t read_dynamic_header(BitReader& br, TT& T, int lane, int* n_ll_out, int* n_d_out) {
   uint32_t h = br.take(14);
   int n_ll = (int)(h & 31u) + 257, n_d = (int)((h >> 5) & 31u) + 1;
   int n_clc = (int)(h >> 10) + 4;
@@ -421,6 +422,421 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
       if (err) atomicCAS(err_flag, 0u, (bi << 4) | err | 0x80000000u);
     }
     __syncwarp();
+  }
+}
+
+// =============================================================================================
+// Lane-group inflate.  The warp-per-member kernel above spends all 32 lanes' issue slots on ONE symbol at a time and is
+// issue bound.  Here a warp carries 32/G members at once: G lanes form a group that owns one member, every lane of a
+// group holds the same reader state, and one pass through the (warp-uniform, predicated) loop body decodes up to
+// NLIT + 1 symbols for EVERY group, so an instruction issued once advances 32/G independent DEFLATE streams.  The G
+// lanes of a group share the LZ77 copy; its stores are deferred by one pass so the L2 round trip of the source bytes
+// overlaps the next pass's Huffman decode.  Tables are 16-bit entries (1280 B per member) so that 160 members fit in one
+// SM's shared memory; the rare canonical walk for codes longer than the LUT index reads a small global scratch (L1
+// resident).  Block headers, table builds, stored blocks and member hand-over are done by the whole warp for one group at
+// a time (`service`), exactly as parallel as in the warp-per-member kernel.  CRC-32 moves to crc_kernel.
+//
+// 16-bit LUT entries:
+//   litlen  literal : 0x8000 | byte << 4 | nb                       length : (base - 3) << 7 | xb << 4 | nb   (xb <= 5)
+//           end of block : 0x0070 | nb        not in the LUT (longer code / unused prefix) : 0x0060
+//   dist    m << 8 | xb << 4 | nb  with distance = 1 + (m << xb) + extra            not in the LUT : 0
+//   precode sym << 4 | nb
+constexpr uint32_t L16_LIT = 0x8000u, L16_EOB = 0x0070u, L16_MISS = 0x0060u;
+constexpr int LG_SORTED = 320;                    // u16 entries per member slot: 288 litlen + 32 distance
+constexpr int LG_SLOT_BYTES = LG_SORTED * 2;                 // global scratch per member slot: sorted16[]
+constexpr int LG_CANON_LL = 15 - INF_LL_BITS, LG_CANON_D = 15 - INF_D_BITS;   // canonical rows kept in shared memory (lengths above the LUT index)
+
+template <int TK>
+__device__ __forceinline__ uint32_t make_entry16(uint32_t sym, uint32_t len) {
+  if (TK == TK_PRECODE) return (sym << 4) | len;
+  if (TK == TK_LITLEN) {
+    if (sym < 256u) return L16_LIT | (sym << 4) | len;
+    if (sym == 256u) return L16_EOB | len;
+    uint32_t s = sym - 257u;
+    if (s > 28u) return L16_MISS;
+    uint32_t extra = (s < 8u || s == 28u) ? 0u : (s - 4u) >> 2;
+    uint32_t base = s == 28u ? 258u : (s < 8u ? 3u + s : 3u + ((4u + (s & 3u)) << extra));
+    return ((base - 3u) << 7) | (extra << 4) | len;
+  }
+  if (sym > 29u) return 0u;
+  uint32_t extra = sym < 4u ? 0u : (sym - 2u) >> 1;
+  uint32_t m = sym < 4u ? sym : 2u + (sym & 1u);
+  return (m << 8) | (extra << 4) | len;
+}
+
+struct WarpScratch16 {
+  uint16_t nxt[16], cnt[16], first[16], offs[16];
+  uint8_t cl[320];
+};
+
+// Canonical Huffman build into a 16-bit LUT + the long-code arrays (canon[len] = first | cnt << 16 | offs << 32, sorted16[]).
+template <int PBITS, int TK>
+__device__ __forceinline__ bool build_table16(const uint8_t* cl, int n, uint16_t* lut, uint16_t* sorted, unsigned long long* canon,
+                                              WarpScratch16& S, int lane) {
+  constexpr uint32_t MISS = TK == TK_LITLEN ? L16_MISS : 0u;
+  if (lane < 16) { S.cnt[lane] = 0; S.nxt[lane] = 0; }
+  for (int i = lane; i < (1 << PBITS) / 2; i += 32) reinterpret_cast<uint32_t*>(lut)[i] = MISS | (MISS << 16);
+  __syncwarp();
+  for (int s = lane; s < n; s += 32) {
+    uint32_t L = cl[s];
+    if (L) atomicAdd(reinterpret_cast<unsigned int*>(S.cnt) + (L >> 1), (L & 1) ? 0x10000u : 1u);
+  }
+  __syncwarp();
+  uint32_t code = 0, off = 0, left = 1;
+  bool over = false;
+  for (int len = 1; len <= 15; len++) {
+    uint32_t c = S.cnt[len];
+    code = (code + S.cnt[len - 1]) << 1;
+    left <<= 1;
+    if (c > left) over = true;
+    left -= c;
+    if (lane == len) {
+      S.first[len] = (uint16_t)code; S.offs[len] = (uint16_t)off;
+      if (len > PBITS) canon[len - PBITS - 1] = (unsigned long long)code | ((unsigned long long)c << 16) | ((unsigned long long)off << 32);
+    }
+    off += c;
+  }
+  if (over) return false;
+  __syncwarp();
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int b = 0; b < n; b += 32) {
+    int s = b + lane;
+    uint32_t L = (s < n) ? cl[s] : 0u;
+    uint32_t m = __match_any_sync(FULL, L);
+    uint32_t r = S.nxt[L] + __popc(m & lt);
+    __syncwarp();
+    if (L && (m & lt) == 0) S.nxt[L] = (uint16_t)(S.nxt[L] + __popc(m));
+    __syncwarp();
+    if (L) {
+      const uint32_t e = make_entry16<TK>((uint32_t)s, L);
+      sorted[S.offs[L] + r] = (uint16_t)e;
+      uint32_t cd = S.first[L] + r;
+      uint32_t rev = __brev(cd) >> (32 - L);
+      if (L <= (uint32_t)PBITS)
+        for (uint32_t idx = rev; idx < (1u << PBITS); idx += (1u << L)) lut[idx] = (uint16_t)e;
+    }
+  }
+  __syncwarp();
+  return true;
+}
+
+// Canonical walk for codes longer than the LUT index; returns the 16-bit entry, or the "miss" value for an invalid code.
+template <int PBITS, int TK>
+__device__ __noinline__ uint32_t decode_long16(uint32_t bits, const unsigned long long* canon, const uint16_t* __restrict__ sorted) {
+  const uint32_t c15 = __brev(bits) >> 17;
+  #pragma unroll
+  for (int len = PBITS + 1; len <= 15; len++) {
+    const unsigned long long q = canon[len - PBITS - 1];
+    const uint32_t d = (c15 >> (15 - len)) - (uint32_t)(q & 0xffffu);
+    if (d < (uint32_t)((q >> 16) & 0xffffu)) return sorted[(uint32_t)(q >> 32) + d];
+  }
+  return TK == TK_LITLEN ? L16_MISS : 0u;
+}
+
+struct Tables16 { uint16_t* lut_ll; uint16_t* lut_d; uint16_t* sorted_ll; uint16_t* sorted_d; unsigned long long* canon_ll; unsigned long long* canon_d; };
+
+__device__ __forceinline__ uint32_t read_dynamic_header16(BitReader& br, const Tables16& T, WarpScratch16& S, int lane, int* n_ll_out, int* n_d_out) {
+  uint32_t h = br.take(14);
+  int n_ll = (int)(h & 31u) + 257, n_d = (int)((h >> 5) & 31u) + 1;
+  int n_clc = (int)(h >> 10) + 4;
+  if (n_ll > 286 || n_d > 30) return INF_ERR_TABLE;
+  if (lane < 19) S.cl[lane] = 0;
+  __syncwarp();
+  for (int i = 0; i < n_clc; i++) {
+    uint32_t v = br.take(3);
+    if (lane == 0) S.cl[c_clc_order[i]] = (uint8_t)v;
+  }
+  __syncwarp();
+  // pre-code (max length 7) goes into the distance LUT; the decoded lengths then overwrite cl[]
+  if (!build_table16<7, TK_PRECODE>(S.cl, 19, T.lut_d, T.sorted_d, T.canon_d, S, lane)) return INF_ERR_TABLE;
+  int total = n_ll + n_d, i = 0;
+  uint32_t prev = 0;
+  while (i < total) {
+    uint32_t bits = br.peek();
+    uint32_t e = T.lut_d[bits & 127u];
+    uint32_t L = e & 15u, s = e >> 4;
+    if (L == 0) return INF_ERR_TABLE;
+    uint32_t rep, val, xb;
+    if (s < 16) { rep = 1; val = s; prev = s; xb = 0; }
+    else if (s == 16) { if (i == 0) return INF_ERR_TABLE; xb = 2; rep = 3 + ((bits >> L) & 3u); val = prev; }
+    else if (s == 17) { xb = 3; rep = 3 + ((bits >> L) & 7u); val = 0; prev = 0; }
+    else { xb = 7; rep = 11 + ((bits >> L) & 127u); val = 0; prev = 0; }
+    br.consume(L + xb);
+    if (i + (int)rep > total) return INF_ERR_TABLE;
+    for (uint32_t k = lane; k < rep; k += 32) S.cl[i + k] = (uint8_t)val;
+    i += (int)rep;
+  }
+  __syncwarp();
+  if (S.cl[256] == 0) return INF_ERR_TABLE;
+  *n_ll_out = n_ll; *n_d_out = n_d;
+  return INF_OK;
+}
+
+template <int G, int W> struct LgConfig {
+  static constexpr int GROUPS = 32 / G;
+  static constexpr int THREADS = W * 32;
+  static constexpr size_t LUT_BYTES = 2 * ((1 << INF_LL_BITS) + (1 << INF_D_BITS));
+  static constexpr size_t MEMBER_SMEM = LUT_BYTES + 8 * (LG_CANON_LL + LG_CANON_D);
+  static constexpr size_t SMEM = (size_t)W * (GROUPS * MEMBER_SMEM + sizeof(WarpScratch16));
+};
+
+enum : uint32_t { ST_SYMBOLS = 0, ST_HEADER = 1, ST_MEMBER = 2, ST_DONE = 3 };
+
+template <int G, int W, int NLIT, int CTAS>
+__global__ void __launch_bounds__(W * 32, CTAS)
+inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
+                  uint8_t* __restrict__ infl, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                  uint32_t* __restrict__ err_flag, uint8_t* __restrict__ slot_scratch) {
+  constexpr int GROUPS = 32 / G;
+  constexpr int U = (16 / G) < 1 ? 1 : (16 / G);                 // deferred bytes per lane: one pass covers 16 bytes
+  constexpr uint32_t LLMASK = (1u << INF_LL_BITS) - 1u, DMASK = (1u << INF_D_BITS) - 1u;
+  constexpr uint32_t MEMBER_SMEM = (uint32_t)LgConfig<G, W>::MEMBER_SMEM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / G, glane = lane % G;
+  unsigned char* const wtab = smem_raw + (size_t)warp * GROUPS * MEMBER_SMEM;
+  WarpScratch16& WS = *reinterpret_cast<WarpScratch16*>(smem_raw + (size_t)W * GROUPS * MEMBER_SMEM + (size_t)warp * sizeof(WarpScratch16));
+  uint8_t* const wslots = slot_scratch + (size_t)(blockIdx.x * W + warp) * GROUPS * LG_SLOT_BYTES;
+  const uint16_t* const ll16 = reinterpret_cast<const uint16_t*>(wtab + grp * MEMBER_SMEM);
+  const uint16_t* const d16 = ll16 + (1 << INF_LL_BITS);
+  unsigned long long my_slot_bits = reinterpret_cast<unsigned long long>(wslots + (size_t)grp * LG_SLOT_BYTES);
+  asm volatile("" : "+l"(my_slot_bits));                        // opaque: keep it in registers instead of re-deriving it every pass
+  const uint16_t* const my_sorted = reinterpret_cast<const uint16_t*>(my_slot_bits);
+  const unsigned long long* const my_canon = reinterpret_cast<const unsigned long long*>(wtab + grp * MEMBER_SMEM + LgConfig<G, W>::LUT_BYTES);
+
+  // member state, replicated over the G lanes of the group
+  const uint32_t* wbase = reinterpret_cast<const uint32_t*>(comp);
+  uint32_t lo = 0, hi = 0, nxt = 0, bp = 0, wi = 0, wlimit = 0;
+  uint32_t outpos = 0, isize = 0, bi = 0, err = INF_OK, state = ST_MEMBER, final_block = 0;
+  uint8_t* obase = infl;
+  // deferred copy: U bytes per lane loaded in the previous pass, not yet stored
+  // two deferred copies per group (q0 older, q1 newer): position in the member, length, U bytes per lane
+  uint32_t ppos0 = 0, plen0 = 0, ppos1 = 0, plen1 = 0; uint8_t pv0[U], pv1[U];
+  uint32_t rem = 0, cdist = 0;                                  // a copy longer than one chunk continues in the next passes
+  uint32_t tog = 0;                                             // warp-uniform: which deferred slot is the older one
+  #pragma unroll
+  for (int k = 0; k < U; k++) { pv0[k] = 0; pv1[k] = 0; }
+
+  for (;;) {
+    // ---------------- service: one group at a time, whole warp ----------------
+    uint32_t need = __ballot_sync(FULL, state == ST_HEADER || state == ST_MEMBER);
+    while (need) {
+      const int src = __ffs(need) - 1;               // first lane of the group
+      const int g = src / G;
+      need &= ~(((G == 32) ? FULL : ((1u << G) - 1u)) << (g * G));
+      BitReader br;
+      {
+        unsigned long long a = reinterpret_cast<unsigned long long>(wbase);
+        a = __shfl_sync(FULL, a, src);
+        br.base = reinterpret_cast<const uint32_t*>(a);
+      }
+      br.lo = __shfl_sync(FULL, lo, src); br.hi = __shfl_sync(FULL, hi, src); br.nxt = __shfl_sync(FULL, nxt, src);
+      br.bp = __shfl_sync(FULL, bp, src); br.wi = __shfl_sync(FULL, wi, src); br.limit_words = __shfl_sync(FULL, wlimit, src);
+      uint32_t s_outpos = __shfl_sync(FULL, outpos, src), s_isize = __shfl_sync(FULL, isize, src), s_bi = __shfl_sync(FULL, bi, src);
+      uint32_t s_err = __shfl_sync(FULL, err, src), s_state = __shfl_sync(FULL, state, src), s_final = __shfl_sync(FULL, final_block, src);
+      unsigned long long s_ob = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(obase), src);
+      uint8_t* s_obase = reinterpret_cast<uint8_t*>(s_ob);
+      Tables16 T;
+      T.lut_ll = reinterpret_cast<uint16_t*>(wtab + g * MEMBER_SMEM); T.lut_d = T.lut_ll + (1 << INF_LL_BITS);
+      T.canon_ll = reinterpret_cast<unsigned long long*>(wtab + g * MEMBER_SMEM + LgConfig<G, W>::LUT_BYTES); T.canon_d = T.canon_ll + LG_CANON_LL;
+      T.sorted_ll = reinterpret_cast<uint16_t*>(wslots + (size_t)g * LG_SLOT_BYTES); T.sorted_d = T.sorted_ll + 288;
+
+      for (;;) {
+        if (s_state == ST_MEMBER) {
+          uint32_t t = 0;
+          if (lane == 0) t = atomicAdd(ticket, 1u);
+          t = __shfl_sync(FULL, t, 0);
+          if (t >= n_blocks) { s_state = ST_DONE; break; }
+          const BlockDesc bd = blocks[t];
+          s_bi = t; s_obase = infl + bd.uoff; s_isize = bd.isize; s_outpos = 0; s_final = 0; s_err = INF_OK;
+          br.init(comp + bd.cdata_off, bd.cdata_len);
+          s_state = ST_HEADER;
+        }
+        if (s_err == INF_OK && s_final && s_outpos != s_isize) s_err = s_outpos > s_isize ? INF_ERR_OVERRUN : INF_ERR_ISIZE;
+        if (s_err != INF_OK || s_final) {             // member finished (or failed): publish, take the next one
+          if (lane == 0) {
+            status[s_bi] = s_err;
+            if (s_err) atomicCAS(err_flag, 0u, (s_bi << 4) | s_err | 0x80000000u);
+          }
+          s_state = ST_MEMBER;
+          continue;
+        }
+        if (br.exhausted()) { s_err = INF_ERR_INPUT; continue; }
+        const uint32_t hdr = br.take(3);
+        s_final = hdr & 1u;
+        const uint32_t btype = hdr >> 1;
+        if (btype == 0) {
+          br.consume((8 - (br.bp & 7)) & 7);
+          const uint32_t len = br.take(16), nlen = br.take(16);
+          if ((len ^ nlen) != 0xffffu || s_outpos + len > s_isize) { s_err = INF_ERR_STORED; continue; }
+          const BlockDesc bd = blocks[s_bi];
+          const uint8_t* sp = br.byte_ptr();
+          const uint32_t used = (uint32_t)(sp + len - (comp + bd.cdata_off));
+          if (used > bd.cdata_len) { s_err = INF_ERR_INPUT; continue; }
+          for (uint32_t i = lane; i < len; i += 32) s_obase[s_outpos + i] = sp[i];
+          s_outpos += len;
+          br.init(sp + len, bd.cdata_len - used);
+          continue;
+        }
+        if (btype == 3) { s_err = INF_ERR_BTYPE; continue; }
+        int n_ll = 288, n_d = 30;
+        __syncwarp();
+        if (btype == 1) {
+          for (int i = lane; i < 288; i += 32) WS.cl[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+          if (lane < 30) WS.cl[288 + lane] = 5;
+          __syncwarp();
+        } else {
+          s_err = read_dynamic_header16(br, T, WS, lane, &n_ll, &n_d);
+          if (s_err) continue;
+        }
+        if (!build_table16<INF_LL_BITS, TK_LITLEN>(WS.cl, n_ll, T.lut_ll, T.sorted_ll, T.canon_ll, WS, lane)) { s_err = INF_ERR_TABLE; continue; }
+        if (!build_table16<INF_D_BITS, TK_DIST>(WS.cl + n_ll, n_d, T.lut_d, T.sorted_d, T.canon_d, WS, lane)) { s_err = INF_ERR_TABLE; continue; }
+        s_state = ST_SYMBOLS;
+        break;
+      }
+      if (grp == g) {
+        wbase = br.base; lo = br.lo; hi = br.hi; nxt = br.nxt; bp = br.bp; wi = br.wi; wlimit = br.limit_words;
+        outpos = s_outpos; isize = s_isize; bi = s_bi; err = s_err; state = s_state; final_block = s_final; obase = s_obase; rem = 0;
+      }
+      __syncwarp();
+    }
+    if (__all_sync(FULL, state == ST_DONE)) break;
+
+    // ---------------- symbols: every group advances by up to NLIT + 1 symbols per pass ----------------
+    // Branch-free refill: bp < 64 here.  The load writes straight into nxt's register (no move waits for it), one word
+    // ahead of its first use.
+#define LG_REFILL()                                                                                              \
+    {                                                                                                            \
+      const bool rf = bp >= 32u;                                                                                 \
+      const uint32_t* const ra = wbase + wi;                                                                     \
+      lo = rf ? hi : lo; hi = rf ? nxt : hi;                                                                     \
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.u32 %0, [%2];\n\t}"          \
+                   : "+r"(nxt) : "r"((uint32_t)rf), "l"(ra));                                                     \
+      wi += bp >> 5; bp &= 31u;                                                                                  \
+    }
+#define LG_STORE(PPOS, PLEN, PV)                                                                                 \
+    if (PLEN) {                                                                                                  \
+      uint8_t* const pd = obase + PPOS + glane;                                                                  \
+      _Pragma("unroll")                                                                                          \
+      for (int k = 0; k < U; k++) if ((uint32_t)(glane + k * G) < PLEN) pd[k * G] = PV[k];                       \
+      PLEN = 0;                                                                                                  \
+    }
+    // One chunk (<= U*G bytes per group) of LZ77 copy.  Slot X holds the copy deferred two match passes ago: it is stored
+    // now and refilled with this pass's loads; slot Y (one pass old) is stored too only when a new chunk reads bytes that
+    // are still deferred.  Byte i of a chunk is src[i mod dist], so only bytes that already exist are ever read.
+#define LG_COPY(PX, LX, VX, PY, LY, VY)                                                                          \
+    {                                                                                                            \
+      const uint32_t pmin = LX ? PX : (LY ? PY : 0xffffffffu);                                                   \
+      const bool hazard = cur != 0 && outpos - dist + cur > pmin;                                                \
+      LG_STORE(PX, LX, VX);                                                                                      \
+      if (__any_sync(FULL, hazard)) { LG_STORE(PY, LY, VY); }                                                    \
+      __syncwarp();                                                                                              \
+      const uint8_t* const s0 = obase + outpos - dist;                                                           \
+      if (!__any_sync(FULL, dist < cur)) {                                                                       \
+        _Pragma("unroll")                                                                                        \
+        for (int k = 0; k < U; k++) if ((uint32_t)(glane + k * G) < cur) VX[k] = __ldcg(s0 + glane + k * G);     \
+      } else {                                                                                                   \
+        const bool ovl = dist < cur;                                                                             \
+        _Pragma("unroll")                                                                                        \
+        for (int k = 0; k < U; k++) {                                                                            \
+          const uint32_t i = glane + k * G;                                                                      \
+          if (i < cur) VX[k] = __ldcg(s0 + (ovl ? i % dist : i));                                                \
+        }                                                                                                        \
+      }                                                                                                          \
+      PX = outpos; LX = cur;                                                                                     \
+    }
+    for (;;) {
+      const bool act = state == ST_SYMBOLS;
+      const bool dec = act && rem == 0;                     // a group in the middle of a long copy does not decode this pass
+      uint32_t bits = __funnelshift_r(lo, hi, bp);
+      uint32_t e = ll16[bits & LLMASK];
+      #pragma unroll
+      for (int k = 0; k < NLIT; k++) {
+        if (dec && (e & L16_LIT)) {
+          if (glane == 0) obase[outpos] = (uint8_t)(e >> 4);
+          outpos++;
+          bp += e & 15u;
+          LG_REFILL();
+          bits = __funnelshift_r(lo, hi, bp);
+          e = ll16[bits & LLMASK];
+        }
+      }
+      uint32_t len = 0;
+      if (dec) {
+        if ((e & (L16_LIT | 0x70u)) == L16_MISS) e = decode_long16<INF_LL_BITS, TK_LITLEN>(bits, my_canon, my_sorted);
+        if (e & L16_LIT) {
+          if (glane == 0) obase[outpos] = (uint8_t)(e >> 4);
+          outpos++;
+          bp += e & 15u;
+        } else if ((e & 0x60u) != 0x60u) {
+          const uint32_t nb = e & 15u, xb = (e >> 4) & 7u;
+          len = (e >> 7) + 3u + ((bits >> nb) & ~(0xffffffffu << xb));
+          bp += nb + xb;
+        } else {                                            // end of block, or an invalid code
+          bp += e & 15u;
+          if ((e & 15u) == 0) err = INF_ERR_SYMBOL;
+          state = ST_HEADER;
+        }
+        LG_REFILL();
+      }
+      if (__any_sync(FULL, (len | rem) != 0)) {
+        if (len) {
+          bits = __funnelshift_r(lo, hi, bp);
+          uint32_t de = d16[bits & DMASK];
+          if ((de & 15u) == 0) de = decode_long16<INF_D_BITS, TK_DIST>(bits, my_canon + LG_CANON_LL, my_sorted + 288);
+          const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
+          const uint32_t d = 1u + ((de >> 8) << dxb) + ((bits >> dnb) & ~(0xffffffffu << dxb));
+          bp += dnb + dxb;
+          if (dnb == 0 || d > outpos || outpos + len > isize) {
+            err = (dnb == 0 || d > outpos) ? INF_ERR_DIST : INF_ERR_OVERRUN;
+            state = ST_HEADER;
+          } else { rem = len; cdist = d; }
+        }
+        const uint32_t cur = min(rem, (uint32_t)(U * G));
+        const uint32_t dist = rem ? cdist : 0u;
+        if (tog) { LG_COPY(ppos1, plen1, pv1, ppos0, plen0, pv0); } else { LG_COPY(ppos0, plen0, pv0, ppos1, plen1, pv1); }
+        tog ^= 1u;
+        outpos += cur; rem -= cur;
+        LG_REFILL();
+      }
+      if (wi > wlimit && act) { if (state == ST_SYMBOLS) err = INF_ERR_INPUT; state = ST_HEADER; rem = 0; }
+      if (__any_sync(FULL, state == ST_HEADER)) break;
+    }
+    LG_STORE(ppos0, plen0, pv0);
+    LG_STORE(ppos1, plen1, pv1);
+#undef LG_COPY
+#undef LG_REFILL
+#undef LG_STORE
+  }
+}
+
+// CRC-32 of every inflated member against its BGZF trailer: one warp per member (32 lane-chunks by slicing-by-4, combined
+// with x^(8k) mod P multiplies).  Runs right behind the inflate kernel while the bytes are still in L2.
+__global__ void __launch_bounds__(256)
+crc_kernel(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const uint8_t* __restrict__ infl,
+           uint32_t* __restrict__ status, uint32_t* __restrict__ err_flag) {
+  __shared__ uint32_t tab[4][256];
+  {
+    uint32_t c = threadIdx.x;
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+    tab[0][threadIdx.x] = c;
+  }
+  __syncthreads();
+  {
+    uint32_t c = tab[0][threadIdx.x];
+    for (int t = 1; t < 4; t++) { c = tab[0][c & 0xff] ^ (c >> 8); tab[t][threadIdx.x] = c; }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t bi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bi < n_blocks; bi += wpg) {
+    if (status[bi] != INF_OK) continue;
+    const BlockDesc bd = blocks[bi];
+    const uint32_t crc = warp_crc32(infl + bd.uoff, bd.isize, tab, lane);
+    if (crc != bd.crc && lane == 0) {
+      status[bi] = INF_ERR_CRC;
+      atomicCAS(err_flag, 0u, (bi << 4) | INF_ERR_CRC | 0x80000000u);
+    }
   }
 }
 
