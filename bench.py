@@ -11,7 +11,7 @@ repo's own writer (tools/bamgen.cpp, seed 2, zlib level 6) under /dev/shm.
 value   : reads/s, device resident (compressed bytes already in HBM, Arrow buffers stay in HBM), CUDA-event time, max over ranks
 e2e     : same scan through the public provider API: H2D of the compressed bytes from pinned host memory and D2H of every
           Arrow buffer inside the timed region
-roofline: inflate_kernel (dominant), algorithmic bytes = compressed bytes read + inflated bytes written, per launch
+roofline: inflate_lg_kernel (dominant), algorithmic bytes = compressed bytes read + inflated bytes written, per launch
 N > 1   : weak scaling -- every rank scans one copy of the file on its own GPU (BGZF files concatenate, so this equals block-
           range sharding of the N-fold concatenation); no collective on the data path.
 """
@@ -298,7 +298,7 @@ def main():
         "inflated_gbps": world * st["inflated_bytes"] * args.steps / dev_s_max / 1e9,
         "scan_roofline_frac": (scan_alg / (st["ms_total"] / 1000.0) / 1e9) / peak,
         "stage_ms": {"inflate": st["ms_inflate"], "boundary": st["ms_boundary"], "decode": st["ms_decode"], "total": st["ms_total"]},
-        "roofline": {"kernel": "inflate_kernel", "bound": "hbm", "achieved": infl_gbs, "peak": peak, "unit": "GB/s", "frac": infl_gbs / peak,
+        "roofline": {"kernel": "inflate_lg_kernel (+ crc_kernel in the same event bracket)", "bound": "hbm", "achieved": infl_gbs, "peak": peak, "unit": "GB/s", "frac": infl_gbs / peak,
                      "traffic": None, "peak_source": peak_src, "launches": launches_inflate,
                      "alg_bytes_per_launch": infl_alg / launches_inflate, "ms_per_launch": st["ms_inflate"] / launches_inflate},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],

@@ -200,6 +200,7 @@ struct BamScanStream {
   BlockDesc* h_descs[2] = {nullptr, nullptr}; size_t h_descs_cap[2] = {0, 0}; uint32_t n_descs[2] = {0, 0}; uint32_t chunk_data_hi[2] = {0, 0};
   int arena_flip = 0;
   // rows of the current chunk that are not decoded yet: a chunk is one inflate wave, a batch is one slice of its rows
+  int64_t launched_chunk = -1;   // index in `chunks` of a chunk whose inflate + boundary kernels are already queued (run_chunk phase 1)
   struct { const uint8_t* U = nullptr; const uint32_t* recoff = nullptr; uint32_t n = 0, pos = 0, rows_per_slice = 0; bool long_records = false; uint64_t ubytes = 0; } cur;
   PendingBatch pending;
   std::vector<ReadyBatch> ready; size_t ready_pos = 0;
@@ -276,7 +277,7 @@ static int stream_init(BamScanStream* s) {
   // per-scan state
   s->range_idx = 0; s->chunks.clear(); s->chunk_idx = 0; s->range_open = false; s->finished = false;
   s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = false; s->tail_seen = false; s->range_stop = false;
-  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->cur.n = s->cur.pos = 0; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
+  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->cur.n = s->cur.pos = 0; s->launched_chunk = -1; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
   s->st = BamScanStats{}; s->error = 0; s->d_comp_all = nullptr; s->comp_all_c0 = 0;
   if (!s->resources_ready) {
   rc = init_device_constants(f->device);
@@ -605,7 +606,9 @@ static int decode_slice(BamScanStream* s, bool* produced) {
 }
 
 // Runs one chunk.  On success *produced tells whether a batch went into s->pending (previous pending must have been consumed).
-static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& range, int slot, bool first_of_range, bool* produced, uint32_t* new_carry, bool* owned_done) {
+// phase 1 queues H2D wait + inflate + record boundaries and returns without waiting (the host can then wait for an older
+// batch's D2H while the GPU works); phase 2 picks the chunk up from there; phase 0 does both.
+static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& range, int slot, bool first_of_range, bool* produced, uint32_t* new_carry, bool* owned_done, int phase) {
   BamFile* f = s->f;
   *produced = false;
   static const bool trace2 = getenv("BAMSCAN_TRACE") && atoi(getenv("BAMSCAN_TRACE")) >= 2;
@@ -634,23 +637,8 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   const uint8_t* d_comp;
   if (s->device_resident) d_comp = s->d_comp_all + (c.c0 - s->comp_all_c0);
   else d_comp = s->d_comp[slot].as<uint8_t>();
-  CU_TRY(cudaStreamWaitEvent(cs, s->ev_h2d[slot], 0));   // descriptors (+ compressed bytes) of this chunk have landed
-  CU_TRY(cudaMemsetAsync(d_flags, 0, 64, cs));
-  CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
-  CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
-  CU_TRY(cudaMemsetAsync(d_flags + 11, 0xff, 4, cs));    // [11] first disagreeing seam
-  CU_TRY(cudaEventRecord(s->ev_t[0], cs));
-  tw1 = wall_ms();
   uint8_t* U = s->d_infl.as<uint8_t>();
-  if (nb) {
-    int nl = 0;
-    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, &s->d_sorted, &nl))) return rc;
-    s->st.kernel_launches += nl;
-  }
-  CU_TRY(cudaEventRecord(s->ev_t[1], cs));
-  // ---- carry-in
   const uint32_t carry = s->carry_len;
-  if (carry) CU_TRY(cudaMemcpyAsync(U + HEADROOM - carry, s->d_carry.p, carry, cudaMemcpyDeviceToDevice, cs));
   // ---- boundaries
   BoundaryParams BP;
   BP.U = U; BP.data_lo = HEADROOM - carry; BP.data_hi = data_hi; BP.seg0 = seg0; BP.seg_bytes = seg_bytes; BP.n_seg = n_seg;
@@ -664,6 +652,22 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   if (c.extension) own = seg0;
   if (range.stop_uoff != ~0ull && range.stop_uoff < c.u0 + c.ubytes) own = std::min<uint64_t>(own, range.stop_uoff >= c.u0 ? HEADROOM + (range.stop_uoff - c.u0) : seg0);
   BP.own_hi = (uint32_t)own;
+  if (phase != 2) {
+  CU_TRY(cudaStreamWaitEvent(cs, s->ev_h2d[slot], 0));   // descriptors (+ compressed bytes) of this chunk have landed
+  CU_TRY(cudaMemsetAsync(d_flags, 0, 64, cs));
+  CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
+  CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
+  CU_TRY(cudaMemsetAsync(d_flags + 11, 0xff, 4, cs));    // [11] first disagreeing seam
+  CU_TRY(cudaEventRecord(s->ev_t[0], cs));
+  tw1 = wall_ms();
+  if (nb) {
+    int nl = 0;
+    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, &s->d_sorted, &nl))) return rc;
+    s->st.kernel_launches += nl;
+  }
+  CU_TRY(cudaEventRecord(s->ev_t[1], cs));
+  // ---- carry-in
+  if (carry) CU_TRY(cudaMemcpyAsync(U + HEADROOM - carry, s->d_carry.p, carry, cudaMemcpyDeviceToDevice, cs));
   WalkOut W{d_seg_start, d_seg_exit, d_seg_count, d_seg_tail, d_flags};
   seg_candidates_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, cs>>>(BP, d_seg_start, (f->debug_flags & 1) ? 1 : 0);
   seg_walk_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
@@ -673,6 +677,8 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   s->st.kernel_launches += 5;
   publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
   CU_TRY(cudaEventRecord(s->ev_flags, cs));
+    if (phase == 1) return BAMSCAN_OK;
+  }
   CU_TRY(cudaEventSynchronize(s->ev_flags));
   CU_TRY(cudaGetLastError());
   // ---- host: decisions
@@ -758,12 +764,41 @@ timing:
   return BAMSCAN_OK;
 }
 
+// H2D of chunk k (unless it was prefetched) and prefetch of chunk k + 1.
+static int issue_chunk_h2d(BamScanStream* s, size_t k) {
+  const int slot = (int)(k & 1);
+  int rc;
+  if (!s->have_h2d_ahead) { if ((rc = issue_h2d(s, s->chunks[k], slot))) return rc; }
+  s->have_h2d_ahead = false;
+  if (k + 1 < s->chunks.size()) { if ((rc = issue_h2d(s, s->chunks[k + 1], slot ^ 1))) return rc; s->have_h2d_ahead = true; }
+  return BAMSCAN_OK;
+}
+
+// Once every row of the current chunk is decoded, queue the next chunk's inflate + boundary kernels right away: the caller
+// is about to block on an older batch's D2H, and the GPU should not sit idle meanwhile.
+static int launch_next_chunk_early(BamScanStream* s) {
+  if (s->cur.pos < s->cur.n || !s->range_open || s->finished || s->launched_chunk >= 0) return BAMSCAN_OK;
+  if (s->chunk_idx >= s->chunks.size()) return BAMSCAN_OK;          // extension chunks are planned when their turn comes
+  const size_t k = s->chunk_idx;
+  int rc = issue_chunk_h2d(s, k);
+  if (rc) return rc;
+  bool produced = false, owned_done = false; uint32_t new_carry = 0;
+  rc = run_chunk(s, s->chunks[k], s->part->ranges[s->range_idx], (int)(k & 1), k == 0, &produced, &new_carry, &owned_done, 1);
+  if (rc) return rc;
+  s->launched_chunk = (int64_t)k;
+  return BAMSCAN_OK;
+}
+
 // Advances the partition by one chunk.  Returns 1 when a chunk ran (a batch may be pending), 0 when the partition is exhausted.
 static int advance(BamScanStream* s, bool* produced) {
   *produced = false;
   BamFile* f = s->f;
   for (;;) {
-    if (s->cur.pos < s->cur.n) { int rc = decode_slice(s, produced); return rc ? rc : 1; }   // rows of the current chunk still to decode
+    if (s->cur.pos < s->cur.n) {   // rows of the current chunk still to decode
+      int rc = decode_slice(s, produced);
+      if (!rc) rc = launch_next_chunk_early(s);
+      return rc ? rc : 1;
+    }
     if (s->finished) return 0;
     if (!s->range_open) {
       if (s->range_idx >= s->part->ranges.size()) { s->finished = true; return 0; }
@@ -797,18 +832,19 @@ static int advance(BamScanStream* s, bool* produced) {
     const size_t k = s->chunk_idx;
     const int slot = (int)(k & 1);
     int rc;
-    if (!s->have_h2d_ahead) { if ((rc = issue_h2d(s, s->chunks[k], slot))) return rc; }
-    s->have_h2d_ahead = false;
-    if (k + 1 < s->chunks.size()) { if ((rc = issue_h2d(s, s->chunks[k + 1], slot ^ 1))) return rc; s->have_h2d_ahead = true; }
+    const bool launched = s->launched_chunk == (int64_t)k;
+    if (!launched && (rc = issue_chunk_h2d(s, k))) return rc;
     uint32_t new_carry = 0; bool owned_done = false;
     s->cur.n = s->cur.pos = 0;
-    rc = run_chunk(s, s->chunks[k], r, slot, k == 0, produced, &new_carry, &owned_done);
+    rc = run_chunk(s, s->chunks[k], r, slot, k == 0, produced, &new_carry, &owned_done, launched ? 2 : 0);
+    s->launched_chunk = -1;
     if (rc) return rc;
     if (s->cur.pos < s->cur.n && (rc = decode_slice(s, produced))) return rc;   // first slice now, the others on the next calls
     s->carry_len = new_carry;
     s->chunk_idx++;
     if (owned_done && s->chunks[k].extension) { s->carry_len = 0; s->range_open = false; s->range_idx++; }   // the tail record is complete
     else if (s->range_stop) { s->carry_len = 0; s->range_open = false; s->range_idx++; }                      // unmapped tail: another reference began
+    if ((rc = launch_next_chunk_early(s))) return rc;
     return 1;
   }
 }
@@ -1135,7 +1171,7 @@ int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t re
   double best_total = 0;
   BamScanStats acc{};
   for (int rep = 0; rep < std::max(1, repeats); rep++) {
-    s->st = BamScanStats{}; s->range_idx = 0; s->range_open = false; s->finished = false; s->carry_len = 0;
+    s->st = BamScanStats{}; s->range_idx = 0; s->range_open = false; s->finished = false; s->carry_len = 0; s->launched_chunk = -1; s->cur.n = s->cur.pos = 0;
     cudaEventRecord(e0, s->s_compute);
     bool produced;
     while ((rc = advance(s, &produced)) == 1) {}

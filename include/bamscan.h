@@ -64,7 +64,7 @@ typedef struct BamScanOptions {
   const char* const* tag_type_hints;      /* "TAG:TYPE" | "TAG:B:SUBTYPE", tag_registry.rs:698-752 */
   int32_t device_id;                      /* CUDA device ordinal for this handle */
   int32_t batch_rows;                     /* rows per emitted batch; 0 = one batch per device chunk (reference default 8192) */
-  uint64_t chunk_inflated_bytes;          /* device chunk size cap (inflated bytes); 0 = default 640 MiB, max 768 MiB */
+  uint64_t chunk_inflated_bytes;          /* device chunk size cap (inflated bytes), max 768 MiB; 0 = one inflate wave per chunk (~1.5 GiB on a B200), decoded in slices of <= 768 MiB: one batch per slice */
   uint32_t segment_bytes;                 /* record-boundary segment size; 0 = default 16 KiB */
   int32_t skip_crc;                       /* 0 (default): verify CRC32 of every BGZF member on the device; 1: skip */
   int32_t debug_flags;                    /* bit0: poison boundary candidates (exercises the repair path in tests); bit1: force the long-record decode kernel */
