@@ -236,10 +236,9 @@ static const InflateVariant& inflate_variant() {
     int k = e ? atoi(e) : 1;
     switch (k) {
       case 0: return InflateVariant{0, 0, 0, 0, nullptr};
-      case 2: return lg_variant<4, 20, 1, 1>();
+      case 2: return lg_variant<4, 19, 1, 1>();
       case 3: return lg_variant<4, 16, 2, 1>();
-      case 4: return lg_variant<8, 32, 2, 1>();
-      default: return lg_variant<4, 20, 2, 1>();
+      default: return lg_variant<4, 19, 2, 1>();
     }
   }();
   return v;

@@ -444,6 +444,7 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
 constexpr uint32_t L16_LIT = 0x8000u, L16_EOB = 0x0070u, L16_MISS = 0x0060u;
 constexpr int LG_SORTED = 320;                    // u16 entries per member slot: 288 litlen + 32 distance
 constexpr int LG_SLOT_BYTES = LG_SORTED * 2;                 // global scratch per member slot: sorted16[]
+constexpr int LG_RING_BYTES = 64;                // compressed-stream ring per member: four 16-byte chunks filled by cp.async
 constexpr int LG_CANON_LL = 15 - INF_LL_BITS, LG_CANON_D = 15 - INF_D_BITS;   // canonical rows kept in shared memory (lengths above the LUT index)
 
 template <int TK>
@@ -576,7 +577,8 @@ template <int G, int W> struct LgConfig {
   static constexpr int GROUPS = 32 / G;
   static constexpr int THREADS = W * 32;
   static constexpr size_t LUT_BYTES = 2 * ((1 << INF_LL_BITS) + (1 << INF_D_BITS));
-  static constexpr size_t MEMBER_SMEM = LUT_BYTES + 8 * (LG_CANON_LL + LG_CANON_D);
+  static constexpr size_t RING_OFF = LUT_BYTES + 8 * (LG_CANON_LL + LG_CANON_D);
+  static constexpr size_t MEMBER_SMEM = RING_OFF + LG_RING_BYTES;
   static constexpr size_t SMEM = (size_t)W * (GROUPS * MEMBER_SMEM + sizeof(WarpScratch16));
 };
 
@@ -605,8 +607,12 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
   const unsigned long long* const my_canon = reinterpret_cast<const unsigned long long*>(wtab + grp * MEMBER_SMEM + LgConfig<G, W>::LUT_BYTES);
 
   // member state, replicated over the G lanes of the group
-  const uint32_t* wbase = reinterpret_cast<const uint32_t*>(comp);
-  uint32_t lo = 0, hi = 0, nxt = 0, bp = 0, wi = 0, wlimit = 0;
+  const uint32_t* wbase = reinterpret_cast<const uint32_t*>(blocks);   // any valid, aligned address until a member is taken
+  // reader: lo:hi hold the two current words; the following words come from the member's shared-memory ring, which cp.async
+  // keeps 2-3 chunks ahead (no register is the destination of an in-flight global load, so no pass waits for one).
+  // wbase is 16-byte aligned; wi = index (from wbase) of the word after hi; fill = next 16-byte chunk to fetch.
+  uint32_t lo = 0, hi = 0, bp = 0, wi = 0, wlimit = 0, fill = 0;
+  const uint32_t my_ring = (uint32_t)__cvta_generic_to_shared(wtab + grp * MEMBER_SMEM + LgConfig<G, W>::RING_OFF);
   uint32_t outpos = 0, isize = 0, bi = 0, err = INF_OK, state = ST_MEMBER, final_block = 0;
   uint8_t* obase = infl;
   // deferred copy: U bytes per lane loaded in the previous pass, not yet stored
@@ -630,8 +636,9 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
         a = __shfl_sync(FULL, a, src);
         br.base = reinterpret_cast<const uint32_t*>(a);
       }
-      br.lo = __shfl_sync(FULL, lo, src); br.hi = __shfl_sync(FULL, hi, src); br.nxt = __shfl_sync(FULL, nxt, src);
-      br.bp = __shfl_sync(FULL, bp, src); br.wi = __shfl_sync(FULL, wi, src); br.limit_words = __shfl_sync(FULL, wlimit, src);
+      br.lo = __shfl_sync(FULL, lo, src); br.hi = __shfl_sync(FULL, hi, src);
+      br.bp = __shfl_sync(FULL, bp, src); br.wi = __shfl_sync(FULL, wi, src); br.limit_words = __shfl_sync(FULL, wlimit, src) + 1u;
+      br.nxt = __ldg(br.base + br.wi); br.wi += 1u;          // back to the three-word reader of the header code
       uint32_t s_outpos = __shfl_sync(FULL, outpos, src), s_isize = __shfl_sync(FULL, isize, src), s_bi = __shfl_sync(FULL, bi, src);
       uint32_t s_err = __shfl_sync(FULL, err, src), s_state = __shfl_sync(FULL, state, src), s_final = __shfl_sync(FULL, final_block, src);
       unsigned long long s_ob = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(obase), src);
@@ -694,8 +701,20 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
         s_state = ST_SYMBOLS;
         break;
       }
+      // re-base the reader on a 16-byte boundary and prime the ring with the first three chunks
+      const uint32_t* s_wbase; uint32_t s_wi, s_wlimit;
+      {
+        const uint32_t* const plo = br.base + (br.wi - 3u);                   // the word held in lo
+        const unsigned long long a16 = reinterpret_cast<unsigned long long>(plo) & ~15ull;
+        const uint32_t k0 = (uint32_t)((reinterpret_cast<unsigned long long>(plo) - a16) >> 2);
+        s_wbase = reinterpret_cast<const uint32_t*>(a16);
+        s_wi = k0 + 2u;
+        s_wlimit = br.limit_words - ((br.wi - 3u) - k0) - 1u;
+        uint32_t* const rg = reinterpret_cast<uint32_t*>(wtab + g * MEMBER_SMEM + LgConfig<G, W>::RING_OFF);
+        if (s_state == ST_SYMBOLS && lane < 12) rg[lane] = __ldg(s_wbase + lane);
+      }
       if (grp == g) {
-        wbase = br.base; lo = br.lo; hi = br.hi; nxt = br.nxt; bp = br.bp; wi = br.wi; wlimit = br.limit_words;
+        wbase = s_wbase; lo = br.lo; hi = br.hi; bp = br.bp; wi = s_wi; wlimit = s_wlimit; fill = 3u;
         outpos = s_outpos; isize = s_isize; bi = s_bi; err = s_err; state = s_state; final_block = s_final; obase = s_obase; rem = 0;
       }
       __syncwarp();
@@ -703,15 +722,13 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
     if (__all_sync(FULL, state == ST_DONE)) break;
 
     // ---------------- symbols: every group advances by up to NLIT + 1 symbols per pass ----------------
-    // Branch-free refill: bp < 64 here.  The load writes straight into nxt's register (no move waits for it), one word
-    // ahead of its first use.
+    // Branch-free refill from the ring: bp < 64 here.
 #define LG_REFILL()                                                                                              \
     {                                                                                                            \
       const bool rf = bp >= 32u;                                                                                 \
-      const uint32_t* const ra = wbase + wi;                                                                     \
-      lo = rf ? hi : lo; hi = rf ? nxt : hi;                                                                     \
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.u32 %0, [%2];\n\t}"          \
-                   : "+r"(nxt) : "r"((uint32_t)rf), "l"(ra));                                                     \
+      lo = rf ? hi : lo;                                                                                         \
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.shared.u32 %0, [%2];\n\t}"              \
+                   : "+r"(hi) : "r"((uint32_t)rf), "r"(my_ring + ((wi & 15u) << 2)));                             \
       wi += bp >> 5; bp &= 31u;                                                                                  \
     }
 #define LG_STORE(PPOS, PLEN, PV)                                                                                 \
@@ -800,8 +817,20 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
         LG_REFILL();
       }
       if (wi > wlimit && act) { if (state == ST_SYMBOLS) err = INF_ERR_INPUT; state = ST_HEADER; rem = 0; }
+      // ring top-up: the chunk requested one pass ago has landed; request the next one when its slot is free (every
+      // word of the chunk it replaces has been consumed)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      {
+        const bool want = act && 4u * fill <= wi + 10u;
+        if (want && glane == 0)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(my_ring + ((fill & 3u) << 4)), "l"(wbase + 4u * fill) : "memory");
+        fill += want ? 1u : 0u;
+      }
+      __syncwarp();
       if (__any_sync(FULL, state == ST_HEADER)) break;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
     LG_STORE(ppos0, plen0, pv0);
     LG_STORE(ppos1, plen1, pv1);
 #undef LG_COPY
