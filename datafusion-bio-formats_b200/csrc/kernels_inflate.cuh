@@ -444,7 +444,7 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
 constexpr uint32_t L16_LIT = 0x8000u, L16_EOB = 0x0070u, L16_MISS = 0x0060u;
 constexpr int LG_SORTED = 320;                    // u16 entries per member slot: 288 litlen + 32 distance
 constexpr int LG_SLOT_BYTES = LG_SORTED * 2;                 // global scratch per member slot: sorted16[]
-constexpr int LG_RING_BYTES = 64;                // compressed-stream ring per member: four 16-byte chunks filled by cp.async
+constexpr int LG_RING_BYTES = 64;                // compressed-stream ring per member: four 16-byte chunks
 constexpr int LG_CANON_LL = 15 - INF_LL_BITS, LG_CANON_D = 15 - INF_D_BITS;   // canonical rows kept in shared memory (lengths above the LUT index)
 
 template <int TK>
@@ -608,10 +608,11 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
 
   // member state, replicated over the G lanes of the group
   const uint32_t* wbase = reinterpret_cast<const uint32_t*>(blocks);   // any valid, aligned address until a member is taken
-  // reader: lo:hi hold the two current words; the following words come from the member's shared-memory ring, which cp.async
-  // keeps 2-3 chunks ahead (no register is the destination of an in-flight global load, so no pass waits for one).
+  // reader: lo:hi hold the two current words; the following words come from the member's shared-memory ring, which is
+  // kept 2-3 chunks ahead by loads that are given a whole pass to complete (see the ring top-up at the end of a pass).
   // wbase is 16-byte aligned; wi = index (from wbase) of the word after hi; fill = next 16-byte chunk to fetch.
   uint32_t lo = 0, hi = 0, bp = 0, wi = 0, wlimit = 0, fill = 0;
+  uint32_t rq[4 / G + (4 % G != 0)], rq_slot = 0xffffffffu;     // ring chunk in flight (one word per lane) and its slot
   const uint32_t my_ring = (uint32_t)__cvta_generic_to_shared(wtab + grp * MEMBER_SMEM + LgConfig<G, W>::RING_OFF);
   uint32_t outpos = 0, isize = 0, bi = 0, err = INF_OK, state = ST_MEMBER, final_block = 0;
   uint8_t* obase = infl;
@@ -714,7 +715,7 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
         if (s_state == ST_SYMBOLS && lane < 12) rg[lane] = __ldg(s_wbase + lane);
       }
       if (grp == g) {
-        wbase = s_wbase; lo = br.lo; hi = br.hi; bp = br.bp; wi = s_wi; wlimit = s_wlimit; fill = 3u;
+        wbase = s_wbase; lo = br.lo; hi = br.hi; bp = br.bp; wi = s_wi; wlimit = s_wlimit; fill = 3u; rq_slot = 0xffffffffu;
         outpos = s_outpos; isize = s_isize; bi = s_bi; err = s_err; state = s_state; final_block = s_final; obase = s_obase; rem = 0;
       }
       __syncwarp();
@@ -817,20 +818,26 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
         LG_REFILL();
       }
       if (wi > wlimit && act) { if (state == ST_SYMBOLS) err = INF_ERR_INPUT; state = ST_HEADER; rem = 0; }
-      // ring top-up: the chunk requested one pass ago has landed; request the next one when its slot is free (every
-      // word of the chunk it replaces has been consumed)
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      {
-        const bool want = act && 4u * fill <= wi + 10u;
-        if (want && glane == 0)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(my_ring + ((fill & 3u) << 4)), "l"(wbase + 4u * fill) : "memory");
-        fill += want ? 1u : 0u;
+      // ring top-up, software pipelined through one register per lane: the chunk loaded one pass ago goes into its slot now
+      // (its four words sit in the group's G lanes), then the next chunk is requested when its slot is free (every word of
+      // the chunk it replaces has been consumed).  The load has a whole pass to complete.
+      if (rq_slot != 0xffffffffu) {
+        #pragma unroll
+        for (int k = 0; k < 4 / G + (4 % G != 0); k++)
+          if (glane + k * G < 4) asm volatile("st.shared.u32 [%0], %1;" :: "r"(my_ring + (rq_slot << 4) + ((glane + k * G) << 2)), "r"(rq[k]) : "memory");
+        rq_slot = 0xffffffffu;
+      }
+      if (act && 4u * fill <= wi + 10u) {
+        #pragma unroll
+        for (int k = 0; k < 4 / G + (4 % G != 0); k++)
+          if (glane + k * G < 4) rq[k] = __ldg(wbase + 4u * fill + glane + k * G);
+        rq_slot = fill & 3u;
+        fill++;
       }
       __syncwarp();
       if (__any_sync(FULL, state == ST_HEADER)) break;
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
+
     LG_STORE(ppos0, plen0, pv0);
     LG_STORE(ppos1, plen1, pv1);
 #undef LG_COPY
