@@ -521,13 +521,17 @@ __device__ __forceinline__ bool build_table16(const uint8_t* cl, int n, uint16_t
   return true;
 }
 
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr)); return v; }
+
 // Canonical walk for codes longer than the LUT index; returns the 16-bit entry, or the "miss" value for an invalid code.
+// canon_s: shared-window address of the rows first | cnt << 16 | offs << 32 for lengths PBITS+1 .. 15.
 template <int PBITS, int TK>
-__device__ __noinline__ uint32_t decode_long16(uint32_t bits, const unsigned long long* canon, const uint16_t* __restrict__ sorted) {
+__device__ __forceinline__ uint32_t decode_long16(uint32_t bits, uint32_t canon_s, const uint16_t* __restrict__ sorted) {
   const uint32_t c15 = __brev(bits) >> 17;
   #pragma unroll
   for (int len = PBITS + 1; len <= 15; len++) {
-    const unsigned long long q = canon[len - PBITS - 1];
+    const unsigned long long q = lds_u64(canon_s + 8u * (uint32_t)(len - PBITS - 1));
     const uint32_t d = (c15 >> (15 - len)) - (uint32_t)(q & 0xffffu);
     if (d < (uint32_t)((q >> 16) & 0xffffu)) return sorted[(uint32_t)(q >> 32) + d];
   }
@@ -595,16 +599,20 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
   constexpr uint32_t MEMBER_SMEM = (uint32_t)LgConfig<G, W>::MEMBER_SMEM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = lane / G, glane = lane % G;
+  const int grp = lane / G;
+  int glane = lane % G;
+  asm volatile("" : "+r"(glane));                               // keep it in a register (the compiler would re-read %tid in every pass)
   unsigned char* const wtab = smem_raw + (size_t)warp * GROUPS * MEMBER_SMEM;
   WarpScratch16& WS = *reinterpret_cast<WarpScratch16*>(smem_raw + (size_t)W * GROUPS * MEMBER_SMEM + (size_t)warp * sizeof(WarpScratch16));
   uint8_t* const wslots = slot_scratch + (size_t)(blockIdx.x * W + warp) * GROUPS * LG_SLOT_BYTES;
-  const uint16_t* const ll16 = reinterpret_cast<const uint16_t*>(wtab + grp * MEMBER_SMEM);
-  const uint16_t* const d16 = ll16 + (1 << INF_LL_BITS);
+  uint32_t ll_s = (uint32_t)__cvta_generic_to_shared(wtab + grp * MEMBER_SMEM);   // shared-window address of this group's tables
+  asm volatile("" : "+r"(ll_s));
+#define LL16(i) lds_u16(ll_s + ((i) << 1))
+#define D16(i) lds_u16(ll_s + (2u << INF_LL_BITS) + ((i) << 1))
   unsigned long long my_slot_bits = reinterpret_cast<unsigned long long>(wslots + (size_t)grp * LG_SLOT_BYTES);
   asm volatile("" : "+l"(my_slot_bits));                        // opaque: keep it in registers instead of re-deriving it every pass
   const uint16_t* const my_sorted = reinterpret_cast<const uint16_t*>(my_slot_bits);
-  const unsigned long long* const my_canon = reinterpret_cast<const unsigned long long*>(wtab + grp * MEMBER_SMEM + LgConfig<G, W>::LUT_BYTES);
+  const uint32_t my_canon = ll_s + (uint32_t)LgConfig<G, W>::LUT_BYTES;     // shared-window address of the canonical rows
 
   // member state, replicated over the G lanes of the group
   const uint32_t* wbase = reinterpret_cast<const uint32_t*>(blocks);   // any valid, aligned address until a member is taken
@@ -613,7 +621,7 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
   // wbase is 16-byte aligned; wi = index (from wbase) of the word after hi; fill = next 16-byte chunk to fetch.
   uint32_t lo = 0, hi = 0, bp = 0, wi = 0, wlimit = 0, fill = 0;
   uint32_t rq[4 / G + (4 % G != 0)], rq_slot = 0xffffffffu;     // ring chunk in flight (one word per lane) and its slot
-  const uint32_t my_ring = (uint32_t)__cvta_generic_to_shared(wtab + grp * MEMBER_SMEM + LgConfig<G, W>::RING_OFF);
+  const uint32_t my_ring = ll_s + (uint32_t)LgConfig<G, W>::RING_OFF;
   uint32_t outpos = 0, isize = 0, bi = 0, err = INF_OK, state = ST_MEMBER, final_block = 0;
   uint8_t* obase = infl;
   // deferred copy: U bytes per lane loaded in the previous pass, not yet stored
@@ -767,7 +775,7 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
       const bool act = state == ST_SYMBOLS;
       const bool dec = act && rem == 0;                     // a group in the middle of a long copy does not decode this pass
       uint32_t bits = __funnelshift_r(lo, hi, bp);
-      uint32_t e = ll16[bits & LLMASK];
+      uint32_t e = LL16(bits & LLMASK);
       #pragma unroll
       for (int k = 0; k < NLIT; k++) {
         if (dec && (e & L16_LIT)) {
@@ -776,7 +784,7 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
           bp += e & 15u;
           LG_REFILL();
           bits = __funnelshift_r(lo, hi, bp);
-          e = ll16[bits & LLMASK];
+          e = LL16(bits & LLMASK);
         }
       }
       uint32_t len = 0;
@@ -800,8 +808,8 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
       if (__any_sync(FULL, (len | rem) != 0)) {
         if (len) {
           bits = __funnelshift_r(lo, hi, bp);
-          uint32_t de = d16[bits & DMASK];
-          if ((de & 15u) == 0) de = decode_long16<INF_D_BITS, TK_DIST>(bits, my_canon + LG_CANON_LL, my_sorted + 288);
+          uint32_t de = D16(bits & DMASK);
+          if ((de & 15u) == 0) de = decode_long16<INF_D_BITS, TK_DIST>(bits, my_canon + 8u * LG_CANON_LL, my_sorted + 288);
           const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
           const uint32_t d = 1u + ((de >> 8) << dxb) + ((bits >> dnb) & ~(0xffffffffu << dxb));
           bp += dnb + dxb;
@@ -841,6 +849,8 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
     LG_STORE(ppos0, plen0, pv0);
     LG_STORE(ppos1, plen1, pv1);
 #undef LG_COPY
+#undef LL16
+#undef D16
 #undef LG_REFILL
 #undef LG_STORE
   }
