@@ -226,44 +226,37 @@ static int init_device_constants(int dev) {
   return BAMSCAN_OK;
 }
 
-// ---- inflate kernel selection (BAMSCAN_INFLATE_VARIANT: experiment switch; 0 = warp-per-member kernel) ----
-typedef void (*InflateLgFn)(const uint8_t*, const BlockDesc*, uint32_t, uint8_t*, uint32_t*, uint32_t*, uint32_t*, uint8_t*);
-struct InflateVariant { int groups, warps, ctas; size_t smem; InflateLgFn fn; };
-template <int G, int W, int NLIT, int CTAS> static InflateVariant lg_variant() { return {32 / G, W, CTAS, LgConfig<G, W>::SMEM, inflate_lg_kernel<G, W, NLIT, CTAS>}; }
-static const InflateVariant& inflate_variant() {
-  static InflateVariant v = [] {
-    const char* e = getenv("BAMSCAN_INFLATE_VARIANT");
-    int k = e ? atoi(e) : 1;
-    switch (k) {
-      case 0: return InflateVariant{0, 0, 0, 0, nullptr};
-      case 2: return lg_variant<4, 19, 1, 1>();
-      case 3: return lg_variant<4, 16, 2, 1>();
-      default: return lg_variant<4, 19, 2, 1>();
-    }
-  }();
-  return v;
-}
+// ---- inflate: two kernels, chosen per launch by the number of members ----
+//   inflate_lg_kernel  throughput: 4 lanes per member, 152 members per SM; a member takes ~17 ms, a full wave of 22 496 too
+//   inflate_kernel     latency:    a warp per member, 48 per SM; a member takes ~7 ms
+// A launch of up to two warp-per-member waves finishes sooner on the latency kernel (region queries, tail chunks).
+constexpr int LG_G = 4, LG_W = 19, LG_NLIT = 2;
+using LgCfg = LgConfig<LG_G, LG_W>;
 static int device_sms(int device) { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); return sms; }
+static bool use_lane_group_kernel(const BamFile* f, uint32_t nb) {
+  if (f->debug_flags & 8) return true;       // tests: force the throughput kernel
+  if (f->debug_flags & 4) return false;      // tests: force the latency kernel
+  return nb > 2u * (uint32_t)device_sms(f->device) * INF_CTAS_PER_SM * INF_WARPS;
+}
 
 // Inflates the nb members described by d_blk (and verifies their CRC-32 unless skip_crc) on stream cs.
 static int launch_inflate(const BamFile* f, cudaStream_t cs, const uint8_t* d_comp, const BlockDesc* d_blk, uint32_t nb, uint8_t* U,
                           uint32_t* d_status, uint32_t* d_ticket, uint32_t* d_err, DeviceBuf* slots, int* launches) {
-  const InflateVariant& v = inflate_variant();
-  if (!v.fn) {
-    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)device_sms(f->device) * INF_CTAS_PER_SM);
+  const uint32_t sms = (uint32_t)device_sms(f->device);
+  if (!use_lane_group_kernel(f, nb)) {
+    uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, sms * INF_CTAS_PER_SM);
     inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, f->skip_crc ? 0 : 1);
     *launches += 1;
     return BAMSCAN_OK;
   }
-  const uint32_t per_cta = (uint32_t)(v.groups * v.warps);
-  const uint32_t max_grid = (uint32_t)(device_sms(f->device) * v.ctas);
-  const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, max_grid);
-  int rc = slots->ensure((size_t)max_grid * per_cta * LG_SLOT_BYTES);
+  const uint32_t per_cta = (uint32_t)(LgCfg::GROUPS * LG_W);
+  const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, sms);
+  int rc = slots->ensure((size_t)sms * per_cta * LG_SLOT_BYTES);
   if (rc) return rc;
-  v.fn<<<grid, v.warps * 32, v.smem, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, slots->as<uint8_t>());
+  inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1><<<grid, LG_W * 32, LgCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, slots->as<uint8_t>());
   *launches += 1;
   if (!f->skip_crc) {
-    crc_kernel<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)device_sms(f->device) * 8), 256, 0, cs>>>(d_blk, nb, U, d_status, d_err);
+    crc_kernel<<<std::min<uint32_t>((nb + 7) / 8, sms * 8), 256, 0, cs>>>(d_blk, nb, U, d_status, d_err);
     *launches += 1;
   }
   return BAMSCAN_OK;
@@ -291,7 +284,7 @@ static int stream_init(BamScanStream* s) {
   CU_TRY(cudaHostAlloc((void**)&s->h_flags, 4096, cudaHostAllocPortable | cudaHostAllocMapped));
   CU_TRY(cudaHostGetDevicePointer((void**)&s->d_hflags, s->h_flags, 0));
   CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
-  if (inflate_variant().fn) CU_TRY(cudaFuncSetAttribute(inflate_variant().fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inflate_variant().smem));
+  CU_TRY(cudaFuncSetAttribute(inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LgCfg::SMEM));
   // reference dictionary: lengths + names blob
   size_t n_ref = f->ref_names.size();
   std::vector<uint32_t> offs(n_ref + 1, 0);
@@ -349,17 +342,9 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
   delete s;
 }
 
-// Members the inflate kernel keeps in flight: one per resident warp.  A member takes milliseconds, so a chunk whose member
-// count is not a whole number of such waves leaves most of the GPU idle in its last wave.
-static uint32_t g_inflate_wave = 0;
-static uint32_t inflate_wave_members(int device) {
-  if (g_inflate_wave) return g_inflate_wave;
-  int sms = device_sms(device), ctas = 0;
-  if (inflate_variant().fn) { g_inflate_wave = (uint32_t)sms * inflate_variant().ctas * inflate_variant().groups * inflate_variant().warps; return g_inflate_wave; }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, inflate_kernel, INF_WARPS * 32, sizeof(InflateShared)) != cudaSuccess || ctas < 1) { cudaGetLastError(); ctas = INF_CTAS_PER_SM; }
-  g_inflate_wave = (uint32_t)sms * (uint32_t)ctas * INF_WARPS;
-  return g_inflate_wave;
-}
+// Members the throughput inflate kernel keeps in flight (one per lane group).  A member takes milliseconds, so a chunk whose
+// member count is not a whole number of such waves leaves most of the GPU idle in its last wave.
+static uint32_t inflate_wave_members(int device) { return (uint32_t)device_sms(device) * LgCfg::GROUPS * LG_W; }
 
 // A chunk is the unit of H2D, inflate and record-boundary resolution; its rows are decoded in slices of <= SLICE_BYTES
 // inflated (Arrow offsets are i32).  Default: one whole inflate wave per chunk (a member takes milliseconds, so a chunk

@@ -20,9 +20,24 @@ def _oracle(path, **kw):
     return OracleBam(str(path), **kw)
 
 
+# Every test of this module runs twice: once per inflate kernel (debug_flags bit 2 forces the warp-per-member "latency"
+# kernel, bit 3 the lane-group "throughput" kernel; without either the engine picks by member count, which on these small
+# fixtures would always be the latency kernel).
+_FORCE_INFLATE = 0
+
+
+@pytest.fixture(autouse=True, params=[4, 8], ids=["warp_per_member", "lane_group"])
+def inflate_kernel(request):
+    global _FORCE_INFLATE
+    _FORCE_INFLATE = request.param
+    yield request.param
+    _FORCE_INFLATE = 0
+
+
 def _provider(path, **kw):
     import bamscan
     zero_based = kw.pop("zero_based", True)
+    kw["debug_flags"] = kw.get("debug_flags", 0) | _FORCE_INFLATE
     kw.setdefault("index_path", "")      # these tests pin the sequential path (physical_exec.rs:371-598); indexed scans: test_gpu_indexed.py
     return bamscan.BamTableProvider(str(path), None, zero_based, kw.pop("tag_fields", None), kw.pop("binary_cigar", False),
                                     kw.pop("infer_tag_types", True), kw.pop("infer_tag_sample_size", 100),
@@ -230,3 +245,13 @@ def test_long_record_decode_kernel_matches_on_short_records(name, tags):
     o = _oracle(path, tag_fields=tags)
     p = _provider(path, tag_fields=tags, debug_flags=2)
     _assert_tables_equal(p.scan(None, [], None).collect(), o.scan(), f"warp decode {name}")
+
+
+@pytest.mark.parametrize("level", [0, 1, 9])
+def test_deflate_block_types(syn_dir, level):
+    """Stored blocks (level 0), fixed-Huffman-heavy output (level 1) and the densest dynamic codes (level 9)."""
+    path = gen_bam(syn_dir, "short", 6000, seed=11, level=level)
+    tags = ["NM", "MD", "AS", "RG"]
+    o = _oracle(path, tag_fields=tags)
+    p = _provider(path, tag_fields=tags, chunk_inflated_bytes=1 << 20)
+    _assert_tables_equal(p.scan(None, [], None).collect(), o.scan(), f"level {level}")
