@@ -299,7 +299,8 @@ def main():
         "scan_roofline_frac": (scan_alg / (st["ms_total"] / 1000.0) / 1e9) / peak,
         "stage_ms": {"inflate": st["ms_inflate"], "boundary": st["ms_boundary"], "decode": st["ms_decode"], "total": st["ms_total"]},
         "roofline": {"kernel": "inflate_lg_kernel (+ crc_kernel in the same event bracket)", "bound": "hbm", "achieved": infl_gbs, "peak": peak, "unit": "GB/s", "frac": infl_gbs / peak,
-                     "traffic": None, "peak_source": peak_src, "launches": launches_inflate,
+                     "traffic": 12.11e9, "traffic_note": "dram read 10.60 GB + write 1.51 GB per full-wave launch (22496 members, 1.98 GB algorithmic), ncu --set full, profiles/r1_inflate_lg_final.md",
+                     "peak_source": peak_src, "launches": launches_inflate,
                      "alg_bytes_per_launch": infl_alg / launches_inflate, "ms_per_launch": st["ms_inflate"] / launches_inflate},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],
                 "ms_per_step": 1000 * float(tmax2.item()) / args.steps},

@@ -3,20 +3,24 @@
 // Replaces: noodles-bgzf 0.49.0 io::Reader block inflate + libdeflate `deflate_decompress`/`crc32`
 // (reference call sites: datafusion/bio-format-bam/src/storage.rs:161-169, physical_exec.rs:409).
 //
-// Mapping to the machine (sm_100a):
-//   * one WARP decodes one BGZF member (<= 64 KiB out); warps pull members from a global atomic
-//     ticket so a persistent grid of 148 x CTAS_PER_SM CTAs stays balanced;
-//   * Huffman state lives in shared memory, ~3.6 KB per warp: 10-bit litlen LUT + 8-bit distance
-//     LUT (16-bit entries) + canonical (sorted-symbol) arrays for the rare codes longer than the
-//     LUT index -> 48 resident warps / SM;
-//   * tables are built warp-cooperatively (match_any ranks, brev canonical codes, strided fill);
-//   * the symbol loop is warp-UNIFORM (no divergence): the bit reader is two 32-bit registers plus
-//     a 128-byte register window (one word per lane, double buffered) refilled by shuffles, so the
-//     compressed stream is read from HBM exactly once, in full 128-byte lines;
-//   * literals are parked one per lane and flushed as 32-byte coalesced stores; LZ77 copies are
-//     done by all 32 lanes (dist==1 broadcast, dist<32 modular, else strided with warp fences);
-//   * CRC-32 of the member is computed by the same warp while the bytes are still in L1/L2:
-//     32 lane-chunks by slicing-by-4 on shared tables, then combined with x^(8k) mod P multiplies.
+// Two kernels share the table builder, the header parser and the CRC code; engine.cu::launch_inflate picks one per launch:
+//
+//   inflate_kernel     "latency" kernel: one WARP decodes one BGZF member, 48 warps / SM.  Per-warp Huffman state in shared
+//                      memory (~3.9 KB): 9-bit litlen LUT + 7-bit distance LUT of self-contained 32-bit entries, canonical
+//                      (sorted-symbol) arrays for the rare longer codes.  The symbol loop is warp-uniform; LZ77 copies are
+//                      done by all 32 lanes; CRC-32 of the member is computed by the same warp.  Issue bound (all 32 lanes
+//                      repeat the same decode), but a member is done in ~7 ms: used for launches of up to two of its waves
+//                      (region queries, tail chunks).
+//   inflate_lg_kernel  "throughput" kernel: FOUR LANES decode one member, eight members per warp, 152 members / SM (16-bit
+//                      LUT entries, 1456 B per member).  One pass of the predicated loop body advances every group by up to
+//                      three symbols, so an issued instruction serves eight DEFLATE streams: 2.3x fewer instructions per
+//                      byte.  Used for whole waves (22 496 members on a B200).  Details at its definition below.
+//   crc_kernel         CRC-32 of each member after inflate_lg_kernel (one warp per member).
+//
+// Common: members are pulled from a global atomic ticket by a persistent grid; tables are built warp-cooperatively
+// (match_any ranks, brev canonical codes, strided fill); CRC-32 is slicing-by-4 on 32 lane-chunks combined with
+// x^(8k) mod P multiplies; every loop is bounded by the member's input length and ISIZE (corrupt data ends in an error code,
+// never in a fault).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
