@@ -97,7 +97,12 @@ seg_candidates_kernel(BoundaryParams P, uint32_t* __restrict__ seg_start, int po
   const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= P.n_seg) return;
-  if (s == 0 && P.first_start != SEG_NONE) { if (lane == 0) seg_start[0] = P.first_start; return; }
+  if (P.first_start != SEG_NONE) {
+    // the exact first record start may lie several segments into the chunk (an indexed range starts anywhere inside its
+    // first BGZF member): the segments before it hold no owned record, the one containing it starts there
+    const uint32_t k = P.first_start > P.seg0 ? min((P.first_start - P.seg0) / P.seg_bytes, P.n_seg - 1u) : 0u;
+    if (s <= k) { if (lane == 0) seg_start[s] = s == k ? P.first_start : SEG_NONE; return; }
+  }
   uint32_t lo = P.seg0 + s * P.seg_bytes;
   uint32_t hi = min(min(lo + P.seg_bytes, P.data_hi), P.own_hi);
   uint32_t found = SEG_NONE;
