@@ -261,7 +261,8 @@ def main():
             del b
         return n, nb
 
-    e2e_step()   # warm-up (pinned arena pool, allocations)
+    for _ in range(max(1, args.warmup)):   # warm-up: the pinned arena pool settles after a few scans
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_rows = 0

@@ -123,7 +123,10 @@ static HostArena arena_acquire(size_t bytes) {
     if (best >= 0) { HostArena a = g_pool[best]; g_pool.erase(g_pool.begin() + best); return a; }
   }
   HostArena a;
-  size_t cap = std::max<size_t>(bytes + bytes / 16, 1 << 16);
+  // coarse sizes, so that the slices of a scan (whose byte counts differ a little) reuse each other's arenas and the pool
+  // stops allocating after the first few batches: page-locking a GB costs ~0.1 s, several times that with 8 ranks at it
+  size_t cap = bytes + bytes / 8;
+  cap = cap > (64u << 20) ? (cap + (64u << 20) - 1) / (64u << 20) * (64u << 20) : std::max<size_t>(cap, 1 << 16);
   a.p = (uint8_t*)pinned_alloc(cap);
   a.cap = a.p ? cap : 0;
   return a;
