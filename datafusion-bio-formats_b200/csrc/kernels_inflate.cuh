@@ -218,10 +218,14 @@ __device__ __noinline__ uint32_t warp_crc32(const uint8_t* out, uint32_t n, cons
   uint32_t len = e - b;
   while (len && (reinterpret_cast<uintptr_t>(p) & 3)) { st = tab[0][(st ^ *p) & 0xff] ^ (st >> 8); p++; len--; }
   const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
-  for (; len >= 4; len -= 4) {
-    st ^= *pw++;
-    st = tab[3][st & 0xff] ^ tab[2][(st >> 8) & 0xff] ^ tab[1][(st >> 16) & 0xff] ^ tab[0][st >> 24];
+#define CRC_WORD(w) { st ^= (w); st = tab[3][st & 0xff] ^ tab[2][(st >> 8) & 0xff] ^ tab[1][(st >> 16) & 0xff] ^ tab[0][st >> 24]; }
+  for (; len >= 4 && (reinterpret_cast<uintptr_t>(pw) & 15); len -= 4) CRC_WORD(*pw++);
+  for (; len >= 16; len -= 16) {                            // 16-byte loads: a quarter of the load instructions, next one in flight
+    const uint4 v = *reinterpret_cast<const uint4*>(pw); pw += 4;
+    CRC_WORD(v.x); CRC_WORD(v.y); CRC_WORD(v.z); CRC_WORD(v.w);
   }
+  for (; len >= 4; len -= 4) CRC_WORD(*pw++);
+#undef CRC_WORD
   p = reinterpret_cast<const uint8_t*>(pw);
   while (len) { st = tab[0][(st ^ *p) & 0xff] ^ (st >> 8); p++; len--; }
   st = crc_shift(st, n - e);
