@@ -438,11 +438,15 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
 // issue bound.  Here a warp carries 32/G members at once: G lanes form a group that owns one member, every lane of a
 // group holds the same reader state, and one pass through the (warp-uniform, predicated) loop body decodes up to
 // NLIT + 1 symbols for EVERY group, so an instruction issued once advances 32/G independent DEFLATE streams.  The G
-// lanes of a group share the LZ77 copy; its stores are deferred by one pass so the L2 round trip of the source bytes
-// overlaps the next pass's Huffman decode.  Tables are 16-bit entries (1280 B per member) so that 160 members fit in one
-// SM's shared memory; the rare canonical walk for codes longer than the LUT index reads a small global scratch (L1
-// resident).  Block headers, table builds, stored blocks and member hand-over are done by the whole warp for one group at
-// a time (`service`), exactly as parallel as in the warp-per-member kernel.  CRC-32 moves to crc_kernel.
+// lanes of a group share the LZ77 copy: it is cut into chunks of <= 16 bytes per pass (a longer copy continues in the next
+// pass instead of decoding), the source bytes are loaded into registers and stored two match passes later (two ping-pong
+// slots; a chunk that would read bytes still held in a slot retires the slots first), so the L2 / DRAM round trip of
+// the history read overlaps the following Huffman decode.  The compressed stream is read through a 64-byte shared-memory
+// ring per member that is topped up through a register one pass ahead.  Tables are 16-bit entries; with the canonical
+// rows and the ring a member needs 1456 B, so 152 members fit in one SM's shared memory.  The rare canonical walk for
+// codes longer than the LUT index takes its rows from shared memory and the symbol entry from a small global scratch (L2).
+// Block headers, table builds, stored blocks and member hand-over are done by the whole warp for one group at a time
+// (`service`), exactly as parallel as in the warp-per-member kernel.  CRC-32 moves to crc_kernel.
 //
 // 16-bit LUT entries:
 //   litlen  literal : 0x8000 | byte << 4 | nb                       length : (base - 3) << 7 | xb << 4 | nb   (xb <= 5)
