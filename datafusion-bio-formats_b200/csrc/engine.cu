@@ -233,7 +233,13 @@ static int init_device_constants(int dev) {
 //   inflate_lg_kernel  throughput: 4 lanes per member, 152 members per SM; a member takes ~17 ms, a full wave of 22 496 too
 //   inflate_kernel     latency:    a warp per member, 48 per SM; a member takes ~7 ms
 // A launch of up to two warp-per-member waves finishes sooner on the latency kernel (region queries, tail chunks).
-constexpr int LG_G = 4, LG_W = 19, LG_NLIT = 2;
+#ifndef BAMSCAN_LG_W
+#define BAMSCAN_LG_W 19
+#endif
+#ifndef BAMSCAN_LG_NLIT
+#define BAMSCAN_LG_NLIT 2
+#endif
+constexpr int LG_G = 4, LG_W = BAMSCAN_LG_W, LG_NLIT = BAMSCAN_LG_NLIT;
 using LgCfg = LgConfig<LG_G, LG_W>;
 static int device_sms(int device) { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); return sms; }
 static bool use_lane_group_kernel(const BamFile* f, uint32_t nb) {

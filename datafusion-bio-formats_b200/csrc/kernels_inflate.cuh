@@ -42,7 +42,10 @@ enum InflateStatus : uint32_t {
 
 constexpr int INF_WARPS = 8;                 // warps per CTA
 constexpr int INF_CTAS_PER_SM = 6;
-constexpr int INF_LL_BITS = 9, INF_D_BITS = 7;
+#ifndef BAMSCAN_D_BITS
+#define BAMSCAN_D_BITS 7
+#endif
+constexpr int INF_LL_BITS = 9, INF_D_BITS = BAMSCAN_D_BITS;
 constexpr uint32_t FULL = 0xffffffffu;
 
 // 32-bit LUT entry, decoded without table look-ups or branches:
