@@ -265,7 +265,7 @@ static int launch_inflate(const BamFile* f, cudaStream_t cs, const uint8_t* d_co
   inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1><<<grid, LG_W * 32, LgCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, slots->as<uint8_t>());
   *launches += 1;
   if (!f->skip_crc) {
-    crc_kernel<<<std::min<uint32_t>((nb + 7) / 8, sms * 8), 256, 0, cs>>>(d_blk, nb, U, d_status, d_err);
+    crc_kernel<<<std::min<uint32_t>((nb + CRC_WARPS - 1) / CRC_WARPS, sms), CRC_WARPS * 32, CRC_SMEM, cs>>>(d_blk, nb, U, d_status, d_err);
     *launches += 1;
   }
   return BAMSCAN_OK;
@@ -294,6 +294,7 @@ static int stream_init(BamScanStream* s) {
   CU_TRY(cudaHostGetDevicePointer((void**)&s->d_hflags, s->h_flags, 0));
   CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
   CU_TRY(cudaFuncSetAttribute(inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LgCfg::SMEM));
+  CU_TRY(cudaFuncSetAttribute(crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_SMEM));
   // reference dictionary: lengths + names blob
   size_t n_ref = f->ref_names.size();
   std::vector<uint32_t> offs(n_ref + 1, 0);

@@ -872,33 +872,58 @@ inflate_lg_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict_
 }
 
 // CRC-32 of every inflated member against its BGZF trailer: one warp per member (32 lane-chunks by slicing-by-4, combined
-// with x^(8k) mod P multiplies).  Runs right behind the inflate kernel while the bytes are still in L2.
-__global__ void __launch_bounds__(256)
+// with x^(8k) mod P multiplies).  Runs right behind the inflate kernel while the bytes are still in L2.  The four 256-entry
+// tables are replicated per lane (entry (t, v) of lane l at word ((t * 256 + v) * 32 + l): bank == lane), so the 32
+// data-dependent look-ups of a warp never conflict: 128 KB of shared memory, one CTA of 32 warps per SM.
+constexpr int CRC_WARPS = 32;
+constexpr size_t CRC_SMEM = 4 * 256 * 32 * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(CRC_WARPS * 32, 1)
 crc_kernel(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const uint8_t* __restrict__ infl,
            uint32_t* __restrict__ status, uint32_t* __restrict__ err_flag) {
-  __shared__ uint32_t tab[4][256];
-  {
-    uint32_t c = threadIdx.x;
-    for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
-    tab[0][threadIdx.x] = c;
-  }
-  __syncthreads();
-  {
-    uint32_t c = tab[0][threadIdx.x];
-    for (int t = 1; t < 4; t++) { c = tab[0][c & 0xff] ^ (c >> 8); tab[t][threadIdx.x] = c; }
-  }
-  __syncthreads();
+  extern __shared__ __align__(16) uint32_t ctab[];
   const int lane = threadIdx.x & 31;
-  const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t bi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bi < n_blocks; bi += wpg) {
+  for (int v = threadIdx.x >> 5; v < 256; v += CRC_WARPS) {           // tab[0][v], one copy per lane
+    uint32_t c = (uint32_t)v;
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+    ctab[(v << 5) + lane] = c;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x >> 5; v < 256; v += CRC_WARPS) {
+    uint32_t c = ctab[(v << 5) + lane];
+    for (int t = 1; t < 4; t++) { c = ctab[((c & 0xffu) << 5) + lane] ^ (c >> 8); ctab[(((t << 8) + v) << 5) + lane] = c; }
+  }
+  __syncthreads();
+  const uint32_t* const T = ctab + lane;
+#define CRC_T(t, b) T[(((t) << 8) + (b)) << 5]
+#define CRC_BYTE(x) { st = CRC_T(0, (st ^ (x)) & 0xffu) ^ (st >> 8); }
+#define CRC_WORD(w) { st ^= (w); st = CRC_T(3, st & 0xffu) ^ CRC_T(2, (st >> 8) & 0xffu) ^ CRC_T(1, (st >> 16) & 0xffu) ^ CRC_T(0, st >> 24); }
+  const uint32_t wpg = gridDim.x * CRC_WARPS;
+  for (uint32_t bi = blockIdx.x * CRC_WARPS + (threadIdx.x >> 5); bi < n_blocks; bi += wpg) {
     if (status[bi] != INF_OK) continue;
     const BlockDesc bd = blocks[bi];
-    const uint32_t crc = warp_crc32(infl + bd.uoff, bd.isize, tab, lane);
-    if (crc != bd.crc && lane == 0) {
+    const uint32_t n = bd.isize;
+    const uint32_t chunk = ((n + 31) / 32 + 15) & ~15u;               // lane chunks of whole 16-byte units
+    const uint32_t b = min(n, chunk * lane), e = min(n, b + chunk);
+    uint32_t st = (lane == 0) ? 0xffffffffu : 0u;
+    const uint8_t* p = infl + bd.uoff + b;
+    uint32_t len = e - b;
+    while (len && (reinterpret_cast<uintptr_t>(p) & 15)) { CRC_BYTE(*p); p++; len--; }
+    const uint4* pq = reinterpret_cast<const uint4*>(p);
+    for (; len >= 16; len -= 16) { const uint4 v = *pq++; CRC_WORD(v.x); CRC_WORD(v.y); CRC_WORD(v.z); CRC_WORD(v.w); }
+    p = reinterpret_cast<const uint8_t*>(pq);
+    while (len) { CRC_BYTE(*p); p++; len--; }
+    st = crc_shift(st, n - e);
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) st ^= __shfl_xor_sync(FULL, st, o);
+    if (~st != bd.crc && lane == 0) {
       status[bi] = INF_ERR_CRC;
       atomicCAS(err_flag, 0u, (bi << 4) | INF_ERR_CRC | 0x80000000u);
     }
   }
+#undef CRC_T
+#undef CRC_BYTE
+#undef CRC_WORD
 }
 
 }  // namespace bamscan
