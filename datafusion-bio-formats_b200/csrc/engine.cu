@@ -430,7 +430,6 @@ static int decode_slice(BamScanStream* s, bool* produced) {
   s->cur.pos += n;
   uint32_t* d_flags = s->d_flags.as<uint32_t>();
   (void)d_flags;
-  double tw3 = 0; (void)tw3;
   CU_TRY(cudaEventRecord(s->ev_t[5], cs));
   {
     // ---- arena region A
@@ -523,7 +522,6 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       CU_TRY(cudaEventSynchronize(s->ev_flags));
       CU_TRY(cudaGetLastError());
       // ---- arena region B
-      tw3 = wall_ms();
       for (int k = 0; k < SC.n_cols; k++) {
         ColLayout& L = cols[scan_owner[k]];
         uint64_t tot = h_totals[k];
@@ -606,7 +604,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   BamFile* f = s->f;
   *produced = false;
   static const bool trace2 = getenv("BAMSCAN_TRACE") && atoi(getenv("BAMSCAN_TRACE")) >= 2;
-  const double tw0 = wall_ms(); double tw1 = 0, tw2 = 0, tw3 = 0;
+  const double tw0 = wall_ms();
   const uint32_t nb_all = c.b1 - c.b0;
   (void)nb_all;
   const uint32_t data_hi = s->chunk_data_hi[slot], seg0 = HEADROOM;
@@ -653,7 +651,6 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
   CU_TRY(cudaMemsetAsync(d_flags + 11, 0xff, 4, cs));    // [11] first disagreeing seam
   CU_TRY(cudaEventRecord(s->ev_t[0], cs));
-  tw1 = wall_ms();
   if (nb) {
     int nl = 0;
     if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, &s->d_sorted, &nl))) return rc;
@@ -676,7 +673,6 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaEventSynchronize(s->ev_flags));
   CU_TRY(cudaGetLastError());
   // ---- host: decisions
-  tw2 = wall_ms();
   const uint32_t* hf = s->h_flags;
   if (hf[9]) {
     uint32_t bi = (hf[9] & 0x7fffffffu) >> 4, code = hf[9] & 15u;
@@ -752,8 +748,7 @@ timing:
     cudaEventElapsedTime(&b, s->ev_t[1], s->ev_t[2]);
     cudaEventElapsedTime(&d, s->ev_t[2], s->ev_t[3]);
     s->st.ms_inflate += a; s->st.ms_boundary += b; s->st.ms_decode += d;
-    if (trace2) fprintf(stderr, "[bamscan chunk] prep %.2f | inflate+boundary(sync) %.2f | fixed+scan(sync) %.2f | var+end %.2f ms wall ; gpu inflate %.2f boundary %.2f decode %.2f\n",
-                        tw1 - tw0, tw2 - tw1, tw3 - tw2, wall_ms() - tw3, a, b, d);
+    if (trace2) fprintf(stderr, "[bamscan chunk] phase %d: %.2f ms wall in this call ; gpu inflate %.2f boundary %.2f emit+rules %.2f ms\n", phase, wall_ms() - tw0, a, b, d);
   }
   return BAMSCAN_OK;
 }
