@@ -805,8 +805,6 @@ static int advance(BamScanStream* s, bool* produced) {
       uint32_t last = s->chunks.back().b1;
       if (s->carry_len == 0 || last >= f->blocks.size()) {
         if (s->carry_len) {
-          bool only_empty = true;
-          (void)only_empty;
           set_error("BAM read error: unexpected EOF inside a record (%u trailing bytes)", s->carry_len);
           return BAMSCAN_ERR_FORMAT;
         }
