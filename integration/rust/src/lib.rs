@@ -96,7 +96,7 @@ impl GpuBamTableProvider {
             n_tag_type_hints: hints_p.len() as i32,
             tag_type_hints: hints_p.as_ptr(),
             device_id,
-            batch_rows: 0, // set per execute() from the session's batch_size
+            batch_rows: 0, // 0 = one batch per decode slice; pass SessionConfig::batch_size here for the reference's batch shape
             chunk_inflated_bytes: 0,
             segment_bytes: 0,
             skip_crc: 0,
