@@ -28,6 +28,7 @@
 #include "kernels_decode.cuh"
 #include "kernels_filter.cuh"
 #include "kernels_inflate.cuh"
+#include "kernels_inflate_cta.cuh"
 
 namespace bamscan {
 
@@ -216,23 +217,31 @@ namespace bamscan {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static double wall_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
+constexpr int ICTA_NT = 256;                      // threads of the CTA-per-member inflate kernel
+using IctaCfg = icta::Cfg<ICTA_NT>;
 static bool g_crc_init[64] = {};
+static uint32_t* g_crc_tabs[64] = {};             // per device: tables of the in-window CRC stage (kernels_inflate_cta.cuh)
 static int init_device_constants(int dev) {
-  if (dev < 64 && g_crc_init[dev]) return BAMSCAN_OK;
+  if (dev >= 64) { set_error("device id %d out of range", dev); return BAMSCAN_ERR_CUDA; }
+  if (g_crc_init[dev]) return BAMSCAN_OK;
+  CU_TRY(cudaMalloc((void**)&g_crc_tabs[dev], icta::CrcTabs<ICTA_NT>::WORDS * 4));
+  icta::crc_tables_init_kernel<ICTA_NT><<<1, 256>>>(g_crc_tabs[dev]);
+  CU_TRY(cudaDeviceSynchronize());
   // x^(8 * 2^j) mod P in the reflected domain
   auto mulmod = [](uint32_t a, uint32_t b) { uint32_t p = 0; for (int i = 0; i < 32; i++) { if (b & 0x80000000u) p ^= a; a = (a >> 1) ^ ((a & 1u) ? 0xEDB88320u : 0u); b <<= 1; } return p; };
   uint32_t tab[18];
   tab[0] = 0x00800000u;   // x^8
   for (int j = 1; j < 18; j++) tab[j] = mulmod(tab[j - 1], tab[j - 1]);
   CU_TRY(cudaMemcpyToSymbol(c_crc_xpow8, tab, sizeof tab));
-  if (dev < 64) g_crc_init[dev] = true;
+  g_crc_init[dev] = true;
   return BAMSCAN_OK;
 }
 
-// ---- inflate: two kernels, chosen per launch by the number of members ----
-//   inflate_lg_kernel  throughput: 4 lanes per member, 152 members per SM; a member takes ~17 ms, a full wave of 22 496 too
-//   inflate_kernel     latency:    a warp per member, 48 per SM; a member takes ~7 ms
-// A launch of up to two warp-per-member waves finishes sooner on the latency kernel (region queries, tail chunks).
+// ---- inflate ----
+//   inflate_cta_kernel (default)  one CTA per member, parallel inside the member, output window in shared memory, CRC fused
+//                                 (kernels_inflate_cta.cuh); members it refuses (INF_RETRY) are redone by inflate_kernel
+//   inflate_kernel                a warp per member (kernels_inflate.cuh): the retry path; debug_flags bit 2 forces it
+//   inflate_lg_kernel             4 lanes per member, 152 members per SM (round-1 throughput kernel): debug_flags bit 3, A/B baseline
 #ifndef BAMSCAN_LG_W
 #define BAMSCAN_LG_W 19
 #endif
@@ -242,30 +251,39 @@ static int init_device_constants(int dev) {
 constexpr int LG_G = 4, LG_W = BAMSCAN_LG_W, LG_NLIT = BAMSCAN_LG_NLIT;
 using LgCfg = LgConfig<LG_G, LG_W>;
 static int device_sms(int device) { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); return sms; }
-static bool use_lane_group_kernel(const BamFile* f, uint32_t nb) {
-  if (f->debug_flags & 8) return true;       // tests: force the throughput kernel
-  if (f->debug_flags & 4) return false;      // tests: force the latency kernel
-  return nb > 2u * (uint32_t)device_sms(f->device) * INF_CTAS_PER_SM * INF_WARPS;
-}
 
 // Inflates the nb members described by d_blk (and verifies their CRC-32 unless skip_crc) on stream cs.
+// d_aux: two zeroed words (ticket of the retry launch, retry count).
 static int launch_inflate(const BamFile* f, cudaStream_t cs, const uint8_t* d_comp, const BlockDesc* d_blk, uint32_t nb, uint8_t* U,
-                          uint32_t* d_status, uint32_t* d_ticket, uint32_t* d_err, DeviceBuf* slots, int* launches) {
+                          uint32_t* d_status, uint32_t* d_ticket, uint32_t* d_err, uint32_t* d_aux, DeviceBuf* slots, int* launches) {
   const uint32_t sms = (uint32_t)device_sms(f->device);
-  if (!use_lane_group_kernel(f, nb)) {
+  const int check_crc = f->skip_crc ? 0 : 1;
+  if (f->debug_flags & 4) {          // tests: the warp-per-member kernel on everything
     uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, sms * INF_CTAS_PER_SM);
-    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, f->skip_crc ? 0 : 1);
+    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, check_crc, 0xffffffffu);
     *launches += 1;
     return BAMSCAN_OK;
   }
-  const uint32_t per_cta = (uint32_t)(LgCfg::GROUPS * LG_W);
-  const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, sms);
-  int rc = slots->ensure((size_t)sms * per_cta * LG_SLOT_BYTES);
-  if (rc) return rc;
-  inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1><<<grid, LG_W * 32, LgCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, slots->as<uint8_t>());
-  *launches += 1;
-  if (!f->skip_crc) {
-    crc_kernel<<<std::min<uint32_t>((nb + CRC_WARPS - 1) / CRC_WARPS, sms), CRC_WARPS * 32, CRC_SMEM, cs>>>(d_blk, nb, U, d_status, d_err);
+  if (f->debug_flags & 8) {          // tests / A-B: the round-1 lane-group kernel + separate CRC kernel
+    const uint32_t per_cta = (uint32_t)(LgCfg::GROUPS * LG_W);
+    const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, sms);
+    int rc = slots->ensure((size_t)sms * per_cta * LG_SLOT_BYTES);
+    if (rc) return rc;
+    inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1><<<grid, LG_W * 32, LgCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, slots->as<uint8_t>());
+    *launches += 1;
+    if (check_crc) {
+      crc_kernel<<<std::min<uint32_t>((nb + CRC_WARPS - 1) / CRC_WARPS, sms), CRC_WARPS * 32, CRC_SMEM, cs>>>(d_blk, nb, U, d_status, d_err);
+      *launches += 1;
+    }
+    return BAMSCAN_OK;
+  }
+  {
+    const uint32_t grid = std::min<uint32_t>(nb, sms * 2u);
+    icta::inflate_cta_kernel<ICTA_NT><<<grid, ICTA_NT, IctaCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, d_aux + 1, g_crc_tabs[f->device], check_crc);
+    *launches += 1;
+    // members flagged INF_RETRY (none on ordinary files); the launch finds nothing to do otherwise
+    uint32_t rgrid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, sms);
+    inflate_kernel<<<rgrid, INF_WARPS * 32, sizeof(InflateShared), cs>>>(d_comp, d_blk, nb, U, d_status, d_aux, d_err, check_crc, icta::INF_RETRY);
     *launches += 1;
   }
   return BAMSCAN_OK;
@@ -295,6 +313,8 @@ static int stream_init(BamScanStream* s) {
   CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
   CU_TRY(cudaFuncSetAttribute(inflate_lg_kernel<LG_G, LG_W, LG_NLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LgCfg::SMEM));
   CU_TRY(cudaFuncSetAttribute(crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_SMEM));
+  CU_TRY(cudaFuncSetAttribute(icta::inflate_cta_kernel<ICTA_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IctaCfg::SMEM));
+  CU_TRY(cudaFuncSetAttribute(icta::inflate_cta_kernel<ICTA_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   // reference dictionary: lengths + names blob
   size_t n_ref = f->ref_names.size();
   std::vector<uint32_t> offs(n_ref + 1, 0);
@@ -653,7 +673,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaEventRecord(s->ev_t[0], cs));
   if (nb) {
     int nl = 0;
-    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, &s->d_sorted, &nl))) return rc;
+    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, d_flags + 12, &s->d_sorted, &nl))) return rc;
     s->st.kernel_launches += nl;
   }
   CU_TRY(cudaEventRecord(s->ev_t[1], cs));
@@ -677,7 +697,11 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   if (hf[9]) {
     uint32_t bi = (hf[9] & 0x7fffffffu) >> 4, code = hf[9] & 15u;
     static const char* names[] = {"ok", "reserved block type", "stored block LEN/NLEN", "Huffman table", "invalid literal/length code", "invalid distance", "output overrun", "ISIZE mismatch", "CRC32 mismatch", "input overrun"};
-    set_error("BAM read error: BGZF member %u (file offset %llu): inflate failed: %s", c.b0 + bi, (unsigned long long)0, code < 10 ? names[code] : "?");
+    // bi indexes the chunk's descriptors, which skip empty members: map it back to the block table
+    uint32_t blk = c.b0;
+    for (uint32_t k = 0; blk < c.b1; blk++) if (f->blocks[blk].isize && k++ == bi) break;
+    blk = std::min(blk, c.b1 - 1);
+    set_error("BAM read error: BGZF member %u (file offset %llu): inflate failed: %s", blk, (unsigned long long)f->blocks[blk].coff, code < 10 ? names[code] : "?");
     return BAMSCAN_ERR_CRC;
   }
   if (hf[1]) { set_error("BAM read error: invalid record block_size at inflated offset %llu", (unsigned long long)(c.u0 + ((hf[1] & ~1u) - HEADROOM))); return BAMSCAN_ERR_FORMAT; }
@@ -1236,7 +1260,7 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
     cudaMemsetAsync(flags.p, 0, 64, s->s_compute);
     cudaEventRecord(e0, s->s_compute);
     int nl = 0;
-    launch_inflate(f, s->s_compute, comp.as<uint8_t>(), blk.as<BlockDesc>(), nb, infl.as<uint8_t>(), status.as<uint32_t>(), flags.as<uint32_t>() + 8, flags.as<uint32_t>() + 9, &s->d_sorted, &nl);
+    launch_inflate(f, s->s_compute, comp.as<uint8_t>(), blk.as<BlockDesc>(), nb, infl.as<uint8_t>(), status.as<uint32_t>(), flags.as<uint32_t>() + 8, flags.as<uint32_t>() + 9, flags.as<uint32_t>() + 12, &s->d_sorted, &nl);
     cudaEventRecord(e1, s->s_compute);
     cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

@@ -280,7 +280,8 @@ __device__ __forceinline__ uint32_t read_dynamic_header(BitReader& br, TT& T, in
 __global__ void __launch_bounds__(INF_WARPS * 32, INF_CTAS_PER_SM)
 inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
                uint8_t* __restrict__ infl, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-               uint32_t* __restrict__ err_flag, int check_crc) {
+               uint32_t* __restrict__ err_flag, int check_crc, uint32_t only_status) {
+  // only_status != 0xffffffff: redo only the members whose status[] holds that value (the CTA-per-member kernel's INF_RETRY)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   InflateShared& sh = *reinterpret_cast<InflateShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -304,6 +305,7 @@ inflate_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ b
     if (lane0) bi = atomicAdd(ticket, 1u);
     bi = __shfl_sync(FULL, bi, 0);
     if (bi >= n_blocks) break;
+    if (only_status != 0xffffffffu && status[bi] != only_status) continue;
     const BlockDesc bd = blocks[bi];
     uint8_t* const out = infl + bd.uoff;
     const uint32_t isize = bd.isize;

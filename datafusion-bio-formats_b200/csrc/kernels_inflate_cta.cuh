@@ -1,0 +1,720 @@
+// kernels_inflate_cta.cuh -- CTA-per-member raw-DEFLATE inflate for BGZF, parallel INSIDE the member, sm_100a.
+//
+// Replaces: noodles-bgzf 0.49.0 io::Reader block inflate + libdeflate `deflate_decompress` / `crc32`
+// (reference call sites: datafusion/bio-format-bam/src/storage.rs:161-169, physical_exec.rs:409).
+//
+// One CTA (NT threads, two CTAs per SM) owns one BGZF member at a time (persistent grid, atomic ticket):
+//   1. the deflate payload is brought into shared memory by ONE cp.async.bulk (TMA) + mbarrier;
+//   2. per deflate block: warp 0 reads the block header, warps 0/1 build two-level Huffman LUTs in shared memory;
+//   3. the block's symbol stream is cut into NT sub-streams which all lanes decode speculatively and then re-anchor on
+//      their predecessor's end until nothing changes (inflate_cta_core.h explains why that converges in ~2 rounds);
+//   4. a CTA scan of the per-lane byte counts gives output offsets; the lanes decode again and EMIT literals and parked
+//      matches into the member's 64 KB OUTPUT WINDOW, which lives in shared memory;
+//   5. all warps RESOLVE the parked matches in output order, each warp over its own part of the window, ordered by
+//      per-warp frontiers (every LZ77 source read is a shared-memory read);
+//   6. CRC-32 is computed from the window (no second pass over HBM), ISIZE is checked, and the window leaves the SM once:
+//      cp.async.bulk shared -> global for the 16-byte aligned body, byte stores for the ragged ends.
+// HBM traffic is therefore the algorithmic minimum: payload read once, inflated bytes written once.
+//
+// Members this kernel cannot take (ISIZE > 65536, a Huffman code whose second-level tables exceed the shared-memory budget)
+// are flagged INF_RETRY in status[] and redone by the warp-per-member kernel of kernels_inflate.cuh.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "inflate_cta_core.h"
+#include "kernels_inflate.cuh"
+
+namespace bamscan {
+namespace icta {
+
+constexpr uint32_t INF_RETRY = 15;          // status: redo this member with the warp-per-member kernel
+constexpr uint32_t FRONT_DONE = 0xffffffffu;
+constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is given
+
+// global constant tables of the CRC stage, filled once per device by crc_tables_init_kernel:
+//   [0, 1024)     four 256-entry tables of the operator "multiply by x^(32*NT)" (strided slicing-by-4)
+//   [1024, 1024+NT] x^(32*j) mod P for j = 0..NT
+template <int NT> struct CrcTabs { static constexpr uint32_t WORDS = 1024 + NT + 1; };
+
+template <int NT>
+struct Cfg {
+  static constexpr int WARPS = NT / 32;
+  static constexpr uint32_t WIN_BYTES = 65536 + 32;
+  static constexpr uint32_t PAY_BYTES = 29 * 1024;            // payload buffer (larger payloads are streamed through it)
+  static constexpr uint32_t PAY_SLACK = 64;
+  static constexpr uint32_t HB_WORDS = 2052;                  // head bitmap: one bit per window byte
+  static constexpr uint32_t LUT_LL_WORDS = ROOT_LL + SUB_LL, LUT_D_WORDS = ROOT_D + SUB_D;
+  static constexpr uint32_t STAGE_PER_WARP = 352;             // heads of one 1 KB stripe (u16 each)
+  static constexpr uint32_t OFF_WIN = 0;
+  static constexpr uint32_t OFF_PAY = OFF_WIN + WIN_BYTES;
+  static constexpr uint32_t OFF_HB = OFF_PAY + PAY_BYTES + PAY_SLACK;
+  static constexpr uint32_t OFF_LUT_LL = OFF_HB + HB_WORDS * 4;
+  static constexpr uint32_t OFF_LUT_D = OFF_LUT_LL + LUT_LL_WORDS * 4;
+  static constexpr uint32_t OFF_LANE_E = OFF_LUT_D + LUT_D_WORDS * 4;
+  static constexpr uint32_t OFF_LANE_N = OFF_LANE_E + NT * 4;
+  static constexpr uint32_t OFF_CTL = OFF_LANE_N + NT * 4;
+  static constexpr uint32_t CTL_BYTES = 1024;
+  static constexpr uint32_t SMEM = OFF_CTL + CTL_BYTES;
+  static_assert(STAGE_PER_WARP * 2 * WARPS <= (LUT_LL_WORDS + LUT_D_WORDS) * 4, "resolver staging aliases the LUTs");
+  static_assert(CrcTabs<NT>::WORDS * 4 <= PAY_BYTES, "CRC tables alias the payload buffer");
+  static_assert(SMEM <= 113 * 1024, "two CTAs per SM");
+};
+
+struct Ctl {
+  unsigned long long mbar;
+  uint32_t ticket, err, btype, final_block, hdr_end, stored_len, n_ll, n_d;
+  uint32_t first_term[2];            // lowest lane whose chain does not hand over (double buffered per round)
+  uint32_t last_lane, last_info;
+  uint32_t warp_tot[32];
+  uint32_t front[32];
+  uint32_t crc_part[32];
+  uint16_t cnt[2][16], first[2][16], nxt[2][16];
+  uint8_t cl[320];
+};
+static_assert(sizeof(Ctl) <= 1024, "Ctl fits its slot");
+
+// ---- PTX helpers: mbarrier + 1-D bulk copies (TMA) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded: a transfer that never completes becomes an error code instead of a hung kernel
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity) {
+  for (uint32_t tries = 0; tries < (1u << 22); tries++) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t brev_n(uint32_t v, uint32_t bits) { return __brev(v) >> (32u - bits); }
+
+// Canonical Huffman build into a two-level LUT (format: inflate_cta_core.h), one warp.  `S` selects the scratch rows.
+// Returns 0 ok, INF_ERR_TABLE for an over-subscribed code, INF_RETRY when the second-level tables do not fit.
+template <int RBITS, bool DIST>
+__device__ __noinline__ uint32_t build_lut_warp(const uint8_t* cl, int n, uint32_t* lut, uint32_t sub_cap, Ctl* C, int S, int lane) {
+  constexpr uint32_t ROOT = 1u << RBITS;
+  uint16_t* cnt = C->cnt[S]; uint16_t* first = C->first[S]; uint16_t* nxt = C->nxt[S];
+  if (lane < 16) { cnt[lane] = 0; nxt[lane] = 0; }
+  for (uint32_t i = lane; i < ROOT + sub_cap; i += 32) lut[i] = E_BAD;
+  __syncwarp();
+  for (int s = lane; s < n; s += 32) {
+    const uint32_t L = cl[s];
+    if (L) atomicAdd(reinterpret_cast<unsigned int*>(cnt) + (L >> 1), (L & 1) ? 0x10000u : 1u);   // 16-bit counters packed in pairs
+  }
+  __syncwarp();
+  uint32_t code = 0, left = 1;
+  bool over = false;
+  for (int len = 1; len <= 15; len++) {
+    const uint32_t c = cnt[len];
+    code = (code + cnt[len - 1]) << 1;
+    left <<= 1;
+    if (c > left) over = true;
+    left -= c;
+    if (lane == len) first[len] = (uint16_t)code;
+  }
+  if (over) return INF_ERR_TABLE;
+  __syncwarp();
+  // pass 1: canonical code of every symbol (kept in registers: <= 9 symbols per lane); root entries of short codes;
+  //         per root prefix of a long code, the widest remainder (atomicMax on the root slot, E_SUB | bits > E_BAD)
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t my_code[9];
+  #pragma unroll
+  for (int b = 0; b < 9; b++) {
+    if (b * 32 >= n) { my_code[b] = 0; continue; }           // (uniform: the distance alphabet needs one pass)
+    const int s = b * 32 + lane;
+    const uint32_t L = (s < n) ? cl[s] : 0u;
+    const uint32_t m = __match_any_sync(FULL, L);
+    const uint32_t r = nxt[L] + __popc(m & lt);
+    __syncwarp();
+    if (L && (m & lt) == 0) nxt[L] = (uint16_t)(nxt[L] + __popc(m));
+    __syncwarp();
+    const uint32_t cd = first[L] + r;
+    my_code[b] = cd;
+    if (L) {
+      if (L <= (uint32_t)RBITS) {
+        const uint32_t e = DIST ? entry_dist((uint32_t)s, L) : entry_litlen((uint32_t)s, L);
+        for (uint32_t idx = brev_n(cd, L); idx < ROOT; idx += (1u << L)) lut[idx] = e;
+      } else {
+        atomicMax(lut + brev_n(cd >> (L - RBITS), RBITS), E_SUB | (L - RBITS));
+      }
+    }
+  }
+  __syncwarp();
+  // second-level tables: one per root prefix that carries long codes; prefixes of long codes are the top of the code space
+  uint32_t any_long = 0;
+  for (int len = RBITS + 1; len <= 15; len++) any_long += cnt[len];
+  if (any_long) {
+    const uint32_t q_min = (uint32_t)first[RBITS + 1] >> 1;
+    uint32_t base = ROOT;
+    for (uint32_t q0 = q_min; q0 < ROOT; q0 += 32) {
+      const uint32_t q = q0 + lane;
+      uint32_t slot = 0, sz = 0, sb = 0;
+      if (q < ROOT) {
+        slot = brev_n(q, RBITS);
+        const uint32_t e = lut[slot];
+        if (e & E_SUB) { sb = e & 15u; sz = 1u << sb; }
+      }
+      uint32_t incl = sz;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+      if (sz) lut[slot] = E_SUB | (sb << 12) | ((base + incl - sz) << 16) | (uint32_t)RBITS;
+      base += __shfl_sync(FULL, incl, 31);
+    }
+    if (base > ROOT + sub_cap) return INF_RETRY;          // (entries past the budget were never written: see the guard below)
+    __syncwarp();
+    #pragma unroll
+    for (int b = 0; b < 9; b++) {
+      const int s = b * 32 + lane;
+      const uint32_t L = (s < n) ? cl[s] : 0u;
+      if (L > (uint32_t)RBITS) {
+        const uint32_t cd = my_code[b], l2 = L - RBITS;
+        const uint32_t pe = lut[brev_n(cd >> l2, RBITS)];
+        const uint32_t sbits = (pe >> 12) & 15u, sbase = pe >> 16;
+        const uint32_t e = DIST ? entry_dist((uint32_t)s, L) : entry_litlen((uint32_t)s, L);
+        for (uint32_t idx = brev_n(cd & ((1u << l2) - 1u), l2); idx < (1u << sbits); idx += (1u << l2)) lut[sbase + idx] = e;
+      }
+    }
+  }
+  __syncwarp();
+  return INF_OK;
+}
+
+// warp-uniform bit reader over the payload words in shared memory (block headers only)
+struct SBits {
+  const uint32_t* w; uint32_t pos;
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w[pos >> 5], w[(pos >> 5) + 1], pos & 31u); }
+  __device__ __forceinline__ uint32_t take(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); pos += n; return v; }
+};
+
+// Dynamic block header (RFC 1951 3.2.7) by one warp: code lengths into C->cl.  The 7-bit precode LUT is built in lut_d.
+__device__ __noinline__ uint32_t read_dynamic_header_smem(SBits& br, uint32_t limit_bit, uint32_t* lut_d, Ctl* C, int lane) {
+  const uint32_t h = br.take(14);
+  const int n_ll = (int)(h & 31u) + 257, n_d = (int)((h >> 5) & 31u) + 1, n_clc = (int)(h >> 10) + 4;
+  if (n_ll > 286 || n_d > 30) return INF_ERR_TABLE;
+  if (lane < 19) C->cl[lane] = 0;
+  __syncwarp();
+  {
+    const uint32_t v = (lane < n_clc) ? ((__funnelshift_r(br.w[(br.pos + 3u * lane) >> 5], br.w[((br.pos + 3u * lane) >> 5) + 1], (br.pos + 3u * lane) & 31u)) & 7u) : 0u;
+    if (lane < n_clc) C->cl[c_clc_order[lane]] = (uint8_t)v;
+    br.pos += 3u * (uint32_t)n_clc;
+  }
+  __syncwarp();
+  // precode: max length 7, no second level
+  {
+    uint16_t* cnt = C->cnt[1]; uint16_t* first = C->first[1]; uint16_t* nxt = C->nxt[1];
+    if (lane < 16) { cnt[lane] = 0; nxt[lane] = 0; }
+    for (int i = lane; i < 128; i += 32) lut_d[i] = 0;
+    __syncwarp();
+    const uint32_t L = lane < 19 ? C->cl[lane] : 0u;
+    if (L) atomicAdd(reinterpret_cast<unsigned int*>(cnt) + (L >> 1), (L & 1) ? 0x10000u : 1u);
+    __syncwarp();
+    uint32_t code = 0, left = 1; bool over = false;
+    for (int len = 1; len <= 7; len++) {
+      const uint32_t c = cnt[len];
+      code = (code + cnt[len - 1]) << 1; left <<= 1;
+      if (c > left) over = true;
+      left -= c;
+      if (lane == len) first[len] = (uint16_t)code;
+    }
+    if (over) return INF_ERR_TABLE;
+    __syncwarp();
+    const uint32_t m = __match_any_sync(FULL, L);
+    const uint32_t r = __popc(m & ((1u << lane) - 1u));
+    if (L) {
+      const uint32_t cd = first[L] + r;
+      for (uint32_t idx = brev_n(cd, L); idx < 128u; idx += (1u << L)) lut_d[idx] = L | ((uint32_t)lane << 16);
+    }
+    __syncwarp();
+  }
+  const int total = n_ll + n_d;
+  int i = 0;
+  uint32_t prev = 0;
+  // 64-bit bit buffer in registers: the serial chain per code-length symbol is one LUT look-up
+  uint32_t wi = br.pos >> 5;
+  const uint32_t sh = br.pos & 31u;
+  uint64_t buf = (((uint64_t)br.w[wi + 1] << 32) | br.w[wi]) >> sh;
+  uint32_t cntb = 64u - sh, pos = br.pos;
+  wi += 2;
+  while (i < total) {
+    if (cntb <= 32u) { buf |= (uint64_t)br.w[wi] << cntb; cntb += 32u; wi++; }
+    const uint32_t bits = (uint32_t)buf;
+    const uint32_t e = lut_d[bits & 127u];
+    const uint32_t L = e & 15u, s = e >> 16;
+    if (L == 0) return INF_ERR_TABLE;
+    uint32_t rep, val, xb;
+    if (s < 16) { rep = 1; val = s; prev = s; xb = 0; }
+    else if (s == 16) { if (i == 0) return INF_ERR_TABLE; xb = 2; rep = 3 + ((bits >> L) & 3u); val = prev; }
+    else if (s == 17) { xb = 3; rep = 3 + ((bits >> L) & 7u); val = 0; prev = 0; }
+    else { xb = 7; rep = 11 + ((bits >> L) & 127u); val = 0; prev = 0; }
+    const uint32_t used = L + xb;
+    buf >>= used; cntb -= used; pos += used;
+    if (i + (int)rep > total) return INF_ERR_TABLE;
+    if (pos > limit_bit) return INF_ERR_INPUT;
+    for (uint32_t k = lane; k < rep; k += 32) C->cl[i + k] = (uint8_t)val;
+    i += (int)rep;
+  }
+  br.pos = pos;
+  __syncwarp();
+  if (C->cl[256] == 0) return INF_ERR_TABLE;
+  C->n_ll = (uint32_t)n_ll; C->n_d = (uint32_t)n_d;
+  return INF_OK;
+}
+
+// One warp resolves the parked matches whose heads lie in its part of the window, in position order.
+//   front[p]: every match of part p headed below front[p] is complete (FRONT_DONE: the whole part).
+// A source byte x of part p is final once x < front[p] and no unfinished match of part p-1 can still reach it.
+template <int NT>
+__device__ __forceinline__ void resolve_part_warp(uint8_t* win, uint32_t* hb, uint16_t* stage, volatile uint32_t* front,
+                                                  uint32_t obase, uint32_t wbeg, uint32_t wend, uint32_t PW, int part, int lane, volatile uint32_t* err_out) {
+  const uint32_t p_beg = wbeg + (uint32_t)part * PW;
+  const uint32_t p_end = min(wend, p_beg + PW);
+  if (p_beg >= wend) { if (lane == 0) front[part] = FRONT_DONE; return; }
+  for (uint32_t cw = p_beg; cw < p_end; cw += 32) {
+    // heads of this 1 KB stripe, compacted in position order
+    const uint32_t widx = cw + lane;
+    uint32_t hw = 0;
+    if (widx < p_end) { hw = hb[widx]; hb[widx] = 0; }
+    const uint32_t c = __popc(hw);
+    uint32_t incl = c;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    {
+      uint32_t k = incl - c, w = hw;
+      while (w) { stage[k++] = (uint16_t)(widx * 32u + (uint32_t)__ffs((int)w) - 1u - obase); w &= w - 1u; }
+    }
+    __syncwarp();
+    for (uint32_t b = 0; b < total; b += 32) {
+      const uint32_t r = b + lane;
+      const bool valid = r < total;
+      uint32_t o = 0xffffffffu, dist = 1, len = 0;
+      if (valid) {
+        o = obase + stage[r];
+        const uint32_t v = (uint32_t)win[o] | ((uint32_t)win[o + 1] << 8) | ((uint32_t)win[o + 2] << 16);
+        dist = (v & 0x7fffu) + 1u; len = (v >> 15) + 3u;
+      }
+      const uint32_t oend = valid ? o + len : 0xffffffffu;
+      const uint32_t sa = o - dist, sb = min(o, sa + len);          // the bytes this match needs from outside itself
+      // earlier lanes of this batch whose range intersects [sa, sb): positions are sorted, so two rank searches
+      uint32_t dep = 0;
+      const uint32_t batch_start = __shfl_sync(FULL, o, 0);
+      {
+        const bool inside = valid && sb > batch_start;
+        if (__any_sync(FULL, inside)) {
+          uint32_t j_lo = 0, j_hi = 0;
+          #pragma unroll
+          for (int s = 16; s; s >>= 1) {
+            const uint32_t ve = __shfl_sync(FULL, oend, (j_lo + s - 1) & 31), vo = __shfl_sync(FULL, o, (j_hi + s - 1) & 31);
+            if (ve <= sa) j_lo += s;
+            if (vo < sb) j_hi += s;
+          }
+          j_hi = min(j_hi, (uint32_t)lane);
+          if (inside && j_hi > j_lo) dep = ((j_hi >= 32u ? 0u : (1u << j_hi)) - 1u) & ~((1u << j_lo) - 1u);
+        }
+      }
+      // sources in another warp's part: wait for that warp's frontier (and, near a part start, for the part before it)
+      int need1 = -1, need2 = -1;
+      if (valid) {
+        const uint32_t wlast = (sb - 1u) >> 5;
+        int pw = 0;
+        #pragma unroll
+        for (int k = 1; k < NT / 32; k++) pw += (wlast >= wbeg + (uint32_t)k * PW) ? 1 : 0;
+        if (pw != part) need1 = pw;
+        if (pw > 0 && sa < (wbeg + (uint32_t)pw * PW) * 32u + 257u) need2 = pw - 1;
+      }
+      bool pend = valid;
+      uint32_t spins = 0;
+      for (;;) {
+        const uint32_t pmask = __ballot_sync(FULL, pend);
+        if (!pmask) break;
+        bool ok = pend && (pmask & dep) == 0;
+        if (ok && need1 >= 0) { if (front[need1] >= sb) need1 = -1; else ok = false; }
+        if (ok && need2 >= 0) { if (front[need2] == FRONT_DONE) need2 = -1; else ok = false; }
+        if (!__any_sync(FULL, ok)) {                                 // every remaining lane waits for another warp
+          if (++spins > (1u << 24)) { if (lane == 0) { *err_out = INF_ERR_INPUT; front[part] = FRONT_DONE; } return; }   // safety valve, never taken
+          continue;
+        }
+        __threadfence_block();
+        // up to RESOLVE_PIECE bytes per ready lane: all loads first (sources are final), then the stores
+        const uint32_t n = ok ? min(len, RESOLVE_PIECE) : 0u;
+        const uint32_t nmax = __reduce_max_sync(FULL, n);
+        {
+          uint8_t v[RESOLVE_PIECE];
+          uint32_t j = 0;
+          #pragma unroll
+          for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
+            if (k < nmax) {
+              if (k < n) { v[k] = win[sa + j]; j++; if (j == dist) j = 0; }
+            }
+          }
+          #pragma unroll
+          for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
+            if (k < nmax) { if (k < n) win[o + k] = v[k]; }
+          }
+        }
+        // the rest of a long match: all 32 lanes copy it
+        uint32_t lmask = __ballot_sync(FULL, ok && len > RESOLVE_PIECE);
+        while (lmask) {
+          const int src = __ffs((int)lmask) - 1;
+          lmask &= lmask - 1u;
+          const uint32_t lo_ = __shfl_sync(FULL, o, src), ld = __shfl_sync(FULL, dist, src), ll = __shfl_sync(FULL, len, src);
+          __syncwarp();
+          if (ld >= 32u) {
+            for (uint32_t kb = RESOLVE_PIECE; kb < ll; kb += 32) {    // a stripe only reads bytes written by earlier stripes
+              const uint32_t k = kb + lane;
+              if (k < ll) win[lo_ + k] = win[lo_ + k - ld];
+              __syncwarp();
+            }
+          } else {
+            for (uint32_t k = RESOLVE_PIECE + lane; k < ll; k += 32) win[lo_ + k] = win[lo_ - ld + (k % ld)];
+          }
+        }
+        pend = pend && !ok;
+        __syncwarp();
+        __threadfence_block();
+        // publish the frontier: head of the first unfinished match, or the next place a head can be
+        const uint32_t pm2 = __ballot_sync(FULL, pend);
+        uint32_t f;
+        if (pm2) f = __shfl_sync(FULL, o, __ffs((int)pm2) - 1);
+        else if (b + 32 < total) f = obase + stage[b + 32];
+        else f = (cw + 32 < p_end) ? (cw + 32) * 32u : FRONT_DONE;
+        if (lane == 0) front[part] = f;
+      }
+    }
+    __syncwarp();
+  }
+  __threadfence_block();
+  if (lane == 0) front[part] = FRONT_DONE;
+}
+
+// CRC tables of the strided CRC (see Cfg / the CRC stage below); one launch per device at init.
+template <int NT>
+__global__ void crc_tables_init_kernel(uint32_t* __restrict__ tabs) {
+  const int t = threadIdx.x;      // 256 threads
+  // standard byte table
+  uint32_t c = (uint32_t)t;
+  for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+  __shared__ uint32_t t0[256];
+  t0[t] = c;
+  __syncthreads();
+  // x^(32*j) mod P: x^32 is the state after feeding 0x00000001... use repeated multiplication by x^32
+  const uint32_t x32 = crc_mulmod(0x00800000u, crc_mulmod(0x00800000u, crc_mulmod(0x00800000u, 0x00800000u)));   // (x^8)^4
+  if (t == 0) {
+    uint32_t p = 0x80000000u;     // x^0 in the reflected domain
+    for (int j = 0; j <= NT; j++) { tabs[1024 + j] = p; p = crc_mulmod(p, x32); }
+  }
+  __syncthreads();
+  __threadfence();
+  // slicing-by-4 tables T_k[b] = (b * x^(8k+8)) * x^(32*(NT-1)): standard tables times the stride operator
+  uint32_t e = t0[t];
+  const uint32_t stride = tabs[1024 + NT - 1];
+  for (int k = 0; k < 4; k++) {
+    tabs[k * 256 + t] = crc_mulmod(e, stride);
+    e = t0[e & 0xffu] ^ (e >> 8);
+  }
+}
+
+__device__ __forceinline__ uint32_t crc_byte_bitwise(uint32_t st, uint32_t b) {
+  st ^= b;
+  #pragma unroll
+  for (int k = 0; k < 8; k++) st = (st >> 1) ^ ((st & 1u) ? 0xEDB88320u : 0u);
+  return st;
+}
+
+// =============================================================================================
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
+                   uint8_t* __restrict__ infl, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                   uint32_t* __restrict__ err_flag, uint32_t* __restrict__ retry_count, const uint32_t* __restrict__ crc_tabs, int check_crc) {
+  using K = Cfg<NT>;
+  constexpr int WARPS = K::WARPS;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint8_t* const win = smem + K::OFF_WIN;
+  uint32_t* const pay = reinterpret_cast<uint32_t*>(smem + K::OFF_PAY);
+  uint32_t* const hb = reinterpret_cast<uint32_t*>(smem + K::OFF_HB);
+  uint32_t* const lut_ll = reinterpret_cast<uint32_t*>(smem + K::OFF_LUT_LL);
+  uint32_t* const lut_d = reinterpret_cast<uint32_t*>(smem + K::OFF_LUT_D);
+  uint32_t* const laneE = reinterpret_cast<uint32_t*>(smem + K::OFF_LANE_E);
+  uint32_t* const laneN = reinterpret_cast<uint32_t*>(smem + K::OFF_LANE_N);
+  Ctl* const C = reinterpret_cast<Ctl*>(smem + K::OFF_CTL);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (uint32_t i = tid; i < K::HB_WORDS; i += NT) hb[i] = 0;
+  if (tid == 0) mbar_init(&C->mbar, 1);
+  __syncthreads();
+  uint32_t bar_parity = 0;
+  bool store_pending = false;
+
+  for (;;) {
+    if (tid == 0) { C->ticket = atomicAdd(ticket, 1u); C->err = INF_OK; }
+    __syncthreads();
+    const uint32_t bi = C->ticket;
+    if (bi >= n_blocks) break;
+    const BlockDesc bd = blocks[bi];
+    const uint8_t* const gpay = comp + bd.cdata_off;
+    const uint32_t isize = bd.isize, clen = bd.cdata_len;
+    const uint32_t obase = bd.uoff & 15u, olimit = obase + isize;
+    uint32_t err = INF_OK;
+    if (isize > 65536u) err = INF_RETRY;
+
+    // ---- payload window: buffer byte 0 <-> payload byte buf_lo (negative: bytes in front of the payload, for 16-byte alignment)
+    int32_t buf_lo = 0; uint32_t loaded = 0;
+    auto load_payload = [&](uint32_t from_byte) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(gpay + from_byte);
+      const uint32_t ph = (uint32_t)(a & 15u);
+      buf_lo = (int32_t)from_byte - (int32_t)ph;
+      const uint32_t want = (clen - from_byte) + ph + 32u;                  // + slack: the reader looks up to 18 bytes ahead
+      loaded = min((want + 15u) & ~15u, K::PAY_BYTES);
+      __syncthreads();                                                     // everyone is done with the old contents
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&C->mbar, loaded);
+        bulk_load(pay, reinterpret_cast<const void*>(a - ph), loaded, &C->mbar);
+      }
+      if (!mbar_wait(&C->mbar, bar_parity)) C->err = INF_ERR_INPUT;
+      bar_parity ^= 1u;
+      __syncthreads();
+      if (C->err) err = C->err;
+    };
+    uint32_t abs_bit = 0;                                                  // position in the payload, in bits
+    const uint32_t end_bit = clen * 8u;
+    if (!err) load_payload(0);
+    if (store_pending) {                                                   // the previous member's bulk store must have read the window
+      if (tid == 0) bulk_store_wait_read();
+      store_pending = false;
+      __syncthreads();
+    }
+    auto buf_bit = [&](uint32_t abit) { return abit - (uint32_t)(buf_lo * 8); };   // payload bit -> buffer bit (two's complement handles buf_lo < 0)
+    auto has_tail = [&]() { return (int64_t)buf_lo + (int64_t)loaded >= (int64_t)clen + 32; };   // the buffer reaches the end of the payload
+    auto covers = [&](uint32_t abit_end) {                                  // is [.., abit_end) inside the buffer (with look-ahead margin)?
+      return has_tail() ? abit_end <= end_bit : (int64_t)abit_end <= ((int64_t)buf_lo + (int64_t)loaded - 32) * 8;
+    };
+
+    uint32_t outpos = obase;
+    bool final_block = false;
+    while (!final_block && !err) {
+      // ---- block header (warp 0) ----
+      if (abs_bit + 3u > end_bit) { err = INF_ERR_INPUT; break; }
+      if (!covers(min(end_bit, abs_bit + 8u * 1024u))) { load_payload(abs_bit >> 3); if (err) break; }
+      if (warp == 0) {
+        SBits br; br.w = pay; br.pos = buf_bit(abs_bit);
+        const uint32_t hdr = br.take(3);
+        uint32_t e = INF_OK, btype = hdr >> 1, slen = 0;
+        if (btype == 3) e = INF_ERR_BTYPE;
+        else if (btype == 0) {
+          br.pos = (br.pos + 7u) & ~7u;
+          const uint32_t len = br.take(16), nlen = br.take(16);
+          slen = len;
+          if ((len ^ nlen) != 0xffffu) e = INF_ERR_STORED;
+        } else if (btype == 1) {
+          for (int i = lane; i < 288; i += 32) C->cl[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+          if (lane < 30) C->cl[288 + lane] = 5;
+          if (lane == 0) { C->n_ll = 288; C->n_d = 30; }
+        } else {
+          e = read_dynamic_header_smem(br, buf_bit(end_bit), lut_d, C, lane);
+        }
+        if (lane == 0) { C->btype = btype; C->final_block = hdr & 1u; C->hdr_end = br.pos + (uint32_t)(buf_lo * 8); C->stored_len = slen; if (e) C->err = e; }
+      }
+      __syncthreads();
+      err = C->err;
+      if (err) break;
+      final_block = C->final_block != 0;
+      abs_bit = C->hdr_end;
+      const uint32_t btype = C->btype;
+      if (btype == 0) {
+        const uint32_t len = C->stored_len, from = abs_bit >> 3;
+        if (from + len > clen || outpos + len > olimit) { err = INF_ERR_STORED; break; }
+        for (uint32_t i = tid; i < len; i += NT) win[outpos + i] = __ldg(gpay + from + i);     // straight from global: any length
+        outpos += len; abs_bit += 8u * len;
+        __syncthreads();
+        continue;
+      }
+      // ---- tables: litlen by warp 0, distance by warp 1 ----
+      {
+        const int n_ll = (int)C->n_ll, n_d = (int)C->n_d;
+        uint32_t e = INF_OK;
+        if (warp == 0) e = build_lut_warp<R_LL, false>(C->cl, n_ll, lut_ll, SUB_LL, C, 0, lane);
+        else if (warp == 1 % WARPS) e = build_lut_warp<R_D, true>(C->cl + n_ll, n_d, lut_d, SUB_D, C, 1, lane);
+        if (WARPS == 1 && !e) e = build_lut_warp<R_D, true>(C->cl + n_ll, n_d, lut_d, SUB_D, C, 1, lane);
+        if (e && lane == 0) atomicMax(&C->err, e);          // INF_RETRY (15) wins over a format error of the other table
+        __syncthreads();
+        err = C->err;
+        if (err) break;
+      }
+      // ---- spans of the symbol stream ----
+      bool block_done = false;
+      while (!block_done && !err) {
+        if (abs_bit >= end_bit) { err = INF_ERR_INPUT; break; }
+        if (!has_tail() && !covers(abs_bit + (K::PAY_BYTES / 2u) * 8u)) { load_payload(abs_bit >> 3); if (err) break; }
+        const uint32_t span_beg = buf_bit(abs_bit);
+        const bool to_end = has_tail();
+        const uint32_t span_end = to_end ? buf_bit(end_bit) : (uint32_t)(((int64_t)loaded - 32) * 8);
+        uint32_t S = (span_end - span_beg + NT - 1) / NT;
+        if (S < MIN_SUB_BITS) S = MIN_SUB_BITS;
+        const uint32_t my_p = span_beg + (uint32_t)tid * S;
+        const bool active = my_p < span_end;
+        const uint32_t my_stop = min(my_p + S, span_end);
+        uint32_t my_s = my_p;
+        bool need = active;
+        uint32_t my_e = 0, my_t = T_CROSS, my_n = 0, F = 0;
+        for (int round = 0;; round++) {
+          if (need) {
+            const SubResult r = decode_sub<false>(pay, lut_ll, lut_d, my_s, my_stop, nullptr, nullptr, 0, 0, 0, nullptr);
+            my_e = r.end_bit; my_t = r.term; my_n = r.n_out;
+            laneE[tid] = my_e;
+          }
+          if (tid == 0) C->first_term[round & 1] = NT - 1;
+          __syncthreads();
+          {
+            const uint32_t m = __ballot_sync(FULL, !active || my_t != T_CROSS);
+            if (m && lane == 0) {
+              const int l = __ffs((int)m) - 1;
+              atomicMin(&C->first_term[round & 1], (uint32_t)(warp * 32 + l));
+            }
+          }
+          __syncthreads();
+          // the lane found above is either inactive (chain ends one before it) or terminates the chain itself
+          F = C->first_term[round & 1];
+          need = false;
+          if (active && tid > 0 && (uint32_t)tid <= F) {
+            const uint32_t pe = laneE[tid - 1];
+            if (pe != my_s) { my_s = pe; need = true; }
+          }
+          if (!__syncthreads_or(need ? 1 : 0)) break;
+          if (round > NT + 2) { err = INF_ERR_INPUT; break; }
+        }
+        if (err) break;
+        // F may name the first INACTIVE lane: the chain then ends at F - 1
+        if ((uint32_t)tid == F) C->last_lane = active ? F : F - 1;
+        __syncthreads();
+        const uint32_t last = C->last_lane;
+        if ((uint32_t)tid == last) C->last_info = my_t | (my_e << 2);
+        // ---- exclusive scan of the byte counts of lanes 0..last ----
+        const uint32_t cnt_n = ((uint32_t)tid <= last) ? my_n : 0u;
+        uint32_t incl = cnt_n;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) C->warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+        #pragma unroll
+        for (int w = 0; w < WARPS; w++) { const uint32_t t = C->warp_tot[w]; if (w < warp) wbase += t; total += t; }
+        const uint32_t last_t = C->last_info & 3u, last_e = C->last_info >> 2;
+        if (last_t == T_BAD) { err = INF_ERR_SYMBOL; break; }
+        if (outpos + total > olimit || total > 65536u) { err = INF_ERR_OVERRUN; break; }
+        // ---- emit ----
+        if ((uint32_t)tid <= last) {
+          uint32_t e2 = 0;
+          decode_sub<true>(pay, lut_ll, lut_d, my_s, my_stop, win, hb, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
+          if (e2) atomicMax(&C->err, e2);
+        }
+        __syncthreads();
+        err = C->err;
+        if (err) break;
+        outpos += total;
+        abs_bit = last_e + (uint32_t)(buf_lo * 8);
+        if (last_t == T_EOB) block_done = true;
+        else if (to_end) { err = INF_ERR_INPUT; break; }
+      }
+    }
+    if (!err && outpos != olimit) err = outpos > olimit ? INF_ERR_OVERRUN : INF_ERR_ISIZE;
+
+    if (!err) {
+      // ---- resolve: every warp takes one part of the window ----
+      const uint32_t wbeg = obase >> 5, wend = (olimit + 31u) >> 5;
+      const uint32_t PW = (((wend - wbeg) + WARPS - 1) / WARPS + 31u) & ~31u;
+      if (tid < WARPS) C->front[tid] = (wbeg + (uint32_t)tid * PW) * 32u;
+      __syncthreads();
+      uint16_t* const stage = reinterpret_cast<uint16_t*>(lut_ll) + (uint32_t)warp * K::STAGE_PER_WARP;
+      resolve_part_warp<NT>(win, hb, stage, C->front, obase, wbeg, wend, PW, warp, lane, &C->err);
+      __syncthreads();
+      err = C->err;
+
+      // ---- CRC-32 from the window (strided slicing-by-4: thread t owns words t, t+NT, ...; tables in the payload buffer) ----
+      if (check_crc && !err) {
+        uint32_t* const ctab = pay;
+        for (uint32_t i = tid; i < CrcTabs<NT>::WORDS; i += NT) ctab[i] = __ldg(crc_tabs + i);
+        __syncthreads();
+        const uint32_t head = min(isize, (4u - (obase & 3u)) & 3u);           // bytes in front of the first aligned word
+        const uint32_t nw = (isize - head) >> 2, tail = (isize - head) & 3u;
+        const uint32_t* const words = reinterpret_cast<const uint32_t*>(win + obase + head);
+        uint32_t st = 0;
+        if (tid == 0) { st = 0xffffffffu; for (uint32_t k = 0; k < head; k++) st = crc_byte_bitwise(st, win[obase + k]); }
+        uint32_t acc = 0, part = 0;
+        if ((uint32_t)tid < nw) {
+          acc = words[tid] ^ st;                                               // the running state folds into the first word
+          uint32_t k = tid + NT;
+          for (; k < nw; k += NT) {
+            acc = ctab[3 * 256 + (acc & 0xffu)] ^ ctab[2 * 256 + ((acc >> 8) & 0xffu)] ^ ctab[256 + ((acc >> 16) & 0xffu)] ^ ctab[acc >> 24];
+            acc ^= words[k];
+          }
+          // acc sits at word k_last = k - NT; it still has to cross (nw - k_last) words
+          part = crc_mulmod(acc, ctab[1024 + (nw - (k - NT))]);
+        } else if (tid == 0) {
+          part = st;                                                           // fewer than one word: only the head bytes
+        }
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) part ^= __shfl_xor_sync(FULL, part, o);
+        if (lane == 0) C->crc_part[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t crc = 0;
+          for (int w = 0; w < WARPS; w++) crc ^= C->crc_part[w];
+          for (uint32_t k = 0; k < tail; k++) crc = crc_byte_bitwise(crc, win[obase + head + 4u * nw + k]);
+          if (~crc != bd.crc) C->err = INF_ERR_CRC;
+        }
+        __syncthreads();
+        err = C->err;
+      }
+    }
+    if (!err) {
+      // ---- the window leaves the SM once: 16-byte aligned body by cp.async.bulk, ragged ends by byte stores ----
+      uint8_t* const gout = infl + bd.uoff;                                    // (gout + k) and (win + obase + k) are congruent mod 16
+      const uint32_t head = min(isize, (16u - obase) & 15u);
+      const uint32_t body = (isize - head) & ~15u, tailb = isize - head - body;
+      if ((uint32_t)tid < head) gout[tid] = win[obase + tid];
+      if ((uint32_t)tid < tailb) gout[head + body + tid] = win[obase + head + body + tid];
+      if (body) {
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) bulk_store(gout + head, win + obase + head, body);
+        store_pending = true;
+      }
+    } else {
+      // leave clean state behind: no head bits, no half-done store
+      __syncthreads();
+      for (uint32_t i = tid; i < K::HB_WORDS; i += NT) hb[i] = 0;
+    }
+    if (tid == 0) {
+      status[bi] = err;
+      if (err == INF_RETRY) atomicAdd(retry_count, 1u);
+      else if (err) atomicCAS(err_flag, 0u, (bi << 4) | err | 0x80000000u);
+    }
+    __syncthreads();
+  }
+  if (store_pending && tid == 0) bulk_store_wait_read();
+  // a bulk store must have finished reading shared memory before the CTA exits; writes complete with the grid
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace icta
+}  // namespace bamscan

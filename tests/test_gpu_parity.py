@@ -20,13 +20,12 @@ def _oracle(path, **kw):
     return OracleBam(str(path), **kw)
 
 
-# Every test of this module runs twice: once per inflate kernel (debug_flags bit 2 forces the warp-per-member "latency"
-# kernel, bit 3 the lane-group "throughput" kernel; without either the engine picks by member count, which on these small
-# fixtures would always be the latency kernel).
+# Every test of this module runs once per inflate kernel: 0 = the default CTA-per-member kernel (kernels_inflate_cta.cuh),
+# debug_flags bit 2 forces the warp-per-member kernel (the retry path), bit 3 the round-1 lane-group kernel (A/B baseline).
 _FORCE_INFLATE = 0
 
 
-@pytest.fixture(autouse=True, params=[4, 8], ids=["warp_per_member", "lane_group"])
+@pytest.fixture(autouse=True, params=[0, 4, 8], ids=["cta_per_member", "warp_per_member", "lane_group"])
 def inflate_kernel(request):
     global _FORCE_INFLATE
     _FORCE_INFLATE = request.param

@@ -1,0 +1,282 @@
+// inflate_sim.cpp -- host model of the CTA-per-member inflate kernel (kernels_inflate_cta.cuh).
+//
+// Runs the kernel's algorithm (speculative sub-stream decode -> restart rounds -> scan -> emit -> resolve) with the
+// lanes of a CTA executed in a loop, using the very same per-lane code (csrc/inflate_cta_core.h), and compares every
+// BGZF member of a file with zlib.  Test/verification tool only: nothing in the product links it.
+//
+//   inflate_sim file.bam [--lanes 256] [--max-members N] [--span-bytes B] [--stats]
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../datafusion-bio-formats_b200/csrc/inflate_cta_core.h"
+
+using namespace bamscan::icta;
+
+static const uint8_t kClcOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct Bits {
+  const uint32_t* w; uint32_t pos;
+  uint32_t peek(int n) const { uint64_t v = (((uint64_t)w[(pos >> 5) + 1] << 32) | w[pos >> 5]) >> (pos & 31); return (uint32_t)(v & ((1ull << n) - 1)); }
+  uint32_t take(int n) { uint32_t v = peek(n); pos += n; return v; }
+};
+
+// serial canonical build in the kernel's table format: root LUT of RBITS index bits + second-level tables behind it.
+// Returns 0 ok, 1 over-subscribed, 2 second-level space exhausted.
+template <int RBITS, bool DIST>
+static int build_lut(const uint8_t* cl, int n, uint32_t* lut, uint32_t sub_cap) {
+  const uint32_t ROOT = 1u << RBITS;
+  int cnt[16] = {0};
+  for (int i = 0; i < n; i++) cnt[cl[i]]++;
+  cnt[0] = 0;
+  uint32_t first[17], code = 0; int left = 1;
+  for (int L = 1; L <= 15; L++) { code = (code + (L > 1 ? cnt[L - 1] : 0)) << 1; first[L] = code; left <<= 1; left -= cnt[L]; if (left < 0) return 1; }
+  for (uint32_t i = 0; i < ROOT + sub_cap; i++) lut[i] = E_BAD;
+  uint32_t next[16]; for (int L = 1; L <= 15; L++) next[L] = first[L];
+  // per root prefix: index bits of its second-level table
+  std::vector<uint8_t> sub_bits(ROOT, 0);
+  std::vector<uint32_t> codes(n, 0);
+  for (int s = 0; s < n; s++) {
+    int L = cl[s]; if (!L) continue;
+    uint32_t c = next[L]++; codes[s] = c;
+    if (L > RBITS) { uint32_t q = c >> (L - RBITS); sub_bits[q] = std::max<uint8_t>(sub_bits[q], (uint8_t)(L - RBITS)); }
+  }
+  std::vector<uint32_t> sub_base(ROOT, 0);
+  uint32_t used = 0;
+  for (uint32_t q = 0; q < ROOT; q++) if (sub_bits[q]) { sub_base[q] = ROOT + used; used += 1u << sub_bits[q]; }
+  if (used > sub_cap) return 2;
+  auto rev = [](uint32_t v, int bits) { uint32_t r = 0; for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i); return r; };
+  for (uint32_t q = 0; q < ROOT; q++) if (sub_bits[q]) lut[rev(q, RBITS)] = E_SUB | ((uint32_t)sub_bits[q] << 12) | (sub_base[q] << 16) | RBITS;
+  for (int s = 0; s < n; s++) {
+    int L = cl[s]; if (!L) continue;
+    uint32_t e = DIST ? entry_dist((uint32_t)s, (uint32_t)L) : entry_litlen((uint32_t)s, (uint32_t)L);
+    uint32_t c = codes[s];
+    if (L <= RBITS) { for (uint32_t idx = rev(c, L); idx < ROOT; idx += 1u << L) lut[idx] = e; }
+    else {
+      uint32_t q = c >> (L - RBITS); int sb = sub_bits[q], l2 = L - RBITS;
+      uint32_t low = rev(c & ((1u << l2) - 1), l2);
+      for (uint32_t idx = low; idx < (1u << sb); idx += 1u << l2) lut[sub_base[q] + idx] = e;
+    }
+  }
+  return 0;
+}
+
+struct Stats { long members = 0, blocks = 0, spans = 0, rounds = 0, lane_decodes = 0, lane_slots = 0, resolve_iters = 0, resolve_steps_max = 0, sub_overflow = 0, resolve_batches = 0; };
+
+
+// Host model of the kernel's one-warp resolver (same structure as resolve_member_warp in kernels_inflate_cta.cuh):
+// lanes are array slots, ballots / shuffles are loops.
+static int resolve_member_warp_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint32_t olimit, Stats& S) {
+  const uint32_t wend = (olimit + 31) >> 5;
+  for (uint32_t cw = obase >> 5; cw < wend; cw += 32) {
+    uint32_t hw[32], incl[32], total = 0;
+    for (int l = 0; l < 32; l++) { hw[l] = cw + l < wend ? hb[cw + l] : 0; if (cw + l < wend) hb[cw + l] = 0; total += __builtin_popcount(hw[l]); incl[l] = total; }
+    for (uint32_t b = 0; b < total; b += 32) {
+      S.resolve_batches++;
+      uint32_t o[32], dist[32], len[32], done[32]; bool pending[32];
+      for (int l = 0; l < 32; l++) {
+        uint32_t r = b + l; pending[l] = r < total; o[l] = dist[l] = len[l] = done[l] = 0;
+        if (!pending[l]) continue;
+        int j = 0; while (incl[j] <= r) j++;
+        uint32_t n = r - (incl[j] - __builtin_popcount(hw[j])), w = hw[j];
+        while (n--) w &= w - 1;
+        o[l] = (cw + j) * 32 + __builtin_ctz(w);
+        uint32_t v = win[o[l]] | (win[o[l] + 1] << 8) | (win[o[l] + 2] << 16);
+        dist[l] = (v & 0x7fff) + 1; len[l] = (v >> 15) + 3;
+      }
+      // dependency mask: the earlier lanes of this batch whose output range intersects this lane's source range
+      uint32_t dep[32];
+      for (int l = 0; l < 32; l++) {
+        dep[l] = 0;
+        if (!pending[l]) continue;
+        const uint32_t sa = o[l] - dist[l], sb = std::min(o[l], sa + len[l]);
+        for (int j = 0; j < l; j++) if (o[j] < sb && o[j] + len[j] > sa) dep[l] |= 1u << j;
+      }
+      for (;;) {
+        uint32_t pmask = 0; for (int l = 0; l < 32; l++) if (pending[l]) pmask |= 1u << l;
+        if (!pmask) break;
+        S.resolve_iters++;
+        bool ready[32];
+        for (int l = 0; l < 32; l++) ready[l] = pending[l] && (pmask & dep[l]) == 0;
+        // ready lanes read only final bytes (below their own match, outside every pending match) and write their own match
+        for (int l = 0; l < 32; l++) if (ready[l]) {
+          for (uint32_t k = 0; k < len[l]; k++) win[o[l] + k] = win[o[l] + k - dist[l]];
+          pending[l] = false;
+          if (len[l] > RESOLVE_PIECE) S.resolve_steps_max++;
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// One member through the modelled CTA.  Returns 0 ok, else an error code (string in *why).
+static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t isize, int NT, uint32_t span_bytes, std::vector<uint8_t>& out, Stats& S, std::string* why) {
+  // payload as words, with slack
+  std::vector<uint32_t> pay((clen + 3) / 4 + 16, 0);
+  memcpy(pay.data(), payload, clen);
+  const uint32_t obase = 5;                                     // any window offset (the kernel uses uoff & 15)
+  std::vector<uint8_t> win(obase + 65536 + 64, 0);
+  std::vector<uint32_t> bm((obase + 65536) / 32 + 4, 0);
+  std::vector<uint32_t> lut_ll(ROOT_LL + SUB_LL), lut_d(ROOT_D + SUB_D);
+  const uint32_t olimit = obase + isize;
+  const uint32_t end_bit = clen * 8;
+  uint32_t outpos = obase;
+  Bits br{pay.data(), 0};
+  bool final_block = false;
+  S.members++;
+  while (!final_block) {
+    if (br.pos + 3 > end_bit) { *why = "input exhausted at block header"; return 9; }
+    uint32_t hdr = br.take(3); final_block = hdr & 1; uint32_t btype = hdr >> 1;
+    S.blocks++;
+    if (btype == 3) { *why = "btype 3"; return 1; }
+    if (btype == 0) {
+      br.pos = (br.pos + 7) & ~7u;
+      if (br.pos + 32 > end_bit) { *why = "stored header past end"; return 9; }
+      uint32_t len = br.take(16), nlen = br.take(16);
+      if ((len ^ nlen) != 0xffff || outpos + len > olimit || br.pos / 8 + len > clen) { *why = "stored"; return 2; }
+      memcpy(win.data() + outpos, payload + br.pos / 8, len);
+      outpos += len; br.pos += 8 * len;
+      continue;
+    }
+    uint8_t cl[320] = {0}; int n_ll = 288, n_d = 30;
+    if (btype == 1) { for (int i = 0; i < 288; i++) cl[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8; for (int i = 0; i < 30; i++) cl[288 + i] = 5; }
+    else {
+      uint32_t h = br.take(14); n_ll = (h & 31) + 257; n_d = ((h >> 5) & 31) + 1; int n_clc = (h >> 10) + 4;
+      if (n_ll > 286 || n_d > 30) { *why = "hlit/hdist"; return 3; }
+      uint8_t pcl[19] = {0}; for (int i = 0; i < n_clc; i++) pcl[kClcOrder[i]] = (uint8_t)br.take(3);
+      std::vector<uint32_t> plut(128 + 8);
+      // precode: 7-bit root, no second level needed (max length 7)
+      {
+        int cnt[8] = {0}; for (int i = 0; i < 19; i++) cnt[pcl[i]]++; cnt[0] = 0;
+        uint32_t code = 0, first[8]; int left = 1;
+        for (int L = 1; L <= 7; L++) { code = (code + (L > 1 ? cnt[L - 1] : 0)) << 1; first[L] = code; left <<= 1; left -= cnt[L]; if (left < 0) { *why = "precode oversubscribed"; return 3; } }
+        for (auto& v : plut) v = 0;
+        for (int s = 0; s < 19; s++) { int L = pcl[s]; if (!L) continue; uint32_t c = first[L]++; uint32_t r = 0; for (int i = 0; i < L; i++) r |= ((c >> i) & 1u) << (L - 1 - i); for (uint32_t idx = r; idx < 128; idx += 1u << L) plut[idx] = (uint32_t)L | ((uint32_t)s << 16); }
+      }
+      int i = 0, total = n_ll + n_d; uint32_t prev = 0;
+      while (i < total) {
+        if (br.pos > end_bit) { *why = "input exhausted in code lengths"; return 9; }
+        uint32_t e = plut[br.peek(7)]; uint32_t L = e & 15, s = e >> 16;
+        if (!L) { *why = "bad precode"; return 3; }
+        br.pos += L;
+        uint32_t rep, val;
+        if (s < 16) { rep = 1; val = s; prev = s; }
+        else if (s == 16) { if (i == 0) { *why = "rep at 0"; return 3; } rep = 3 + br.take(2); val = prev; }
+        else if (s == 17) { rep = 3 + br.take(3); val = 0; prev = 0; }
+        else { rep = 11 + br.take(7); val = 0; prev = 0; }
+        if (i + (int)rep > total) { *why = "code lengths overrun"; return 3; }
+        while (rep--) cl[i++] = (uint8_t)val;
+      }
+      if (cl[256] == 0) { *why = "no EOB code"; return 3; }
+    }
+    int rc = build_lut<R_LL, false>(cl, n_ll, lut_ll.data(), SUB_LL);
+    if (!rc) rc = build_lut<R_D, true>(cl + n_ll, n_d, lut_d.data(), SUB_D);
+    if (rc == 2) { S.sub_overflow++; *why = "second-level table space exhausted"; return 100; }
+    if (rc) { *why = "oversubscribed"; return 3; }
+
+    // ---- spans: the symbol stream of this block, NT lanes at a time ----
+    uint32_t cur = br.pos;
+    bool block_done = false;
+    while (!block_done) {
+      S.spans++;
+      const uint32_t span_end = std::min<uint64_t>(end_bit, (uint64_t)cur + (uint64_t)span_bytes * 8);
+      if (cur >= end_bit) { *why = "input exhausted before end of block"; return 9; }
+      uint32_t Sbits = (span_end - cur + NT - 1) / NT; if (Sbits < 256) Sbits = 256;
+      std::vector<uint32_t> ls(NT), le(NT), lt(NT), ln(NT); std::vector<char> active(NT), need(NT);
+      for (int i = 0; i < NT; i++) { uint64_t p = (uint64_t)cur + (uint64_t)i * Sbits; active[i] = p < span_end; ls[i] = (uint32_t)p; need[i] = active[i]; }
+      int F = 0;
+      for (int round = 0;; round++) {
+        S.rounds++;
+        for (int i = 0; i < NT; i++) {
+          S.lane_slots++;
+          if (!need[i]) continue;
+          S.lane_decodes++;
+          uint32_t stop = std::min<uint64_t>(span_end, (uint64_t)cur + (uint64_t)(i + 1) * Sbits);
+          SubResult r = decode_sub<false>(pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, nullptr, nullptr, 0, 0, 0, nullptr);
+          le[i] = r.end_bit; lt[i] = r.term; ln[i] = r.n_out;
+        }
+        // first lane of the chain that does not hand over to a successor
+        F = NT - 1;
+        for (int i = 0; i < NT; i++) if (!active[i]) { F = i - 1; break; } else if (lt[i] != T_CROSS) { F = i; break; }
+        bool any = false;
+        for (int i = 0; i < NT; i++) {
+          need[i] = 0;
+          if (i == 0 || i > F) continue;
+          if (le[i - 1] != ls[i]) {
+            // the predecessor's chain may step over this lane's whole sub-stream (a long token): then this lane owns nothing
+            ls[i] = le[i - 1]; need[i] = 1; any = true;
+          }
+        }
+        if (!any) break;
+        if (round > NT + 2) { *why = "restart rounds did not converge"; return 50; }
+      }
+      // lanes 0..F are the true chain
+      if (lt[F] == T_BAD) { *why = "unused code on the true chain"; return 4; }
+      uint64_t total = 0; std::vector<uint32_t> lo(NT, 0);
+      for (int i = 0; i <= F; i++) { lo[i] = outpos + (uint32_t)total; total += ln[i]; }
+      if (outpos + total > olimit) { *why = "output overrun"; return 6; }
+      uint32_t err = 0;
+      for (int i = 0; i <= F; i++) {
+        uint32_t stop = std::min<uint64_t>(span_end, (uint64_t)cur + (uint64_t)(i + 1) * Sbits);
+        SubResult r = decode_sub<true>(pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, win.data(), bm.data(), lo[i], obase, olimit, &err);
+        if (err) { *why = err == CE_DIST ? "distance too far back" : "overrun in emit"; return (int)err; }
+        if (r.end_bit != le[i] || r.n_out != ln[i]) { *why = "emit pass disagrees with count pass"; return 51; }
+      }
+      outpos += (uint32_t)total;
+      if (lt[F] == T_EOB) { block_done = true; br.pos = le[F]; }
+      else {
+        cur = le[F];
+        if (span_end >= end_bit) { *why = "input exhausted before end of block"; return 9; }
+      }
+    }
+  }
+  if (outpos != olimit) { *why = "isize mismatch"; return 7; }
+  if (int rr = resolve_member_warp_model(win.data(), bm.data(), obase, olimit, S)) { *why = "resolver"; return rr; }
+  for (auto v : bm) if (v) { *why = "head bits left"; return 53; }
+  out.assign(win.begin() + obase, win.begin() + obase + isize);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: inflate_sim file.bam [--lanes N] [--max-members N] [--span-bytes B] [--stats]\n"); return 2; }
+  int NT = 256; long maxm = 1L << 40; uint32_t span_bytes = 28 * 1024; bool stats = false;
+  for (int i = 2; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "--lanes") NT = atoi(argv[++i]); else if (a == "--max-members") maxm = atol(argv[++i]);
+    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true;
+  }
+  FILE* f = fopen(argv[1], "rb"); if (!f) { perror("open"); return 2; }
+  fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> d(sz + 64, 0); if (fread(d.data(), 1, sz, f) != (size_t)sz) return 2; fclose(f);
+  Stats S; long off = 0, nm = 0, bad = 0; std::vector<uint8_t> out, ref(65536 + 16);
+  while (off + 28 <= sz && nm < maxm) {
+    if (d[off] != 0x1f || d[off + 1] != 0x8b) { fprintf(stderr, "not a gzip member at %ld\n", off); return 2; }
+    uint32_t xlen = d[off + 10] | (d[off + 11] << 8);
+    uint32_t bsize = 0; for (uint32_t x = 0; x + 4 <= xlen;) { const uint8_t* p = &d[off + 12 + x]; uint32_t slen = p[2] | (p[3] << 8); if (p[0] == 'B' && p[1] == 'C') bsize = p[4] | (p[5] << 8); x += 4 + slen; }
+    uint32_t hdr = 12 + xlen, clen = bsize + 1 - hdr - 8;
+    const uint8_t* payload = &d[off + hdr];
+    uint32_t isize; memcpy(&isize, &d[off + bsize + 1 - 4], 4);
+    if (isize) {
+      z_stream zs; memset(&zs, 0, sizeof zs); inflateInit2(&zs, -15);
+      zs.next_in = (Bytef*)payload; zs.avail_in = clen; zs.next_out = ref.data(); zs.avail_out = 65536 + 16;
+      int zr = inflate(&zs, Z_FINISH); inflateEnd(&zs);
+      std::string why;
+      int rc = inflate_member_sim(payload, clen, isize, NT, span_bytes, out, S, &why);
+      bool zok = zr == Z_STREAM_END && zs.total_out == isize;
+      if (rc == 100) { /* refused: second-level space */ }
+      else if (zok && (rc != 0 || memcmp(out.data(), ref.data(), isize))) { bad++; if (bad < 10) fprintf(stderr, "member %ld at %ld: MISMATCH rc=%d (%s)\n", nm, off, rc, why.c_str()); }
+      else if (!zok && rc == 0) { bad++; if (bad < 10) fprintf(stderr, "member %ld: zlib failed (%d) but the model succeeded\n", nm, zr); }
+    }
+    off += bsize + 1; nm++;
+  }
+  printf("%s: members=%ld bad=%ld refused(sub-table)=%ld | deflate blocks=%ld spans=%ld rounds/span=%.2f lane-decodes/span=%.1f (of %d) resolver rounds/member=%.0f batches/member=%.0f long-copies/member=%.0f\n", argv[1], S.members, bad, S.sub_overflow,
+         S.blocks, S.spans, (double)S.rounds / std::max(1L, S.spans), (double)S.lane_decodes / std::max(1L, S.spans), NT, (double)S.resolve_iters / std::max(1L, S.members), (double)S.resolve_batches / std::max(1L, S.members), (double)S.resolve_steps_max / std::max(1L, S.members));
+  (void)stats;
+  return bad ? 1 : 0;
+}
