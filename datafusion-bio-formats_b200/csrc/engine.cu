@@ -220,7 +220,8 @@ static double wall_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); retu
 constexpr int ICTA_NT = 256;                      // threads of the CTA-per-member inflate kernel
 using IctaCfg = icta::Cfg<ICTA_NT>;
 static bool g_crc_init[64] = {};
-static uint32_t* g_crc_tabs[64] = {};             // per device: tables of the in-window CRC stage (kernels_inflate_cta.cuh)
+static uint32_t* g_crc_tabs[64] = {};
+static unsigned long long* g_icta_prof = nullptr;   // bamscan_bench_inflate with BAMSCAN_ICTA_PROF=1: per-phase cycle counters             // per device: tables of the in-window CRC stage (kernels_inflate_cta.cuh)
 static int init_device_constants(int dev) {
   if (dev >= 64) { set_error("device id %d out of range", dev); return BAMSCAN_ERR_CUDA; }
   if (g_crc_init[dev]) return BAMSCAN_OK;
@@ -279,7 +280,7 @@ static int launch_inflate(const BamFile* f, cudaStream_t cs, const uint8_t* d_co
   }
   {
     const uint32_t grid = std::min<uint32_t>(nb, sms * 2u);
-    icta::inflate_cta_kernel<ICTA_NT><<<grid, ICTA_NT, IctaCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, d_aux + 1, g_crc_tabs[f->device], check_crc);
+    icta::inflate_cta_kernel<ICTA_NT><<<grid, ICTA_NT, IctaCfg::SMEM, cs>>>(d_comp, d_blk, nb, U, d_status, d_ticket, d_err, d_aux + 1, g_crc_tabs[f->device], check_crc, g_icta_prof);
     *launches += 1;
     // members flagged INF_RETRY (none on ordinary files); the launch finds nothing to do otherwise
     uint32_t rgrid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, sms);
@@ -1256,7 +1257,11 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   cudaMemcpy(blk.p, descs.data(), sizeof(BlockDesc) * nb, cudaMemcpyHostToDevice);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float total = 0;
+  const bool want_prof = getenv("BAMSCAN_ICTA_PROF") != nullptr;
+  const size_t prof_n = (size_t)device_sms(f->device) * 2 * 16;
+  if (want_prof) { cudaMalloc((void**)&g_icta_prof, prof_n * 8); }
   for (int rep = 0; rep < repeats + 1; rep++) {
+    if (want_prof) cudaMemsetAsync(g_icta_prof, 0, prof_n * 8, s->s_compute);
     cudaMemsetAsync(flags.p, 0, 64, s->s_compute);
     cudaEventRecord(e0, s->s_compute);
     int nl = 0;
@@ -1268,6 +1273,18 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
   }
   uint32_t hflags[16];
   cudaMemcpy(hflags, flags.p, 64, cudaMemcpyDeviceToHost);
+  if (want_prof) {   // last repetition: per-phase cycles of thread 0, summed over the CTAs, per member
+    std::vector<unsigned long long> h(prof_n);
+    cudaMemcpy(h.data(), g_icta_prof, prof_n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(g_icta_prof); g_icta_prof = nullptr;
+    unsigned long long sum[16] = {};
+    for (size_t i = 0; i < prof_n; i++) sum[i % 16] += h[i];
+    static const char* names[] = {"ticket", "payload load", "block header", "tables", "count rounds", "scan+emit", "resolve", "crc", "store+status"};
+    const double m = (double)std::max<unsigned long long>(1, sum[13]);
+    fprintf(stderr, "[icta prof] members %llu, count rounds/member %.2f; cycles per member:", sum[13], sum[12] / m);
+    for (int k = 0; k < 9; k++) fprintf(stderr, " %s %.0f |", names[k], sum[k] / m);
+    fprintf(stderr, "\n");
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (cudaGetLastError() != cudaSuccess || hflags[9]) { set_error("inflate benchmark failed (flag %u)", hflags[9]); return fail(BAMSCAN_ERR_CRC); }
   *ms_per_launch = total / std::max(1, repeats); *inflated_bytes = c.ubytes; *compressed_bytes = c.c1 - c.c0;

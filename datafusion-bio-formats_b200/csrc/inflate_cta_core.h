@@ -87,59 +87,73 @@ struct SubResult { uint32_t end_bit, term, n_out; };
 // Decodes tokens from bit `start_bit` of `pay` until the first token boundary at or after `stop_bit`, an end-of-block
 // symbol or an unused code.  EMIT = false: count only.  EMIT = true: literals and parked matches go into win[opos...]
 // (obase = window offset of the member's first byte, olimit = window offset one past the member's last byte).
-// A token is at most 48 bits; the caller guarantees that `pay` is readable 16 bytes past the word holding stop_bit.
+// A token is at most 48 bits; the caller guarantees that `pay` is readable 18 bytes past stop_bit.
+//
+// On the device ALL 32 lanes of a warp call this together (`enabled` = false for a lane with nothing to do): the loop
+// condition is a warp vote, so the lanes re-converge after every token.  (A per-lane `while` with `continue` / `break`
+// compiles to code whose lanes never re-converge inside the loop: measured, one active thread per issued instruction.)
+#if defined(__CUDA_ARCH__)
+#define ICTA_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define ICTA_ANY(x) (x)
+#endif
 template <bool EMIT>
-ICTA_HD SubResult decode_sub(const uint32_t* __restrict__ pay, const uint32_t* __restrict__ lut_ll, const uint32_t* __restrict__ lut_d,
+ICTA_HD SubResult decode_sub(bool enabled, const uint32_t* __restrict__ pay, const uint32_t* __restrict__ lut_ll, const uint32_t* __restrict__ lut_d,
                              uint32_t start_bit, uint32_t stop_bit,
                              uint8_t* win, uint32_t* hb, uint32_t opos, uint32_t obase, uint32_t olimit, uint32_t* err) {
-  uint32_t wi = start_bit >> 5;
+  uint32_t wi = enabled ? (start_bit >> 5) : 0u;
   const uint32_t sh = start_bit & 31u;
   uint64_t buf = (((uint64_t)pay[wi + 1] << 32) | pay[wi]) >> sh;
   uint32_t cnt = 64u - sh;                                   // valid bits in buf
   wi += 2;
   uint32_t pos = start_bit, n_out = 0, term = T_CROSS;
-  while (pos < stop_bit) {
-    if (cnt <= 32u) { buf |= (uint64_t)pay[wi] << cnt; cnt += 32u; wi++; }
-    uint32_t bits = (uint32_t)buf;
-    uint32_t e = lut_ll[bits & (ROOT_LL - 1u)];
-    if (e & E_SUB) e = lut_ll[(e >> 16) + ((bits >> R_LL) & ((1u << ((e >> 12) & 15u)) - 1u))];
-    const uint32_t nb = e & 15u;
-    if ((int32_t)e < 0) {                                    // literal
-      if (EMIT) {
-        if (opos >= olimit) { *err = CE_OVERRUN; term = T_BAD; break; }
-        win[opos] = (uint8_t)(e >> 16);
-        opos++;
+  bool live = enabled && pos < stop_bit;
+  while (ICTA_ANY(live)) {
+    if (live) {
+      if (cnt <= 32u) { buf |= (uint64_t)pay[wi] << cnt; cnt += 32u; wi++; }
+      uint32_t bits = (uint32_t)buf;
+      uint32_t e = lut_ll[bits & (ROOT_LL - 1u)];
+      if (e & E_SUB) e = lut_ll[(e >> 16) + ((bits >> R_LL) & ((1u << ((e >> 12) & 15u)) - 1u))];
+      const uint32_t nb = e & 15u;
+      if ((int32_t)e < 0) {                                    // literal
+        if (EMIT) {
+          if (opos >= olimit) { *err = CE_OVERRUN; term = T_BAD; }
+          else { win[opos] = (uint8_t)(e >> 16); opos++; }
+        }
+        n_out++;
+        buf >>= nb; cnt -= nb; pos += nb;
+      } else if (!(e & E_SYM)) {                               // end of block, or an unused code
+        if (e & E_EOB) { pos += nb; term = T_EOB; } else term = T_BAD;
+      } else {
+        const uint32_t xb = (e >> 4) & 15u;
+        const uint32_t len = ((e >> 16) & 0x7fffu) + ((bits >> nb) & ((1u << xb) - 1u));
+        uint32_t used = nb + xb;
+        buf >>= used; cnt -= used; pos += used;
+        if (cnt <= 32u) { buf |= (uint64_t)pay[wi] << cnt; cnt += 32u; wi++; }
+        bits = (uint32_t)buf;
+        uint32_t de = lut_d[bits & (ROOT_D - 1u)];
+        if (de & E_SUB) de = lut_d[(de >> 16) + ((bits >> R_D) & ((1u << ((de >> 12) & 15u)) - 1u))];
+        if (!(de & E_SYM)) term = T_BAD;
+        else {
+          const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
+          const uint32_t dist = ((de >> 16) & 0x7fffu) + ((bits >> dnb) & ((1u << dxb) - 1u));
+          used = dnb + dxb;
+          buf >>= used; cnt -= used; pos += used;
+          if (EMIT) {
+            if (dist > opos - obase) { *err = CE_DIST; term = T_BAD; }
+            else if (opos + len > olimit) { *err = CE_OVERRUN; term = T_BAD; }
+            else {
+              const uint32_t v = (dist - 1u) | ((len - 3u) << 15);   // parked in the match's own first three bytes
+              win[opos] = (uint8_t)v; win[opos + 1] = (uint8_t)(v >> 8); win[opos + 2] = (uint8_t)(v >> 16);
+              bm_or(hb + (opos >> 5), 1u << (opos & 31u));          // head bit
+              opos += len;
+            }
+          }
+          n_out += len;
+        }
       }
-      n_out++;
-      buf >>= nb; cnt -= nb; pos += nb;
-      continue;
+      live = term == T_CROSS && pos < stop_bit;
     }
-    if (!(e & E_SYM)) {                                      // end of block, or an unused code
-      if (e & E_EOB) { pos += nb; term = T_EOB; } else term = T_BAD;
-      break;
-    }
-    const uint32_t xb = (e >> 4) & 15u;
-    const uint32_t len = ((e >> 16) & 0x7fffu) + ((bits >> nb) & ((1u << xb) - 1u));
-    uint32_t used = nb + xb;
-    buf >>= used; cnt -= used; pos += used;
-    if (cnt <= 32u) { buf |= (uint64_t)pay[wi] << cnt; cnt += 32u; wi++; }
-    bits = (uint32_t)buf;
-    uint32_t de = lut_d[bits & (ROOT_D - 1u)];
-    if (de & E_SUB) de = lut_d[(de >> 16) + ((bits >> R_D) & ((1u << ((de >> 12) & 15u)) - 1u))];
-    if (!(de & E_SYM)) { term = T_BAD; break; }
-    const uint32_t dnb = de & 15u, dxb = (de >> 4) & 15u;
-    const uint32_t dist = ((de >> 16) & 0x7fffu) + ((bits >> dnb) & ((1u << dxb) - 1u));
-    used = dnb + dxb;
-    buf >>= used; cnt -= used; pos += used;
-    if (EMIT) {
-      if (dist > opos - obase) { *err = CE_DIST; term = T_BAD; break; }
-      if (opos + len > olimit) { *err = CE_OVERRUN; term = T_BAD; break; }
-      const uint32_t v = (dist - 1u) | ((len - 3u) << 15);   // parked in the match's own first three bytes
-      win[opos] = (uint8_t)v; win[opos + 1] = (uint8_t)(v >> 8); win[opos + 2] = (uint8_t)(v >> 16);
-      bm_or(hb + (opos >> 5), 1u << (opos & 31u));          // head bit
-      opos += len;
-    }
-    n_out += len;
   }
   SubResult r; r.end_bit = pos; r.term = term; r.n_out = n_out;
   return r;

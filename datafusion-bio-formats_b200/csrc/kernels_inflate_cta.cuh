@@ -45,18 +45,18 @@ struct Cfg {
   static constexpr uint32_t PAY_SLACK = 64;
   static constexpr uint32_t HB_WORDS = 2052;                  // head bitmap: one bit per window byte
   static constexpr uint32_t LUT_LL_WORDS = ROOT_LL + SUB_LL, LUT_D_WORDS = ROOT_D + SUB_D;
-  static constexpr uint32_t STAGE_PER_WARP = 352;             // heads of one 1 KB stripe (u16 each)
   static constexpr uint32_t OFF_WIN = 0;
-  static constexpr uint32_t OFF_PAY = OFF_WIN + WIN_BYTES;
-  static constexpr uint32_t OFF_HB = OFF_PAY + PAY_BYTES + PAY_SLACK;
-  static constexpr uint32_t OFF_LUT_LL = OFF_HB + HB_WORDS * 4;
+  static constexpr uint32_t OFF_HB = OFF_WIN + WIN_BYTES;
+  static constexpr uint32_t OFF_PAY = OFF_HB + HB_WORDS * 4;
+  static constexpr uint32_t OFF_LUT_LL = OFF_PAY + PAY_BYTES + PAY_SLACK;
   static constexpr uint32_t OFF_LUT_D = OFF_LUT_LL + LUT_LL_WORDS * 4;
   static constexpr uint32_t OFF_LANE_E = OFF_LUT_D + LUT_D_WORDS * 4;
   static constexpr uint32_t OFF_LANE_N = OFF_LANE_E + NT * 4;
   static constexpr uint32_t OFF_CTL = OFF_LANE_N + NT * 4;
   static constexpr uint32_t CTL_BYTES = 1024;
   static constexpr uint32_t SMEM = OFF_CTL + CTL_BYTES;
-  static_assert(STAGE_PER_WARP * 2 * WARPS <= (LUT_LL_WORDS + LUT_D_WORDS) * 4, "resolver staging aliases the LUTs");
+  // the resolver's in-order list of match heads (u16 each) aliases the payload buffer and the LUTs, which are dead by then
+  static constexpr uint32_t LIST_CAP = (OFF_LANE_E - OFF_PAY) / 2;
   static_assert(CrcTabs<NT>::WORDS * 4 <= PAY_BYTES, "CRC tables alias the payload buffer");
   static_assert(SMEM <= 113 * 1024, "two CTAs per SM");
 };
@@ -67,7 +67,7 @@ struct Ctl {
   uint32_t first_term[2];            // lowest lane whose chain does not hand over (double buffered per round)
   uint32_t last_lane, last_info;
   uint32_t warp_tot[32];
-  uint32_t front[32];
+  uint32_t n_matches;
   uint32_t crc_part[32];
   uint16_t cnt[2][16], first[2][16], nxt[2][16];
   uint8_t cl[320];
@@ -278,131 +278,109 @@ __device__ __noinline__ uint32_t read_dynamic_header_smem(SBits& br, uint32_t li
   return INF_OK;
 }
 
-// One warp resolves the parked matches whose heads lie in its part of the window, in position order.
-//   front[p]: every match of part p headed below front[p] is complete (FRONT_DONE: the whole part).
-// A source byte x of part p is final once x < front[p] and no unfinished match of part p-1 can still reach it.
+// RESOLVE, whole member, all warps.  `hb` holds one bit per parked match head on entry.
+//   A  every thread ranks the heads of its share of the bitmap words; a CTA scan turns that into an in-order list of
+//      head positions (u16, relative to obase); the bitmap words are zeroed on the way;
+//   B  the bitmap becomes the UNRESOLVED map: every byte of every parked match is flagged;
+//   C  dataflow: warp w takes the groups w, w + WARPS, ... of 32 consecutive matches.  A lane copies a piece (<= 16 bytes)
+//      of its match as soon as the map shows that the piece's source bytes are final, then clears the piece's bits.
+//      The lowest unresolved piece of the member always has final sources, and all warps work within a few hundred
+//      bytes of that frontier, so the wait of a lane is the real LZ77 dependency chain and nothing else.
+// Returns INF_OK or INF_RETRY (more matches than the list holds).
 template <int NT>
-__device__ __forceinline__ void resolve_part_warp(uint8_t* win, uint32_t* hb, uint16_t* stage, volatile uint32_t* front,
-                                                  uint32_t obase, uint32_t wbeg, uint32_t wend, uint32_t PW, int part, int lane, volatile uint32_t* err_out) {
-  const uint32_t p_beg = wbeg + (uint32_t)part * PW;
-  const uint32_t p_end = min(wend, p_beg + PW);
-  if (p_beg >= wend) { if (lane == 0) front[part] = FRONT_DONE; return; }
-  for (uint32_t cw = p_beg; cw < p_end; cw += 32) {
-    // heads of this 1 KB stripe, compacted in position order
-    const uint32_t widx = cw + lane;
-    uint32_t hw = 0;
-    if (widx < p_end) { hw = hb[widx]; hb[widx] = 0; }
-    const uint32_t c = __popc(hw);
-    uint32_t incl = c;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    {
-      uint32_t k = incl - c, w = hw;
-      while (w) { stage[k++] = (uint16_t)(widx * 32u + (uint32_t)__ffs((int)w) - 1u - obase); w &= w - 1u; }
+__device__ __forceinline__ uint32_t resolve_member(uint8_t* win, uint32_t* hb, uint16_t* list, uint32_t list_cap, Ctl* C,
+                                                   uint32_t obase, uint32_t olimit, int tid) {
+  constexpr int WARPS = NT / 32;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t wbeg = obase >> 5, wend = (olimit + 31u) >> 5;
+  const uint32_t WPT = (wend - wbeg + NT - 1) / NT;                 // bitmap words per thread (<= 9)
+  // ---- A: rank + list
+  const uint32_t w0 = wbeg + (uint32_t)tid * WPT, w1 = min(wend, w0 + WPT);
+  uint32_t cnt = 0;
+  for (uint32_t w = w0; w < w1; w++) cnt += __popc(hb[w]);
+  uint32_t incl = cnt;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) C->warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+  #pragma unroll
+  for (int w = 0; w < WARPS; w++) { const uint32_t t = C->warp_tot[w]; if (w < warp) base += t; total += t; }
+  if (total > list_cap) return INF_RETRY;                           // (uniform; the caller wipes the bitmap)
+  {
+    uint32_t k = base + incl - cnt;
+    for (uint32_t w = w0; w < w1; w++) {
+      uint32_t bits = hb[w];
+      hb[w] = 0;
+      while (bits) { list[k++] = (uint16_t)(w * 32u + (uint32_t)__ffs((int)bits) - 1u - obase); bits &= bits - 1u; }
     }
-    __syncwarp();
-    for (uint32_t b = 0; b < total; b += 32) {
-      const uint32_t r = b + lane;
-      const bool valid = r < total;
-      uint32_t o = 0xffffffffu, dist = 1, len = 0;
-      if (valid) {
-        o = obase + stage[r];
-        const uint32_t v = (uint32_t)win[o] | ((uint32_t)win[o + 1] << 8) | ((uint32_t)win[o + 2] << 16);
-        dist = (v & 0x7fffu) + 1u; len = (v >> 15) + 3u;
-      }
-      const uint32_t oend = valid ? o + len : 0xffffffffu;
-      const uint32_t sa = o - dist, sb = min(o, sa + len);          // the bytes this match needs from outside itself
-      // earlier lanes of this batch whose range intersects [sa, sb): positions are sorted, so two rank searches
-      uint32_t dep = 0;
-      const uint32_t batch_start = __shfl_sync(FULL, o, 0);
-      {
-        const bool inside = valid && sb > batch_start;
-        if (__any_sync(FULL, inside)) {
-          uint32_t j_lo = 0, j_hi = 0;
-          #pragma unroll
-          for (int s = 16; s; s >>= 1) {
-            const uint32_t ve = __shfl_sync(FULL, oend, (j_lo + s - 1) & 31), vo = __shfl_sync(FULL, o, (j_hi + s - 1) & 31);
-            if (ve <= sa) j_lo += s;
-            if (vo < sb) j_hi += s;
-          }
-          j_hi = min(j_hi, (uint32_t)lane);
-          if (inside && j_hi > j_lo) dep = ((j_hi >= 32u ? 0u : (1u << j_hi)) - 1u) & ~((1u << j_lo) - 1u);
-        }
-      }
-      // sources in another warp's part: wait for that warp's frontier (and, near a part start, for the part before it)
-      int need1 = -1, need2 = -1;
-      if (valid) {
-        const uint32_t wlast = (sb - 1u) >> 5;
-        int pw = 0;
-        #pragma unroll
-        for (int k = 1; k < NT / 32; k++) pw += (wlast >= wbeg + (uint32_t)k * PW) ? 1 : 0;
-        if (pw != part) need1 = pw;
-        if (pw > 0 && sa < (wbeg + (uint32_t)pw * PW) * 32u + 257u) need2 = pw - 1;
-      }
-      bool pend = valid;
-      uint32_t spins = 0;
-      for (;;) {
-        const uint32_t pmask = __ballot_sync(FULL, pend);
-        if (!pmask) break;
-        bool ok = pend && (pmask & dep) == 0;
-        if (ok && need1 >= 0) { if (front[need1] >= sb) need1 = -1; else ok = false; }
-        if (ok && need2 >= 0) { if (front[need2] == FRONT_DONE) need2 = -1; else ok = false; }
-        if (!__any_sync(FULL, ok)) {                                 // every remaining lane waits for another warp
-          if (++spins > (1u << 24)) { if (lane == 0) { *err_out = INF_ERR_INPUT; front[part] = FRONT_DONE; } return; }   // safety valve, never taken
-          continue;
-        }
-        __threadfence_block();
-        // up to RESOLVE_PIECE bytes per ready lane: all loads first (sources are final), then the stores
-        const uint32_t n = ok ? min(len, RESOLVE_PIECE) : 0u;
-        const uint32_t nmax = __reduce_max_sync(FULL, n);
-        {
-          uint8_t v[RESOLVE_PIECE];
-          uint32_t j = 0;
-          #pragma unroll
-          for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
-            if (k < nmax) {
-              if (k < n) { v[k] = win[sa + j]; j++; if (j == dist) j = 0; }
-            }
-          }
-          #pragma unroll
-          for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
-            if (k < nmax) { if (k < n) win[o + k] = v[k]; }
-          }
-        }
-        // the rest of a long match: all 32 lanes copy it
-        uint32_t lmask = __ballot_sync(FULL, ok && len > RESOLVE_PIECE);
-        while (lmask) {
-          const int src = __ffs((int)lmask) - 1;
-          lmask &= lmask - 1u;
-          const uint32_t lo_ = __shfl_sync(FULL, o, src), ld = __shfl_sync(FULL, dist, src), ll = __shfl_sync(FULL, len, src);
-          __syncwarp();
-          if (ld >= 32u) {
-            for (uint32_t kb = RESOLVE_PIECE; kb < ll; kb += 32) {    // a stripe only reads bytes written by earlier stripes
-              const uint32_t k = kb + lane;
-              if (k < ll) win[lo_ + k] = win[lo_ + k - ld];
-              __syncwarp();
-            }
-          } else {
-            for (uint32_t k = RESOLVE_PIECE + lane; k < ll; k += 32) win[lo_ + k] = win[lo_ - ld + (k % ld)];
-          }
-        }
-        pend = pend && !ok;
-        __syncwarp();
-        __threadfence_block();
-        // publish the frontier: head of the first unfinished match, or the next place a head can be
-        const uint32_t pm2 = __ballot_sync(FULL, pend);
-        uint32_t f;
-        if (pm2) f = __shfl_sync(FULL, o, __ffs((int)pm2) - 1);
-        else if (b + 32 < total) f = obase + stage[b + 32];
-        else f = (cw + 32 < p_end) ? (cw + 32) * 32u : FRONT_DONE;
-        if (lane == 0) front[part] = f;
-      }
-    }
-    __syncwarp();
   }
-  __threadfence_block();
-  if (lane == 0) front[part] = FRONT_DONE;
+  __syncthreads();
+  // ---- B: unresolved map
+  for (uint32_t r = tid; r < total; r += NT) {
+    const uint32_t o = obase + list[r];
+    const uint32_t len = ((((uint32_t)win[o + 1] << 8) | ((uint32_t)win[o + 2] << 16)) >> 15) + 3u;
+    uint32_t w = o >> 5, b = o & 31u, rem = len;
+    while (rem) {
+      const uint32_t n = min(rem, 32u - b);
+      atomicOr(hb + w, (n == 32u ? 0xffffffffu : ((1u << n) - 1u)) << b);
+      rem -= n; w++; b = 0;
+    }
+  }
+  __syncthreads();
+  // ---- C: dataflow
+  volatile uint32_t* const ub = hb;
+  for (uint32_t g = warp; g * 32u < total; g += WARPS) {
+    const uint32_t r = g * 32u + lane;
+    const bool valid = r < total;
+    uint32_t o = 0, dist = 1, len = 0;
+    if (valid) {
+      o = obase + list[r];
+      const uint32_t v = (uint32_t)win[o] | ((uint32_t)win[o + 1] << 8) | ((uint32_t)win[o + 2] << 16);
+      dist = (v & 0x7fffu) + 1u; len = (v >> 15) + 3u;
+    }
+    uint32_t done = 0, spins = 0;
+    bool pend = valid;
+    while (__any_sync(FULL, pend)) {
+      const uint32_t cur = o + done;
+      const uint32_t n = pend ? min(len - done, RESOLVE_PIECE) : 0u;
+      const uint32_t sa = cur - dist, sb = min(cur, sa + n);        // the piece's bytes that come from outside itself
+      bool ok = false;
+      if (pend) {
+        const uint32_t x = __funnelshift_r(ub[sa >> 5], ub[(sa >> 5) + 1], sa & 31u);
+        ok = (x & ((1u << (sb - sa)) - 1u)) == 0;
+      }
+      if (!__any_sync(FULL, ok)) {
+        __nanosleep(20);
+        if (++spins > (1u << 22)) { if (lane == 0) C->err = INF_ERR_INPUT; break; }    // safety valve, never taken
+        continue;
+      }
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+      const uint32_t nn = ok ? n : 0u;
+      const uint32_t nmax = __reduce_max_sync(FULL, nn);
+      {
+        uint8_t v[RESOLVE_PIECE];
+        uint32_t j = 0;
+        #pragma unroll
+        for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
+          if (k < nmax) { if (k < nn) { v[k] = win[sa + j]; j++; if (j == dist) j = 0; } }
+        }
+        #pragma unroll
+        for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
+          if (k < nmax) { if (k < nn) win[cur + k] = v[k]; }
+        }
+      }
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+      if (ok) {
+        const uint32_t w = cur >> 5, b = cur & 31u, m = (1u << n) - 1u;      // n <= 16
+        atomicAnd(hb + w, ~(m << b));
+        if (b + n > 32u) atomicAnd(hb + w + 1, ~(m >> (32u - b)));
+        done += n;
+        pend = done < len;
+      }
+    }
+  }
+  return INF_OK;
 }
 
 // CRC tables of the strided CRC (see Cfg / the CRC stage below); one launch per device at init.
@@ -444,7 +422,9 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 2)
 inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
                    uint8_t* __restrict__ infl, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                   uint32_t* __restrict__ err_flag, uint32_t* __restrict__ retry_count, const uint32_t* __restrict__ crc_tabs, int check_crc) {
+                   uint32_t* __restrict__ err_flag, uint32_t* __restrict__ retry_count, const uint32_t* __restrict__ crc_tabs, int check_crc,
+                   unsigned long long* __restrict__ prof) {
+  // prof (optional, profiling builds of the bench only): per-phase clock64() sums of thread 0, 16 slots per CTA
   using K = Cfg<NT>;
   constexpr int WARPS = K::WARPS;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -463,6 +443,8 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
   __syncthreads();
   uint32_t bar_parity = 0;
   bool store_pending = false;
+  long long t_prev = prof ? clock64() : 0;
+#define ICTA_PROF(slot) do { if (prof && tid == 0) { const long long t_now = clock64(); prof[blockIdx.x * 16 + (slot)] += (unsigned long long)(t_now - t_prev); t_prev = t_now; } } while (0)
 
   for (;;) {
     if (tid == 0) { C->ticket = atomicAdd(ticket, 1u); C->err = INF_OK; }
@@ -497,7 +479,9 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
     };
     uint32_t abs_bit = 0;                                                  // position in the payload, in bits
     const uint32_t end_bit = clen * 8u;
+    ICTA_PROF(0);
     if (!err) load_payload(0);
+    ICTA_PROF(1);
     if (store_pending) {                                                   // the previous member's bulk store must have read the window
       if (tid == 0) bulk_store_wait_read();
       store_pending = false;
@@ -535,6 +519,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         if (lane == 0) { C->btype = btype; C->final_block = hdr & 1u; C->hdr_end = br.pos + (uint32_t)(buf_lo * 8); C->stored_len = slen; if (e) C->err = e; }
       }
       __syncthreads();
+      ICTA_PROF(2);
       err = C->err;
       if (err) break;
       final_block = C->final_block != 0;
@@ -557,6 +542,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         if (WARPS == 1 && !e) e = build_lut_warp<R_D, true>(C->cl + n_ll, n_d, lut_d, SUB_D, C, 1, lane);
         if (e && lane == 0) atomicMax(&C->err, e);          // INF_RETRY (15) wins over a format error of the other table
         __syncthreads();
+        ICTA_PROF(3);
         err = C->err;
         if (err) break;
       }
@@ -577,10 +563,9 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         bool need = active;
         uint32_t my_e = 0, my_t = T_CROSS, my_n = 0, F = 0;
         for (int round = 0;; round++) {
-          if (need) {
-            const SubResult r = decode_sub<false>(pay, lut_ll, lut_d, my_s, my_stop, nullptr, nullptr, 0, 0, 0, nullptr);
-            my_e = r.end_bit; my_t = r.term; my_n = r.n_out;
-            laneE[tid] = my_e;
+          if (__any_sync(FULL, need)) {                       // (all lanes of a warp enter together: see decode_sub)
+            const SubResult r = decode_sub<false>(need, pay, lut_ll, lut_d, my_s, my_stop, nullptr, nullptr, 0, 0, 0, nullptr);
+            if (need) { my_e = r.end_bit; my_t = r.term; my_n = r.n_out; laneE[tid] = my_e; }
           }
           if (tid == 0) C->first_term[round & 1] = NT - 1;
           __syncthreads();
@@ -599,9 +584,11 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
             const uint32_t pe = laneE[tid - 1];
             if (pe != my_s) { my_s = pe; need = true; }
           }
+          if (prof && tid == 0) prof[blockIdx.x * 16 + 12] += 1;
           if (!__syncthreads_or(need ? 1 : 0)) break;
           if (round > NT + 2) { err = INF_ERR_INPUT; break; }
         }
+        ICTA_PROF(4);
         if (err) break;
         // F may name the first INACTIVE lane: the chain then ends at F - 1
         if ((uint32_t)tid == F) C->last_lane = active ? F : F - 1;
@@ -622,12 +609,13 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         if (last_t == T_BAD) { err = INF_ERR_SYMBOL; break; }
         if (outpos + total > olimit || total > 65536u) { err = INF_ERR_OVERRUN; break; }
         // ---- emit ----
-        if ((uint32_t)tid <= last) {
+        if ((uint32_t)(warp * 32) <= last) {
           uint32_t e2 = 0;
-          decode_sub<true>(pay, lut_ll, lut_d, my_s, my_stop, win, hb, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
+          decode_sub<true>((uint32_t)tid <= last, pay, lut_ll, lut_d, my_s, my_stop, win, hb, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
           if (e2) atomicMax(&C->err, e2);
         }
         __syncthreads();
+        ICTA_PROF(5);
         err = C->err;
         if (err) break;
         outpos += total;
@@ -639,15 +627,14 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
     if (!err && outpos != olimit) err = outpos > olimit ? INF_ERR_OVERRUN : INF_ERR_ISIZE;
 
     if (!err) {
-      // ---- resolve: every warp takes one part of the window ----
-      const uint32_t wbeg = obase >> 5, wend = (olimit + 31u) >> 5;
-      const uint32_t PW = (((wend - wbeg) + WARPS - 1) / WARPS + 31u) & ~31u;
-      if (tid < WARPS) C->front[tid] = (wbeg + (uint32_t)tid * PW) * 32u;
-      __syncthreads();
-      uint16_t* const stage = reinterpret_cast<uint16_t*>(lut_ll) + (uint32_t)warp * K::STAGE_PER_WARP;
-      resolve_part_warp<NT>(win, hb, stage, C->front, obase, wbeg, wend, PW, warp, lane, &C->err);
-      __syncthreads();
-      err = C->err;
+      // ---- resolve ----
+      {
+        uint16_t* const list = reinterpret_cast<uint16_t*>(smem + K::OFF_PAY);
+        const uint32_t e = resolve_member<NT>(win, hb, list, K::LIST_CAP, C, obase, olimit, tid);
+        __syncthreads();
+        err = e ? e : C->err;
+      }
+      ICTA_PROF(6);
 
       // ---- CRC-32 from the window (strided slicing-by-4: thread t owns words t, t+NT, ...; tables in the payload buffer) ----
       if (check_crc && !err) {
@@ -684,6 +671,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         }
         __syncthreads();
         err = C->err;
+        ICTA_PROF(7);
       }
     }
     if (!err) {
@@ -708,9 +696,12 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
       status[bi] = err;
       if (err == INF_RETRY) atomicAdd(retry_count, 1u);
       else if (err) atomicCAS(err_flag, 0u, (bi << 4) | err | 0x80000000u);
+      if (prof) prof[blockIdx.x * 16 + 13] += 1;
     }
     __syncthreads();
+    ICTA_PROF(8);
   }
+#undef ICTA_PROF
   if (store_pending && tid == 0) bulk_store_wait_read();
   // a bulk store must have finished reading shared memory before the CTA exits; writes complete with the grid
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

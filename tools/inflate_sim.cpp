@@ -69,48 +69,64 @@ static int build_lut(const uint8_t* cl, int n, uint32_t* lut, uint32_t sub_cap) 
 struct Stats { long members = 0, blocks = 0, spans = 0, rounds = 0, lane_decodes = 0, lane_slots = 0, resolve_iters = 0, resolve_steps_max = 0, sub_overflow = 0, resolve_batches = 0; };
 
 
-// Host model of the kernel's one-warp resolver (same structure as resolve_member_warp in kernels_inflate_cta.cuh):
-// lanes are array slots, ballots / shuffles are loops.
-static int resolve_member_warp_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint32_t olimit, Stats& S) {
-  const uint32_t wend = (olimit + 31) >> 5;
-  for (uint32_t cw = obase >> 5; cw < wend; cw += 32) {
-    uint32_t hw[32], incl[32], total = 0;
-    for (int l = 0; l < 32; l++) { hw[l] = cw + l < wend ? hb[cw + l] : 0; if (cw + l < wend) hb[cw + l] = 0; total += __builtin_popcount(hw[l]); incl[l] = total; }
-    for (uint32_t b = 0; b < total; b += 32) {
-      S.resolve_batches++;
-      uint32_t o[32], dist[32], len[32], done[32]; bool pending[32];
-      for (int l = 0; l < 32; l++) {
-        uint32_t r = b + l; pending[l] = r < total; o[l] = dist[l] = len[l] = done[l] = 0;
-        if (!pending[l]) continue;
-        int j = 0; while (incl[j] <= r) j++;
-        uint32_t n = r - (incl[j] - __builtin_popcount(hw[j])), w = hw[j];
-        while (n--) w &= w - 1;
-        o[l] = (cw + j) * 32 + __builtin_ctz(w);
-        uint32_t v = win[o[l]] | (win[o[l] + 1] << 8) | (win[o[l] + 2] << 16);
-        dist[l] = (v & 0x7fff) + 1; len[l] = (v >> 15) + 3;
-      }
-      // dependency mask: the earlier lanes of this batch whose output range intersects this lane's source range
-      uint32_t dep[32];
-      for (int l = 0; l < 32; l++) {
-        dep[l] = 0;
-        if (!pending[l]) continue;
-        const uint32_t sa = o[l] - dist[l], sb = std::min(o[l], sa + len[l]);
-        for (int j = 0; j < l; j++) if (o[j] < sb && o[j] + len[j] > sa) dep[l] |= 1u << j;
-      }
-      for (;;) {
-        uint32_t pmask = 0; for (int l = 0; l < 32; l++) if (pending[l]) pmask |= 1u << l;
-        if (!pmask) break;
-        S.resolve_iters++;
-        bool ready[32];
-        for (int l = 0; l < 32; l++) ready[l] = pending[l] && (pmask & dep[l]) == 0;
-        // ready lanes read only final bytes (below their own match, outside every pending match) and write their own match
-        for (int l = 0; l < 32; l++) if (ready[l]) {
-          for (uint32_t k = 0; k < len[l]; k++) win[o[l] + k] = win[o[l] + k - dist[l]];
-          pending[l] = false;
-          if (len[l] > RESOLVE_PIECE) S.resolve_steps_max++;
+// Host model of the kernel's resolver (resolve_member in kernels_inflate_cta.cuh): in-order list of match heads, the
+// head bitmap turned into an "unresolved" map, then W warps taking groups of 32 consecutive matches round-robin.  The
+// warps are stepped one iteration at a time in turn, so a lane really does wait for another warp's progress here.
+static int resolve_member_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint32_t olimit, int W, Stats& S) {
+  const uint32_t wbeg = obase >> 5, wend = (olimit + 31) >> 5;
+  std::vector<uint16_t> list;
+  for (uint32_t w = wbeg; w < wend; w++) { uint32_t bits = hb[w]; hb[w] = 0; while (bits) { list.push_back((uint16_t)(w * 32 + __builtin_ctz(bits) - obase)); bits &= bits - 1; } }
+  const uint32_t total = (uint32_t)list.size();
+  for (uint32_t r = 0; r < total; r++) {
+    uint32_t o = obase + list[r], len = (((win[o + 1] << 8) | (win[o + 2] << 16)) >> 15) + 3;
+    for (uint32_t k = 0; k < len; k++) hb[(o + k) >> 5] |= 1u << ((o + k) & 31);
+  }
+  struct Lane { uint32_t o, dist, len, done; bool pend; };
+  struct Warp { uint32_t g; bool loaded, finished; Lane l[32]; };
+  std::vector<Warp> ws(W);
+  for (int w = 0; w < W; w++) { ws[w].g = w; ws[w].loaded = false; ws[w].finished = (uint32_t)w * 32 >= total; }
+  int left = 0; for (auto& w : ws) if (!w.finished) left++;
+  long idle_turns = 0;
+  while (left) {
+    bool progressed = false;
+    for (int wi = 0; wi < W; wi++) {
+      Warp& w = ws[wi];
+      if (w.finished) continue;
+      if (!w.loaded) {
+        for (int l = 0; l < 32; l++) {
+          uint32_t r = w.g * 32 + l; Lane& L = w.l[l]; L.pend = r < total; L.done = 0; L.o = 0; L.dist = 1; L.len = 0;
+          if (L.pend) { L.o = obase + list[r]; uint32_t v = win[L.o] | (win[L.o + 1] << 8) | (win[L.o + 2] << 16); L.dist = (v & 0x7fff) + 1; L.len = (v >> 15) + 3; }
         }
+        w.loaded = true; S.resolve_batches++;
+      }
+      // one iteration of the warp's loop
+      bool ok[32]; uint32_t n[32]; bool any_ok = false, any_pend = false;
+      for (int l = 0; l < 32; l++) {
+        Lane& L = w.l[l]; ok[l] = false; n[l] = 0;
+        if (!L.pend) continue;
+        any_pend = true;
+        uint32_t cur = L.o + L.done; n[l] = std::min(L.len - L.done, RESOLVE_PIECE);
+        uint32_t sa = cur - L.dist, sb = std::min(cur, sa + n[l]);
+        bool clear = true; for (uint32_t x = sa; x < sb; x++) if (hb[x >> 5] >> (x & 31) & 1) clear = false;
+        ok[l] = clear; any_ok |= clear;
+      }
+      if (!any_pend) { w.g += W; w.loaded = false; if (w.g * 32 >= total) { w.finished = true; left--; } progressed = true; continue; }
+      S.resolve_iters++;
+      if (!any_ok) continue;
+      progressed = true;
+      for (int l = 0; l < 32; l++) if (ok[l]) {            // loads first (all sources are final), then stores
+        Lane& L = w.l[l]; uint32_t cur = L.o + L.done, sa = cur - L.dist; uint8_t v[16]; uint32_t j = 0;
+        for (uint32_t k = 0; k < n[l]; k++) { v[k] = win[sa + j]; if (++j == L.dist) j = 0; }
+        for (uint32_t k = 0; k < n[l]; k++) win[cur + k] = v[k];
+      }
+      for (int l = 0; l < 32; l++) if (ok[l]) {
+        Lane& L = w.l[l]; uint32_t cur = L.o + L.done;
+        for (uint32_t k = 0; k < n[l]; k++) hb[(cur + k) >> 5] &= ~(1u << ((cur + k) & 31));
+        L.done += n[l]; L.pend = L.done < L.len;
       }
     }
+    if (!progressed && ++idle_turns > 4) return 52;       // stalled: cannot happen (the lowest unresolved piece is always ready)
+    if (progressed) idle_turns = 0;
   }
   return 0;
 }
@@ -198,7 +214,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
           if (!need[i]) continue;
           S.lane_decodes++;
           uint32_t stop = std::min<uint64_t>(span_end, (uint64_t)cur + (uint64_t)(i + 1) * Sbits);
-          SubResult r = decode_sub<false>(pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, nullptr, nullptr, 0, 0, 0, nullptr);
+          SubResult r = decode_sub<false>(true, pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, nullptr, nullptr, 0, 0, 0, nullptr);
           le[i] = r.end_bit; lt[i] = r.term; ln[i] = r.n_out;
         }
         // first lane of the chain that does not hand over to a successor
@@ -224,7 +240,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
       uint32_t err = 0;
       for (int i = 0; i <= F; i++) {
         uint32_t stop = std::min<uint64_t>(span_end, (uint64_t)cur + (uint64_t)(i + 1) * Sbits);
-        SubResult r = decode_sub<true>(pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, win.data(), bm.data(), lo[i], obase, olimit, &err);
+        SubResult r = decode_sub<true>(true, pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, win.data(), bm.data(), lo[i], obase, olimit, &err);
         if (err) { *why = err == CE_DIST ? "distance too far back" : "overrun in emit"; return (int)err; }
         if (r.end_bit != le[i] || r.n_out != ln[i]) { *why = "emit pass disagrees with count pass"; return 51; }
       }
@@ -237,7 +253,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
     }
   }
   if (outpos != olimit) { *why = "isize mismatch"; return 7; }
-  if (int rr = resolve_member_warp_model(win.data(), bm.data(), obase, olimit, S)) { *why = "resolver"; return rr; }
+  if (int rr = resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
   for (auto v : bm) if (v) { *why = "head bits left"; return 53; }
   out.assign(win.begin() + obase, win.begin() + obase + isize);
   return 0;
@@ -275,8 +291,8 @@ int main(int argc, char** argv) {
     }
     off += bsize + 1; nm++;
   }
-  printf("%s: members=%ld bad=%ld refused(sub-table)=%ld | deflate blocks=%ld spans=%ld rounds/span=%.2f lane-decodes/span=%.1f (of %d) resolver rounds/member=%.0f batches/member=%.0f long-copies/member=%.0f\n", argv[1], S.members, bad, S.sub_overflow,
-         S.blocks, S.spans, (double)S.rounds / std::max(1L, S.spans), (double)S.lane_decodes / std::max(1L, S.spans), NT, (double)S.resolve_iters / std::max(1L, S.members), (double)S.resolve_batches / std::max(1L, S.members), (double)S.resolve_steps_max / std::max(1L, S.members));
+  printf("%s: members=%ld bad=%ld refused(sub-table)=%ld | deflate blocks=%ld spans=%ld rounds/span=%.2f lane-decodes/span=%.1f (of %d) resolver warp-iterations/member=%.0f groups/member=%.0f\n", argv[1], S.members, bad, S.sub_overflow,
+         S.blocks, S.spans, (double)S.rounds / std::max(1L, S.spans), (double)S.lane_decodes / std::max(1L, S.spans), NT, (double)S.resolve_iters / std::max(1L, S.members), (double)S.resolve_batches / std::max(1L, S.members));
   (void)stats;
   return bad ? 1 : 0;
 }

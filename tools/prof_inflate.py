@@ -8,7 +8,7 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "datafusion-bio-for
 import bench, bamscan
 reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 path, info = bench.ensure_bam(reads, 2, True)
-p = bamscan.BamTableProvider(str(path), None, True, bench.TAGS, False, True, 100, None, debug_flags=int(os.environ.get("BAMSCAN_DEBUG_FLAGS", "0")))
+p = bamscan.BamTableProvider(str(path), None, True, bench.TAGS, False, True, 100, None, debug_flags=int(os.environ.get("BAMSCAN_DEBUG_FLAGS", "0")), skip_crc=bool(int(os.environ.get("BAMSCAN_SKIP_CRC", "0"))))
 plan = p.scan(None, [], None, target_partitions=1, partition_mode="block_range")
 r = plan.bench_inflate(0, 5)
 gb = (r["inflated_bytes"] + r["compressed_bytes"]) / 1e9
