@@ -170,12 +170,12 @@ __device__ __noinline__ uint32_t build_lut_warp(const uint8_t* cl, int n, uint32
       if (q < ROOT) {
         slot = brev_n(q, RBITS);
         const uint32_t e = lut[slot];
-        if (e & E_SUB) { sb = e & 15u; sz = 1u << sb; }
+        if (e & E_SUB) { sb = e & 31u; sz = 1u << sb; }
       }
       uint32_t incl = sz;
       #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-      if (sz) lut[slot] = E_SUB | (sb << 12) | ((base + incl - sz) << 16) | (uint32_t)RBITS;
+      if (sz) lut[slot] = entry_sub((uint32_t)RBITS, sb, base + incl - sz);
       base += __shfl_sync(FULL, incl, 31);
     }
     if (base > ROOT + sub_cap) return INF_RETRY;          // (entries past the budget were never written: see the guard below)
@@ -187,7 +187,7 @@ __device__ __noinline__ uint32_t build_lut_warp(const uint8_t* cl, int n, uint32
       if (L > (uint32_t)RBITS) {
         const uint32_t cd = my_code[b], l2 = L - RBITS;
         const uint32_t pe = lut[brev_n(cd >> l2, RBITS)];
-        const uint32_t sbits = (pe >> 12) & 15u, sbase = pe >> 16;
+        const uint32_t sbits = pe & 31u, sbase = pe >> 16;
         const uint32_t e = DIST ? entry_dist((uint32_t)s, L) : entry_litlen((uint32_t)s, L);
         for (uint32_t idx = brev_n(cd & ((1u << l2) - 1u), l2); idx < (1u << sbits); idx += (1u << l2)) lut[sbase + idx] = e;
       }
@@ -204,8 +204,9 @@ struct SBits {
   __device__ __forceinline__ uint32_t take(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); pos += n; return v; }
 };
 
-// Dynamic block header (RFC 1951 3.2.7) by one warp: code lengths into C->cl.  The 7-bit precode LUT is built in lut_d.
-__device__ __noinline__ uint32_t read_dynamic_header_smem(SBits& br, uint32_t limit_bit, uint32_t* lut_d, Ctl* C, int lane) {
+// Dynamic block header (RFC 1951 3.2.7), part 1, one warp: HLIT / HDIST / HCLEN, the code-length code and its 7-bit LUT
+// (128 entries at `plut`: length | symbol << 16, 0 = unused).  Leaves br.pos at the first code-length symbol.
+__device__ __noinline__ uint32_t read_precode_warp(SBits& br, uint32_t* plut, Ctl* C, int lane) {
   const uint32_t h = br.take(14);
   const int n_ll = (int)(h & 31u) + 257, n_d = (int)((h >> 5) & 31u) + 1, n_clc = (int)(h >> 10) + 4;
   if (n_ll > 286 || n_d > 30) return INF_ERR_TABLE;
@@ -217,66 +218,102 @@ __device__ __noinline__ uint32_t read_dynamic_header_smem(SBits& br, uint32_t li
     br.pos += 3u * (uint32_t)n_clc;
   }
   __syncwarp();
-  // precode: max length 7, no second level
-  {
-    uint16_t* cnt = C->cnt[1]; uint16_t* first = C->first[1]; uint16_t* nxt = C->nxt[1];
-    if (lane < 16) { cnt[lane] = 0; nxt[lane] = 0; }
-    for (int i = lane; i < 128; i += 32) lut_d[i] = 0;
-    __syncwarp();
-    const uint32_t L = lane < 19 ? C->cl[lane] : 0u;
-    if (L) atomicAdd(reinterpret_cast<unsigned int*>(cnt) + (L >> 1), (L & 1) ? 0x10000u : 1u);
-    __syncwarp();
-    uint32_t code = 0, left = 1; bool over = false;
-    for (int len = 1; len <= 7; len++) {
-      const uint32_t c = cnt[len];
-      code = (code + cnt[len - 1]) << 1; left <<= 1;
-      if (c > left) over = true;
-      left -= c;
-      if (lane == len) first[len] = (uint16_t)code;
-    }
-    if (over) return INF_ERR_TABLE;
-    __syncwarp();
-    const uint32_t m = __match_any_sync(FULL, L);
-    const uint32_t r = __popc(m & ((1u << lane) - 1u));
-    if (L) {
-      const uint32_t cd = first[L] + r;
-      for (uint32_t idx = brev_n(cd, L); idx < 128u; idx += (1u << L)) lut_d[idx] = L | ((uint32_t)lane << 16);
-    }
-    __syncwarp();
-  }
-  const int total = n_ll + n_d;
-  int i = 0;
-  uint32_t prev = 0;
-  // 64-bit bit buffer in registers: the serial chain per code-length symbol is one LUT look-up
-  uint32_t wi = br.pos >> 5;
-  const uint32_t sh = br.pos & 31u;
-  uint64_t buf = (((uint64_t)br.w[wi + 1] << 32) | br.w[wi]) >> sh;
-  uint32_t cntb = 64u - sh, pos = br.pos;
-  wi += 2;
-  while (i < total) {
-    if (cntb <= 32u) { buf |= (uint64_t)br.w[wi] << cntb; cntb += 32u; wi++; }
-    const uint32_t bits = (uint32_t)buf;
-    const uint32_t e = lut_d[bits & 127u];
-    const uint32_t L = e & 15u, s = e >> 16;
-    if (L == 0) return INF_ERR_TABLE;
-    uint32_t rep, val, xb;
-    if (s < 16) { rep = 1; val = s; prev = s; xb = 0; }
-    else if (s == 16) { if (i == 0) return INF_ERR_TABLE; xb = 2; rep = 3 + ((bits >> L) & 3u); val = prev; }
-    else if (s == 17) { xb = 3; rep = 3 + ((bits >> L) & 7u); val = 0; prev = 0; }
-    else { xb = 7; rep = 11 + ((bits >> L) & 127u); val = 0; prev = 0; }
-    const uint32_t used = L + xb;
-    buf >>= used; cntb -= used; pos += used;
-    if (i + (int)rep > total) return INF_ERR_TABLE;
-    if (pos > limit_bit) return INF_ERR_INPUT;
-    for (uint32_t k = lane; k < rep; k += 32) C->cl[i + k] = (uint8_t)val;
-    i += (int)rep;
-  }
-  br.pos = pos;
+  uint16_t* cnt = C->cnt[1]; uint16_t* first = C->first[1];
+  if (lane < 16) cnt[lane] = 0;
+  for (int i = lane; i < 128; i += 32) plut[i] = 0;
   __syncwarp();
-  if (C->cl[256] == 0) return INF_ERR_TABLE;
+  const uint32_t L = lane < 19 ? C->cl[lane] : 0u;
+  if (L) atomicAdd(reinterpret_cast<unsigned int*>(cnt) + (L >> 1), (L & 1) ? 0x10000u : 1u);
+  __syncwarp();
+  uint32_t code = 0, left = 1; bool over = false;
+  for (int len = 1; len <= 7; len++) {
+    const uint32_t c = cnt[len];
+    code = (code + cnt[len - 1]) << 1; left <<= 1;
+    if (c > left) over = true;
+    left -= c;
+    if (lane == len) first[len] = (uint16_t)code;
+  }
+  if (over) return INF_ERR_TABLE;
+  __syncwarp();
+  const uint32_t m = __match_any_sync(FULL, L);
+  const uint32_t r = __popc(m & ((1u << lane) - 1u));
+  if (L) {
+    const uint32_t cd = first[L] + r;
+    for (uint32_t idx = brev_n(cd, L); idx < 128u; idx += (1u << L)) plut[idx] = L | ((uint32_t)lane << 16);
+  }
+  __syncwarp();
   C->n_ll = (uint32_t)n_ll; C->n_d = (uint32_t)n_d;
   return INF_OK;
 }
+
+// Part 2, whole CTA: the run-length coded code lengths.  One code-length symbol takes a warp ~300 cycles when it is decoded
+// serially (one LUT look-up per symbol on a dependent chain, sharing the issue slots with 15 other warps), and a member has
+// ~500 of them.  Here every thread decodes the symbol that WOULD start at its bit offsets (a table of 16-bit records:
+// bits consumed - 1 [3:0], kind [5:4] = 0 length / 1 repeat previous / 2 zeros / 3 invalid, value or run length [13:6]),
+// one thread then follows the chain of real symbols through that table (a handful of instructions per symbol), and all
+// threads expand the runs into C->cl.  Returns the error code; *end_pos = bit position behind the code lengths.
+template <int NT>
+__device__ __forceinline__ uint32_t read_code_lengths_cta(const uint32_t* pay, uint32_t start_pos, uint32_t limit_pos, const uint32_t* plut,
+                                                          uint16_t* tab, uint32_t tab_cap, uint32_t* chain, Ctl* C, int tid, uint32_t* end_pos) {
+  const uint32_t total = C->n_ll + C->n_d;
+  const uint32_t n_tab = min(tab_cap, limit_pos > start_pos ? limit_pos - start_pos : 0u);
+  for (uint32_t q = tid; q < n_tab; q += NT) {
+    const uint32_t p = start_pos + q;
+    const uint32_t bits = __funnelshift_r(pay[p >> 5], pay[(p >> 5) + 1], p & 31u);
+    const uint32_t e = plut[bits & 127u];
+    const uint32_t L = e & 15u, sy = e >> 16;
+    uint32_t rec;
+    if (L == 0) rec = 3u << 4;
+    else if (sy < 16u) rec = (L - 1u) | (sy << 6);
+    else if (sy == 16u) rec = (L + 2u - 1u) | (1u << 4) | ((3u + ((bits >> L) & 3u)) << 6);
+    else if (sy == 17u) rec = (L + 3u - 1u) | (2u << 4) | ((3u + ((bits >> L) & 7u)) << 6);
+    else rec = (L + 7u - 1u) | (2u << 4) | ((11u + ((bits >> L) & 127u)) << 6);
+    tab[q] = (uint16_t)rec;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t q = 0, i = 0, prev = 0, k = 0, e = INF_OK;
+    while (i < total) {
+      if (q >= n_tab) { e = n_tab == tab_cap ? INF_RETRY : INF_ERR_INPUT; break; }
+      const uint32_t t = tab[q];
+      const uint32_t kind = (t >> 4) & 3u, pl = t >> 6;
+      if (kind == 3u || (kind == 1u && i == 0u)) { e = INF_ERR_TABLE; break; }
+      const uint32_t rep = kind ? pl : 1u;
+      const uint32_t val = kind == 0u ? pl : (kind == 1u ? prev : 0u);
+      prev = val;
+      if (i + rep > total) { e = INF_ERR_TABLE; break; }
+      chain[k++] = i | (rep << 9) | (val << 17);
+      i += rep;
+      q += (t & 15u) + 1u;
+    }
+    C->last_lane = k;                 // (scratch: number of chain records)
+    C->last_info = q;
+    if (e) C->err = e;
+  }
+  __syncthreads();
+  if (C->err) return C->err;
+  const uint32_t k = C->last_lane;
+  for (uint32_t j = tid; j < k; j += NT) {
+    const uint32_t c = chain[j];
+    const uint32_t i0 = c & 511u, rep = (c >> 9) & 255u, val = c >> 17;
+    for (uint32_t r = 0; r < rep; r++) C->cl[i0 + r] = (uint8_t)val;
+  }
+  *end_pos = start_pos + C->last_info;
+  __syncthreads();
+  if (C->cl[256] == 0) return INF_ERR_TABLE;
+  return INF_OK;
+}
+
+// Ordering between a piece's data stores and the clearing of its map bits (writer), and between the map load and the data
+// loads (reader).  All of it is shared memory of ONE SM: a warp's shared-memory instructions are issued and performed in
+// program order, and the reader's data loads are control-dependent on the value its map load returned, so a compiler
+// barrier is what is needed in practice; BAMSCAN_ICTA_FENCES=1 puts fence.acq_rel.cta (MEMBAR.ALL.CTA, ~100 cycles on the
+// dependency chain, twice per hop) back.  Every member's CRC-32 is checked behind this stage either way.
+#if defined(BAMSCAN_ICTA_FENCES) && BAMSCAN_ICTA_FENCES
+#define ICTA_ORDER() asm volatile("fence.acq_rel.cta;" ::: "memory")
+#else
+#define ICTA_ORDER() asm volatile("" ::: "memory")
+#endif
 
 // RESOLVE, whole member, all warps.  `hb` holds one bit per parked match head on entry.
 //   A  every thread ranks the heads of its share of the bitmap words; a CTA scan turns that into an in-order list of
@@ -351,26 +388,37 @@ __device__ __forceinline__ uint32_t resolve_member(uint8_t* win, uint32_t* hb, u
         ok = (x & ((1u << (sb - sa)) - 1u)) == 0;
       }
       if (!__any_sync(FULL, ok)) {
-        __nanosleep(20);
-        if (++spins > (1u << 22)) { if (lane == 0) C->err = INF_ERR_INPUT; break; }    // safety valve, never taken
+#ifdef BAMSCAN_ICTA_SLEEP
+        if ((spins & 15u) == 15u) __nanosleep(BAMSCAN_ICTA_SLEEP);          // (a sleep is ~1 us: far longer than one hop of the dependency chain)
+#endif
+        if (++spins > (1u << 24)) { if (lane == 0) C->err = INF_ERR_INPUT; break; }    // safety valve, never taken
         continue;
       }
-      asm volatile("fence.acq_rel.cta;" ::: "memory");
-      const uint32_t nn = ok ? n : 0u;
-      const uint32_t nmax = __reduce_max_sync(FULL, nn);
-      {
-        uint8_t v[RESOLVE_PIECE];
-        uint32_t j = 0;
+      ICTA_ORDER();
+      // copy: source and destination of a ready piece are disjoint when dist >= n (the common case): head bytes up to
+      // the destination's word boundary, whole words (two aligned loads + funnel shift each), tail bytes
+      const bool wrap = ok && dist < n;
+      if (ok && !wrap) {
+        const uint32_t h = min(n, (4u - (cur & 3u)) & 3u);
         #pragma unroll
-        for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
-          if (k < nmax) { if (k < nn) { v[k] = win[sa + j]; j++; if (j == dist) j = 0; } }
-        }
+        for (uint32_t k = 0; k < 3; k++) if (k < h) win[cur + k] = win[sa + k];
+        const uint32_t mid = (n - h) >> 2;
+        const uint32_t s0 = sa + h, sh8 = (s0 & 3u) * 8u;
+        const uint32_t* const sw = reinterpret_cast<const uint32_t*>(win + (s0 & ~3u));
+        uint32_t* const dw = reinterpret_cast<uint32_t*>(win + cur + h);
         #pragma unroll
-        for (uint32_t k = 0; k < RESOLVE_PIECE; k++) {
-          if (k < nmax) { if (k < nn) win[cur + k] = v[k]; }
+        for (uint32_t jw = 0; jw < RESOLVE_PIECE / 4; jw++) if (jw < mid) dw[jw] = __funnelshift_r(sw[jw], sw[jw + 1], sh8);
+        const uint32_t t = h + 4u * mid;
+        #pragma unroll
+        for (uint32_t k = 0; k < 3; k++) if (t + k < n) win[cur + t + k] = win[sa + t + k];
+      }
+      if (__any_sync(FULL, wrap)) {            // a piece that overlaps its own source: byte k is src[k mod dist]
+        if (wrap) {
+          uint32_t j = 0;
+          for (uint32_t k = 0; k < n; k++) { win[cur + k] = win[sa + j]; j = j + 1 == dist ? 0 : j + 1; }
         }
       }
-      asm volatile("fence.acq_rel.cta;" ::: "memory");
+      ICTA_ORDER();
       if (ok) {
         const uint32_t w = cur >> 5, b = cur & 31u, m = (1u << n) - 1u;      // n <= 16
         atomicAnd(hb + w, ~(m << b));
@@ -437,6 +485,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
   uint32_t* const laneN = reinterpret_cast<uint32_t*>(smem + K::OFF_LANE_N);
   Ctl* const C = reinterpret_cast<Ctl*>(smem + K::OFF_CTL);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t win_s = smem_u32(win), pay_s = smem_u32(pay), hb_s = smem_u32(hb), ll_s = smem_u32(lut_ll), d_s = smem_u32(lut_d);
 
   for (uint32_t i = tid; i < K::HB_WORDS; i += NT) hb[i] = 0;
   if (tid == 0) mbar_init(&C->mbar, 1);
@@ -514,9 +563,17 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
           if (lane < 30) C->cl[288 + lane] = 5;
           if (lane == 0) { C->n_ll = 288; C->n_d = 30; }
         } else {
-          e = read_dynamic_header_smem(br, buf_bit(end_bit), lut_d, C, lane);
+          e = read_precode_warp(br, lut_d + ROOT_D, C, lane);
         }
         if (lane == 0) { C->btype = btype; C->final_block = hdr & 1u; C->hdr_end = br.pos + (uint32_t)(buf_lo * 8); C->stored_len = slen; if (e) C->err = e; }
+      }
+      __syncthreads();
+      if (C->btype == 2u && !C->err) {
+        // code lengths, whole CTA; the symbol table aliases the (not yet built) LUTs, the chain records the lane arrays
+        uint32_t endp = 0;
+        const uint32_t e = read_code_lengths_cta<NT>(pay, buf_bit(C->hdr_end), buf_bit(end_bit), lut_d + ROOT_D, reinterpret_cast<uint16_t*>(lut_ll),
+                                                     (K::LUT_LL_WORDS + ROOT_D) * 2u, laneE, C, tid, &endp);
+        if (tid == 0) { if (e) C->err = e; else C->hdr_end = endp + (uint32_t)(buf_lo * 8); }
       }
       __syncthreads();
       ICTA_PROF(2);
@@ -564,7 +621,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         uint32_t my_e = 0, my_t = T_CROSS, my_n = 0, F = 0;
         for (int round = 0;; round++) {
           if (__any_sync(FULL, need)) {                       // (all lanes of a warp enter together: see decode_sub)
-            const SubResult r = decode_sub<false>(need, pay, lut_ll, lut_d, my_s, my_stop, nullptr, nullptr, 0, 0, 0, nullptr);
+            const SubResult r = decode_sub<false>(need, pay_s, ll_s, d_s, my_s, my_stop, 0, 0, 0, 0, 0, nullptr);
             if (need) { my_e = r.end_bit; my_t = r.term; my_n = r.n_out; laneE[tid] = my_e; }
           }
           if (tid == 0) C->first_term[round & 1] = NT - 1;
@@ -611,7 +668,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         // ---- emit ----
         if ((uint32_t)(warp * 32) <= last) {
           uint32_t e2 = 0;
-          decode_sub<true>((uint32_t)tid <= last, pay, lut_ll, lut_d, my_s, my_stop, win, hb, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
+          decode_sub<true>((uint32_t)tid <= last, pay_s, ll_s, d_s, my_s, my_stop, win_s, hb_s, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
           if (e2) atomicMax(&C->err, e2);
         }
         __syncthreads();

@@ -51,7 +51,7 @@ static int build_lut(const uint8_t* cl, int n, uint32_t* lut, uint32_t sub_cap) 
   for (uint32_t q = 0; q < ROOT; q++) if (sub_bits[q]) { sub_base[q] = ROOT + used; used += 1u << sub_bits[q]; }
   if (used > sub_cap) return 2;
   auto rev = [](uint32_t v, int bits) { uint32_t r = 0; for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i); return r; };
-  for (uint32_t q = 0; q < ROOT; q++) if (sub_bits[q]) lut[rev(q, RBITS)] = E_SUB | ((uint32_t)sub_bits[q] << 12) | (sub_base[q] << 16) | RBITS;
+  for (uint32_t q = 0; q < ROOT; q++) if (sub_bits[q]) lut[rev(q, RBITS)] = entry_sub(RBITS, sub_bits[q], sub_base[q]);
   for (int s = 0; s < n; s++) {
     int L = cl[s]; if (!L) continue;
     uint32_t e = DIST ? entry_dist((uint32_t)s, (uint32_t)L) : entry_litlen((uint32_t)s, (uint32_t)L);
