@@ -238,11 +238,15 @@ static int init_device_constants(int dev) {
   return BAMSCAN_OK;
 }
 
-// ---- inflate ----
-//   inflate_cta_kernel (default)  one CTA per member, parallel inside the member, output window in shared memory, CRC fused
-//                                 (kernels_inflate_cta.cuh); members it refuses (INF_RETRY) are redone by inflate_kernel
-//   inflate_kernel                a warp per member (kernels_inflate.cuh): the retry path; debug_flags bit 2 forces it
-//   inflate_lg_kernel             4 lanes per member, 152 members per SM (round-1 throughput kernel): debug_flags bit 3, A/B baseline
+// ---- inflate: three kernels, one picked per launch ----
+//   inflate_cta_kernel   one CTA per member, parallel INSIDE the member (kernels_inflate_cta.cuh): 296 members in flight, a member
+//                        is done in ~0.3 ms.  Members it refuses (INF_RETRY) are redone by inflate_kernel.  Picked for every
+//                        launch of up to ICTA_MAX_MEMBERS members: region queries, tail chunks, small and long-read files.
+//   inflate_lg_kernel    4 lanes per member, 152 members per SM (22 496 in flight), a member takes ~17 ms: more members per
+//                        second on a FULL wave (15.9 ms against 20.1 ms measured), so whole-wave chunks of a big scan use it.
+//   inflate_kernel       a warp per member: the retry path of the first.
+//   debug_flags: bit 2 forces inflate_kernel, bit 3 inflate_lg_kernel, bit 4 inflate_cta_kernel (tests and A/B runs).
+constexpr uint32_t ICTA_MAX_MEMBERS = 16384;
 #ifndef BAMSCAN_LG_W
 #define BAMSCAN_LG_W 19
 #endif
@@ -265,7 +269,7 @@ static int launch_inflate(const BamFile* f, cudaStream_t cs, const uint8_t* d_co
     *launches += 1;
     return BAMSCAN_OK;
   }
-  if (f->debug_flags & 8) {          // tests / A-B: the round-1 lane-group kernel + separate CRC kernel
+  if ((f->debug_flags & 8) || (!(f->debug_flags & 16) && nb > ICTA_MAX_MEMBERS)) {   // lane-group kernel + separate CRC kernel
     const uint32_t per_cta = (uint32_t)(LgCfg::GROUPS * LG_W);
     const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, sms);
     int rc = slots->ensure((size_t)sms * per_cta * LG_SLOT_BYTES);

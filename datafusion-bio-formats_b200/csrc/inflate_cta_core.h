@@ -83,7 +83,7 @@ ICTA_HD uint32_t ld_volatile(const uint32_t* p) { return *p; }
 ICTA_HD uint32_t ffs32(uint32_t v) { return (uint32_t)__builtin_ffs((int)v); }
 #endif
 
-struct SubResult { uint32_t end_bit, term, n_out; };
+struct SubResult { uint32_t end_bit, term, n_out, first_bit; };   // first_bit: first token boundary at or after count_from (0xffffffff: the chain ended before it)
 
 // Decodes tokens from bit `start_bit` of `pay` until the first token boundary at or after `stop_bit`, an end-of-block
 // symbol or an unused code.  EMIT = false: count only.  EMIT = true: literals and parked matches go into win[opos...]
@@ -96,16 +96,18 @@ struct SubResult { uint32_t end_bit, term, n_out; };
 #if !defined(__CUDACC__)
 template <bool EMIT>
 inline SubResult decode_sub(bool enabled, const uint32_t* pay, const uint32_t* lut_ll, const uint32_t* lut_d,
-                            uint32_t start_bit, uint32_t stop_bit,
+                            uint32_t start_bit, uint32_t count_from, uint32_t stop_bit,
                             uint8_t* win, uint32_t* hb, uint32_t opos, uint32_t obase, uint32_t olimit, uint32_t* err) {
   uint32_t wi = enabled ? (start_bit >> 5) : 0u;
   const uint32_t sh = start_bit & 31u;
   uint64_t buf = (((uint64_t)pay[wi + 1] << 32) | pay[wi]) >> sh;
   uint32_t cnt = 64u - sh;                                   // valid bits in buf
   wi += 2;
-  uint32_t pos = start_bit, n_out = 0, term = T_CROSS;
+  uint32_t pos = start_bit, n_out = 0, term = T_CROSS, first_bit = 0xffffffffu;
   bool live = enabled && pos < stop_bit;
   while (live) {
+    const bool counting = pos >= count_from;                 // tokens in front of count_from only warm the chain up
+    if (counting && first_bit == 0xffffffffu) first_bit = pos;
     if (cnt <= 32u) { buf |= (uint64_t)pay[wi] << cnt; cnt += 32u; wi++; }
     uint32_t bits = (uint32_t)buf;
     uint32_t e = lut_ll[bits & (ROOT_LL - 1u)];
@@ -118,7 +120,7 @@ inline SubResult decode_sub(bool enabled, const uint32_t* pay, const uint32_t* l
         if (opos >= olimit) { *err = CE_OVERRUN; term = T_BAD; }
         else { win[opos] = (uint8_t)len; opos++; }
       }
-      n_out++;
+      if (counting) n_out++;
     } else if (e & E_SYM) {
       if (cnt <= 32u) { buf |= (uint64_t)pay[wi] << cnt; cnt += 32u; wi++; }
       bits = (uint32_t)buf;
@@ -139,14 +141,15 @@ inline SubResult decode_sub(bool enabled, const uint32_t* pay, const uint32_t* l
             opos += len;
           }
         }
-        n_out += len;
+        if (counting) n_out += len;
       }
     } else {
       term = (e & E_EOB) ? T_EOB : T_BAD;
     }
     live = term == T_CROSS && pos < stop_bit;
   }
-  SubResult r; r.end_bit = pos; r.term = term; r.n_out = n_out;
+  if (first_bit == 0xffffffffu && term == T_CROSS && pos >= count_from) first_bit = pos;
+  SubResult r; r.end_bit = pos; r.term = term; r.n_out = n_out; r.first_bit = first_bit;
   return r;
 }
 #else
@@ -159,16 +162,18 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volati
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 template <bool EMIT>
 __device__ __forceinline__ SubResult decode_sub(bool enabled, uint32_t pay_s, uint32_t ll_s, uint32_t d_s,
-                                                uint32_t start_bit, uint32_t stop_bit,
+                                                uint32_t start_bit, uint32_t count_from, uint32_t stop_bit,
                                                 uint32_t win_s, uint32_t hb_s, uint32_t opos, uint32_t obase, uint32_t olimit, uint32_t* err) {
   uint32_t wa = pay_s + ((enabled ? start_bit : 0u) >> 5) * 4u;
   const uint32_t sh = start_bit & 31u;
   uint64_t buf = (((uint64_t)lds_u32(wa + 4u) << 32) | lds_u32(wa)) >> sh;
   uint32_t cnt = 64u - sh;
   wa += 8u;
-  uint32_t pos = start_bit, n_out = 0, term = T_CROSS;
+  uint32_t pos = start_bit, n_out = 0, term = T_CROSS, first_bit = 0xffffffffu;
   bool live = enabled && pos < stop_bit;
   while (__any_sync(0xffffffffu, live)) {
+    const bool counting = live && pos >= count_from;           // tokens in front of count_from only warm the chain up
+    first_bit = min(first_bit, counting ? pos : 0xffffffffu);
     if (cnt <= 32u) { buf |= (uint64_t)lds_u32(wa) << cnt; cnt += 32u; wa += 4u; }     // (a finished lane refills at most once more)
     uint32_t bits = (uint32_t)buf;
     uint32_t e = lds_u32(ll_s + ((bits & (ROOT_LL - 1u)) << 2));
@@ -183,7 +188,7 @@ __device__ __forceinline__ SubResult decode_sub(bool enabled, uint32_t pay_s, ui
         if (opos >= olimit) { *err = CE_OVERRUN; term = T_BAD; }
         else { sts_u8(win_s + opos, len); opos++; }
       }
-      n_out++;
+      n_out += counting ? 1u : 0u;
     }
     if (cnt <= 32u) { buf |= (uint64_t)lds_u32(wa) << cnt; cnt += 32u; wa += 4u; }
     bits = (uint32_t)buf;
@@ -206,10 +211,11 @@ __device__ __forceinline__ SubResult decode_sub(bool enabled, uint32_t pay_s, ui
       }
     }
     buf >>= tot; cnt -= tot; pos += tot;
-    if (dok) n_out += len;
+    if (dok && counting) n_out += len;
     live = live && term == T_CROSS && pos < stop_bit;
   }
-  SubResult r; r.end_bit = pos; r.term = term; r.n_out = n_out;
+  if (first_bit == 0xffffffffu && term == T_CROSS && pos >= count_from) first_bit = pos;
+  SubResult r; r.end_bit = pos; r.term = term; r.n_out = n_out; r.first_bit = first_bit;
   return r;
 }
 #endif

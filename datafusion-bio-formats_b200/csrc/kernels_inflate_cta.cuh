@@ -31,6 +31,7 @@ namespace icta {
 constexpr uint32_t INF_RETRY = 15;          // status: redo this member with the warp-per-member kernel
 constexpr uint32_t FRONT_DONE = 0xffffffffu;
 constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is given
+constexpr uint32_t WARMUP_BITS = 640;       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
 
 // global constant tables of the CRC stage, filled once per device by crc_tables_init_kernel:
 //   [0, 1024)     four 256-entry tables of the operator "multiply by x^(32*NT)" (strided slicing-by-4)
@@ -616,13 +617,24 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         const uint32_t my_p = span_beg + (uint32_t)tid * S;
         const bool active = my_p < span_end;
         const uint32_t my_stop = min(my_p + S, span_end);
-        uint32_t my_s = my_p;
+        // round 0 starts every lane but the first `ov` bits EARLY and only warms the chain up until the lane's own cut is
+        // reached: by then it is almost always the true chain (self-synchronisation), so most spans need no second round
+        const uint32_t ov = min(WARMUP_BITS, S);
+        uint32_t my_s = (tid == 0 || my_p - span_beg <= ov) ? span_beg : my_p - ov;
         bool need = active;
         uint32_t my_e = 0, my_t = T_CROSS, my_n = 0, F = 0;
         for (int round = 0;; round++) {
           if (__any_sync(FULL, need)) {                       // (all lanes of a warp enter together: see decode_sub)
-            const SubResult r = decode_sub<false>(need, pay_s, ll_s, d_s, my_s, my_stop, 0, 0, 0, 0, 0, nullptr);
-            if (need) { my_e = r.end_bit; my_t = r.term; my_n = r.n_out; laneE[tid] = my_e; }
+            const uint32_t from = round == 0 ? (tid == 0 ? span_beg : my_p) : my_s;
+            const SubResult r = decode_sub<false>(need, pay_s, ll_s, d_s, my_s, from, my_stop, 0, 0, 0, 0, 0, nullptr);
+            if (need) {
+              my_e = r.end_bit; my_t = r.term; my_n = r.n_out;
+              if (round == 0) {
+                my_s = r.first_bit;                           // 0xffffffff (chain ended inside the warm-up) never equals a predecessor's end
+                if (r.first_bit == 0xffffffffu) { my_e = my_p; my_t = T_CROSS; my_n = 0; }
+              }
+              laneE[tid] = my_e;
+            }
           }
           if (tid == 0) C->first_term[round & 1] = NT - 1;
           __syncthreads();
@@ -668,7 +680,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         // ---- emit ----
         if ((uint32_t)(warp * 32) <= last) {
           uint32_t e2 = 0;
-          decode_sub<true>((uint32_t)tid <= last, pay_s, ll_s, d_s, my_s, my_stop, win_s, hb_s, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
+          decode_sub<true>((uint32_t)tid <= last, pay_s, ll_s, d_s, my_s, my_s, my_stop, win_s, hb_s, outpos + wbase + incl - cnt_n, obase, olimit, &e2);
           if (e2) atomicMax(&C->err, e2);
         }
         __syncthreads();

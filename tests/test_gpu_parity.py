@@ -20,12 +20,13 @@ def _oracle(path, **kw):
     return OracleBam(str(path), **kw)
 
 
-# Every test of this module runs once per inflate kernel: 0 = the default CTA-per-member kernel (kernels_inflate_cta.cuh),
-# debug_flags bit 2 forces the warp-per-member kernel (the retry path), bit 3 the round-1 lane-group kernel (A/B baseline).
+# Every test of this module runs once per inflate kernel (debug_flags): bit 4 forces the CTA-per-member kernel
+# (kernels_inflate_cta.cuh, what every launch of <= 16384 members uses), bit 2 the warp-per-member kernel (its retry path),
+# bit 3 the lane-group kernel (full waves of a big scan).
 _FORCE_INFLATE = 0
 
 
-@pytest.fixture(autouse=True, params=[0, 4, 8], ids=["cta_per_member", "warp_per_member", "lane_group"])
+@pytest.fixture(autouse=True, params=[16, 4, 8], ids=["cta_per_member", "warp_per_member", "lane_group"])
 def inflate_kernel(request):
     global _FORCE_INFLATE
     _FORCE_INFLATE = request.param

@@ -132,6 +132,7 @@ static int resolve_member_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint
 }
 
 // One member through the modelled CTA.  Returns 0 ok, else an error code (string in *why).
+static uint32_t overlap = 448;
 static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t isize, int NT, uint32_t span_bytes, std::vector<uint8_t>& out, Stats& S, std::string* why) {
   // payload as words, with slack
   std::vector<uint32_t> pay((clen + 3) / 4 + 16, 0);
@@ -205,7 +206,8 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
       if (cur >= end_bit) { *why = "input exhausted before end of block"; return 9; }
       uint32_t Sbits = (span_end - cur + NT - 1) / NT; if (Sbits < 256) Sbits = 256;
       std::vector<uint32_t> ls(NT), le(NT), lt(NT), ln(NT); std::vector<char> active(NT), need(NT);
-      for (int i = 0; i < NT; i++) { uint64_t p = (uint64_t)cur + (uint64_t)i * Sbits; active[i] = p < span_end; ls[i] = (uint32_t)p; need[i] = active[i]; }
+      std::vector<uint32_t> lp(NT);
+      for (int i = 0; i < NT; i++) { uint64_t p = (uint64_t)cur + (uint64_t)i * Sbits; active[i] = p < span_end; lp[i] = ls[i] = (uint32_t)p; need[i] = active[i]; }
       int F = 0;
       for (int round = 0;; round++) {
         S.rounds++;
@@ -214,7 +216,16 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
           if (!need[i]) continue;
           S.lane_decodes++;
           uint32_t stop = std::min<uint64_t>(span_end, (uint64_t)cur + (uint64_t)(i + 1) * Sbits);
-          SubResult r = decode_sub<false>(true, pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, nullptr, nullptr, 0, 0, 0, nullptr);
+          SubResult r;
+          if (round == 0 && i > 0) {
+            // warm-up: start `overlap` bits early so that the chain is (almost always) the true one when it reaches the lane's cut
+            const uint32_t from = lp[i] - cur > overlap ? lp[i] - overlap : cur;
+            r = decode_sub<false>(true, pay.data(), lut_ll.data(), lut_d.data(), from, lp[i], stop, nullptr, nullptr, 0, 0, 0, nullptr);
+            ls[i] = r.first_bit;                      // 0xffffffff: ended during the warm-up -> never equals a predecessor's end
+            if (r.first_bit == 0xffffffffu) { r.term = T_CROSS; r.end_bit = lp[i]; r.n_out = 0; }
+          } else {
+            r = decode_sub<false>(true, pay.data(), lut_ll.data(), lut_d.data(), ls[i], ls[i], stop, nullptr, nullptr, 0, 0, 0, nullptr);
+          }
           le[i] = r.end_bit; lt[i] = r.term; ln[i] = r.n_out;
         }
         // first lane of the chain that does not hand over to a successor
@@ -240,7 +251,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
       uint32_t err = 0;
       for (int i = 0; i <= F; i++) {
         uint32_t stop = std::min<uint64_t>(span_end, (uint64_t)cur + (uint64_t)(i + 1) * Sbits);
-        SubResult r = decode_sub<true>(true, pay.data(), lut_ll.data(), lut_d.data(), ls[i], stop, win.data(), bm.data(), lo[i], obase, olimit, &err);
+        SubResult r = decode_sub<true>(true, pay.data(), lut_ll.data(), lut_d.data(), ls[i], ls[i], stop, win.data(), bm.data(), lo[i], obase, olimit, &err);
         if (err) { *why = err == CE_DIST ? "distance too far back" : "overrun in emit"; return (int)err; }
         if (r.end_bit != le[i] || r.n_out != ln[i]) { *why = "emit pass disagrees with count pass"; return 51; }
       }
@@ -265,7 +276,7 @@ int main(int argc, char** argv) {
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--lanes") NT = atoi(argv[++i]); else if (a == "--max-members") maxm = atol(argv[++i]);
-    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true;
+    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--overlap") overlap = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true;
   }
   FILE* f = fopen(argv[1], "rb"); if (!f) { perror("open"); return 2; }
   fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
