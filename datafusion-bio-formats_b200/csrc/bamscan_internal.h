@@ -52,7 +52,7 @@ struct BaiIndex { std::vector<BaiRef> refs; bool has_no_coor = false; uint64_t n
 // == BamTableProvider (table_provider.rs:314-335)
 struct BamFile {
   std::string path, index_path;
-  uint8_t* data = nullptr;   // whole file: read-only mapping page-locked in place (cudaHostRegister), or a pinned copy
+  uint8_t* data = nullptr;   // whole file: read-only mapping (O_RDONLY / PROT_READ, not page-locked); small files: a plain copy
   uint64_t size = 0;
   bool pinned = false, mapped = false, registered = false;
   int device = 0;

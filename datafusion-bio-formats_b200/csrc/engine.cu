@@ -23,6 +23,8 @@
 #include <cstring>
 #include <ctime>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "bamscan_internal.h"
 #include "kernels_decode.cuh"
@@ -60,33 +62,38 @@ void* pinned_alloc(size_t bytes) {
 }
 void pinned_free(void* p) { if (!p) return; if (g_have_device) cudaFreeHost(p); else free(p); }
 
-// Maps the file and page-locks the mapping in place (cudaHostRegister): no private copy is made, and the N processes
-// of one node that scan the same file (one per GPU) share its page-cache pages.  The driver only accepts writable shared
-// mappings (measured on this stack: PROT_READ mappings are refused even with cudaHostRegisterReadOnly), so the file is
-// opened O_RDWR; nothing is ever written through the mapping.  Returns nullptr when this is not possible (read-only
-// file, no device): the caller then falls back to a page-locked copy.
+// Maps the file READ-ONLY (O_RDONLY, PROT_READ): the scan never needs write permission on the user's BAM, and nothing a
+// stray host or driver write could do reaches the file.  The mapping is not page-locked: compressed bytes reach the GPU
+// through a small ring of pinned staging buffers (issue_h2d), so pinned memory does not grow with the file, and the
+// per-GPU processes of one node share the page cache.
 void* map_file_pinned(const char* path, uint64_t size, bool* registered) {
   *registered = false;
-  if (!g_have_device) {
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) return nullptr;
-    void* p = mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
-    close(fd);
-    return p == MAP_FAILED ? nullptr : p;
-  }
-  int fd = open(path, O_RDWR);
+  int fd = open(path, O_RDONLY);
   if (fd < 0) return nullptr;
-  void* p = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+  void* p = mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
   close(fd);
   if (p == MAP_FAILED) return nullptr;
-  if (cudaHostRegister(p, size, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); munmap(p, size); return nullptr; }
-  *registered = true;
+  madvise(p, size, MADV_SEQUENTIAL);
   return p;
 }
 void unmap_file_pinned(void* p, uint64_t size, bool registered) {
+  (void)registered;
   if (!p) return;
-  if (registered) cudaHostUnregister(p);
   munmap(p, size);
+}
+
+// memcpy with a few threads: page cache -> pinned staging runs at ~10 GB/s per core, a chunk is ~0.5 GB
+static void parallel_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+  const size_t piece = 32u << 20;
+  unsigned t = (unsigned)std::min<size_t>(4, (n + piece - 1) / piece);
+  if (t <= 1) { memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((n + t - 1) / t + 4095) & ~size_t(4095);
+  for (unsigned i = 0; i < t; i++) {
+    const size_t a = std::min(n, (size_t)i * per), b = std::min(n, a + per);
+    if (a < b) th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+  }
+  for (auto& x : th) x.join();
 }
 
 // Tiny results (row counts, totals, error words) reach the host through mapped pinned memory written by a kernel:
@@ -202,6 +209,7 @@ struct BamScanStream {
   uint32_t* d_hflags = nullptr;           // device alias of h_flags (mapped)
   uint32_t* h_flags = nullptr;            // pinned mirror: [0..15] boundary flags / inflate err, [16..] totals (u64)
   BlockDesc* h_descs[2] = {nullptr, nullptr}; size_t h_descs_cap[2] = {0, 0}; uint32_t n_descs[2] = {0, 0}; uint32_t chunk_data_hi[2] = {0, 0};
+  uint8_t* h_stage[2] = {nullptr, nullptr}; size_t h_stage_cap[2] = {0, 0};   // pinned staging ring for the compressed bytes (the file mapping is read-only, not page-locked)
   int arena_flip = 0;
   // rows of the current chunk that are not decoded yet: a chunk is one inflate wave, a batch is one slice of its rows
   int64_t launched_chunk = -1;   // index in `chunks` of a chunk whose inflate + boundary kernels are already queued (run_chunk phase 1)
@@ -367,6 +375,7 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
                   &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf, &s->d_sorted}) b->release();
   if (s->h_flags) cudaFreeHost(s->h_flags);
   for (auto& hd : s->h_descs) if (hd) cudaFreeHost(hd);
+  for (auto& hs : s->h_stage) if (hs) cudaFreeHost(hs);
   for (auto& e : s->ev_h2d) if (e) cudaEventDestroy(e);
   if (s->ev_compute) cudaEventDestroy(s->ev_compute);
   if (s->ev_flags) cudaEventDestroy(s->ev_flags);
@@ -431,7 +440,17 @@ static int issue_h2d(BamScanStream* s, const ChunkPlan& c, int slot) {
   if (!s->device_resident) {
     size_t bytes = (size_t)(c.c1 - c.c0);
     if ((rc = s->d_comp[slot].ensure(bytes + 1024))) return rc;
-    CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->f->data + c.c0, bytes, cudaMemcpyHostToDevice, s->s_h2d));
+    // page cache -> pinned staging buffer of this slot (its previous transfer has long finished) -> one async copy
+    CU_TRY(cudaEventSynchronize(s->ev_h2d[slot]));
+    if (s->h_stage_cap[slot] < bytes) {
+      if (s->h_stage[slot]) cudaFreeHost(s->h_stage[slot]);
+      const size_t cap = bytes + bytes / 8 + 4096;
+      s->h_stage[slot] = (uint8_t*)pinned_alloc(cap);
+      if (!s->h_stage[slot]) { s->h_stage_cap[slot] = 0; return BAMSCAN_ERR_CUDA; }
+      s->h_stage_cap[slot] = cap;
+    }
+    parallel_copy(s->h_stage[slot], s->f->data + c.c0, bytes);
+    CU_TRY(cudaMemcpyAsync(s->d_comp[slot].p, s->h_stage[slot], bytes, cudaMemcpyHostToDevice, s->s_h2d));
     CU_TRY(cudaMemsetAsync(s->d_comp[slot].as<uint8_t>() + bytes, 0, 1024, s->s_h2d));   // the bit reader may look a few words past the last member
     s->st.h2d_bytes += bytes;
   }
@@ -932,7 +951,7 @@ static int decode_error_to_rc(uint32_t code, uint32_t row) {
     case DEC_ERR_TAG_RANGE: set_error("tag value in record %u does not fit the column type", row); return BAMSCAN_ERR_SCHEMA;
     case DEC_ERR_TAG_TYPE: set_error("tag value type mismatch in record %u", row); return BAMSCAN_ERR_SCHEMA;
     case DEC_ERR_UNSUPPORTED_F2S: set_error("record %u: float tag into a Utf8 column is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
-    case DEC_ERR_QUAL: set_error("record %u: quality score >= 95 (multi-byte char) is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
+    case DEC_ERR_QUAL: set_error("record %u: quality score in 95..222 (char::from(q + 33) is a two-byte UTF-8 sequence) is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
     case DEC_ERR_NAME: set_error("record %u: non-ASCII read name is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
   }
   set_error("decode error %u at record %u", code, row);

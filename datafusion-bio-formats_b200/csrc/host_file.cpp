@@ -99,11 +99,12 @@ int load_file(BamFile* f) {
   struct stat st;
   if (fstat(fileno(fp), &st) != 0) { fclose(fp); set_error("cannot stat %s", f->path.c_str()); return BAMSCAN_ERR_IO; }
   f->size = (uint64_t)st.st_size;
-  if (f->size >= (1u << 20)) {   // large files: map + page-lock in place (shared between the per-GPU processes of one node)
+  if (f->size >= (1u << 20)) {   // large files: read-only mapping (page cache shared between the per-GPU processes of one node)
     f->data = (uint8_t*)map_file_pinned(f->path.c_str(), f->size, &f->registered);
     f->mapped = f->data != nullptr;
+    if (!f->data) { fclose(fp); set_error("cannot map %s read-only", f->path.c_str()); return BAMSCAN_ERR_IO; }
   }
-  if (!f->data) {
+  if (!f->data) {                 // small file: a private copy (at most 1 MiB)
     f->data = (uint8_t*)pinned_alloc(f->size + 4096);
     if (!f->data) { fclose(fp); return BAMSCAN_ERR_CUDA; }
     f->pinned = true;

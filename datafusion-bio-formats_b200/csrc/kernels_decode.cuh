@@ -33,7 +33,7 @@ enum ColKind : int32_t {
 enum DecodeErr : uint32_t {
   DEC_OK = 0, DEC_ERR_FIELDS = 1 /* record fields exceed block_size */, DEC_ERR_REF = 2 /* reference id out of range */,
   DEC_ERR_CIGAR_OP = 3, DEC_ERR_TAG_RANGE = 4 /* value does not fit the column type */, DEC_ERR_TAG_TYPE = 5 /* value kind vs column kind */,
-  DEC_ERR_UNSUPPORTED_F2S = 6 /* float tag into Utf8 column */, DEC_ERR_QUAL = 7 /* quality >= 95: multi-byte char (unpinned) */,
+  DEC_ERR_UNSUPPORTED_F2S = 6 /* float tag into Utf8 column */, DEC_ERR_QUAL = 7 /* quality in 95..222: char::from(q + 33) is a two-byte UTF-8 sequence (unpinned; 0xFF wraps to ' ' and is fine) */,
   DEC_ERR_NAME = 8 /* non-ASCII read name (unpinned) */
 };
 
@@ -448,18 +448,20 @@ multi_scan_apply_kernel(ScanCols C, const uint64_t* __restrict__ tile_sums, uint
 
 // ---------------------------------------------------------------------------------------------
 // phase 3: one warp per record
-// out[i] = in[i] + add (byte-wise), 4 bytes per lane and step on destination-aligned words; the source word is assembled from
-// two aligned loads.  Returns (per lane) the OR of the "bad byte" masks: a byte >= 0x80 on input, or on output when add != 0.
+// out[i] = (in[i] + add) mod 256 (byte-wise, no carry between bytes), 4 bytes per lane and step on destination-aligned
+// words; the source word is assembled from two aligned loads.  Returns (per lane) the OR of the "bad byte" masks: an OUTPUT
+// byte >= 0x80 (a non-ASCII name byte; a quality q with 95 <= q <= 222, whose char::from(q + 33) is a two-byte UTF-8
+// sequence).  The missing-quality fill 0xFF wraps to 0x20 exactly as the reference's u8 addition does in a release build.
 // Reads up to 3 bytes past src + n (the inflated buffer carries slack).
 __device__ __forceinline__ uint32_t warp_map4(uint8_t* dst, const uint8_t* src, uint32_t n, int lane, uint32_t add4) {
   uint32_t bad = 0;
   const uint32_t add1 = add4 & 0xffu;
   if (n <= 32u) {                                              // names, short tags: one predicated byte load / store
-    if ((uint32_t)lane < n) { uint32_t c = src[lane]; bad = (c | ((c & 0x7fu) + add1)) & 0x80u; dst[lane] = (uint8_t)(c + add1); }
+    if ((uint32_t)lane < n) { const uint32_t c = (src[lane] + add1) & 0xffu; bad = c & 0x80u; dst[lane] = (uint8_t)c; }
     return bad;
   }
   const uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
-  if ((uint32_t)lane < head) { uint32_t c = src[lane]; bad |= (c | ((c & 0x7fu) + add1)) & 0x80u; dst[lane] = (uint8_t)(c + add1); }
+  if ((uint32_t)lane < head) { const uint32_t c = (src[lane] + add1) & 0xffu; bad |= c & 0x80u; dst[lane] = (uint8_t)c; }
   dst += head; src += head; n -= head;
   const uint32_t nw = n >> 2;
   const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
@@ -469,11 +471,12 @@ __device__ __forceinline__ uint32_t warp_map4(uint8_t* dst, const uint8_t* src, 
   for (uint32_t j = lane; j < nw; j += 32) {
     const uint32_t lo = sw[j];
     const uint32_t v = sh ? __funnelshift_r(lo, sw[j + 1], sh) : lo;
-    bad |= (v | ((v & 0x7f7f7f7fu) + add4)) & 0x80808080u;
-    dw[j] = v + add4;                                          // no inter-byte carry unless a byte is "bad" (then the scan fails anyway)
+    const uint32_t o = ((v & 0x7f7f7f7fu) + add4) ^ (v & 0x80808080u);     // per-byte sum mod 256 (add4 bytes are < 0x80)
+    bad |= o & 0x80808080u;
+    dw[j] = o;
   }
   const uint32_t t0 = nw << 2;
-  if (t0 + (uint32_t)lane < n) { uint32_t c = src[t0 + lane]; bad |= (c | ((c & 0x7fu) + add1)) & 0x80u; dst[t0 + lane] = (uint8_t)(c + add1); }
+  if (t0 + (uint32_t)lane < n) { const uint32_t c = (src[t0 + lane] + add1) & 0xffu; bad |= c & 0x80u; dst[t0 + lane] = (uint8_t)c; }
   return bad;
 }
 __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) { (void)warp_map4(dst, src, n, lane, 0u); }

@@ -31,6 +31,10 @@ namespace icta {
 constexpr uint32_t INF_RETRY = 15;          // status: redo this member with the warp-per-member kernel
 constexpr uint32_t FRONT_DONE = 0xffffffffu;
 constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is given
+#ifndef BAMSCAN_ICTA_RESOLVE_WARPS
+#define BAMSCAN_ICTA_RESOLVE_WARPS 8
+#endif
+constexpr int RESOLVE_WARPS = BAMSCAN_ICTA_RESOLVE_WARPS;
 constexpr uint32_t WARMUP_BITS = 640;       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
 
 // global constant tables of the CRC stage, filled once per device by crc_tables_init_kernel:
@@ -367,8 +371,11 @@ __device__ __forceinline__ uint32_t resolve_member(uint8_t* win, uint32_t* hb, u
   }
   __syncthreads();
   // ---- C: dataflow
+  // Only RESOLVE_WARPS warps take groups: a warp iterates about once per dependency level of the member whatever their
+  // number is, so more warps cost more issued instructions without shortening the chain.
   volatile uint32_t* const ub = hb;
-  for (uint32_t g = warp; g * 32u < total; g += WARPS) {
+  if (warp < RESOLVE_WARPS)
+  for (uint32_t g = warp; g * 32u < total; g += RESOLVE_WARPS) {
     const uint32_t r = g * 32u + lane;
     const bool valid = r < total;
     uint32_t o = 0, dist = 1, len = 0;

@@ -1,6 +1,8 @@
 import os
+import struct
 import subprocess
 import sys
+import zlib
 from pathlib import Path
 
 import pytest
@@ -49,3 +51,43 @@ def gen_bam(tmpdir: Path, mode="short", reads=20000, seed=1, bai=False, unmapped
 @pytest.fixture(scope="session")
 def syn_dir(tmp_path_factory):
     return tmp_path_factory.mktemp("syn")
+
+
+# ---- hand-made BAM with the edge cases the reference pins through write->read round trips (sam_read_test.rs) ----
+def _bgzf(payload: bytes) -> bytes:
+    out = b""
+    for i in range(0, max(1, len(payload)), 0xff00):
+        chunk = payload[i:i + 0xff00]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        cd = c.compress(chunk) + c.flush()
+        out += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    return out + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _rec(ref, pos, name, mapq, flag, cigar, seq, qual, nref, npos, tlen, aux=b""):
+    codes = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    cg = b"".join(struct.pack("<I", (l << 4) | "MIDNSHP=X".index(o)) for l, o in cigar)
+    sb = bytearray((len(seq) + 1) // 2)
+    for i, ch in enumerate(seq):
+        sb[i >> 1] |= codes[ch] << (4 if i % 2 == 0 else 0)
+    body = struct.pack("<iiBBHHHiiii", ref, pos, len(name) + 1, mapq, 4680, len(cigar), flag, len(seq), nref, npos, tlen) + name.encode() + b"\0" + cg + bytes(sb) + bytes(qual) + aux
+    return struct.pack("<i", len(body)) + body
+
+
+def make_edge_bam(path, missing_qual=False):
+    text = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chrA\tLN:1000\tM5:abc\n@SQ\tSN:chrB\tLN:2000\n@RG\tID:g1\tSM:s\tPL:ILLUMINA\tXX:y\n@PG\tID:p\tPN:prog\tVN:1\tCL:cmd \"q\"\n@CO\thello\tworld\n"
+    hdr = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 2)
+    for n, l in (("chrA", 1000), ("chrB", 2000)):
+        hdr += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    aux1 = b"NMC\x05" + b"MDZ10A5\0" + b"XSc\xfe" + b"XFf" + struct.pack("<f", 1.5) + b"XBBS" + struct.pack("<iHH", 2, 7, 65535) + b"XAAq" + b"XIi" + struct.pack("<i", -70000) + b"XUI" + struct.pack("<I", 4000000000)
+    recs = [
+        _rec(0, 99, "r1", 255, 99, [(5, "S"), (10, "M"), (2, "I"), (3, "D"), (4, "N"), (1, "="), (1, "X")], "ACGTNACGTNACGTNACGT", range(19), 1, 199, -160, aux1),
+        _rec(-1, -1, "*", 0, 4, [], "", [], -1, -1, 0),                       # name "*", unmapped, l_seq 0 (sam_read_test.rs:902-907)
+        _rec(1, 0, "r3", 60, 16, [(268435455, "M")], "A", [40], 0, 5, 160),   # max CIGAR length, odd l_seq
+        _rec(0, 5, "placed_no_cigar", 3, 133, [], "AC", [1, 2], 0, 5, 0),     # CIGAR-less placed read: end NULL (unpinned default)
+    ]
+    if missing_qual:   # SAM spec 4.2.3: SEQ present, QUAL '*' is stored as 0xFF bytes; char::from(q + 33) wraps to ' ' in a release build
+        recs.append(_rec(1, 7, "no_qual", 20, 0, [(40, "M")], "ACGT" * 10, [0xFF] * 40, -1, -1, 0))
+    path.write_bytes(_bgzf(hdr + b"".join(recs)))
+
+
