@@ -11,9 +11,13 @@ repo's own writer (tools/bamgen.cpp, seed 2, zlib level 6) under /dev/shm.
 value   : reads/s, device resident (compressed bytes already in HBM, Arrow buffers stay in HBM), CUDA-event time, max over ranks
 e2e     : same scan through the public provider API: H2D of the compressed bytes from pinned host memory and D2H of every
           Arrow buffer inside the timed region
-roofline: inflate_lg_kernel (dominant), algorithmic bytes = compressed bytes read + inflated bytes written, per launch
-N > 1   : weak scaling -- every rank scans one copy of the file on its own GPU (BGZF files concatenate, so this equals block-
-          range sharding of the N-fold concatenation); no collective on the data path.
+roofline: the inflate stage (dominant), algorithmic bytes = compressed bytes read + inflated bytes written, per launch
+N > 1   : STRONG scaling of the ONE file (BASELINE config 2, "by BGZF block range"): the plan has N block-range partitions,
+          rank r scans partition r on its own GPU (ranks > 0 find their first record by speculation); no collective on the
+          data path.  `replicas` keeps the round-1 number (every rank scans a whole copy) beside it.
+--verify: (outside every timed region) the default product path over a <= 10 M-read file of the same generator is compared
+          with the oracle, every row of every column (oracle/verify.py); the result goes into the line's "verify" key.
+--config: 2 (default) full projection | 3 fixed-width projection | 4 BAI region query chr1:50M-150M | 5 long reads
 """
 import argparse
 import json
@@ -39,10 +43,10 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def ensure_bam(reads: int, seed: int, want_bai: bool) -> tuple[Path, dict]:
+def ensure_bam(reads: int, seed: int, want_bai: bool, mode: str = "short") -> tuple[Path, dict]:
     base = Path(os.environ.get("BAMSCAN_BENCH_DIR", "/dev/shm/bamscan_bench"))
     base.mkdir(parents=True, exist_ok=True)
-    path = base / f"wgs_short_{reads}_s{seed}.bam"
+    path = base / f"wgs_{mode}_{reads}_s{seed}.bam"
     meta = path.with_suffix(".json")
     if path.exists() and meta.exists() and (not want_bai or Path(str(path) + ".bai").exists()):
         return path, json.loads(meta.read_text())
@@ -52,7 +56,7 @@ def ensure_bam(reads: int, seed: int, want_bai: bool) -> tuple[Path, dict]:
         exe.parent.mkdir(exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", str(exe), str(src), "-lz"])
     t0 = time.time()
-    out = subprocess.check_output([str(exe), "--mode", "short", "--reads", str(reads), "--seed", str(seed), "--out", str(path),
+    out = subprocess.check_output([str(exe), "--mode", mode, "--reads", str(reads), "--seed", str(seed), "--out", str(path),
                                    "--level", "6", "--bai"])
     info = json.loads(out.decode().strip().splitlines()[-1])
     info["generate_s"] = round(time.time() - t0, 1)
@@ -138,6 +142,63 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+CONFIG_KEYS = ("workload", "reads", "projection", "tags", "partitioning", "sample_reads_per_step")
+
+
+def make_config(reads, projection, partitioning, sample):
+    return {"workload": f"synthetic {reads}-read 150bp WGS-like BAM (BGZF lvl 6, tools/bamgen.cpp seed 2)", "reads": reads,
+            "projection": "all 12 core columns + tags" if projection is None else "chrom,start,end,mapping_quality,flags",
+            "tags": TAGS if projection is None else [], "partitioning": partitioning, "sample_reads_per_step": sample}
+
+
+def inflate_only_cpu(path, members=3000):
+    """zlib raw inflate + crc32 of the first `members` BGZF members on one thread (the reference links libdeflate,
+    which is ~2x faster than zlib and absent from this image)."""
+    import zlib
+    data = open(path, "rb").read(members * 30000)
+    off, n, out_bytes = 0, 0, 0
+    t0 = time.perf_counter()
+    while off + 28 <= len(data) and n < members:
+        bsize = struct.unpack_from("<H", data, off + 16)[0]
+        xlen = struct.unpack_from("<H", data, off + 10)[0]
+        if off + bsize + 1 > len(data):
+            break
+        payload = data[off + 12 + xlen: off + bsize + 1 - 8]
+        raw = zlib.decompress(payload, -15)
+        zlib.crc32(raw)
+        out_bytes += len(raw); off += bsize + 1; n += 1
+    dt = time.perf_counter() - t0
+    return {"inflated_gbps": out_bytes / dt / 1e9, "members": n, "threads": 1, "library": "zlib (python binding)"}
+
+
+def oracle_threads_scan(o, offs, total_reads, sample_reads, threads, steps=1, warmup=0):
+    """`threads` block-range partitions of a bounded prefix, one sequential decode loop each (the reference's one-thread-per-
+    partition model), batches of 8192 rows built and dropped."""
+    frac = min(1.0, sample_reads / total_reads)
+    hi = max(threads + 1, min(int(len(offs) * frac), len(offs) - 1))
+    cuts = [o.first_record_voffset] + [offs[(hi * k) // threads] for k in range(1, threads)] + [offs[hi] if frac < 1.0 else 0]
+    results = [None] * threads
+
+    def work(i):
+        _b, st = o.scan(None, start_voffset=cuts[i], stop_voffset=cuts[i + 1], batch_rows=8192, want_stats=True)
+        results[i] = st
+
+    def step():
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        t0 = time.perf_counter()
+        for t in ths: t.start()
+        for t in ths: t.join()
+        return time.perf_counter() - t0, sum(r["rows"] for r in results), sum(r["inflated_bytes"] for r in results)
+
+    for _ in range(warmup):
+        step()
+    tt, rows, infl = 0.0, 0, 0
+    for _ in range(steps):
+        dt, r, ib = step()
+        tt += dt; rows += r; infl += ib
+    return tt, rows, infl
+
+
 def run_reference(args, path, info, rank, world):
     """The reference's CPU path, restated (oracle/): one sequential decode loop per partition, all host threads."""
     if rank != 0:
@@ -146,45 +207,61 @@ def run_reference(args, path, info, rank, world):
     cores = os.cpu_count() or 1
     offs = bai_linear_offsets(Path(str(path) + ".bai"))
     o = OracleBam(str(path), tag_fields=TAGS)
-    # bounded sample: the first `frac` of the file, cut into `cores` partitions at exact record starts
     total_reads = info["reads"]
     target = min(total_reads, int(os.environ.get("BAMSCAN_REF_SAMPLE_READS", 1_000_000 * cores)))
-    frac = target / total_reads
-    hi = int(len(offs) * frac)
-    hi = max(cores + 1, min(hi, len(offs) - 1))
-    cuts = [o.first_record_voffset] + [offs[(hi * k) // cores] for k in range(1, cores)] + [offs[hi] if frac < 1.0 else 0]
-    results = [None] * cores
-
-    def work2(i):
-        _b, st = o.scan(None, start_voffset=cuts[i], stop_voffset=cuts[i + 1], batch_rows=8192, want_stats=True)
-        results[i] = st
-
-    def step():
-        ths = [threading.Thread(target=work2, args=(i,)) for i in range(cores)]
-        t0 = time.perf_counter()
-        for t in ths: t.start()
-        for t in ths: t.join()
-        return time.perf_counter() - t0, sum(r["rows"] for r in results), sum(r["inflated_bytes"] for r in results)
-
-    for _ in range(args.warmup):
-        step()
-    tt, rows, infl = 0.0, 0, 0
-    for _ in range(args.steps):
-        dt, r, ib = step()
-        tt += dt; rows += r; infl += ib
+    tt, rows, infl = oracle_threads_scan(o, offs, total_reads, target, cores, args.steps, args.warmup)
     value = rows / tt
-    sample = f"first {rows // args.steps} reads of the {total_reads}-read file per step, {cores} block-range partitions seeded from BAI linear-index record starts, batches of 8192 rows built and dropped"
+    per_step = rows // args.steps
+    sample = f"first {per_step} reads of the {total_reads}-read file per step, {cores} block-range partitions seeded from BAI linear-index record starts, batches of 8192 rows built and dropped"
     line = {
         "impl": "reference", "metric": "bam_scan_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * tt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "inflated_gbps": infl / tt / 1e9,
-        "config": {"workload": f"synthetic {total_reads}-read 150bp WGS-like BAM (BGZF lvl 6), full projection + tags {TAGS}",
-                   "reads": total_reads, "note": "CPU restatement of the reference path (noodles+libdeflate not buildable here; zlib inflate)"},
+        "config": make_config(total_reads, None, f"{cores} block-range partitions on {cores} host threads", per_step),
+        "note": "CPU restatement of the reference path (noodles + libdeflate are not buildable here; zlib inflate, ~2x slower than libdeflate); a bounded prefix per step",
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def bind_to_gpu_numa(local):
+    """Pins this rank's threads (and therefore its pinned-memory allocations) to the CPUs next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        cpus = Path(f"/sys/bus/pci/devices/{bus}/local_cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception as e:   # pragma: no cover
+        log(f"[bench] NUMA binding skipped ({e})")
+    return None
+
+
+def traffic_from_profile(kernel_sources):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (tools/ncu_traffic.py), valid only for the
+    kernel source it was taken on: a stale capture reads as null, never as a number."""
+    import hashlib
+    f = ROOT / "profiles" / "r2_inflate_traffic.json"
+    if not f.exists():
+        return None, "no ncu traffic capture committed (profiles/r2_inflate_traffic.json)"
+    d = json.loads(f.read_text())
+    h = hashlib.sha256(b"".join((PKG / "csrc" / k).read_bytes() for k in kernel_sources)).hexdigest()[:16]
+    if d.get("source_sha") != h:
+        return None, f"ncu capture is for kernel source {d.get('source_sha')}, tree has {h}: stale, not reported"
+    return d, "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (tools/ncu_traffic.py)"
 
 
 def main():
@@ -196,7 +273,12 @@ def main():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("BAMSCAN_BENCH_READS", 100_000_000)))
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--projection", default="full", choices=["full", "fixed"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--no-replicas", action="store_true")
     args = ap.parse_args()
+    if args.config == 3:
+        args.projection = "fixed"
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
 
@@ -206,6 +288,7 @@ def main():
             run_reference(args, path, info, rank, world)
         return
 
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     import torch
     dist = None
     if world > 1:
@@ -220,46 +303,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather(obj):
+        if dist is None:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    long_reads = args.config == 5
+    if long_reads:
+        args.reads = min(args.reads, int(os.environ.get("BAMSCAN_BENCH_LONG_READS", 1_000_000)))
     if rank == 0:
-        path, info = ensure_bam(args.reads, args.seed, True)
+        path, info = ensure_bam(args.reads, args.seed if not long_reads else 5, True, mode="long" if long_reads else "short")
     barrier()
     if rank != 0:
-        path, info = ensure_bam(args.reads, args.seed, True)
+        path, info = ensure_bam(args.reads, args.seed if not long_reads else 5, True, mode="long" if long_reads else "short")
 
     import bamscan
+    tags = TAGS if not long_reads else ["NM", "MD", "MM", "ML"]
     t_open = time.time()
-    provider = bamscan.BamTableProvider(str(path), None, True, TAGS, False, True, 100, None, device_id=local)
+    provider = bamscan.BamTableProvider(str(path), None, True, tags, False, True, 100, None, device_id=local,
+                                        index_path=None if args.config == 4 else "")
     projection = None if args.projection == "full" else [1, 2, 3, 6, 4]
-    # block_range with 1 partition == the reference's sequential single-partition scan of the whole file
-    plan = provider.scan(projection, [], None, target_partitions=1, partition_mode="block_range")
-    log(f"[bench r{rank}] open+pin+plan {time.time() - t_open:.1f}s")
+    filters = [("chrom", "=", ["chr1"]), ("start", "between", [50_000_000, 150_000_000])] if args.config == 4 else []
+    if args.config == 4:
+        plan = provider.scan(projection, filters, None, target_partitions=world)          # balance_partitions regions, one per GPU
+        partitioning = f"BAI region query chr1:50000000-150000000, {plan.output_partition_count()} balance_partitions regions over {world} GPU(s)"
+    else:
+        # block_range with N partitions: rank r owns the records that start in its block range (N = 1: the reference's sequential scan)
+        plan = provider.scan(projection, [], None, target_partitions=world, partition_mode="block_range")
+        partitioning = f"{world} BGZF block-range partition(s) of one file, one per GPU"
+    n_parts = plan.output_partition_count()
+    my_parts = [p for p in range(n_parts) if p % world == rank]
+    log(f"[bench r{rank}] open+plan {time.time() - t_open:.1f}s, partitions {my_parts} of {n_parts}, numa cpus {numa}")
+
+    def dev_pass(repeats):
+        tot = None
+        for p in my_parts:
+            st = plan.run_device_resident(p, repeats)
+            if tot is None:
+                tot = dict(st)
+            else:
+                for k, v in st.items():
+                    tot[k] = tot[k] + v
+        return tot or {"rows": 0, "ms_total": 0.0, "ms_inflate": 0.0, "ms_boundary": 0.0, "ms_decode": 0.0, "chunks": 0, "compressed_bytes": 0,
+                       "inflated_bytes": 0, "arrow_bytes": 0, "kernel_launches": 0, "boundary_repairs": 0, "boundary_seam_mismatches": 0, "blocks": 0}
 
     # ---------------- device-resident value ----------------
     if args.warmup > 0:
-        plan.run_device_resident(0, args.warmup)
+        dev_pass(args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    st = plan.run_device_resident(0, args.steps)
+    st = dev_pass(args.steps)
     barrier()
     wall_dev = time.perf_counter() - t0
     clocks = sampler.stop()
-    dev_s = st["ms_total"] / 1000.0 * args.steps
-    tmax = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_s_max = float(tmax.item())
-    rows = st["rows"]
-    value = world * rows * args.steps / dev_s_max
+    dev_s_max = all_max(st["ms_total"] / 1000.0 * args.steps)
+    rows_all = int(all_sum(st["rows"]))
+    value = rows_all * args.steps / dev_s_max
+    per_rank = gather({"rank": rank, "rows": st["rows"], "ms_per_step": st["ms_total"], "ms_inflate": st["ms_inflate"], "ms_boundary": st["ms_boundary"],
+                       "ms_decode": st["ms_decode"], "chunks": st["chunks"], "members": st["blocks"], "boundary_repairs": st["boundary_repairs"],
+                       "seam_mismatches": st["boundary_seam_mismatches"], "first_record": "exact (header end)" if rank == 0 else "speculated",
+                       "last_chunk_members": st["blocks"] % 22496 if st["chunks"] else 0, "kernel_launches": st["kernel_launches"],
+                       "first_record_uoff": st.get("first_record_uoff", 0), "end_chain_uoff": st.get("end_chain_uoff", 0)})
 
     # ---------------- end to end through the provider API ----------------
     def e2e_step():
-        n = 0; nb = 0
-        for b in plan.execute(0):
-            n += b.num_rows; nb += b.nbytes
-            del b
-        return n, nb
+        n = 0
+        for p in my_parts:
+            for b in plan.execute(p):
+                n += b.num_rows
+                del b
+        return n
 
     for _ in range(max(1, args.warmup)):   # warm-up: the pinned arena pool settles after a few scans
         e2e_step()
@@ -267,58 +396,92 @@ def main():
     t0 = time.perf_counter()
     e2e_rows = 0
     for _ in range(args.steps):
-        n, _nb = e2e_step()
-        e2e_rows += n
+        e2e_rows += e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    est = plan.last_stats
-    tmax2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tmax2, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_rows / float(tmax2.item())
+    e2e_s = all_max(time.perf_counter() - t0)
+    est = plan.last_stats if my_parts else {"h2d_bytes": 0, "d2h_bytes": 0}
+    e2e_value = all_sum(e2e_rows) / e2e_s
+    h2d_all, d2h_all = all_sum(est["h2d_bytes"]), all_sum(est["d2h_bytes"])
+
+    # ---------------- round-1 number beside it: every rank scans a whole copy ----------------
+    replicas = None
+    if world > 1 and not args.no_replicas and args.config in (2, 3):
+        rplan = provider.scan(projection, [], None, target_partitions=1, partition_mode="block_range")
+        rplan.run_device_resident(0, 1)
+        barrier()
+        rst = rplan.run_device_resident(0, 2)
+        barrier()
+        r_s = all_max(rst["ms_total"] / 1000.0 * 2)
+        replicas = {"value": world * rst["rows"] * 2 / r_s, "unit": "reads/s", "note": "every rank scans one whole copy of the file (weak scaling, what round 1 reported)"}
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
+    if args.config != 4 and world > 1:
+        # every partition must start where its predecessor's record chain landed: the speculated starts are proven, or the run fails
+        bamscan.check_partition_seams([dict(rows=r["rows"], first_record_uoff=r["first_record_uoff"], end_chain_uoff=r["end_chain_uoff"]) for r in per_rank])
     peak, peak_src = peaks()
     launches_inflate = max(1, st["chunks"])
     infl_alg = st["compressed_bytes"] + st["inflated_bytes"]
     infl_gbs = infl_alg / (st["ms_inflate"] / 1000.0) / 1e9 if st["ms_inflate"] > 0 else 0.0
     scan_alg = st["inflated_bytes"] + st["arrow_bytes"]
+    tr, tr_note = traffic_from_profile(["kernels_inflate.cuh", "kernels_inflate_cta.cuh", "inflate_cta_core.h"])
     line = {
         "metric": "bam_scan_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1000 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"synthetic {rows}-read 150bp WGS-like BAM (BGZF lvl 6), full projection + tags {TAGS}" if projection is None
-                   else f"synthetic {rows}-read BAM, projection chrom,start,end,mapping_quality,flags",
-                   "reads_per_gpu": rows, "compressed_bytes": st["compressed_bytes"], "inflated_bytes": st["inflated_bytes"],
-                   "arrow_bytes": st["arrow_bytes"], "chunks": st["chunks"], "l2": "inputs (>= 10x L2) stream from HBM; no reuse between steps",
-                   "sharding": "one file copy per GPU (block-range sharding of the N-fold concatenation), no collectives"},
-        "inflated_gbps": world * st["inflated_bytes"] * args.steps / dev_s_max / 1e9,
-        "scan_roofline_frac": (scan_alg / (st["ms_total"] / 1000.0) / 1e9) / peak,
-        "stage_ms": {"inflate": st["ms_inflate"], "boundary": st["ms_boundary"], "decode": st["ms_decode"], "total": st["ms_total"]},
-        "roofline": {"kernel": "inflate_lg_kernel (+ crc_kernel in the same event bracket)", "bound": "hbm", "achieved": infl_gbs, "peak": peak, "unit": "GB/s", "frac": infl_gbs / peak,
-                     "traffic": 12.11e9, "traffic_note": "dram read 10.60 GB + write 1.51 GB per full-wave launch (22496 members, 1.98 GB algorithmic), ncu --set full, profiles/r1_inflate_lg_final.md",
+        "config": make_config(info["reads"], projection, partitioning, rows_all) if not long_reads else
+        {"workload": f"synthetic {info['reads']}-read long-read BAM (10 kb, long CIGARs, MM/ML), tools/bamgen.cpp seed 5", "reads": info["reads"],
+         "projection": "all 12 core columns + tags", "tags": tags, "partitioning": partitioning, "sample_reads_per_step": rows_all},
+        "bytes_rank0": {"compressed": st["compressed_bytes"], "inflated": st["inflated_bytes"], "arrow": st["arrow_bytes"],
+                        "l2": "inputs (>= 10x L2) stream from HBM; no reuse between steps"},
+        "inflated_gbps": info["inflated_bytes"] * (rows_all / max(1, info["reads"])) * args.steps / dev_s_max / 1e9,
+        "scan_roofline_frac_rank0": (scan_alg / (st["ms_total"] / 1000.0) / 1e9) / peak if st["ms_total"] else None,
+        "stage_ms_rank0": {"inflate": st["ms_inflate"], "boundary": st["ms_boundary"], "decode": st["ms_decode"], "total": st["ms_total"]},
+        "roofline": {"kernel": "inflate stage of rank 0: inflate_lg_kernel + crc_kernel on full 22496-member waves, inflate_cta_kernel on chunks of <= 16384 members (same event bracket)",
+                     "bound": "hbm", "achieved": infl_gbs, "peak": peak, "unit": "GB/s", "frac": infl_gbs / peak,
+                     "traffic": (tr["dram_bytes_per_launch"] if tr else None), "traffic_note": tr_note,
                      "peak_source": peak_src, "launches": launches_inflate,
                      "alg_bytes_per_launch": infl_alg / launches_inflate, "ms_per_launch": st["ms_inflate"] / launches_inflate},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],
-                "ms_per_step": 1000 * float(tmax2.item()) / args.steps},
-        "gpu_launches": int(st["kernel_launches"] * args.steps),
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                "ms_per_step": 1000 * e2e_s / args.steps, "d2h_gbps_aggregate": d2h_all / (e2e_s / args.steps) / 1e9},
+        "gpu_launches": int(sum(r["kernel_launches"] for r in per_rank) * args.steps),
+        "per_rank": per_rank,
         "clocks": clocks, "wall_s_device_region": wall_dev,
     }
-    if world == 1:
-        # CPU baseline beside it: the oracle port, one thread, bounded sample
+    if replicas:
+        line["replicas"] = replicas
+    if world == 1 and args.config == 2:
+        # CPU baseline beside it (bounded samples): the oracle port on all host threads, on one thread, and inflate alone
         from oracle.bam_oracle import OracleBam
         o = OracleBam(str(path), tag_fields=TAGS)
-        sample_reads = min(rows, int(os.environ.get("BAMSCAN_CPU_SAMPLE_READS", 4_000_000)))
+        cores = os.cpu_count() or 1
+        offs = bai_linear_offsets(Path(str(path) + ".bai"))
+        n_all = min(info["reads"], int(os.environ.get("BAMSCAN_CPU_SAMPLE_READS", 500_000 * cores)))
+        tt, r_all, ib = oracle_threads_scan(o, offs, info["reads"], n_all, cores)
+        n_one = min(info["reads"], 2_000_000)
         t0 = time.perf_counter()
-        cst = o.time_scan(None, max_records=sample_reads, batch_rows=8192)
+        cst = o.time_scan(None, max_records=n_one, batch_rows=8192)
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": cst["rows"] / dt, "unit": "reads/s", "cores": 1, "kind": "port",
-                                "sample": f"first {cst['rows']} reads, sequential single-partition loop, zlib inflate+crc32, batches of 8192 built and dropped",
-                                "inflated_gbps": cst["inflated_bytes"] / dt / 1e9}
+        line["cpu_baseline"] = {"value": r_all / tt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {r_all} reads as {cores} block-range partitions on {cores} threads; zlib inflate + crc32, batches of 8192 built and dropped",
+                                "inflated_gbps": ib / tt / 1e9,
+                                "one_thread": {"value": cst["rows"] / dt, "unit": "reads/s", "cores": 1, "sample": f"first {cst['rows']} reads, one sequential loop",
+                                               "inflated_gbps": cst["inflated_bytes"] / dt / 1e9},
+                                "inflate_only": inflate_only_cpu(path)}
+    if args.verify:
+        from oracle.bam_oracle import OracleBam
+        from oracle.verify import verify_full_scan
+        vreads = min(args.reads, int(os.environ.get("BAMSCAN_VERIFY_READS", 10_000_000)))
+        vpath, _vinfo = ensure_bam(vreads, args.seed, True)
+        vp = bamscan.BamTableProvider(str(vpath), None, True, TAGS, False, True, 100, None, device_id=local, index_path="")
+        vo = OracleBam(str(vpath), tag_fields=TAGS)
+        rep = verify_full_scan(vo, str(vpath) + ".bai", vp.scan(None, [], None).execute(0), n_parts=max(8, vreads // 1_000_000), threads=os.cpu_count())
+        rep.pop("checksums", None)
+        rep["result"] = "bit-exact: per-column checksums over every row + RecordBatch equality on 3 windows"
+        line["verify"] = rep
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "bamscan_plan_range_info", "bamscan_plan_partition_regions", "bamscan_extract_regions", "bamscan_balance_partitions",
     "bamscan_execute", "bamscan_next",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
-    "bamscan_probe_pcie", "bamscan_last_error", "bamscan_version",
+    "bamscan_probe_pcie", "bamscan_check_partition_seams", "bamscan_last_error", "bamscan_version",
 ]
 
 
@@ -77,7 +77,7 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("blocks", C.c_uint64), ("kernel_launches", C.c_uint64), ("boundary_repairs", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_inflate", C.c_double), ("ms_boundary", C.c_double), ("ms_decode", C.c_double),
-                ("boundary_seam_mismatches", C.c_uint64)]
+                ("boundary_seam_mismatches", C.c_uint64), ("first_record_uoff", C.c_uint64), ("end_chain_uoff", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -236,11 +236,16 @@ class BamExec:
             L.bamscan_stream_free(st)
 
     def collect(self) -> pa.Table:
-        """All partitions in partition order (CoalescePartitionsExec over the leaf)."""
+        """All partitions in partition order (CoalescePartitionsExec over the leaf).  Block-range partitions > 0 speculate
+        their first record: the seams are checked (each partition must start where its predecessor's chain landed)."""
         schema = self.schema()
         batches = []
+        stats = []
         for p in range(self.output_partition_count()):
             batches += list(self.execute(p))
+            stats.append(self.last_stats)
+        if len(stats) > 1 and all(len(self.partition_ranges(p)) == 1 and self.partition_ranges(p)[0]["region_mode"] == 0 for p in range(len(stats))):
+            check_partition_seams(stats)
         if len(schema) == 0:
             return batches
         return pa.Table.from_batches(batches, schema=schema)
@@ -344,6 +349,16 @@ class BamTableProvider:
         _check(L.bamscan_plan(self._h, proj, n_proj, pack.arr, pack.n, -1 if limit is None else int(limit),
                               int(target_partitions), mode, C.byref(ph)))
         return BamExec(self, ph)
+
+
+def check_partition_seams(stats_list):
+    """Raises BamScanError unless every block-range partition starts where the chain of the one before it landed
+    (bamscan_check_partition_seams).  stats_list: last_stats dicts (or run_device_resident results) in partition order."""
+    arr = (Stats * len(stats_list))()
+    for i, d in enumerate(stats_list):
+        for k, _t in Stats._fields_:
+            setattr(arr[i], k, d.get(k, 0))
+    _check(load_library().bamscan_check_partition_seams(arr, len(stats_list)))
 
 
 def extract_genomic_regions(filters, coordinate_system_zero_based: bool) -> dict:

@@ -13,6 +13,7 @@
 // Two host syncs per chunk (row count; var-len totals) size the arena exactly.  A batch is handed out one
 // chunk late so its D2H overlaps the next chunk's kernels.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -102,6 +103,10 @@ __global__ void publish_kernel(const uint32_t* __restrict__ src, volatile uint32
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
   __threadfence_system();
 }
+
+// NVTX ranges around the pipeline steps of a chunk (host-side issue of H2D / inflate / boundaries / decode, the D2H wait):
+// an nsys timeline of the end-to-end path shows where a step's wall time goes.
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 struct DeviceBuf {
   void* p = nullptr; size_t cap = 0;
@@ -310,7 +315,7 @@ static int stream_init(BamScanStream* s) {
   s->range_idx = 0; s->chunks.clear(); s->chunk_idx = 0; s->range_open = false; s->finished = false;
   s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = false; s->tail_seen = false; s->range_stop = false;
   s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->cur.n = s->cur.pos = 0; s->launched_chunk = -1; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
-  s->st = BamScanStats{}; s->error = 0; s->d_comp_all = nullptr; s->comp_all_c0 = 0;
+  s->st = BamScanStats{}; s->st.first_record_uoff = ~0ull; s->error = 0; s->d_comp_all = nullptr; s->comp_all_c0 = 0;
   if (!s->resources_ready) {
   rc = init_device_constants(f->device);
   if (rc) return rc;
@@ -417,6 +422,7 @@ static void plan_chunks(const BamFile& f, uint32_t b0, uint32_t b1, bool extensi
 // Everything the compute stream needs from the host for this chunk travels here, so the copy engine never makes the
 // kernels of the previous chunk wait (a pageable copy issued on the compute stream would queue behind the big transfer).
 static int issue_h2d(BamScanStream* s, const ChunkPlan& c, int slot) {
+  NvtxRange nv("bamscan: stage + H2D of a chunk's compressed members");
   const BamFile* f = s->f;
   const uint32_t nb_all = c.b1 - c.b0;
   if (s->h_descs_cap[slot] < nb_all) {
@@ -465,6 +471,7 @@ struct ArenaBuilder {
 
 // Decodes the next slice of the current chunk's rows into a fresh arena and queues its D2H (one batch).
 static int decode_slice(BamScanStream* s, bool* produced) {
+  NvtxRange nv("bamscan: decode slice (fixed, scan, var) + D2H issue");
   BamFile* f = s->f;
   cudaStream_t cs = s->s_compute;
   int rc;
@@ -647,6 +654,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
 static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& range, int slot, bool first_of_range, bool* produced, uint32_t* new_carry, bool* owned_done, int phase) {
   BamFile* f = s->f;
   *produced = false;
+  NvtxRange nv(phase == 1 ? "bamscan: queue inflate + record boundaries (ahead)" : phase == 2 ? "bamscan: chunk boundaries -> rows" : "bamscan: inflate + record boundaries");
   static const bool trace2 = getenv("BAMSCAN_TRACE") && atoi(getenv("BAMSCAN_TRACE")) >= 2;
   const double tw0 = wall_ms();
   const uint32_t nb_all = c.b1 - c.b0;
@@ -694,6 +702,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaMemsetAsync(d_flags + 2, 0xff, 4, cs));     // [2] tail offset
   CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
   CU_TRY(cudaMemsetAsync(d_flags + 11, 0xff, 4, cs));    // [11] first disagreeing seam
+  CU_TRY(cudaMemsetAsync(d_flags + 13, 0xff, 4, cs));    // [13] first owned record of the chunk
   CU_TRY(cudaEventRecord(s->ev_t[0], cs));
   if (nb) {
     int nl = 0;
@@ -739,6 +748,9 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   if (*new_carry > HEADROOM) { set_error("BAM record larger than %u bytes is not supported", HEADROOM); return BAMSCAN_ERR_UNSUPPORTED; }
   if (*new_carry) CU_TRY(cudaMemcpyAsync(s->d_carry.p, U + tail_off, *new_carry, cudaMemcpyDeviceToDevice, cs));
   s->st.chunks++; s->st.blocks += nb; s->st.inflated_bytes += c.ubytes; s->st.compressed_bytes += c.c1 - c.c0;
+  // seam evidence of block-range partitions (BamScanStats): where the first owned record starts, where the chain lands
+  if (n_rec > 0 && s->st.first_record_uoff == ~0ull && hf[13] != 0xffffffffu && hf[13] >= HEADROOM) s->st.first_record_uoff = c.u0 + (hf[13] - HEADROOM);
+  if (*owned_done) s->st.end_chain_uoff = c.u0 + (uint64_t)tail_off - HEADROOM;
   CU_TRY(cudaEventRecord(s->ev_t[2], cs));
   if (n_rec == 0) { CU_TRY(cudaEventRecord(s->ev_t[3], cs)); goto timing; }
   {
@@ -960,6 +972,7 @@ static int decode_error_to_rc(uint32_t code, uint32_t row) {
 
 // waits for the pending batch's D2H and queues it (sliced to batch_rows) for hand-out
 static int finalize_pending(BamScanStream* s) {
+  NvtxRange nv("bamscan: wait for a batch's D2H");
   PendingBatch& P = s->pending;
   if (!P.valid) return BAMSCAN_OK;
   CU_TRY(cudaEventSynchronize(P.done));
@@ -1206,7 +1219,7 @@ int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t re
   double best_total = 0;
   BamScanStats acc{};
   for (int rep = 0; rep < std::max(1, repeats); rep++) {
-    s->st = BamScanStats{}; s->range_idx = 0; s->range_open = false; s->finished = false; s->carry_len = 0; s->launched_chunk = -1; s->cur.n = s->cur.pos = 0;
+    s->st = BamScanStats{}; s->st.first_record_uoff = ~0ull; s->range_idx = 0; s->range_open = false; s->finished = false; s->carry_len = 0; s->launched_chunk = -1; s->cur.n = s->cur.pos = 0;
     cudaEventRecord(e0, s->s_compute);
     bool produced;
     while ((rc = advance(s, &produced)) == 1) {}
@@ -1222,6 +1235,21 @@ int bamscan_run_device_resident(BamScanPlan* plan, int32_t partition, int32_t re
   if (rc >= 0) { acc.ms_total = best_total / std::max(1, repeats); *stats = acc; rc = BAMSCAN_OK; }
   stream_destroy(s);
   return rc;
+}
+
+int bamscan_check_partition_seams(const BamScanStats* stats, int32_t n) {
+  if (!stats || n <= 0) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  uint64_t expect = ~0ull;     // where the next partition that owns a record must start
+  for (int32_t p = 0; p < n; p++) {
+    const BamScanStats& S = stats[p];
+    if (S.first_record_uoff != ~0ull && expect != ~0ull && S.first_record_uoff != expect) {
+      set_error("block-range partition %d starts at inflated offset %llu but the chain of the partition before it lands at %llu: speculative record start rejected",
+                p, (unsigned long long)S.first_record_uoff, (unsigned long long)expect);
+      return BAMSCAN_ERR_FORMAT;
+    }
+    if (S.rows > 0 || S.end_chain_uoff) expect = S.end_chain_uoff;
+  }
+  return BAMSCAN_OK;
 }
 
 int bamscan_probe_pcie(int32_t device_id, uint64_t bytes, double* h2d_gbps, double* d2h_gbps, double* bidir_gbps) {

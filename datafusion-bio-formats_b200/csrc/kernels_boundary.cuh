@@ -210,7 +210,7 @@ __global__ void seg_repair_kernel(BoundaryParams P, WalkOut W) {
   W.flags[0] = 0;
 }
 
-// single-CTA exclusive scan of seg_count -> seg_base ; total -> flags[3]
+// single-CTA exclusive scan of seg_count -> seg_base ; total -> flags[3] ; first owned record -> flags[13] (preset to 0xffffffff)
 __global__ void __launch_bounds__(1024)
 seg_scan_kernel(const uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_exit,
                 const uint8_t* __restrict__ seg_tail, uint32_t* __restrict__ seg_base, uint32_t n_seg, uint32_t* __restrict__ flags) {
@@ -222,6 +222,7 @@ seg_scan_kernel(const uint32_t* __restrict__ seg_count, const uint32_t* __restri
   for (uint32_t base = 0; base < n_seg; base += 1024) {
     uint32_t i = base + tid;
     uint32_t v = i < n_seg ? seg_count[i] : 0u;
+    if (v) atomicMin(&flags[13], seg_start[i]);                        // offset of the first owned record of the chunk
     if (i < n_seg && seg_start[i] != SEG_NONE && seg_tail[i] == 2) atomicExch(&flags[1], seg_exit[i] | 1u);   // corrupt block_size on the live chain
     uint32_t x = v;
     #pragma unroll

@@ -103,7 +103,16 @@ typedef struct BamScanStats {
   uint64_t blocks, kernel_launches, boundary_repairs;
   double ms_total, ms_inflate, ms_boundary, ms_decode;      /* CUDA-event device times */
   uint64_t boundary_seam_mismatches;                        /* seams the parallel check rejected (each triggers the repair walk) */
+  /* Block-range partitions: inflated offset of the first record this partition owned (UINT64_MAX: none) and the offset at
+   * which its record chain landed at or after its stop offset.  Partition p > 0 SPECULATES its first record; the scan of the
+   * whole file is proven exact when end_chain_uoff of partition p - 1 equals first_record_uoff of partition p for every p
+   * (bamscan_check_partition_seams; the python mirror and bench.py do this and fail loudly otherwise). */
+  uint64_t first_record_uoff, end_chain_uoff;
 } BamScanStats;
+
+/* Seam check over the stats of the N block-range partitions of one plan, in partition order.  0 = every partition starts
+ * where its predecessor's chain landed; BAMSCAN_ERR_FORMAT (message names the partition) otherwise. */
+int bamscan_check_partition_seams(const BamScanStats* stats, int32_t n_partitions);
 
 /* == BamTableProvider::new (table_provider.rs:381-529): header read, tag-type inference, schema, index discovery.
  * index_path_or_null: NULL => discover `<path>.bai`, `<stem>.bai` (index_utils.rs:43-76; CSI is not read by this build);

@@ -12,7 +12,6 @@ differently, equality is established in two ways:
 Reference semantics being checked: physical_exec.rs:371-598 (sequential scan), alignment_utils.rs:316-368 (batch assembly).
 """
 import struct
-import threading
 import zlib
 
 import numpy as np
@@ -74,44 +73,47 @@ class ColumnSum:
 
 
 def oracle_partitions(oracle, bai_path, n_parts, projection=None, threads=None):
-    """Scans the whole file with the oracle as n_parts block-range partitions (exact record starts) on host threads.
-    Returns the RecordBatches in file order."""
+    """Scans the whole file with the oracle as n_parts block-range partitions (exact record starts) on host threads and
+    yields the RecordBatches in file order.  At most `threads` partitions are alive at a time (a 100 M-read file does not
+    fit in host memory as Arrow twice over)."""
+    import concurrent.futures as cf
     offs = bai_linear_offsets(bai_path)
     n_parts = max(1, min(n_parts, len(offs)))
-    cuts = [oracle.first_record_voffset] + [offs[(len(offs) * k) // n_parts] for k in range(1, n_parts)] + [0]
-    cuts = [cuts[0]] + sorted(set(cuts[1:-1])) + [0]
-    out = [None] * (len(cuts) - 1)
-    errs = []
-    sem = threading.Semaphore(threads or len(out))
-
-    def work(i):
-        with sem:
-            try:
-                out[i] = oracle.scan(projection, start_voffset=cuts[i], stop_voffset=cuts[i + 1])
-            except Exception as e:   # noqa: BLE001
-                errs.append(e)
-
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(out))]
-    for t in ths: t.start()
-    for t in ths: t.join()
-    if errs:
-        raise errs[0]
-    return out
+    cuts = [offs[(len(offs) * k) // n_parts] for k in range(1, n_parts)]
+    cuts = [oracle.first_record_voffset] + sorted(set(cuts)) + [0]
+    n = len(cuts) - 1
+    threads = max(1, min(threads or n, n))
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+        futs = {}
+        nxt = 0
+        for i in range(n):
+            while nxt < n and nxt < i + threads:
+                futs[nxt] = ex.submit(oracle.scan, projection, cuts[nxt], 0, 0, 0, None, None, cuts[nxt + 1])
+                nxt += 1
+            yield futs.pop(i).result()
 
 
 def verify_full_scan(oracle, bai_path, gpu_batches, n_parts=8, projection=None, threads=None) -> dict:
     """gpu_batches: iterable of RecordBatch in file order.  Raises AssertionError on any difference."""
-    parts = oracle_partitions(oracle, bai_path, n_parts, projection, threads)
-    names = parts[0].schema.names
-    want = {nm: ColumnSum() for nm in names}
-    starts, row0 = [], 0
-    for b in parts:
-        starts.append(row0); row0 += b.num_rows
+    # pass 1 (oracle): checksums of every column over every row; the first, a middle and the last partition are kept
+    picks = sorted({0, n_parts // 2, n_parts - 1})
+    names, want, keep, starts, rows_of = None, None, {}, [], []
+    row0 = 0
+    for k, b in enumerate(oracle_partitions(oracle, bai_path, n_parts, projection, threads)):
+        if names is None:
+            names = b.schema.names
+            want = {nm: ColumnSum() for nm in names}
+        starts.append(row0); rows_of.append(b.num_rows); row0 += b.num_rows
         for nm in names:
             want[nm].update(b.column(nm))
+        if k in picks:
+            keep[k] = b
     total_rows = row0
-    picks = sorted({0, len(parts) // 2, len(parts) - 1})
-    windows = {k: (starts[k], starts[k] + parts[k].num_rows) for k in picks}
+    picks = sorted(keep)
+    if len(starts) - 1 not in keep:                     # fewer partitions than asked for: the last one is whatever came last
+        picks = sorted(set(picks))
+    windows = {k: (starts[k], starts[k] + rows_of[k]) for k in picks}
+    # pass 2 (GPU): same checksums, plus the rows of the kept windows
     got = {nm: ColumnSum() for nm in names}
     kept = {k: [] for k in picks}
     r = 0
@@ -129,10 +131,10 @@ def verify_full_scan(oracle, bai_path, gpu_batches, n_parts=8, projection=None, 
         assert got[nm].digest() == want[nm].digest(), f"column {nm}: checksum (rows, nulls, validity, lengths, values) gpu {got[nm].digest()} != oracle {want[nm].digest()}"
     for k in picks:
         g = pa.Table.from_batches(kept[k], schema=kept[k][0].schema) if kept[k] else None
-        w = pa.Table.from_batches([parts[k]])
+        w = pa.Table.from_batches([keep[k]])
         assert g is not None and g.num_rows == w.num_rows, f"window {k}: rows"
         for nm in names:
             assert g[nm].combine_chunks().equals(w[nm].combine_chunks()), f"window {k} (rows {windows[k]}): column {nm} differs"
-    return {"rows": total_rows, "columns": len(names), "oracle_partitions": len(parts),
+    return {"rows": total_rows, "columns": len(names), "oracle_partitions": len(starts),
             "windows_compared": [list(windows[k]) for k in picks],
             "checksums": {nm: [hex(x) for x in got[nm].digest()[2:]] for nm in names}}

@@ -114,3 +114,16 @@ def test_not_bgzf_and_missing_file(tmp_path):
         prov.scan(None, [], None)
     with pytest.raises(bamscan.BamScanError):
         _provider(tmp_path / "nope.bam")
+
+
+def test_partition_seam_check_rejects_a_wrong_speculative_start():
+    """block-range partitions > 0 speculate their first record; the seam check must fail loudly when a partition does
+    not start where its predecessor's chain landed (bamscan_check_partition_seams)."""
+    import bamscan
+    none = 0xFFFFFFFFFFFFFFFF
+    ok = [dict(rows=10, first_record_uoff=100, end_chain_uoff=5000), dict(rows=7, first_record_uoff=5000, end_chain_uoff=9000),
+          dict(rows=0, first_record_uoff=none, end_chain_uoff=9000), dict(rows=3, first_record_uoff=9000, end_chain_uoff=12000)]
+    bamscan.check_partition_seams(ok)
+    bad = [dict(ok[0]), dict(ok[1], first_record_uoff=5012)]
+    with pytest.raises(bamscan.BamScanError, match="partition 1 starts at inflated offset 5012"):
+        bamscan.check_partition_seams(bad)
