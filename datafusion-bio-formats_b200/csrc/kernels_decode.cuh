@@ -19,6 +19,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "f32_text.h"
+
 #include "kernels_boundary.cuh"
 
 namespace bamscan {
@@ -33,7 +35,7 @@ enum ColKind : int32_t {
 enum DecodeErr : uint32_t {
   DEC_OK = 0, DEC_ERR_FIELDS = 1 /* record fields exceed block_size */, DEC_ERR_REF = 2 /* reference id out of range */,
   DEC_ERR_CIGAR_OP = 3, DEC_ERR_TAG_RANGE = 4 /* value does not fit the column type */, DEC_ERR_TAG_TYPE = 5 /* value kind vs column kind */,
-  DEC_ERR_UNSUPPORTED_F2S = 6 /* float tag into Utf8 column */, DEC_ERR_QUAL = 7 /* quality in 95..222: char::from(q + 33) is a two-byte UTF-8 sequence (unpinned; 0xFF wraps to ' ' and is fine) */,
+  DEC_ERR_UNSUPPORTED_F2S = 6 /* (retired: float tags are rendered into Utf8 columns, f32_text.h) */, DEC_ERR_QUAL = 7 /* quality in 95..222: char::from(q + 33) is a two-byte UTF-8 sequence (unpinned; 0xFF wraps to ' ' and is fine) */,
   DEC_ERR_NAME = 8 /* non-ASCII read name (unpinned) */
 };
 
@@ -122,7 +124,7 @@ __device__ __forceinline__ TagConv convert_tag(const DecodeParams& P, const TagP
     else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
   } else if (ty == 'f') {
     if (kind == K_Float32) val = ld_u32(U, v);
-    else if (kind == K_Utf8) { set_err(P.err, DEC_ERR_UNSUPPORTED_F2S, r); ok = false; }
+    else if (kind == K_Utf8) { len = (int32_t)f32_to_text(ld_u32(U, v), nullptr); src = a + 2u; }     // f32::to_string() (sam_tag_io.rs:670-676)
     else { set_err(P.err, DEC_ERR_TAG_TYPE, r); ok = false; }
   } else if (ty == 'A') {
     if (kind == K_Int32 || kind == K_UInt32) val = U[v];
@@ -585,6 +587,7 @@ decode_var_kernel(const DecodeParams P) {
       if (ty == 'Z' || ty == 'H') warp_copy(dst, U + v, n, lane);
       else if (lane == 0) {
         if (ty == 'A') utf8_put(dst, U[v]);
+        else if (ty == 'f') f32_to_text(ld_u32(U, v), dst);
         else {
           int64_t iv;
           switch (ty) {

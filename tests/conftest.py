@@ -88,6 +88,9 @@ def make_edge_bam(path, missing_qual=False):
     ]
     if missing_qual:   # SAM spec 4.2.3: SEQ present, QUAL '*' is stored as 0xFF bytes; char::from(q + 33) wraps to ' ' in a release build
         recs.append(_rec(1, 7, "no_qual", 20, 0, [(40, "M")], "ACGT" * 10, [0xFF] * 40, -1, -1, 0))
+        floats = [1e-7, 3.4028235e38, 0.1, -1.4e-45, 16777216.0, 0.0, -0.0, 123456.789, 5e-324, float("inf")]
+        aux = b"".join(b"Y" + bytes([ord("a") + i]) + b"f" + struct.pack("<f", v) for i, v in enumerate(floats))
+        recs.append(_rec(0, 9, "floats", 1, 0, [(4, "M")], "ACGT", [30] * 4, -1, -1, 0, aux))
     path.write_bytes(_bgzf(hdr + b"".join(recs)))
 
 

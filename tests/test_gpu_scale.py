@@ -67,8 +67,27 @@ def test_edge_bam_on_gpu(tmp_path, inflate, fixed, zero_based):
     p = bamscan.BamTableProvider(str(path), None, zero_based, tags, False, True, 100, None, index_path="", debug_flags=inflate | fixed)
     assert schema_equal(p.schema(), o.schema)
     got = p.scan(None, [], None).collect()
-    assert got.num_rows == want.num_rows == 5
+    assert got.num_rows == want.num_rows == 6
     for name in want.schema.names:
         assert got[name].combine_chunks().equals(want[name].combine_chunks()), f"{name}: {got[name].to_pylist()} != {want[name].to_pylist()}"
     assert got["quality_scores"].to_pylist()[4] == " " * 40 and got["mapping_quality"].to_pylist()[0] == 255 and got["name"].to_pylist()[1] == "*"
+    p.close()
+
+
+def test_float_tags_into_utf8_columns(tmp_path):
+    """sam_tag_io.rs:670-676: a float tag read into a Utf8 column (unknown tag, inference off) is Rust's f32::to_string():
+    shortest digits that round-trip, no exponent.  GPU (f32_text.h) == oracle (rust_f32_to_string)."""
+    import bamscan
+    from oracle.bam_oracle import OracleBam
+    path = tmp_path / "edge.bam"
+    make_edge_bam(path, missing_qual=True)
+    tags = ["XF"] + ["Y" + chr(ord("a") + i) for i in range(10)]
+    o = OracleBam(str(path), tag_fields=tags, infer_tag_types=False)
+    want = pa.Table.from_batches([o.scan()])
+    p = bamscan.BamTableProvider(str(path), None, True, tags, False, False, 100, None, index_path="")
+    got = p.scan(None, [], None).collect()
+    for name in tags:
+        assert want.schema.field(name).type == pa.string()
+        assert got[name].combine_chunks().equals(want[name].combine_chunks()), f"{name}: {got[name].to_pylist()} != {want[name].to_pylist()}"
+    assert got["XF"].to_pylist()[0] == "1.5" and got["Ya"].to_pylist()[5] == "0.0000001" and got["Yc"].to_pylist()[5] == "0.1"
     p.close()
