@@ -156,11 +156,24 @@ static void arena_release(HostArena a) {
 }
 
 struct BatchOwner {
-  HostArena arena;
+  HostArena arena;                 // host hand-off: pinned arena the batch was copied into
+  void* dev = nullptr;             // device hand-off (bamscan_next_device): the batch's own device allocation ...
+  cudaEvent_t dev_ready = nullptr; // ... and the event behind the kernels / copy that produced it (ArrowDeviceArray::sync_event)
+  int device = 0;
   std::atomic<int> refs{0};
 };
 static void owner_unref(BatchOwner* o) {
-  if (o->refs.fetch_sub(1) == 1) { arena_release(o->arena); delete o; }
+  if (o->refs.fetch_sub(1) == 1) {
+    arena_release(o->arena);
+    if (o->dev || o->dev_ready) {
+      int cur = 0; cudaGetDevice(&cur);
+      if (cur != o->device) cudaSetDevice(o->device);
+      if (o->dev_ready) { cudaEventSynchronize(o->dev_ready); cudaEventDestroy(o->dev_ready); }
+      if (o->dev) cudaFree(o->dev);
+      if (cur != o->device) cudaSetDevice(cur);
+    }
+    delete o;
+  }
 }
 
 // one output column of a chunk (offsets into the arena; same layout on device and host)
@@ -198,6 +211,7 @@ struct BamScanStream {
   Plan* plan = nullptr; BamFile* f = nullptr; const Partition* part = nullptr; BamScanHandle* handle = nullptr;
   bool resources_ready = false;
   bool device_resident = false;
+  bool device_export = false;            // batches stay in HBM and are handed out through the Arrow C Device Data Interface
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute = nullptr, ev_flags = nullptr, ev_t[6] = {};
   // iteration
@@ -623,6 +637,24 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);
       CU_TRY(cudaStreamSynchronize(cs));
       if (s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
+    } else if (s->device_export) {
+      // device hand-off: the batch gets its own exactly-sized device allocation (a device-to-device copy on the side
+      // stream, ~3 TB/s); only the decode error word travels to the host
+      CU_TRY(cudaEventRecord(s->ev_compute, cs));
+      PendingBatch& P = s->pending;
+      P.owner = new BatchOwner();
+      P.owner->device = f->device; P.owner->refs = 1;
+      if (cudaMalloc(&P.owner->dev, arena_bytes) != cudaSuccess) { delete P.owner; P.owner = nullptr; set_error("cudaMalloc(%zu) for a device batch failed", arena_bytes); return BAMSCAN_ERR_CUDA; }
+      P.cols = cols; P.rows = n; P.arena_bytes = arena_bytes; P.err_off = err_off; P.valid = true;
+      if (!P.done) CU_TRY(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&P.owner->dev_ready, cudaEventDisableTiming));
+      CU_TRY(cudaStreamWaitEvent(s->s_d2h, s->ev_compute, 0));
+      CU_TRY(cudaMemcpyAsync(P.owner->dev, A, arena_bytes, cudaMemcpyDeviceToDevice, s->s_d2h));
+      CU_TRY(cudaMemcpyAsync(s->h_flags + 66, A + err_off, 8, cudaMemcpyDeviceToHost, s->s_d2h));
+      CU_TRY(cudaEventRecord(P.owner->dev_ready, s->s_d2h));
+      CU_TRY(cudaEventRecord(P.done, s->s_d2h));
+      s->arena_flip ^= 1;
+      *produced = true;
     } else {
       CU_TRY(cudaEventRecord(s->ev_compute, cs));
       PendingBatch& P = s->pending;
@@ -931,14 +963,15 @@ static int64_t count_nulls(const uint8_t* bm, uint64_t row0, uint64_t n) {
 }
 
 static void export_batch(const BamScanStream* s, const ReadyBatch& rb, ArrowArray* out) {
-  const uint8_t* H = rb.owner->arena.p;
+  const bool on_device = rb.owner->dev != nullptr;     // device hand-off: same layout, device addresses, null counts unknown (-1)
+  const uint8_t* H = on_device ? static_cast<const uint8_t*>(rb.owner->dev) : rb.owner->arena.p;
   const size_t n_out = s->out_to_dec.size();
   new_node(out, rb.owner, (int64_t)rb.nrows, 0, 0, 1, n_out);
   for (size_t i = 0; i < n_out; i++) {
     const ColLayout& L = rb.cols[s->out_to_dec[i]];
     ArrowArray* ch = out->children[i];
     const bool is_list = L.kind >= HK_ListInt8, is_var = L.kind == HK_Utf8 || L.kind == HK_Binary;
-    int64_t nulls = L.has_validity ? count_nulls(H + L.validity_off, rb.row0, rb.nrows) : 0;
+    int64_t nulls = L.has_validity ? (on_device ? -1 : count_nulls(H + L.validity_off, rb.row0, rb.nrows)) : 0;
     const void* validity = (L.has_validity && nulls) ? H + L.validity_off : nullptr;
     if (is_list) {
       NodePriv* p = new_node(ch, rb.owner, (int64_t)rb.nrows, nulls, (int64_t)rb.row0, 2, 1);
@@ -977,7 +1010,7 @@ static int finalize_pending(BamScanStream* s) {
   if (!P.valid) return BAMSCAN_OK;
   CU_TRY(cudaEventSynchronize(P.done));
   P.valid = false;
-  const uint32_t* err = reinterpret_cast<const uint32_t*>(P.owner->arena.p + P.err_off);
+  const uint32_t* err = s->device_export ? s->h_flags + 66 : reinterpret_cast<const uint32_t*>(P.owner->arena.p + P.err_off);
   if (err[0]) { int rc = decode_error_to_rc(err[0], err[1]); owner_unref(P.owner); P.owner = nullptr; return rc; }
   s->ready.clear(); s->ready_pos = 0;
   uint64_t step = s->f->batch_rows > 0 ? (uint64_t)s->f->batch_rows : P.rows;
@@ -1121,7 +1154,7 @@ int bamscan_plan_range_info(const BamScanPlan* plan, int32_t partition, int32_t 
   return BAMSCAN_OK;
 }
 
-static int make_stream(BamScanPlan* plan, int32_t partition, bool device_resident, BamScanStream** out) {
+static int make_stream(BamScanPlan* plan, int32_t partition, bool device_resident, BamScanStream** out, bool device_export = false) {
   if (!plan || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
   if (partition < 0 || partition >= (int32_t)plan->plan->partitions.size()) { set_error("partition %d out of range", partition); return BAMSCAN_ERR_INVALID; }
   if (!g_have_device) { set_error("no CUDA device available: the BAM scan runs on the GPU only (libbamscan has no CPU path)"); return BAMSCAN_ERR_CUDA; }
@@ -1132,7 +1165,7 @@ static int make_stream(BamScanPlan* plan, int32_t partition, bool device_residen
   }
   if (!s) s = new BamScanStream();
   s->plan = plan->plan; s->f = plan->plan->file; s->part = &plan->plan->partitions[partition]; s->handle = plan->handle;
-  s->device_resident = device_resident;
+  s->device_resident = device_resident; s->device_export = device_export;
   int rc = stream_init(s);
   if (rc) { stream_destroy(s, false); return rc; }
   *out = s;
@@ -1140,6 +1173,19 @@ static int make_stream(BamScanPlan* plan, int32_t partition, bool device_residen
 }
 
 int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out) { return make_stream(plan, partition, false, out); }
+int bamscan_execute_device(BamScanPlan* plan, int32_t partition, BamScanStream** out) { return make_stream(plan, partition, false, out, true); }
+
+int bamscan_next_device(BamScanStream* s, struct ArrowDeviceArray* out) {
+  if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  if (!s->device_export) { set_error("bamscan_next_device needs a stream from bamscan_execute_device"); return BAMSCAN_ERR_INVALID; }
+  memset(out, 0, sizeof *out);
+  const int rc = bamscan_next(s, &out->array);
+  if (rc != 1) return rc;
+  BatchOwner* o = static_cast<NodePriv*>(out->array.private_data)->owner;
+  out->device_id = s->f->device; out->device_type = ARROW_DEVICE_CUDA;
+  out->sync_event = o->dev_ready ? &o->dev_ready : nullptr;
+  return 1;
+}
 
 int bamscan_next(BamScanStream* s, struct ArrowArray* out) {
   if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
