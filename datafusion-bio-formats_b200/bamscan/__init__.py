@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "bamscan_open", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
     "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_plan_num_ranges",
     "bamscan_plan_range_info", "bamscan_plan_partition_regions", "bamscan_extract_regions", "bamscan_balance_partitions",
-    "bamscan_execute", "bamscan_next",
+    "bamscan_execute", "bamscan_next", "bamscan_execute_device", "bamscan_next_device",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
     "bamscan_probe_pcie", "bamscan_check_partition_seams", "bamscan_last_error", "bamscan_version",
 ]
@@ -235,6 +235,25 @@ class BamExec:
         finally:
             L.bamscan_stream_free(st)
 
+    def execute_device(self, partition: int):
+        """Generator of DeviceBatch for one partition: the batch stays in HBM (Arrow C Device Data Interface)."""
+        L = load_library()
+        schema = self.schema()
+        st = C.c_void_p()
+        _check(L.bamscan_execute_device(self._h, partition, C.byref(st)))
+        try:
+            while True:
+                dev = ArrowDeviceArrayStruct()
+                rc = _check(L.bamscan_next_device(st, C.byref(dev)))
+                if rc == 0:
+                    break
+                yield DeviceBatch(dev, schema)
+            s = Stats()
+            L.bamscan_stream_stats(st, C.byref(s))
+            self.last_stats = s.as_dict()
+        finally:
+            L.bamscan_stream_free(st)
+
     def collect(self) -> pa.Table:
         """All partitions in partition order (CoalescePartitionsExec over the leaf).  Block-range partitions > 0 speculate
         their first record: the seams are checked (each partition must start where its predecessor's chain landed)."""
@@ -271,6 +290,95 @@ class _ArrowArrayStruct(C.Structure):
     _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
                 ("n_children", C.c_int64), ("buffers", C.c_void_p), ("children", C.c_void_p), ("dictionary", C.c_void_p),
                 ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowDeviceArrayStruct(C.Structure):
+    _fields_ = [("array", _ArrowArrayStruct), ("device_id", C.c_int64), ("device_type", C.c_int32), ("sync_event", C.c_void_p),
+                ("reserved", C.c_int64 * 3)]
+
+
+ARROW_DEVICE_CUDA = 2
+_cudart = None
+
+
+def _cuda_memcpy_d2h(dst_addr: int, src_addr: int, n: int):
+    """cudaMemcpy(dst, src, n, DeviceToHost) through libcudart (tests / debugging of the device hand-off only)."""
+    global _cudart
+    if _cudart is None:
+        import glob
+        cands = glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+        try:
+            import torch
+            cands += glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*"))
+            cands += glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+        except Exception:
+            pass
+        if not cands:
+            raise RuntimeError("libcudart not found")
+        _cudart = C.CDLL(sorted(cands)[-1])
+        _cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        _cudart.cudaDeviceSynchronize.argtypes = []
+    if n:
+        rc = _cudart.cudaMemcpy(dst_addr, src_addr, n, 2)
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpy D2H failed ({rc})")
+
+
+class DeviceBatch:
+    """One batch in HBM: an ArrowDeviceArray (device_type CUDA) plus the projected schema.  `release()` (or garbage collection)
+    returns the device allocation to the engine; `to_host()` copies it back as a pyarrow.RecordBatch (tests, debugging)."""
+
+    def __init__(self, dev: ArrowDeviceArrayStruct, schema: pa.Schema):
+        self._dev = dev
+        self.schema = schema
+        self.num_rows = dev.array.length
+        self.device_id = dev.device_id
+        self.device_type = dev.device_type
+
+    def release(self):
+        a = self._dev.array
+        if a.release:
+            C.CFUNCTYPE(None, C.POINTER(_ArrowArrayStruct))(a.release)(C.byref(a))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _host(addr, nbytes):
+        import numpy as np
+        buf = np.empty(max(1, nbytes), dtype=np.uint8)
+        _cuda_memcpy_d2h(buf.ctypes.data, addr, nbytes)
+        return pa.py_buffer(buf[:nbytes].tobytes())
+
+    def _child(self, node: _ArrowArrayStruct, typ: pa.DataType) -> pa.Array:
+        import numpy as np
+        n, off = node.length, node.offset
+        bufs = C.cast(node.buffers, C.POINTER(C.c_void_p))
+        validity = self._host(bufs[0], (off + n + 7) // 8) if bufs[0] else None
+        if pa.types.is_string(typ) or pa.types.is_binary(typ) or pa.types.is_list(typ):
+            offs = self._host(bufs[1], 4 * (off + n + 1))
+            o = np.frombuffer(offs, dtype=np.int32)
+            if pa.types.is_list(typ):
+                kids = C.cast(node.children, C.POINTER(C.POINTER(_ArrowArrayStruct)))
+                child = self._child(kids[0].contents, typ.value_type)
+                return pa.Array.from_buffers(typ, n, [validity, offs], null_count=-1, offset=off, children=[child])
+            data = self._host(bufs[2], int(o[-1]) if len(o) else 0)
+            return pa.Array.from_buffers(typ, n, [validity, offs, data], null_count=-1, offset=off)
+        return pa.Array.from_buffers(typ, n, [validity, self._host(bufs[1], (off + n) * (typ.bit_width // 8))], null_count=-1, offset=off)
+
+    def to_host(self) -> pa.RecordBatch:
+        if self._dev.sync_event:
+            _cuda_memcpy_d2h(0, 0, 0)
+            _cudart.cudaDeviceSynchronize()           # (a consumer kernel would cudaStreamWaitEvent on *sync_event instead)
+        a = self._dev.array
+        if len(self.schema) == 0:
+            return pa.RecordBatch.from_struct_array(pa.array([{}] * a.length, type=pa.struct([])))
+        kids = C.cast(a.children, C.POINTER(C.POINTER(_ArrowArrayStruct)))
+        cols = [self._child(kids[i].contents, self.schema.field(i).type) for i in range(a.n_children)]
+        return pa.RecordBatch.from_arrays(cols, schema=self.schema)
 
 
 class BamTableProvider:
