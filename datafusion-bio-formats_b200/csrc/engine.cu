@@ -1032,7 +1032,20 @@ extern "C" {
 const char* bamscan_last_error(void) { return last_error_cstr(); }
 const char* bamscan_version(void) { return "bamscan-b200 0.1 (sm_100a)"; }
 
+static int bamscan_open_impl(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
+
+// No C++ exception may cross the C ABI (a corrupt file can ask for absurd allocations): they become BAMSCAN_ERR_FORMAT.
+#define BAMSCAN_GUARD(call)                                                                                          \
+  try { return (call); }                                                                                             \
+  catch (const std::bad_alloc&) { set_error("out of memory (corrupt or oversized input?)"); return BAMSCAN_ERR_FORMAT; } \
+  catch (const std::exception& e) { set_error("internal error: %s", e.what()); return BAMSCAN_ERR_FORMAT; }           \
+  catch (...) { set_error("internal error"); return BAMSCAN_ERR_FORMAT; }
+
 int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out) {
+  BAMSCAN_GUARD(bamscan_open_impl(path, index_path_or_null, options, out))
+}
+
+static int bamscan_open_impl(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out) {
   if (!path || !out) { set_error("bamscan_open: null argument"); return BAMSCAN_ERR_INVALID; }
   BamScanOptions opt;
   memset(&opt, 0, sizeof opt);
@@ -1087,8 +1100,14 @@ int bamscan_classify_filters(BamScanHandle* h, const BamScanFilter* filters, int
   return classify_filters(h->file, filters, n_filters, out_pushdown);
 }
 
+static int bamscan_plan_impl(BamScanHandle* h, const int32_t* projection, int32_t n_projection, const BamScanFilter* filters, int32_t n_filters,
+                             int64_t limit_or_neg, int32_t target_partitions, int32_t partition_mode, BamScanPlan** out);
 int bamscan_plan(BamScanHandle* h, const int32_t* projection, int32_t n_projection, const BamScanFilter* filters, int32_t n_filters,
                  int64_t limit_or_neg, int32_t target_partitions, int32_t partition_mode, BamScanPlan** out) {
+  BAMSCAN_GUARD(bamscan_plan_impl(h, projection, n_projection, filters, n_filters, limit_or_neg, target_partitions, partition_mode, out))
+}
+static int bamscan_plan_impl(BamScanHandle* h, const int32_t* projection, int32_t n_projection, const BamScanFilter* filters, int32_t n_filters,
+                             int64_t limit_or_neg, int32_t target_partitions, int32_t partition_mode, BamScanPlan** out) {
   (void)limit_or_neg;   // stored and never used by the reference either (physical_exec.rs:38,44)
   if (!h || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
   Plan* p = nullptr;
@@ -1172,8 +1191,8 @@ static int make_stream(BamScanPlan* plan, int32_t partition, bool device_residen
   return BAMSCAN_OK;
 }
 
-int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out) { return make_stream(plan, partition, false, out); }
-int bamscan_execute_device(BamScanPlan* plan, int32_t partition, BamScanStream** out) { return make_stream(plan, partition, false, out, true); }
+int bamscan_execute(BamScanPlan* plan, int32_t partition, BamScanStream** out) { BAMSCAN_GUARD(make_stream(plan, partition, false, out)) }
+int bamscan_execute_device(BamScanPlan* plan, int32_t partition, BamScanStream** out) { BAMSCAN_GUARD(make_stream(plan, partition, false, out, true)) }
 
 int bamscan_next_device(BamScanStream* s, struct ArrowDeviceArray* out) {
   if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
@@ -1187,7 +1206,9 @@ int bamscan_next_device(BamScanStream* s, struct ArrowDeviceArray* out) {
   return 1;
 }
 
-int bamscan_next(BamScanStream* s, struct ArrowArray* out) {
+static int bamscan_next_impl(BamScanStream* s, struct ArrowArray* out);
+int bamscan_next(BamScanStream* s, struct ArrowArray* out) { BAMSCAN_GUARD(bamscan_next_impl(s, out)) }
+static int bamscan_next_impl(BamScanStream* s, struct ArrowArray* out) {
   if (!s || !out) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
   static const bool trace = getenv("BAMSCAN_TRACE") != nullptr;
   static thread_local double t_last_return = 0;

@@ -220,6 +220,8 @@ int load_bai(const std::string& path, BaiIndex* out) {
   auto need = [&](size_t k) { return p + k <= d.size(); };
   if (!need(8) || memcmp(d.data(), "BAI\1", 4) != 0) { set_error("%s: missing BAI magic", path.c_str()); return BAMSCAN_ERR_FORMAT; }
   uint32_t n_ref = rd32(d.data() + 4); p = 8;
+  // every reference takes at least 8 bytes (n_bin, n_intv): a count the file cannot hold is a corrupt index, not an allocation
+  if ((uint64_t)n_ref * 8ull > d.size() - p) { set_error("%s: BAI n_ref %u exceeds the file size", path.c_str(), n_ref); return BAMSCAN_ERR_FORMAT; }
   out->refs.resize(n_ref);
   for (uint32_t r = 0; r < n_ref; r++) {
     if (!need(4)) goto trunc;

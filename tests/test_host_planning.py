@@ -127,3 +127,19 @@ def test_partition_seam_check_rejects_a_wrong_speculative_start():
     bad = [dict(ok[0]), dict(ok[1], first_record_uoff=5012)]
     with pytest.raises(bamscan.BamScanError, match="partition 1 starts at inflated offset 5012"):
         bamscan.check_partition_seams(bad)
+
+
+def test_corrupt_bai_is_an_error_not_a_crash(tmp_path):
+    """n_ref from a corrupt .bai must not turn into a multi-GB allocation / an exception across the C ABI."""
+    import shutil
+    import bamscan
+    bam = tmp_path / "x.bam"
+    shutil.copy(GOLDEN / "multi_chrom.bam", bam)
+    (tmp_path / "x.bam.bai").write_bytes(b"BAI\1" + (0x7fffffff).to_bytes(4, "little") + b"\0" * 16)
+    p = bamscan.BamTableProvider(str(bam), None, True, None, False, True, 100, None)
+    try:
+        plan = p.scan(None, [("chrom", "=", ["chr1"])], None, target_partitions=4)
+        assert plan.output_partition_count() == 1        # an unreadable index = no index: the sequential single-partition plan
+    except bamscan.BamScanError as e:
+        assert "BAI" in str(e)                           # ... or a clean error; never a crash
+    p.close()
