@@ -31,10 +31,14 @@ namespace icta {
 constexpr uint32_t INF_RETRY = 15;          // status: redo this member with the warp-per-member kernel
 constexpr uint32_t FRONT_DONE = 0xffffffffu;
 constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is given
+#ifndef BAMSCAN_ICTA_RESOLVE_SLOTS
+#define BAMSCAN_ICTA_RESOLVE_SLOTS 1
+#endif
 #ifndef BAMSCAN_ICTA_RESOLVE_WARPS
 #define BAMSCAN_ICTA_RESOLVE_WARPS 8
 #endif
-constexpr int RESOLVE_WARPS = BAMSCAN_ICTA_RESOLVE_WARPS;
+constexpr int RESOLVE_SLOTS = BAMSCAN_ICTA_RESOLVE_SLOTS;   // matches per lane the resolver keeps in flight
+constexpr int RESOLVE_WARPS = BAMSCAN_ICTA_RESOLVE_WARPS;   // warps of the resolver
 constexpr uint32_t WARMUP_BITS = 640;       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
 
 // global constant tables of the CRC stage, filled once per device by crc_tables_init_kernel:
@@ -50,7 +54,7 @@ struct Cfg {
   static constexpr uint32_t PAY_SLACK = 64;
   static constexpr uint32_t HB_WORDS = 2052;                  // head bitmap: one bit per window byte
   static constexpr uint32_t LUT_LL_WORDS = ROOT_LL + SUB_LL, LUT_D_WORDS = ROOT_D + SUB_D;
-  static constexpr uint32_t OFF_WIN = 0;
+  static constexpr uint32_t OFF_WIN = 16;                     // (the resolver gathers up to 3 bytes in front of the window's first word)
   static constexpr uint32_t OFF_HB = OFF_WIN + WIN_BYTES;
   static constexpr uint32_t OFF_PAY = OFF_HB + HB_WORDS * 4;
   static constexpr uint32_t OFF_LUT_LL = OFF_PAY + PAY_BYTES + PAY_SLACK;
@@ -68,6 +72,7 @@ struct Cfg {
 
 struct Ctl {
   unsigned long long mbar;
+  unsigned long long psel[8];        // psel[d]: sixteen nibbles k mod d (byte selectors of a period-d piece, resolve stage)
   uint32_t ticket, err, btype, final_block, hdr_end, stored_len, n_ll, n_d;
   uint32_t first_term[2];            // lowest lane whose chain does not hand over (double buffered per round)
   uint32_t last_lane, last_info;
@@ -108,6 +113,12 @@ __device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem,
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+// (predicated inside the asm: an `if` around a volatile asm compiles to a branch + reconvergence barrier per statement)
+__device__ __forceinline__ void and_shared_if(uint32_t a, uint32_t v, bool on) { asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.and.b32 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void red_and_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ uint32_t brev_n(uint32_t v, uint32_t bits) { return __brev(v) >> (32u - bits); }
 
@@ -309,25 +320,135 @@ __device__ __forceinline__ uint32_t read_code_lengths_cta(const uint32_t* pay, u
   return INF_OK;
 }
 
-// Ordering between a piece's data stores and the clearing of its map bits (writer), and between the map load and the data
-// loads (reader).  All of it is shared memory of ONE SM: a warp's shared-memory instructions are issued and performed in
-// program order, and the reader's data loads are control-dependent on the value its map load returned, so a compiler
-// barrier is what is needed in practice; BAMSCAN_ICTA_FENCES=1 puts fence.acq_rel.cta (MEMBAR.ALL.CTA, ~100 cycles on the
-// dependency chain, twice per hop) back.  Every member's CRC-32 is checked behind this stage either way.
-#if defined(BAMSCAN_ICTA_FENCES) && BAMSCAN_ICTA_FENCES
-#define ICTA_ORDER() asm volatile("fence.acq_rel.cta;" ::: "memory")
-#else
-#define ICTA_ORDER() asm volatile("" ::: "memory")
-#endif
+
+// RESOLVE stage C: dataflow over the in-order match list.  RESOLVE_WARPS warps x 32 lanes x SLOTS matches are in flight,
+// dealt statically (thread t, slot m takes the matches t + T m, + T SLOTS, ... with T = 32 RESOLVE_WARPS: the lowest
+// unresolved match of the member is therefore always in flight and its sources are final, so the stage always makes
+// progress).  The LZ77 dependency chains of sorted BAM data are 90-190 pieces deep per member (a record copies from the
+// record in front of it): this stage is a latency chain, not a bandwidth problem, and what counts is the length of one
+// hop = the dependent instructions of one loop iteration.  Hence: descriptors are prefetched one match ahead, the source is
+// gathered in the DESTINATION's word frame (one funnel shift per word, no second alignment pass), periods < 8 are expanded
+// in registers with byte permutes, all stores are predicated inside the asm (no branches), and a slot tests the map bits of
+// exactly the source bytes it needs (partial pieces go as soon as their bytes are final).
+// Ordering: a writer stores the piece and then clears its map bits; a reader loads the map and then the bytes.  Both are
+// shared-memory accesses of one SM, performed in program order per warp; every member's CRC-32 is checked behind this stage.
+__device__ __forceinline__ void sts_u32_if(uint32_t a, uint32_t v, bool on) { asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void sts_u8_if(uint32_t a, uint32_t v, bool on) { asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)on) : "memory"); }
+template <int SLOTS, int RWARPS>
+__device__ __forceinline__ void resolve_dataflow(uint32_t win_s, uint32_t hb_s, uint32_t list_s, uint32_t psel_s, uint32_t obase, uint32_t total, int tid, Ctl* C) {
+  constexpr uint32_t T = 32u * RWARPS;
+  uint32_t o[SLOTS], dist[SLOTS], len[SLOTS], done[SLOTS], no[SLOTS], nv[SLOTS], nr[SLOTS];
+  bool pend[SLOTS];
+  auto load_desc = [&](uint32_t r, uint32_t& oo, uint32_t& vv) {
+    oo = obase + lds_u16(list_s + r * 2u);
+    const uint32_t a = win_s + (oo & ~3u);
+    vv = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (oo & 3u) * 8u) & 0xffffffu;
+  };
+  #pragma unroll
+  for (int m = 0; m < SLOTS; m++) {
+    const uint32_t r = (uint32_t)tid + T * m;
+    uint32_t v = 0;
+    pend[m] = r < total; o[m] = obase + 4u; no[m] = obase + 4u; nv[m] = 0;
+    if (pend[m]) load_desc(r, o[m], v);
+    dist[m] = pend[m] ? (v & 0x7fffu) + 1u : 1u; len[m] = pend[m] ? (v >> 15) + 3u : 0u; done[m] = 0;
+    nr[m] = r + T * SLOTS;
+    if (nr[m] < total) load_desc(nr[m], no[m], nv[m]);
+  }
+  uint32_t spins = 0;
+  for (;;) {
+    bool anyp = false;
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) anyp |= pend[m];
+    if (!__any_sync(FULL, anyp)) break;
+    uint32_t cur[SLOTS], sa[SLOTS], x[SLOTS], n[SLOTS], D[SLOTS][5];
+    // phase 1: map bits of the source
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) {
+      cur[m] = o[m] + done[m];
+      sa[m] = cur[m] - dist[m];
+      const uint32_t wa = hb_s + ((sa[m] >> 5) << 2);
+      x[m] = __funnelshift_r(lds_u32(wa), lds_u32(wa + 4u), sa[m] & 31u);
+    }
+    // phase 2: gather in the destination's word frame: D[j] = the source bytes that land in the word at (cur & ~3) + 4 j
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) {
+      const uint32_t f = sa[m] - (cur[m] & 3u);                      // (>= obase - 3: the window starts 16 bytes into shared memory)
+      const uint32_t a = win_s + (f & ~3u), s8 = (f & 3u) * 8u;
+      const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4u), w2 = lds_u32(a + 8u), w3 = lds_u32(a + 12u), w4 = lds_u32(a + 16u), w5 = lds_u32(a + 20u);
+      D[m][0] = __funnelshift_r(w0, w1, s8); D[m][1] = __funnelshift_r(w1, w2, s8); D[m][2] = __funnelshift_r(w2, w3, s8);
+      D[m][3] = __funnelshift_r(w3, w4, s8); D[m][4] = __funnelshift_r(w4, w5, s8);
+    }
+    // phase 3: how many bytes of the piece can go now
+    bool anyn = false, anywrap = false;
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) {
+      uint32_t want = min(len[m] - done[m], RESOLVE_PIECE);
+      if (dist[m] < want && dist[m] >= 8u) want = dist[m];                         // (only periods < 8 are expanded in registers)
+      const uint32_t outn = min(want, dist[m]);                                    // the piece's bytes that come from outside itself
+      const uint32_t avail = x[m] ? (uint32_t)__ffs((int)x[m]) - 1u : 32u;         // final source bytes from sa on
+      n[m] = avail >= outn ? want : (dist[m] >= want ? avail : 0u);
+      if (!pend[m]) n[m] = 0;
+      anyn |= n[m] != 0u; anywrap |= n[m] > dist[m];
+    }
+    if (!__any_sync(FULL, anyn)) {                                                 // nothing ready in this warp: another warp's piece comes first
+      if (RWARPS == 1 || ++spins > (1u << 22)) { C->err = INF_ERR_INPUT; break; }  // (one warp: cannot happen; else a safety valve, never taken)
+      continue;
+    }
+    if (__any_sync(FULL, anywrap)) {                                               // a piece longer than its period: byte k is src[k mod dist]
+      #pragma unroll
+      for (int m = 0; m < SLOTS; m++) if (n[m] > dist[m]) {
+        const uint32_t h8 = (cur[m] & 3u) * 8u;
+        const uint32_t s0 = __funnelshift_r(D[m][0], D[m][1], h8), s1 = __funnelshift_r(D[m][1], D[m][2], h8);   // the 8 bytes at sa
+        const uint32_t m0 = lds_u32(psel_s + dist[m] * 8u), m1 = lds_u32(psel_s + dist[m] * 8u + 4u);
+        const uint32_t V0 = __byte_perm(s0, s1, m0 & 0xffffu), V1 = __byte_perm(s0, s1, m0 >> 16), V2 = __byte_perm(s0, s1, m1 & 0xffffu), V3 = __byte_perm(s0, s1, m1 >> 16);
+        D[m][0] = V0 << h8; D[m][1] = __funnelshift_l(V0, V1, h8); D[m][2] = __funnelshift_l(V1, V2, h8); D[m][3] = __funnelshift_l(V2, V3, h8); D[m][4] = __funnelshift_l(V3, 0u, h8);
+      }
+    }
+    // phase 4: store.  Word j holds the piece's bytes [4j - sh, 4j - sh + 4); whole words, then the ragged head and tail as bytes
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) {
+      const uint32_t sh = cur[m] & 3u, A = win_s + (cur[m] & ~3u), e = sh + n[m], ca = win_s + cur[m];
+      sts_u32_if(A, D[m][0], sh == 0u && n[m] >= 4u);
+      sts_u32_if(A + 4u, D[m][1], e >= 8u);
+      sts_u32_if(A + 8u, D[m][2], e >= 12u);
+      sts_u32_if(A + 12u, D[m][3], e >= 16u);
+      sts_u32_if(A + 16u, D[m][4], e >= 20u);
+      const uint32_t h = sh ? min(n[m], 4u - sh) : 0u, hv = D[m][0] >> (sh * 8u);
+      sts_u8_if(ca, hv, h > 0u); sts_u8_if(ca + 1u, hv >> 8, h > 1u); sts_u8_if(ca + 2u, hv >> 16, h > 2u);
+      const uint32_t jt = e >> 2, t = (e >= 4u || sh == 0u) ? (e & 3u) : 0u;
+      const uint32_t Dt = jt == 0u ? D[m][0] : jt == 1u ? D[m][1] : jt == 2u ? D[m][2] : jt == 3u ? D[m][3] : D[m][4];
+      const uint32_t ta = A + 4u * jt;
+      sts_u8_if(ta, Dt, t > 0u); sts_u8_if(ta + 1u, Dt >> 8, t > 1u); sts_u8_if(ta + 2u, Dt >> 16, t > 2u);
+    }
+    // phase 5: the piece's bytes are final
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) {
+      const uint32_t wa = hb_s + ((cur[m] >> 5) << 2), b = cur[m] & 31u, mk = (1u << n[m]) - 1u;      // n <= 16
+      and_shared_if(wa, ~(mk << b), n[m] != 0u);
+      and_shared_if(wa + 4u, ~__funnelshift_r(mk, 0u, 32u - b), b + n[m] > 32u);
+    }
+    // phase 6: a finished slot adopts its prefetched next match and prefetches the one after
+    #pragma unroll
+    for (int m = 0; m < SLOTS; m++) {
+      done[m] += n[m];
+      if (pend[m] && done[m] == len[m]) {
+        pend[m] = nr[m] < total;
+        o[m] = no[m]; done[m] = 0;
+        dist[m] = pend[m] ? (nv[m] & 0x7fffu) + 1u : 1u; len[m] = pend[m] ? (nv[m] >> 15) + 3u : 0u;
+        nr[m] += T * SLOTS;
+        if (nr[m] < total) load_desc(nr[m], no[m], nv[m]);
+      }
+    }
+  }
+}
 
 // RESOLVE, whole member, all warps.  `hb` holds one bit per parked match head on entry.
 //   A  every thread ranks the heads of its share of the bitmap words; a CTA scan turns that into an in-order list of
 //      head positions (u16, relative to obase); the bitmap words are zeroed on the way;
 //   B  the bitmap becomes the UNRESOLVED map: every byte of every parked match is flagged;
-//   C  dataflow: warp w takes the groups w, w + WARPS, ... of 32 consecutive matches.  A lane copies a piece (<= 16 bytes)
-//      of its match as soon as the map shows that the piece's source bytes are final, then clears the piece's bits.
-//      The lowest unresolved piece of the member always has final sources, and all warps work within a few hundred
-//      bytes of that frontier, so the wait of a lane is the real LZ77 dependency chain and nothing else.
+//   C  dataflow, warp 0: 32 consecutive matches in flight, one per lane.  A lane copies a piece (<= 16 bytes) of its match
+//      as soon as the map shows that the piece's source bytes are final, then clears the piece's bits.  The lowest
+//      unresolved piece of the member always has final sources, so every iteration makes progress.
 // Returns INF_OK or INF_RETRY (more matches than the list holds).
 template <int NT>
 __device__ __forceinline__ uint32_t resolve_member(uint8_t* win, uint32_t* hb, uint16_t* list, uint32_t list_cap, Ctl* C,
@@ -370,72 +491,8 @@ __device__ __forceinline__ uint32_t resolve_member(uint8_t* win, uint32_t* hb, u
     }
   }
   __syncthreads();
-  // ---- C: dataflow
-  // Only RESOLVE_WARPS warps take groups: a warp iterates about once per dependency level of the member whatever their
-  // number is, so more warps cost more issued instructions without shortening the chain.
-  volatile uint32_t* const ub = hb;
-  if (warp < RESOLVE_WARPS)
-  for (uint32_t g = warp; g * 32u < total; g += RESOLVE_WARPS) {
-    const uint32_t r = g * 32u + lane;
-    const bool valid = r < total;
-    uint32_t o = 0, dist = 1, len = 0;
-    if (valid) {
-      o = obase + list[r];
-      const uint32_t v = (uint32_t)win[o] | ((uint32_t)win[o + 1] << 8) | ((uint32_t)win[o + 2] << 16);
-      dist = (v & 0x7fffu) + 1u; len = (v >> 15) + 3u;
-    }
-    uint32_t done = 0, spins = 0;
-    bool pend = valid;
-    while (__any_sync(FULL, pend)) {
-      const uint32_t cur = o + done;
-      const uint32_t n = pend ? min(len - done, RESOLVE_PIECE) : 0u;
-      const uint32_t sa = cur - dist, sb = min(cur, sa + n);        // the piece's bytes that come from outside itself
-      bool ok = false;
-      if (pend) {
-        const uint32_t x = __funnelshift_r(ub[sa >> 5], ub[(sa >> 5) + 1], sa & 31u);
-        ok = (x & ((1u << (sb - sa)) - 1u)) == 0;
-      }
-      if (!__any_sync(FULL, ok)) {
-#ifdef BAMSCAN_ICTA_SLEEP
-        if ((spins & 15u) == 15u) __nanosleep(BAMSCAN_ICTA_SLEEP);          // (a sleep is ~1 us: far longer than one hop of the dependency chain)
-#endif
-        if (++spins > (1u << 24)) { if (lane == 0) C->err = INF_ERR_INPUT; break; }    // safety valve, never taken
-        continue;
-      }
-      ICTA_ORDER();
-      // copy: source and destination of a ready piece are disjoint when dist >= n (the common case): head bytes up to
-      // the destination's word boundary, whole words (two aligned loads + funnel shift each), tail bytes
-      const bool wrap = ok && dist < n;
-      if (ok && !wrap) {
-        const uint32_t h = min(n, (4u - (cur & 3u)) & 3u);
-        #pragma unroll
-        for (uint32_t k = 0; k < 3; k++) if (k < h) win[cur + k] = win[sa + k];
-        const uint32_t mid = (n - h) >> 2;
-        const uint32_t s0 = sa + h, sh8 = (s0 & 3u) * 8u;
-        const uint32_t* const sw = reinterpret_cast<const uint32_t*>(win + (s0 & ~3u));
-        uint32_t* const dw = reinterpret_cast<uint32_t*>(win + cur + h);
-        #pragma unroll
-        for (uint32_t jw = 0; jw < RESOLVE_PIECE / 4; jw++) if (jw < mid) dw[jw] = __funnelshift_r(sw[jw], sw[jw + 1], sh8);
-        const uint32_t t = h + 4u * mid;
-        #pragma unroll
-        for (uint32_t k = 0; k < 3; k++) if (t + k < n) win[cur + t + k] = win[sa + t + k];
-      }
-      if (__any_sync(FULL, wrap)) {            // a piece that overlaps its own source: byte k is src[k mod dist]
-        if (wrap) {
-          uint32_t j = 0;
-          for (uint32_t k = 0; k < n; k++) { win[cur + k] = win[sa + j]; j = j + 1 == dist ? 0 : j + 1; }
-        }
-      }
-      ICTA_ORDER();
-      if (ok) {
-        const uint32_t w = cur >> 5, b = cur & 31u, m = (1u << n) - 1u;      // n <= 16
-        atomicAnd(hb + w, ~(m << b));
-        if (b + n > 32u) atomicAnd(hb + w + 1, ~(m >> (32u - b)));
-        done += n;
-        pend = done < len;
-      }
-    }
-  }
+  // ---- C: dataflow (resolve_dataflow above)
+  if (warp < RESOLVE_WARPS) resolve_dataflow<RESOLVE_SLOTS, RESOLVE_WARPS>(smem_u32(win), smem_u32(hb), smem_u32(list), smem_u32(C->psel), obase, total, tid, C);
   return INF_OK;
 }
 
@@ -497,6 +554,11 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
 
   for (uint32_t i = tid; i < K::HB_WORDS; i += NT) hb[i] = 0;
   if (tid == 0) mbar_init(&C->mbar, 1);
+  if (tid < 8) {
+    unsigned long long m = 0;
+    for (uint32_t k = 0; k < 16; k++) m |= (unsigned long long)(tid ? k % (uint32_t)tid : 0u) << (4u * k);
+    C->psel[tid] = m;
+  }
   __syncthreads();
   uint32_t bar_parity = 0;
   bool store_pending = false;

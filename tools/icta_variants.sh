@@ -1,8 +1,9 @@
 #!/bin/bash
 # A/B of compile-time variants of the CTA-per-member inflate kernel on one wave (builds on the GPU box: nvcc is there).
-reads=${1:-4000000}
+# usage: tools/icta_variants.sh reads "flags1" "flags2" ...
+reads=${1:-4000000}; shift
 cd datafusion-bio-formats_b200/csrc
-for v in "-DBAMSCAN_ICTA_RESOLVE_WARPS=8" "-DBAMSCAN_ICTA_RESOLVE_WARPS=4" "-DBAMSCAN_ICTA_RESOLVE_WARPS=2"; do
+for v in "$@"; do
   echo "== $v"
   rm -f ../libbamscan.so
   make CXXFLAGS="-O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -lineinfo $v" > /dev/null 2>&1 || { echo build failed; continue; }

@@ -8,6 +8,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -131,8 +132,50 @@ static int resolve_member_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint
   return 0;
 }
 
+
+// Host model of the IN-ORDER resolver (one warp, frontier rule).  mode 1: a group of 32 consecutive matches at a time;
+// mode 2: rolling (a lane that finishes takes the next match of the list at once).  Returns warp iterations via S.
+static uint32_t g_piece = 16; static int g_lanes = 32;
+static int resolve_inorder_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint32_t olimit, int mode, Stats& S) {
+  const uint32_t wbeg = obase >> 5, wend = (olimit + 31) >> 5;
+  std::vector<uint16_t> list;
+  for (uint32_t w = wbeg; w < wend; w++) { uint32_t bits = hb[w]; hb[w] = 0; while (bits) { list.push_back((uint16_t)(w * 32 + __builtin_ctz(bits) - obase)); bits &= bits - 1; } }
+  const uint32_t total = (uint32_t)list.size();
+  struct Lane { uint32_t o, dist, len, done; bool pend; };
+  std::vector<Lane> L(g_lanes); for (auto& l : L) l.pend = false;
+  std::vector<uint8_t> fin(olimit + 64, 1);
+  if (mode >= 3) for (uint32_t r = 0; r < total; r++) { uint32_t o = obase + list[r], len = (((win[o + 1] << 8) | (win[o + 2] << 16)) >> 15) + 3; for (uint32_t k = 0; k < len; k++) fin[o + k] = 0; }
+  uint32_t next = 0;
+  std::vector<uint32_t> lane_next(g_lanes); for (int i = 0; i < g_lanes; i++) lane_next[i] = i;
+  auto fetch_static = [&](Lane& l, int i) { if (lane_next[i] >= total) return; l.o = obase + list[lane_next[i]]; lane_next[i] += g_lanes; uint32_t v = win[l.o] | (win[l.o + 1] << 8) | (win[l.o + 2] << 16); l.dist = (v & 0x7fff) + 1; l.len = (v >> 15) + 3; l.done = 0; l.pend = true; };
+  auto fetch = [&](Lane& l) { if (next >= total) return; l.o = obase + list[next++]; uint32_t v = win[l.o] | (win[l.o + 1] << 8) | (win[l.o + 2] << 16); l.dist = (v & 0x7fff) + 1; l.len = (v >> 15) + 3; l.done = 0; l.pend = true; };
+  for (;;) {
+    bool any = false; for (auto& l : L) any |= l.pend;
+    if (mode == 1) { if (!any) { if (next >= total) break; for (auto& l : L) fetch(l); S.resolve_batches++; } }
+    else if (mode == 4) { for (int i = 0; i < g_lanes; i++) if (!L[i].pend) fetch_static(L[i], i); any = false; for (auto& l : L) any |= l.pend; if (!any) break; }
+    else { for (auto& l : L) if (!l.pend) fetch(l); any = false; for (auto& l : L) any |= l.pend; if (!any) break; }
+    S.resolve_iters++;
+    uint32_t F = 0xffffffffu; for (auto& l : L) if (l.pend) F = std::min(F, l.o + l.done);
+    std::vector<uint32_t> n(g_lanes); int nok = 0;
+    for (int i = 0; i < g_lanes; i++) {
+      Lane& l = L[i]; n[i] = 0; if (!l.pend) continue;
+      uint32_t cur = l.o + l.done, sa = cur - l.dist, want = std::min(l.len - l.done, g_piece);
+      if (mode >= 3) { uint32_t k = 0; while (k < want && (sa + k >= cur || fin[sa + k])) k++; n[i] = k; }
+      else if (sa >= l.o || F >= cur) n[i] = want; else if (F > sa) n[i] = std::min(want, F - sa);
+      if (n[i]) nok++;
+    }
+    if (!nok) return 52;
+    S.lane_decodes += nok;
+    std::vector<std::array<uint8_t,64>> v(g_lanes);
+    for (int i = 0; i < g_lanes; i++) if (n[i]) { Lane& l = L[i]; uint32_t cur = l.o + l.done, sa = cur - l.dist, j = 0; for (uint32_t k = 0; k < n[i]; k++) { v[i][k] = win[sa + j]; if (++j == l.dist) j = 0; } }
+    for (int i = 0; i < g_lanes; i++) if (n[i]) { Lane& l = L[i]; uint32_t cur = l.o + l.done; for (uint32_t k = 0; k < n[i]; k++) { win[cur + k] = v[i][k]; fin[cur + k] = 1; } l.done += n[i]; l.pend = l.done < l.len; }
+  }
+  return 0;
+}
+
 // One member through the modelled CTA.  Returns 0 ok, else an error code (string in *why).
 static uint32_t overlap = 448;
+static int g_rmode = 0;
 static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t isize, int NT, uint32_t span_bytes, std::vector<uint8_t>& out, Stats& S, std::string* why) {
   // payload as words, with slack
   std::vector<uint32_t> pay((clen + 3) / 4 + 16, 0);
@@ -264,7 +307,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
     }
   }
   if (outpos != olimit) { *why = "isize mismatch"; return 7; }
-  if (int rr = resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
+  if (int rr = g_rmode ? resolve_inorder_model(win.data(), bm.data(), obase, olimit, g_rmode, S) : resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
   for (auto v : bm) if (v) { *why = "head bits left"; return 53; }
   out.assign(win.begin() + obase, win.begin() + obase + isize);
   return 0;
@@ -276,7 +319,7 @@ int main(int argc, char** argv) {
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--lanes") NT = atoi(argv[++i]); else if (a == "--max-members") maxm = atol(argv[++i]);
-    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--overlap") overlap = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true;
+    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--overlap") overlap = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true; else if (a == "--resolve") g_rmode = atoi(argv[++i]); else if (a == "--rlanes") g_lanes = atoi(argv[++i]); else if (a == "--piece") g_piece = (uint32_t)atol(argv[++i]);
   }
   FILE* f = fopen(argv[1], "rb"); if (!f) { perror("open"); return 2; }
   fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
