@@ -279,7 +279,7 @@ __device__ __forceinline__ uint32_t read_code_lengths_cta(const uint32_t* pay, u
     const uint32_t e = plut[bits & 127u];
     const uint32_t L = e & 15u, sy = e >> 16;
     uint32_t rec;
-    if (L == 0) rec = 3u << 4;
+    if (L == 0) rec = (3u << 4) | (255u << 6);
     else if (sy < 16u) rec = (L - 1u) | (sy << 6);
     else if (sy == 16u) rec = (L + 2u - 1u) | (1u << 4) | ((3u + ((bits >> L) & 3u)) << 6);
     else if (sy == 17u) rec = (L + 3u - 1u) | (2u << 4) | ((3u + ((bits >> L) & 7u)) << 6);
@@ -288,34 +288,39 @@ __device__ __forceinline__ uint32_t read_code_lengths_cta(const uint32_t* pay, u
   }
   __syncthreads();
   if (tid == 0) {
-    uint32_t q = 0, i = 0, prev = 0, k = 0, e = INF_OK;
-    while (i < total) {
-      if (q >= n_tab) { e = n_tab == tab_cap ? INF_RETRY : INF_ERR_INPUT; break; }
-      const uint32_t t = tab[q];
-      const uint32_t kind = (t >> 4) & 3u, pl = t >> 6;
-      if (kind == 3u || (kind == 1u && i == 0u)) { e = INF_ERR_TABLE; break; }
-      const uint32_t rep = kind ? pl : 1u;
-      const uint32_t val = kind == 0u ? pl : (kind == 1u ? prev : 0u);
-      prev = val;
-      if (i + rep > total) { e = INF_ERR_TABLE; break; }
-      chain[k++] = i | (rep << 9) | (val << 17);
-      i += rep;
-      q += (t & 15u) + 1u;
+    // The serial part: follow the chain of real symbols.  Per step only "record -> bits consumed -> next position -> load" is on
+    // the dependency chain (~45 cycles; the next record is loaded before this one is looked at); validity, the value of a
+    // "repeat previous" and the expansion are done by all threads below.  An invalid code has run length 255 and ends the walk.
+    uint32_t q = 0, i = 0, k = 0;
+    uint32_t t = n_tab ? tab[0] : 0u;
+    while (i < total && q < n_tab) {
+      const uint32_t qn = q + (t & 15u) + 1u;
+      const uint32_t tn = tab[min(qn, n_tab - 1u)];
+      chain[k++] = t | (i << 16);
+      i += ((t >> 4) & 3u) ? (t >> 6) : 1u;
+      q = qn; t = tn;
     }
     C->last_lane = k;                 // (scratch: number of chain records)
     C->last_info = q;
-    if (e) C->err = e;
+    if (i < total) C->err = n_tab == tab_cap ? INF_RETRY : INF_ERR_INPUT;     // ran out of table / input (a format error found below wins)
   }
   __syncthreads();
-  if (C->err) return C->err;
   const uint32_t k = C->last_lane;
   for (uint32_t j = tid; j < k; j += NT) {
     const uint32_t c = chain[j];
-    const uint32_t i0 = c & 511u, rep = (c >> 9) & 255u, val = c >> 17;
+    const uint32_t i0 = c >> 16, kind = (c >> 4) & 3u, pl = (c >> 6) & 255u, rep = kind ? pl : 1u;
+    if (kind == 3u || (kind == 1u && i0 == 0u) || i0 + rep > total) { C->err = INF_ERR_TABLE; continue; }
+    uint32_t val = kind == 0u ? pl : 0u;
+    if (kind == 1u) {                  // repeat previous: the value of the nearest earlier symbol that is not a repeat
+      uint32_t jj = j - 1u, cc = chain[jj];
+      while (((cc >> 4) & 3u) == 1u && jj > 0u) cc = chain[--jj];
+      val = ((cc >> 4) & 3u) == 0u ? (cc >> 6) & 255u : 0u;
+    }
     for (uint32_t r = 0; r < rep; r++) C->cl[i0 + r] = (uint8_t)val;
   }
-  *end_pos = start_pos + C->last_info;
   __syncthreads();
+  if (C->err) return C->err;
+  *end_pos = start_pos + C->last_info;
   if (C->cl[256] == 0) return INF_ERR_TABLE;
   return INF_OK;
 }
