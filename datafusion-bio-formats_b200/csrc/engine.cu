@@ -244,7 +244,10 @@ namespace bamscan {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static double wall_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
-constexpr int ICTA_NT = 256;                      // threads of the CTA-per-member inflate kernel
+#ifndef BAMSCAN_ICTA_NT
+#define BAMSCAN_ICTA_NT 256
+#endif
+constexpr int ICTA_NT = BAMSCAN_ICTA_NT;                      // threads of the CTA-per-member inflate kernel
 using IctaCfg = icta::Cfg<ICTA_NT>;
 static bool g_crc_init[64] = {};
 static uint32_t* g_crc_tabs[64] = {};

@@ -35,7 +35,7 @@ constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is giv
 #define BAMSCAN_ICTA_RESOLVE_SLOTS 1
 #endif
 #ifndef BAMSCAN_ICTA_RESOLVE_WARPS
-#define BAMSCAN_ICTA_RESOLVE_WARPS 8
+#define BAMSCAN_ICTA_RESOLVE_WARPS 0          // 0: every warp of the CTA
 #endif
 constexpr int RESOLVE_SLOTS = BAMSCAN_ICTA_RESOLVE_SLOTS;   // matches per lane the resolver keeps in flight
 constexpr int RESOLVE_WARPS = BAMSCAN_ICTA_RESOLVE_WARPS;   // warps of the resolver
@@ -50,7 +50,7 @@ template <int NT>
 struct Cfg {
   static constexpr int WARPS = NT / 32;
   static constexpr uint32_t WIN_BYTES = 65536 + 32;
-  static constexpr uint32_t PAY_BYTES = 29 * 1024;            // payload buffer (larger payloads are streamed through it)
+  static constexpr uint32_t PAY_BYTES = (NT <= 384 ? 29 : 27) * 1024;            // payload buffer (larger payloads are streamed through it)
   static constexpr uint32_t PAY_SLACK = 64;
   static constexpr uint32_t HB_WORDS = 2052;                  // head bitmap: one bit per window byte
   static constexpr uint32_t LUT_LL_WORDS = ROOT_LL + SUB_LL, LUT_D_WORDS = ROOT_D + SUB_D;
@@ -497,7 +497,8 @@ __device__ __forceinline__ uint32_t resolve_member(uint8_t* win, uint32_t* hb, u
   }
   __syncthreads();
   // ---- C: dataflow (resolve_dataflow above)
-  if (warp < RESOLVE_WARPS) resolve_dataflow<RESOLVE_SLOTS, RESOLVE_WARPS>(smem_u32(win), smem_u32(hb), smem_u32(list), smem_u32(C->psel), obase, total, tid, C);
+  constexpr int RW = RESOLVE_WARPS ? RESOLVE_WARPS : WARPS;
+  if (warp < RW) resolve_dataflow<RESOLVE_SLOTS, RW>(smem_u32(win), smem_u32(hb), smem_u32(list), smem_u32(C->psel), obase, total, tid, C);
   return INF_OK;
 }
 

@@ -173,6 +173,61 @@ static int resolve_inorder_model(uint8_t* win, uint32_t* hb, uint32_t obase, uin
   return 0;
 }
 
+// Host model of the multi-warp STATIC dataflow resolver (resolve_dataflow in kernels_inflate_cta.cuh): W warps x 32 lanes,
+// thread t takes matches t, t + 32 W, ...  `group_sync`: a warp adopts its next 32 matches only when all 32 current ones
+// are done, and (gate >= 0) starts polling a group only when the group `gate` groups in front of it is complete.
+// All warps execute one iteration per round (lockstep): rounds ~ latency, polls ~ issued iterations.
+static int g_gate = -1; static bool g_group_sync = false;
+static int resolve_static_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint32_t olimit, int W, Stats& S) {
+  const uint32_t wbeg = obase >> 5, wend = (olimit + 31) >> 5;
+  std::vector<uint16_t> list;
+  for (uint32_t w = wbeg; w < wend; w++) { uint32_t bits = hb[w]; hb[w] = 0; while (bits) { list.push_back((uint16_t)(w * 32 + __builtin_ctz(bits) - obase)); bits &= bits - 1; } }
+  const uint32_t total = (uint32_t)list.size();
+  std::vector<uint8_t> fin(olimit + 64, 1);
+  for (uint32_t r = 0; r < total; r++) { uint32_t o = obase + list[r], len = (((win[o + 1] << 8) | (win[o + 2] << 16)) >> 15) + 3; for (uint32_t k = 0; k < len; k++) fin[o + k] = 0; }
+  const int T = 32 * W;
+  struct Lane { uint32_t o, dist, len, done, r; bool pend; };
+  std::vector<Lane> L(T);
+  const uint32_t ngroups = (total + 31) / 32;
+  std::vector<uint32_t> grp_left(ngroups + 1, 0);
+  for (uint32_t r = 0; r < total; r++) grp_left[r / 32]++;
+  auto load = [&](Lane& l, uint32_t r) { l.r = r; l.pend = r < total; l.done = 0; if (!l.pend) return; l.o = obase + list[r]; uint32_t v = win[l.o] | (win[l.o + 1] << 8) | (win[l.o + 2] << 16); l.dist = (v & 0x7fff) + 1; l.len = (v >> 15) + 3; };
+  for (int t = 0; t < T; t++) load(L[t], t);
+  long rounds = 0, polls = 0, cheap = 0;
+  for (;;) {
+    bool any = false; for (auto& l : L) any |= l.pend;
+    if (!any) break;
+    rounds++;
+    std::vector<std::pair<int, uint32_t>> todo;   // decisions from the state at the start of the round
+    std::vector<char> warp_real(W, 0);
+    for (int w = 0; w < W; w++) {
+      bool wp = false; uint32_t ming = 0xffffffffu;
+      for (int l = 0; l < 32; l++) if (L[w * 32 + l].pend) { wp = true; ming = std::min(ming, L[w * 32 + l].r / 32); }
+      if (!wp) continue;
+      if (g_gate >= 0 && ming >= (uint32_t)g_gate && grp_left[ming - g_gate] != 0) { cheap++; continue; }   // gated: one-word poll
+      polls++; warp_real[w] = 1;
+      for (int l = 0; l < 32; l++) {
+        Lane& a = L[w * 32 + l]; if (!a.pend) continue;
+        uint32_t cur = a.o + a.done, sa = cur - a.dist, want = std::min(a.len - a.done, g_piece);
+        if (a.dist < want && a.dist >= 8) want = a.dist;
+        uint32_t outn = std::min(want, a.dist), k = 0; while (k < outn && fin[sa + k]) k++;
+        uint32_t n = k >= outn ? want : (a.dist >= want ? k : 0);
+        if (n) { todo.push_back({w * 32 + l, n}); warp_real[w] = 2; }
+      }
+      if (warp_real[w] == 2) S.spans++;   // (reused as: productive iterations)
+    }
+    if (todo.empty() && cheap > 100000000) return 52;
+    for (auto& td : todo) { Lane& a = L[td.first]; uint32_t cur = a.o + a.done, sa = cur - a.dist, j = 0; uint8_t v[64]; for (uint32_t k = 0; k < td.second; k++) { v[k] = win[sa + j]; if (++j == a.dist) j = 0; } for (uint32_t k = 0; k < td.second; k++) { win[cur + k] = v[k]; fin[cur + k] = 1; } a.done += td.second; if (a.done == a.len) { a.pend = false; grp_left[a.r / 32]--; } }
+    for (int w = 0; w < W; w++) {
+      if (g_group_sync) { bool wp = false; for (int l = 0; l < 32; l++) wp |= L[w * 32 + l].pend; if (!wp) for (int l = 0; l < 32; l++) { Lane& a = L[w * 32 + l]; if (a.r < total) load(a, a.r + T); } }
+      else for (int l = 0; l < 32; l++) { Lane& a = L[w * 32 + l]; if (!a.pend && a.r < total) load(a, a.r + T); }
+    }
+    if (rounds > 10000000) return 52;
+  }
+  S.resolve_iters += polls; S.resolve_batches += rounds; S.lane_slots += cheap;
+  return 0;
+}
+
 // One member through the modelled CTA.  Returns 0 ok, else an error code (string in *why).
 static uint32_t overlap = 448;
 static int g_rmode = 0;
@@ -307,7 +362,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
     }
   }
   if (outpos != olimit) { *why = "isize mismatch"; return 7; }
-  if (int rr = g_rmode ? resolve_inorder_model(win.data(), bm.data(), obase, olimit, g_rmode, S) : resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
+  if (int rr = g_rmode == 6 ? resolve_static_model(win.data(), bm.data(), obase, olimit, NT / 32, S) : g_rmode ? resolve_inorder_model(win.data(), bm.data(), obase, olimit, g_rmode, S) : resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
   for (auto v : bm) if (v) { *why = "head bits left"; return 53; }
   out.assign(win.begin() + obase, win.begin() + obase + isize);
   return 0;
@@ -319,7 +374,7 @@ int main(int argc, char** argv) {
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--lanes") NT = atoi(argv[++i]); else if (a == "--max-members") maxm = atol(argv[++i]);
-    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--overlap") overlap = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true; else if (a == "--resolve") g_rmode = atoi(argv[++i]); else if (a == "--rlanes") g_lanes = atoi(argv[++i]); else if (a == "--piece") g_piece = (uint32_t)atol(argv[++i]);
+    else if (a == "--span-bytes") span_bytes = (uint32_t)atol(argv[++i]); else if (a == "--overlap") overlap = (uint32_t)atol(argv[++i]); else if (a == "--stats") stats = true; else if (a == "--resolve") g_rmode = atoi(argv[++i]); else if (a == "--gate") g_gate = atoi(argv[++i]); else if (a == "--group-sync") g_group_sync = true; else if (a == "--rlanes") g_lanes = atoi(argv[++i]); else if (a == "--piece") g_piece = (uint32_t)atol(argv[++i]);
   }
   FILE* f = fopen(argv[1], "rb"); if (!f) { perror("open"); return 2; }
   fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
