@@ -79,7 +79,7 @@ struct Ctl {
   uint32_t warp_tot[32];
   uint32_t n_matches;
   uint32_t crc_part[32];
-  uint16_t cnt[2][16], first[2][16], nxt[2][16];
+  uint16_t cnt[2][16], first[2][16], nxt[2][16], offs[2][16];
   uint8_t cl[320];
 };
 static_assert(sizeof(Ctl) <= 1024, "Ctl fits its slot");
@@ -122,21 +122,24 @@ __device__ __forceinline__ void red_and_shared(uint32_t a, uint32_t v) { asm vol
 
 __device__ __forceinline__ uint32_t brev_n(uint32_t v, uint32_t bits) { return __brev(v) >> (32u - bits); }
 
-// Canonical Huffman build into a two-level LUT (format: inflate_cta_core.h), one warp.  `S` selects the scratch rows.
-// Returns 0 ok, INF_ERR_TABLE for an over-subscribed code, INF_RETRY when the second-level tables do not fit.
-template <int RBITS, bool DIST>
-__device__ __noinline__ uint32_t build_lut_warp(const uint8_t* cl, int n, uint32_t* lut, uint32_t sub_cap, Ctl* C, int S, int lane) {
-  constexpr uint32_t ROOT = 1u << RBITS;
-  uint16_t* cnt = C->cnt[S]; uint16_t* first = C->first[S]; uint16_t* nxt = C->nxt[S];
+// Canonical Huffman build into a two-level LUT (format: inflate_cta_core.h), in three steps:
+//   lut_prepare_warp  one warp per table: counts, first codes, every symbol's code and the symbols sorted by (length, symbol);
+//   lut_fill_root     ALL threads: root entry idx is decoded canonically (<= RBITS steps) -- perfectly balanced, where a
+//                     symbol-centric fill leaves one lane writing 2^(RBITS - len) entries for the shortest code;
+//   lut_sub_warp      one warp per table: second-level tables for the codes longer than RBITS bits.
+// `S` selects the scratch rows of Ctl.  Error codes: INF_ERR_TABLE for an over-subscribed code, INF_RETRY when the
+// second-level tables do not fit.
+template <int RBITS>
+__device__ __forceinline__ uint32_t lut_prepare_warp(const uint8_t* cl, int n, Ctl* C, int S, uint16_t* sorted, uint16_t* codes, int lane) {
+  uint16_t* cnt = C->cnt[S]; uint16_t* first = C->first[S]; uint16_t* nxt = C->nxt[S]; uint16_t* offs = C->offs[S];
   if (lane < 16) { cnt[lane] = 0; nxt[lane] = 0; }
-  for (uint32_t i = lane; i < ROOT + sub_cap; i += 32) lut[i] = E_BAD;
   __syncwarp();
   for (int s = lane; s < n; s += 32) {
     const uint32_t L = cl[s];
     if (L) atomicAdd(reinterpret_cast<unsigned int*>(cnt) + (L >> 1), (L & 1) ? 0x10000u : 1u);   // 16-bit counters packed in pairs
   }
   __syncwarp();
-  uint32_t code = 0, left = 1;
+  uint32_t code = 0, left = 1, off = 0;
   bool over = false;
   for (int len = 1; len <= 15; len++) {
     const uint32_t c = cnt[len];
@@ -144,17 +147,15 @@ __device__ __noinline__ uint32_t build_lut_warp(const uint8_t* cl, int n, uint32
     left <<= 1;
     if (c > left) over = true;
     left -= c;
-    if (lane == len) first[len] = (uint16_t)code;
+    if (lane == len) { first[len] = (uint16_t)code; offs[len] = (uint16_t)off; }
+    off += c;
   }
   if (over) return INF_ERR_TABLE;
   __syncwarp();
-  // pass 1: canonical code of every symbol (kept in registers: <= 9 symbols per lane); root entries of short codes;
-  //         per root prefix of a long code, the widest remainder (atomicMax on the root slot, E_SUB | bits > E_BAD)
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t my_code[9];
   #pragma unroll
   for (int b = 0; b < 9; b++) {
-    if (b * 32 >= n) { my_code[b] = 0; continue; }           // (uniform: the distance alphabet needs one pass)
+    if (b * 32 >= n) break;                                    // (uniform: the distance alphabet needs one pass)
     const int s = b * 32 + lane;
     const uint32_t L = (s < n) ? cl[s] : 0u;
     const uint32_t m = __match_any_sync(FULL, L);
@@ -162,51 +163,70 @@ __device__ __noinline__ uint32_t build_lut_warp(const uint8_t* cl, int n, uint32
     __syncwarp();
     if (L && (m & lt) == 0) nxt[L] = (uint16_t)(nxt[L] + __popc(m));
     __syncwarp();
-    const uint32_t cd = first[L] + r;
-    my_code[b] = cd;
-    if (L) {
-      if (L <= (uint32_t)RBITS) {
-        const uint32_t e = DIST ? entry_dist((uint32_t)s, L) : entry_litlen((uint32_t)s, L);
-        for (uint32_t idx = brev_n(cd, L); idx < ROOT; idx += (1u << L)) lut[idx] = e;
-      } else {
-        atomicMax(lut + brev_n(cd >> (L - RBITS), RBITS), E_SUB | (L - RBITS));
-      }
-    }
+    if (L) { sorted[offs[L] + r] = (uint16_t)s; codes[s] = (uint16_t)(first[L] + r); }
   }
-  __syncwarp();
-  // second-level tables: one per root prefix that carries long codes; prefixes of long codes are the top of the code space
+  return INF_OK;
+}
+
+template <int RBITS, bool DIST, int NT>
+__device__ __forceinline__ void lut_fill_root(uint32_t* lut, uint32_t sub_cap, const Ctl* C, int S, const uint16_t* sorted, int tid) {
+  constexpr uint32_t ROOT = 1u << RBITS;
+  const uint16_t* cnt = C->cnt[S]; const uint16_t* first = C->first[S]; const uint16_t* offs = C->offs[S];
+  for (uint32_t idx = tid; idx < ROOT; idx += NT) {
+    const uint32_t rev = __brev(idx) >> (32 - RBITS);          // the code bits, first bit on top
+    uint32_t hl = 0, hd = 0;
+    #pragma unroll
+    for (int L = 1; L <= RBITS; L++) {
+      const uint32_t d = (rev >> (RBITS - L)) - first[L];
+      if (d < cnt[L]) { hl = L; hd = d + offs[L]; }            // (prefix code: at most one length matches)
+    }
+    uint32_t e = E_BAD;
+    if (hl) { const uint32_t sy = sorted[hd]; e = DIST ? entry_dist(sy, hl) : entry_litlen(sy, hl); }
+    lut[idx] = e;
+  }
+  for (uint32_t i = ROOT + tid; i < ROOT + sub_cap; i += NT) lut[i] = E_BAD;
+}
+
+template <int RBITS, bool DIST>
+__device__ __forceinline__ uint32_t lut_sub_warp(const uint8_t* cl, int n, uint32_t* lut, uint32_t sub_cap, Ctl* C, int S, const uint16_t* codes, int lane) {
+  constexpr uint32_t ROOT = 1u << RBITS;
+  const uint16_t* cnt = C->cnt[S]; const uint16_t* first = C->first[S];
   uint32_t any_long = 0;
   for (int len = RBITS + 1; len <= 15; len++) any_long += cnt[len];
-  if (any_long) {
-    const uint32_t q_min = (uint32_t)first[RBITS + 1] >> 1;
-    uint32_t base = ROOT;
-    for (uint32_t q0 = q_min; q0 < ROOT; q0 += 32) {
-      const uint32_t q = q0 + lane;
-      uint32_t slot = 0, sz = 0, sb = 0;
-      if (q < ROOT) {
-        slot = brev_n(q, RBITS);
-        const uint32_t e = lut[slot];
-        if (e & E_SUB) { sb = e & 31u; sz = 1u << sb; }
-      }
-      uint32_t incl = sz;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-      if (sz) lut[slot] = entry_sub((uint32_t)RBITS, sb, base + incl - sz);
-      base += __shfl_sync(FULL, incl, 31);
+  if (!any_long) return INF_OK;
+  // per root prefix of a long code, the widest remainder (atomicMax on the root slot, E_SUB | bits > E_BAD)
+  for (int s = lane; s < n; s += 32) {
+    const uint32_t L = cl[s];
+    if (L > (uint32_t)RBITS) atomicMax(lut + brev_n((uint32_t)codes[s] >> (L - RBITS), RBITS), E_SUB | (L - RBITS));
+  }
+  __syncwarp();
+  // one second-level table per root prefix that carries long codes; prefixes of long codes are the top of the code space
+  const uint32_t q_min = (uint32_t)first[RBITS + 1] >> 1;
+  uint32_t base = ROOT;
+  for (uint32_t q0 = q_min; q0 < ROOT; q0 += 32) {
+    const uint32_t q = q0 + lane;
+    uint32_t slot = 0, sz = 0, sb = 0;
+    if (q < ROOT) {
+      slot = brev_n(q, RBITS);
+      const uint32_t e = lut[slot];
+      if (e & E_SUB) { sb = e & 31u; sz = 1u << sb; }
     }
-    if (base > ROOT + sub_cap) return INF_RETRY;          // (entries past the budget were never written: see the guard below)
-    __syncwarp();
+    uint32_t incl = sz;
     #pragma unroll
-    for (int b = 0; b < 9; b++) {
-      const int s = b * 32 + lane;
-      const uint32_t L = (s < n) ? cl[s] : 0u;
-      if (L > (uint32_t)RBITS) {
-        const uint32_t cd = my_code[b], l2 = L - RBITS;
-        const uint32_t pe = lut[brev_n(cd >> l2, RBITS)];
-        const uint32_t sbits = pe & 31u, sbase = pe >> 16;
-        const uint32_t e = DIST ? entry_dist((uint32_t)s, L) : entry_litlen((uint32_t)s, L);
-        for (uint32_t idx = brev_n(cd & ((1u << l2) - 1u), l2); idx < (1u << sbits); idx += (1u << l2)) lut[sbase + idx] = e;
-      }
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    if (sz && base + incl <= ROOT + sub_cap) lut[slot] = entry_sub((uint32_t)RBITS, sb, base + incl - sz);
+    base += __shfl_sync(FULL, incl, 31);
+  }
+  if (base > ROOT + sub_cap) return INF_RETRY;
+  __syncwarp();
+  for (int s = lane; s < n; s += 32) {
+    const uint32_t L = cl[s];
+    if (L > (uint32_t)RBITS) {
+      const uint32_t cd = codes[s], l2 = L - RBITS;
+      const uint32_t pe = lut[brev_n(cd >> l2, RBITS)];
+      const uint32_t sbits = pe & 31u, sbase = pe >> 16;
+      const uint32_t e = DIST ? entry_dist((uint32_t)s, L) : entry_litlen((uint32_t)s, L);
+      for (uint32_t idx = brev_n(cd & ((1u << l2) - 1u), l2); idx < (1u << sbits); idx += (1u << l2)) lut[sbase + idx] = e;
     }
   }
   __syncwarp();
@@ -666,14 +686,27 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         __syncthreads();
         continue;
       }
-      // ---- tables: litlen by warp 0, distance by warp 1 ----
+      // ---- tables: prepared by warps 0 (litlen) and 1 (distance), root LUTs filled by everyone, second levels by warps 0 / 1 ----
       {
         const int n_ll = (int)C->n_ll, n_d = (int)C->n_d;
+        // scratch in the lane arrays (free until the count pass): symbols sorted by (length, symbol) and every symbol's code
+        uint16_t* const sorted_ll = reinterpret_cast<uint16_t*>(laneE), *const codes_ll = sorted_ll + 288, *const sorted_d = codes_ll + 288, *const codes_d = sorted_d + 32;
         uint32_t e = INF_OK;
-        if (warp == 0) e = build_lut_warp<R_LL, false>(C->cl, n_ll, lut_ll, SUB_LL, C, 0, lane);
-        else if (warp == 1 % WARPS) e = build_lut_warp<R_D, true>(C->cl + n_ll, n_d, lut_d, SUB_D, C, 1, lane);
-        if (WARPS == 1 && !e) e = build_lut_warp<R_D, true>(C->cl + n_ll, n_d, lut_d, SUB_D, C, 1, lane);
-        if (e && lane == 0) atomicMax(&C->err, e);          // INF_RETRY (15) wins over a format error of the other table
+        if (warp == 0) e = lut_prepare_warp<R_LL>(C->cl, n_ll, C, 0, sorted_ll, codes_ll, lane);
+        else if (warp == 1) e = lut_prepare_warp<R_D>(C->cl + n_ll, n_d, C, 1, sorted_d, codes_d, lane);
+        if (e && lane == 0) atomicMax(&C->err, e);
+        __syncthreads();
+        if (!C->err) {
+          lut_fill_root<R_LL, false, NT>(lut_ll, SUB_LL, C, 0, sorted_ll, tid);
+          lut_fill_root<R_D, true, NT>(lut_d, SUB_D, C, 1, sorted_d, tid);
+        }
+        __syncthreads();
+        if (!C->err) {
+          e = INF_OK;
+          if (warp == 0) e = lut_sub_warp<R_LL, false>(C->cl, n_ll, lut_ll, SUB_LL, C, 0, codes_ll, lane);
+          else if (warp == 1) e = lut_sub_warp<R_D, true>(C->cl + n_ll, n_d, lut_d, SUB_D, C, 1, codes_d, lane);
+          if (e && lane == 0) atomicMax(&C->err, e);        // INF_RETRY (15) wins over a format error of the other table
+        }
         __syncthreads();
         ICTA_PROF(3);
         err = C->err;
