@@ -626,7 +626,11 @@ static int decode_slice(BamScanStream* s, bool* produced) {
           default: DP.tags[tag_slot[i]].data = d;
         }
       }
-      decode_var_kernel<<<std::min<uint32_t>((n + VAR_WARPS - 1) / VAR_WARPS, 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
+      // short reads: 8 lanes per record (4 records per warp); long reads (and debug_flags bit 1): a warp per record
+      if (s->cur.long_records)
+        decode_var_kernel<32><<<std::min<uint32_t>((n + VAR_WARPS - 1) / VAR_WARPS, 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
+      else
+        decode_var_kernel<8><<<std::min<uint32_t>((n + VAR_WARPS * 4 - 1) / (VAR_WARPS * 4), 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
       s->st.kernel_launches++;
     }
     const size_t arena_bytes = AB.pos;

@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define F32T_HD __host__ __device__
+#define F32T_NOINLINE __noinline__      // a rare path: its registers and stack must not be charged to the decode kernels' main loops
 #else
 #define F32T_HD
+#define F32T_NOINLINE
 #endif
 
 namespace bamscan {
@@ -49,7 +51,7 @@ F32T_HD inline int f32t_cmp(const uint8_t* a, int na, const uint8_t* b, int nb) 
 }
 
 // Writes the text of the f32 with bit pattern `bits` to out (when out != nullptr) and returns its length (<= 64).
-F32T_HD inline uint32_t f32_to_text(uint32_t bits, uint8_t* out) {
+F32T_HD F32T_NOINLINE inline uint32_t f32_to_text(uint32_t bits, uint8_t* out) {
   const uint32_t sign = bits >> 31, ex = (bits >> 23) & 0xffu, mant = bits & 0x7fffffu;
   uint32_t o = 0;
 #define F32T_PUT(c) do { if (out) out[o] = (uint8_t)(c); o++; } while (0)

@@ -11,7 +11,7 @@
 //                          locates / converts every requested tag.
 //   multi_scan_*         : exclusive prefix sums turning the length arrays into Arrow i32 offsets
 //                          (all var-len columns in one launch, grid.y = column).
-//   decode_var_kernel    : one WARP per record.  Copies / transcodes the var-len payloads to their final
+//   decode_var_kernel    : a group of 8 lanes (short reads) or a whole warp (long reads) per record.  Copies / transcodes the var-len payloads to their final
 //                          offsets: name, chrom / mate_chrom (dictionary expand), CIGAR text (or raw words),
 //                          sequence (4-bit -> ASCII via shared LUT), qualities (+33), Z/H/A/int-as-text tags,
 //                          B arrays with element-wise checked conversion.
@@ -144,7 +144,7 @@ __device__ __forceinline__ TagConv convert_tag(const DecodeParams& P, const TagP
 
 // ---------------------------------------------------------------------------------------------
 // phase 1: one thread per record
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 decode_fixed_kernel(const DecodeParams P) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -449,28 +449,29 @@ multi_scan_apply_kernel(ScanCols C, const uint64_t* __restrict__ tile_sums, uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 3: one warp per record
+// phase 3: a GROUP of G lanes per record (G = 8 for short reads: four records per warp; G = 32 for long reads)
 // out[i] = (in[i] + add) mod 256 (byte-wise, no carry between bytes), 4 bytes per lane and step on destination-aligned
 // words; the source word is assembled from two aligned loads.  Returns (per lane) the OR of the "bad byte" masks: an OUTPUT
 // byte >= 0x80 (a non-ASCII name byte; a quality q with 95 <= q <= 222, whose char::from(q + 33) is a two-byte UTF-8
 // sequence).  The missing-quality fill 0xFF wraps to 0x20 exactly as the reference's u8 addition does in a release build.
-// Reads up to 3 bytes past src + n (the inflated buffer carries slack).
-__device__ __forceinline__ uint32_t warp_map4(uint8_t* dst, const uint8_t* src, uint32_t n, int lane, uint32_t add4) {
+// Reads up to 3 bytes past src + n (the inflated buffer carries slack).  `gl` = lane within the group.
+template <int G>
+__device__ __forceinline__ uint32_t grp_map4(uint8_t* dst, const uint8_t* src, uint32_t n, int gl, uint32_t add4) {
   uint32_t bad = 0;
   const uint32_t add1 = add4 & 0xffu;
-  if (n <= 32u) {                                              // names, short tags: one predicated byte load / store
-    if ((uint32_t)lane < n) { const uint32_t c = (src[lane] + add1) & 0xffu; bad = c & 0x80u; dst[lane] = (uint8_t)c; }
+  if (n <= (uint32_t)G) {                                      // names, short tags: one predicated byte load / store
+    if ((uint32_t)gl < n) { const uint32_t c = (src[gl] + add1) & 0xffu; bad = c & 0x80u; dst[gl] = (uint8_t)c; }
     return bad;
   }
   const uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
-  if ((uint32_t)lane < head) { const uint32_t c = (src[lane] + add1) & 0xffu; bad |= c & 0x80u; dst[lane] = (uint8_t)c; }
+  if ((uint32_t)gl < head) { const uint32_t c = (src[gl] + add1) & 0xffu; bad |= c & 0x80u; dst[gl] = (uint8_t)c; }
   dst += head; src += head; n -= head;
   const uint32_t nw = n >> 2;
   const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
   const uint32_t sh = (uint32_t)(sa & 3u) * 8u;
   uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-  for (uint32_t j = lane; j < nw; j += 32) {
+  for (uint32_t j = gl; j < nw; j += G) {
     const uint32_t lo = sw[j];
     const uint32_t v = sh ? __funnelshift_r(lo, sw[j + 1], sh) : lo;
     const uint32_t o = ((v & 0x7f7f7f7fu) + add4) ^ (v & 0x80808080u);     // per-byte sum mod 256 (add4 bytes are < 0x80)
@@ -478,10 +479,11 @@ __device__ __forceinline__ uint32_t warp_map4(uint8_t* dst, const uint8_t* src, 
     dw[j] = o;
   }
   const uint32_t t0 = nw << 2;
-  if (t0 + (uint32_t)lane < n) { const uint32_t c = (src[t0 + lane] + add1) & 0xffu; bad |= c & 0x80u; dst[t0 + lane] = (uint8_t)c; }
+  if (t0 + (uint32_t)gl < n) { const uint32_t c = (src[t0 + gl] + add1) & 0xffu; bad |= c & 0x80u; dst[t0 + gl] = (uint8_t)c; }
   return bad;
 }
-__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) { (void)warp_map4(dst, src, n, lane, 0u); }
+template <int G>
+__device__ __forceinline__ void grp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int gl) { (void)grp_map4<G>(dst, src, n, gl, 0u); }
 
 __device__ __forceinline__ uint32_t render_u32(uint8_t* dst, uint32_t v) {   // decimal, returns digits written
   uint32_t d = ndigits_u32(v);
@@ -498,7 +500,12 @@ __device__ __forceinline__ uint32_t utf8_put(uint8_t* out, uint32_t cp) {
 
 constexpr int VAR_WARPS = 8;
 
-__global__ void __launch_bounds__(VAR_WARPS * 32)
+// One warp instruction serves 32 / G records.  With a warp per 340-byte record (round 1) most steps moved a handful of bytes
+// (name 20, chrom 4, CIGAR text 4, MD 3, RG 6) with 32 lanes issued: ~700 warp instructions per record, issue bound at
+// 10 % of the HBM roofline.  Eight lanes per record cut that to ~120.  Group-wide shuffles use the width argument; a loop's
+// trip count is the maximum over the warp's groups (records of one file are alike, so little is lost).
+template <int G>
+__global__ void __launch_bounds__(VAR_WARPS * 32, 6)
 decode_var_kernel(const DecodeParams P) {
   __shared__ uint16_t seq_lut[256];
   {
@@ -506,77 +513,83 @@ decode_var_kernel(const DecodeParams P) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) seq_lut[i] = (uint16_t)((uint8_t)codes[i >> 4] | ((uint16_t)(uint8_t)codes[i & 15] << 8));
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  constexpr int GPW = 32 / G;                                  // groups (records) per warp
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1);
   const uint8_t* U = P.U;
-  // grid-stride over records: a resident warp handles many records, so the LUT set-up and launch cost are amortised
-  for (uint32_t r = blockIdx.x * VAR_WARPS + (threadIdx.x >> 5); r < P.n; r += gridDim.x * VAR_WARPS) {
-  const uint32_t o = P.rec_off[r];
-  const uint32_t bs = ld_u32(U, o);
+  // grid-stride over records: a resident warp handles many records, so the LUT set-up and launch cost are amortised.
+  // All lanes of a warp run the same number of iterations (shuffles inside): a group past the end works on nothing.
+  const uint32_t stride = gridDim.x * VAR_WARPS * GPW;
+  for (uint32_t r0 = (blockIdx.x * VAR_WARPS + (threadIdx.x >> 5)) * GPW; r0 < P.n; r0 += stride) {
+  const uint32_t r = r0 + (uint32_t)(lane / G);
+  const bool on = r < P.n;
+  const uint32_t o = on ? P.rec_off[r] : P.rec_off[0];
   const int32_t ref = (int32_t)ld_u32(U, o + 4);
   uint32_t w = ld_u32(U, o + 12);
   const uint32_t l_name = w & 0xffu;
-  const uint32_t n_cig = ld_u32(U, o + 16) & 0xffffu;
-  const uint32_t l_seq = ld_u32(U, o + 20);
+  const uint32_t n_cig = on ? ld_u32(U, o + 16) & 0xffffu : 0u;
+  const uint32_t l_seq = on ? ld_u32(U, o + 20) : 0u;
   const int32_t nref = (int32_t)ld_u32(U, o + 24);
   const uint32_t o_name = o + 36, o_cig = o_name + l_name, o_seq = o_cig + 4u * n_cig;
   const uint32_t o_qual = o_seq + (l_seq + 1u) / 2u;
-  (void)bs;
 
-  if (P.d_name) {
+  if (P.d_name && on) {
     uint8_t* dst = P.d_name + P.l_name[r];
     uint32_t n = l_name ? l_name - 1u : 0u;
-    if (warp_map4(dst, U + o_name, n, lane, 0u)) set_err(P.err, DEC_ERR_NAME, r);
+    if (grp_map4<G>(dst, U + o_name, n, gl, 0u)) set_err(P.err, DEC_ERR_NAME, r);
   }
-  if (P.d_chrom && ref >= 0) warp_copy(P.d_chrom + P.l_chrom[r], P.ref_names + P.ref_name_off[ref], P.ref_name_off[ref + 1] - P.ref_name_off[ref], lane);
-  if (P.d_mchrom && nref >= 0) warp_copy(P.d_mchrom + P.l_mchrom[r], P.ref_names + P.ref_name_off[nref], P.ref_name_off[nref + 1] - P.ref_name_off[nref], lane);
+  if (P.d_chrom && on && ref >= 0) grp_copy<G>(P.d_chrom + P.l_chrom[r], P.ref_names + P.ref_name_off[ref], P.ref_name_off[ref + 1] - P.ref_name_off[ref], gl);
+  if (P.d_mchrom && on && nref >= 0) grp_copy<G>(P.d_mchrom + P.l_mchrom[r], P.ref_names + P.ref_name_off[nref], P.ref_name_off[nref + 1] - P.ref_name_off[nref], gl);
   if (P.d_cigar) {
-    uint8_t* dst = P.d_cigar + P.l_cigar[r];
-    if (P.binary_cigar) warp_copy(dst, U + o_cig, 4u * n_cig, lane);
+    uint8_t* dst = P.d_cigar + (on ? P.l_cigar[r] : 0);
+    if (P.binary_cigar) { if (on) grp_copy<G>(dst, U + o_cig, 4u * n_cig, gl); }
     else {
       uint32_t base = 0;
-      for (uint32_t k0 = 0; k0 < n_cig; k0 += 32) {          // uniform trip count
-        uint32_t k = k0 + lane, len = 0, op = 0, wlen = 0;
+      uint32_t nmax = n_cig;                                    // trip count: the largest op count among the warp's groups
+      #pragma unroll
+      for (int s = G; s < 32; s <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, s));
+      for (uint32_t k0 = 0; k0 < nmax; k0 += G) {
+        uint32_t k = k0 + gl, len = 0, op = 0, wlen = 0;
         if (k < n_cig) { uint32_t cw = ld_u32(U, o_cig + 4u * k); len = cw >> 4; op = cw & 15u; wlen = ndigits_u32(len) + 1u; }
         uint32_t x = wlen;
         #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, s); if (lane >= s) x += y; }
+        for (int s = 1; s < G; s <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, s, G); if (gl >= s) x += y; }
         if (k < n_cig) {
           uint8_t* q = dst + base + x - wlen;
           uint32_t d = render_u32(q, len);
           q[d] = (uint8_t)"MIDNSHP=X"[op > 8u ? 0u : op];
         }
-        base += __shfl_sync(0xffffffffu, x, 31);
+        base += __shfl_sync(0xffffffffu, x, G - 1, G);
       }
     }
   }
-  if (P.d_seq) {
+  if (P.d_seq && on) {
     uint8_t* dst = P.d_seq + P.l_seq[r];
     // 4 output characters (one aligned word) per lane and step: 2 or 3 input bytes through the two-base LUT
     const uint32_t head = min(l_seq, (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
     const uint8_t* ps = U + o_seq;
-    if ((uint32_t)lane < head) { uint16_t two = seq_lut[ps[lane >> 1]]; dst[lane] = (uint8_t)((lane & 1) ? (two >> 8) : two); }
+    if ((uint32_t)gl < head) { uint16_t two = seq_lut[ps[gl >> 1]]; dst[gl] = (uint8_t)((gl & 1) ? (two >> 8) : two); }
     const uint32_t nw = (l_seq - head) >> 2;
     uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
     if ((head & 1u) == 0u) {
       const uint8_t* p2 = ps + (head >> 1);
-      for (uint32_t j = lane; j < nw; j += 32) dw[j] = (uint32_t)seq_lut[p2[2u * j]] | ((uint32_t)seq_lut[p2[2u * j + 1u]] << 16);
+      for (uint32_t j = gl; j < nw; j += G) dw[j] = (uint32_t)seq_lut[p2[2u * j]] | ((uint32_t)seq_lut[p2[2u * j + 1u]] << 16);
     } else {
       const uint8_t* p2 = ps + (head >> 1);                    // char `head` is the LOW nibble of p2[0]
-      for (uint32_t j = lane; j < nw; j += 32) {
+      for (uint32_t j = gl; j < nw; j += G) {
         const uint32_t t0 = seq_lut[p2[2u * j]], t1 = seq_lut[p2[2u * j + 1u]], t2 = seq_lut[p2[2u * j + 2u]];
         dw[j] = (t0 >> 8) | (t1 << 8) | ((t2 & 0xffu) << 24);
       }
     }
     const uint32_t c0 = head + (nw << 2);
-    if (c0 + (uint32_t)lane < l_seq) { const uint32_t c = c0 + lane; uint16_t two = seq_lut[ps[c >> 1]]; dst[c] = (uint8_t)((c & 1u) ? (two >> 8) : two); }
+    if (c0 + (uint32_t)gl < l_seq) { const uint32_t c = c0 + gl; uint16_t two = seq_lut[ps[c >> 1]]; dst[c] = (uint8_t)((c & 1u) ? (two >> 8) : two); }
   }
-  if (P.d_qual) {
+  if (P.d_qual && on) {
     uint8_t* dst = P.d_qual + P.l_qual[r];
-    if (warp_map4(dst, U + o_qual, l_seq, lane, 0x21212121u)) set_err(P.err, DEC_ERR_QUAL, r);
+    if (grp_map4<G>(dst, U + o_qual, l_seq, gl, 0x21212121u)) set_err(P.err, DEC_ERR_QUAL, r);
   }
   for (int t = 0; t < P.n_tags; t++) {
     const TagPlan& T = P.tags[t];
-    if (!T.data || !T.src) continue;
+    if (!T.data || !T.src || !on) continue;
     uint32_t s = T.src[r];
     if (!s) continue;
     const uint8_t ty = U[s];
@@ -584,8 +597,8 @@ decode_var_kernel(const DecodeParams P) {
     if (T.kind == K_Utf8) {
       uint8_t* dst = T.data + T.lens[r];
       uint32_t n = (uint32_t)(T.lens[r + 1] - T.lens[r]);
-      if (ty == 'Z' || ty == 'H') warp_copy(dst, U + v, n, lane);
-      else if (lane == 0) {
+      if (ty == 'Z' || ty == 'H') grp_copy<G>(dst, U + v, n, gl);
+      else if (gl == 0) {
         if (ty == 'A') utf8_put(dst, U[v]);
         else if (ty == 'f') f32_to_text(ld_u32(U, v), dst);
         else {
@@ -608,7 +621,7 @@ decode_var_kernel(const DecodeParams P) {
       const uint32_t first = (uint32_t)T.lens[r];
       const int32_t kind = T.kind;
       bool bad = false;
-      for (uint32_t i = lane; i < cnt; i += 32) {
+      for (uint32_t i = gl; i < cnt; i += G) {
         uint32_t a = e0 + i * es;
         int64_t iv = 0; float fv = 0.f; bool isf = false;
         switch (st) {
