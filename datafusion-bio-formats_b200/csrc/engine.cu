@@ -212,8 +212,12 @@ struct BamScanStream {
   bool resources_ready = false;
   bool device_resident = false;
   bool device_export = false;            // batches stay in HBM and are handed out through the Arrow C Device Data Interface
-  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute = nullptr, ev_flags = nullptr, ev_t[6] = {};
+  // Chunk k runs entirely on s_chunk[k & 1] (inflate, record boundaries, rows, decode): the next chunk's inflate is queued on
+  // the other stream as soon as this chunk's boundaries are known, so it overlaps this chunk's decode kernels -- the inflate
+  // kernel fills the SMs' shared memory but leaves registers, issue slots and nearly all of the HBM bandwidth unused.  Every
+  // per-chunk device buffer is double buffered by the same slot; stream order makes the reuse two chunks later safe.
+  cudaStream_t s_chunk[2] = {nullptr, nullptr}, s_compute = nullptr /* = s_chunk[0] */, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute = nullptr, ev_flags[2] = {nullptr, nullptr}, ev_dflags = nullptr, ev_carry = nullptr, ev_t[2][6] = {}, ev_dt[2] = {};
   // iteration
   size_t range_idx = 0;
   std::vector<ChunkPlan> chunks; size_t chunk_idx = 0; bool range_open = false; bool finished = false;
@@ -222,7 +226,7 @@ struct BamScanStream {
   std::vector<int32_t> dec_cols;          // schema indices, unique
   std::vector<int32_t> out_to_dec;        // projection position -> index into dec_cols
   // device memory
-  DeviceBuf d_comp[2], d_blk[2], d_infl, d_carry, d_status, d_flags, d_seg, d_recoff, d_recoff2, d_keep, d_tiles, d_totals, d_scratch, d_arena[2], d_refs, d_sorted;
+  DeviceBuf d_comp[2], d_blk[2], d_infl[2], d_carry, d_status[2], d_flags[2], d_seg[2], d_recoff[2], d_recoff2[2], d_keep[2], d_tiles, d_totals, d_scratch, d_arena[2], d_refs, d_sorted;
   bool tail_seen = false, range_stop = false;   // per-reference unmapped tail state (physical_exec.rs:1203-1215)
   const uint8_t* d_comp_all = nullptr; DeviceBuf d_comp_all_buf; uint64_t comp_all_c0 = 0;
   uint32_t* d_hflags = nullptr;           // device alias of h_flags (mapped)
@@ -231,8 +235,9 @@ struct BamScanStream {
   uint8_t* h_stage[2] = {nullptr, nullptr}; size_t h_stage_cap[2] = {0, 0};   // pinned staging ring for the compressed bytes (the file mapping is read-only, not page-locked)
   int arena_flip = 0;
   // rows of the current chunk that are not decoded yet: a chunk is one inflate wave, a batch is one slice of its rows
+  bool slice_pending = false;    // a decode slice whose time / error word has not been collected (flush_slice)
   int64_t launched_chunk = -1;   // index in `chunks` of a chunk whose inflate + boundary kernels are already queued (run_chunk phase 1)
-  struct { const uint8_t* U = nullptr; const uint32_t* recoff = nullptr; uint32_t n = 0, pos = 0, rows_per_slice = 0; bool long_records = false; uint64_t ubytes = 0; } cur;
+  struct { const uint8_t* U = nullptr; const uint32_t* recoff = nullptr; uint32_t n = 0, pos = 0, rows_per_slice = 0; bool long_records = false; uint64_t ubytes = 0; cudaStream_t cs = nullptr; } cur;
   PendingBatch pending;
   std::vector<ReadyBatch> ready; size_t ready_pos = 0;
   BamScanStats st{};
@@ -331,18 +336,22 @@ static int stream_init(BamScanStream* s) {
   // per-scan state
   s->range_idx = 0; s->chunks.clear(); s->chunk_idx = 0; s->range_open = false; s->finished = false;
   s->carry_len = 0; s->have_h2d_ahead = false; s->ext_blocks = 8; s->need_spec = false; s->tail_seen = false; s->range_stop = false;
-  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->cur.n = s->cur.pos = 0; s->launched_chunk = -1; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
+  s->dec_cols.clear(); s->out_to_dec.clear(); s->arena_flip = 0; s->cur.n = s->cur.pos = 0; s->launched_chunk = -1; s->slice_pending = false; s->pending = PendingBatch(); s->ready.clear(); s->ready_pos = 0;
   s->st = BamScanStats{}; s->st.first_record_uoff = ~0ull; s->error = 0; s->d_comp_all = nullptr; s->comp_all_c0 = 0;
   if (!s->resources_ready) {
   rc = init_device_constants(f->device);
   if (rc) return rc;
-  CU_TRY(cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
+  for (auto& st : s->s_chunk) CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  s->s_compute = s->s_chunk[0];
   CU_TRY(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) CU_TRY(cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming));
-  CU_TRY(cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming));
-  for (auto& e : s->ev_t) CU_TRY(cudaEventCreate(&e));
+  for (auto& e : s->ev_flags) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&s->ev_dflags, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&s->ev_carry, cudaEventDisableTiming));
+  for (auto& row : s->ev_t) for (auto& e : row) CU_TRY(cudaEventCreate(&e));
+  for (auto& e : s->ev_dt) CU_TRY(cudaEventCreate(&e));
   CU_TRY(cudaHostAlloc((void**)&s->h_flags, 4096, cudaHostAllocPortable | cudaHostAllocMapped));
   CU_TRY(cudaHostGetDevicePointer((void**)&s->d_hflags, s->h_flags, 0));
   CU_TRY(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
@@ -382,7 +391,7 @@ static int stream_init(BamScanStream* s) {
 static void stream_destroy(BamScanStream* s, bool recycle = true) {
   if (!s) return;
   cudaSetDevice(s->f->device);
-  if (s->s_compute) cudaStreamSynchronize(s->s_compute);
+  for (auto st : s->s_chunk) if (st) cudaStreamSynchronize(st);
   if (s->s_h2d) cudaStreamSynchronize(s->s_h2d);
   if (s->s_d2h) cudaStreamSynchronize(s->s_d2h);
   if (s->pending.valid) { owner_unref(s->pending.owner); if (s->pending.done) cudaEventDestroy(s->pending.done); }
@@ -393,16 +402,19 @@ static void stream_destroy(BamScanStream* s, bool recycle = true) {
     std::lock_guard<std::mutex> lk(s->handle->mu);
     if (s->handle->idle_streams.size() < 2) { s->handle->idle_streams.push_back(s); return; }
   }
-  for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl, &s->d_carry, &s->d_status, &s->d_flags, &s->d_seg,
-                  &s->d_recoff, &s->d_recoff2, &s->d_keep, &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf, &s->d_sorted}) b->release();
+  for (auto* b : {&s->d_comp[0], &s->d_comp[1], &s->d_blk[0], &s->d_blk[1], &s->d_infl[0], &s->d_infl[1], &s->d_carry, &s->d_status[0], &s->d_status[1], &s->d_flags[0], &s->d_flags[1], &s->d_seg[0], &s->d_seg[1],
+                  &s->d_recoff[0], &s->d_recoff[1], &s->d_recoff2[0], &s->d_recoff2[1], &s->d_keep[0], &s->d_keep[1], &s->d_tiles, &s->d_totals, &s->d_scratch, &s->d_arena[0], &s->d_arena[1], &s->d_refs, &s->d_comp_all_buf, &s->d_sorted}) b->release();
   if (s->h_flags) cudaFreeHost(s->h_flags);
   for (auto& hd : s->h_descs) if (hd) cudaFreeHost(hd);
   for (auto& hs : s->h_stage) if (hs) cudaFreeHost(hs);
   for (auto& e : s->ev_h2d) if (e) cudaEventDestroy(e);
   if (s->ev_compute) cudaEventDestroy(s->ev_compute);
-  if (s->ev_flags) cudaEventDestroy(s->ev_flags);
-  for (auto& e : s->ev_t) if (e) cudaEventDestroy(e);
-  if (s->s_compute) cudaStreamDestroy(s->s_compute);
+  for (auto& e : s->ev_flags) if (e) cudaEventDestroy(e);
+  if (s->ev_dflags) cudaEventDestroy(s->ev_dflags);
+  if (s->ev_carry) cudaEventDestroy(s->ev_carry);
+  for (auto& row : s->ev_t) for (auto& e : row) if (e) cudaEventDestroy(e);
+  for (auto& e : s->ev_dt) if (e) cudaEventDestroy(e);
+  for (auto st : s->s_chunk) if (st) cudaStreamDestroy(st);
   if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
   if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
   delete s;
@@ -487,18 +499,28 @@ struct ArenaBuilder {
 };
 
 // Decodes the next slice of the current chunk's rows into a fresh arena and queues its D2H (one batch).
+// A decode slice is queued without waiting for it; its time (and, for device-resident runs, its error word) is collected when
+// the next slice starts or the partition ends.
+static int flush_slice(BamScanStream* s) {
+  if (!s->slice_pending) return BAMSCAN_OK;
+  s->slice_pending = false;
+  CU_TRY(cudaEventSynchronize(s->ev_dt[1]));
+  { float d = 0; cudaEventElapsedTime(&d, s->ev_dt[0], s->ev_dt[1]); s->st.ms_decode += d; }
+  if (s->device_resident && s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
+  return BAMSCAN_OK;
+}
+
 static int decode_slice(BamScanStream* s, bool* produced) {
   NvtxRange nv("bamscan: decode slice (fixed, scan, var) + D2H issue");
   BamFile* f = s->f;
-  cudaStream_t cs = s->s_compute;
+  cudaStream_t cs = s->cur.cs;
   int rc;
+  if ((rc = flush_slice(s))) return rc;
   const uint8_t* U = s->cur.U;
   const uint32_t n = std::min<uint32_t>(s->cur.rows_per_slice, s->cur.n - s->cur.pos);
   const uint32_t* d_recoff = s->cur.recoff + s->cur.pos;
   s->cur.pos += n;
-  uint32_t* d_flags = s->d_flags.as<uint32_t>();
-  (void)d_flags;
-  CU_TRY(cudaEventRecord(s->ev_t[5], cs));
+  CU_TRY(cudaEventRecord(s->ev_dt[0], cs));
   {
     // ---- arena region A
     const size_t n_dec = s->dec_cols.size();
@@ -586,8 +608,8 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       multi_scan_apply_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
       s->st.kernel_launches += 3;
       publish_kernel<<<1, 64, 0, cs>>>(s->d_totals.as<uint32_t>(), s->d_hflags + 16, 2 * SC.n_cols);
-      CU_TRY(cudaEventRecord(s->ev_flags, cs));
-      CU_TRY(cudaEventSynchronize(s->ev_flags));
+      CU_TRY(cudaEventRecord(s->ev_dflags, cs));
+      CU_TRY(cudaEventSynchronize(s->ev_dflags));
       CU_TRY(cudaGetLastError());
       // ---- arena region B
       for (int k = 0; k < SC.n_cols; k++) {
@@ -641,9 +663,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
     }
     if (s->device_resident) {
       // keep everything in HBM: only the decode error word travels
-      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);
-      CU_TRY(cudaStreamSynchronize(cs));
-      if (s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
+      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);     // (checked by flush_slice)
     } else if (s->device_export) {
       // device hand-off: the batch gets its own exactly-sized device allocation (a device-to-device copy on the side
       // stream, ~3 TB/s); only the decode error word travels to the host
@@ -681,9 +701,8 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       *produced = true;
     }
     }
-  CU_TRY(cudaEventRecord(s->ev_t[4], cs));
-  CU_TRY(cudaEventSynchronize(s->ev_t[4]));
-  { float d = 0; cudaEventElapsedTime(&d, s->ev_t[5], s->ev_t[4]); s->st.ms_decode += d; }
+  CU_TRY(cudaEventRecord(s->ev_dt[1], cs));
+  s->slice_pending = true;
   return BAMSCAN_OK;
 }
 
@@ -701,26 +720,26 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   const uint32_t data_hi = s->chunk_data_hi[slot], seg0 = HEADROOM;
   const uint32_t nb = s->n_descs[slot];
   int rc;
-  if ((rc = s->d_infl.ensure((size_t)HEADROOM + c.ubytes + INFL_PAD))) return rc;
-  if ((rc = s->d_status.ensure(4 * std::max<uint32_t>(nb, 1)))) return rc;
-  if ((rc = s->d_flags.ensure(256))) return rc;
+  if ((rc = s->d_infl[slot].ensure((size_t)HEADROOM + c.ubytes + INFL_PAD))) return rc;
+  if ((rc = s->d_status[slot].ensure(4 * std::max<uint32_t>(nb, 1)))) return rc;
+  if ((rc = s->d_flags[slot].ensure(256))) return rc;
   if ((rc = s->d_carry.ensure(HEADROOM))) return rc;
   const uint32_t seg_bytes = f->seg_bytes;
   const uint32_t n_seg = std::max<uint32_t>(1, (uint32_t)((c.ubytes + seg_bytes - 1) / seg_bytes));
   // seg arrays: start, exit, count, base (u32 each) + tail (u8)
-  if ((rc = s->d_seg.ensure((size_t)n_seg * 17 + 64))) return rc;
-  uint32_t* d_seg_start = s->d_seg.as<uint32_t>();
+  if ((rc = s->d_seg[slot].ensure((size_t)n_seg * 17 + 64))) return rc;
+  uint32_t* d_seg_start = s->d_seg[slot].as<uint32_t>();
   uint32_t* d_seg_exit = d_seg_start + n_seg;
   uint32_t* d_seg_count = d_seg_exit + n_seg;
   uint32_t* d_seg_base = d_seg_count + n_seg;
   uint8_t* d_seg_tail = reinterpret_cast<uint8_t*>(d_seg_base + n_seg);
-  uint32_t* d_flags = s->d_flags.as<uint32_t>();   // [0..7] boundary flags, [8] inflate ticket, [9] inflate err, [10..11] decode err
+  uint32_t* d_flags = s->d_flags[slot].as<uint32_t>();   // [0..7] boundary flags, [8] inflate ticket, [9] inflate err, [10..11] decode err
 
-  cudaStream_t cs = s->s_compute;
+  cudaStream_t cs = s->s_chunk[slot];
   const uint8_t* d_comp;
   if (s->device_resident) d_comp = s->d_comp_all + (c.c0 - s->comp_all_c0);
   else d_comp = s->d_comp[slot].as<uint8_t>();
-  uint8_t* U = s->d_infl.as<uint8_t>();
+  uint8_t* U = s->d_infl[slot].as<uint8_t>();
   const uint32_t carry = s->carry_len;
   // ---- boundaries
   BoundaryParams BP;
@@ -742,15 +761,18 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   CU_TRY(cudaMemsetAsync(d_flags + 5, 0xff, 8, cs));     // [5] first row of the target reference, [6] stop row
   CU_TRY(cudaMemsetAsync(d_flags + 11, 0xff, 4, cs));    // [11] first disagreeing seam
   CU_TRY(cudaMemsetAsync(d_flags + 13, 0xff, 4, cs));    // [13] first owned record of the chunk
-  CU_TRY(cudaEventRecord(s->ev_t[0], cs));
+  CU_TRY(cudaEventRecord(s->ev_t[slot][0], cs));
   if (nb) {
     int nl = 0;
-    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status.as<uint32_t>(), d_flags + 8, d_flags + 9, d_flags + 12, &s->d_sorted, &nl))) return rc;
+    if ((rc = launch_inflate(f, cs, d_comp, s->d_blk[slot].as<BlockDesc>(), nb, U, s->d_status[slot].as<uint32_t>(), d_flags + 8, d_flags + 9, d_flags + 12, &s->d_sorted, &nl))) return rc;
     s->st.kernel_launches += nl;
   }
-  CU_TRY(cudaEventRecord(s->ev_t[1], cs));
+  CU_TRY(cudaEventRecord(s->ev_t[slot][1], cs));
   // ---- carry-in
-  if (carry) CU_TRY(cudaMemcpyAsync(U + HEADROOM - carry, s->d_carry.p, carry, cudaMemcpyDeviceToDevice, cs));
+  if (carry) {
+    CU_TRY(cudaStreamWaitEvent(cs, s->ev_carry, 0));                  // the previous chunk's tail was copied out on the other stream
+    CU_TRY(cudaMemcpyAsync(U + HEADROOM - carry, s->d_carry.p, carry, cudaMemcpyDeviceToDevice, cs));
+  }
   WalkOut W{d_seg_start, d_seg_exit, d_seg_count, d_seg_tail, d_flags};
   seg_candidates_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, cs>>>(BP, d_seg_start, (f->debug_flags & 1) ? 1 : 0);
   seg_walk_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
@@ -759,10 +781,10 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   seg_scan_kernel<<<1, 1024, 0, cs>>>(d_seg_count, d_seg_start, d_seg_exit, d_seg_tail, d_seg_base, n_seg, d_flags);
   s->st.kernel_launches += 5;
   publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
-  CU_TRY(cudaEventRecord(s->ev_flags, cs));
+  CU_TRY(cudaEventRecord(s->ev_flags[slot], cs));
     if (phase == 1) return BAMSCAN_OK;
   }
-  CU_TRY(cudaEventSynchronize(s->ev_flags));
+  CU_TRY(cudaEventSynchronize(s->ev_flags[slot]));
   CU_TRY(cudaGetLastError());
   // ---- host: decisions
   const uint32_t* hf = s->h_flags;
@@ -785,17 +807,17 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   *owned_done = tail_off >= BP.own_hi;
   *new_carry = *owned_done ? 0 : data_hi - tail_off;
   if (*new_carry > HEADROOM) { set_error("BAM record larger than %u bytes is not supported", HEADROOM); return BAMSCAN_ERR_UNSUPPORTED; }
-  if (*new_carry) CU_TRY(cudaMemcpyAsync(s->d_carry.p, U + tail_off, *new_carry, cudaMemcpyDeviceToDevice, cs));
+  if (*new_carry) { CU_TRY(cudaMemcpyAsync(s->d_carry.p, U + tail_off, *new_carry, cudaMemcpyDeviceToDevice, cs)); CU_TRY(cudaEventRecord(s->ev_carry, cs)); }
   s->st.chunks++; s->st.blocks += nb; s->st.inflated_bytes += c.ubytes; s->st.compressed_bytes += c.c1 - c.c0;
   // seam evidence of block-range partitions (BamScanStats): where the first owned record starts, where the chain lands
   if (n_rec > 0 && s->st.first_record_uoff == ~0ull && hf[13] != 0xffffffffu && hf[13] >= HEADROOM) s->st.first_record_uoff = c.u0 + (hf[13] - HEADROOM);
   if (*owned_done) s->st.end_chain_uoff = c.u0 + (uint64_t)tail_off - HEADROOM;
-  CU_TRY(cudaEventRecord(s->ev_t[2], cs));
-  if (n_rec == 0) { CU_TRY(cudaEventRecord(s->ev_t[3], cs)); goto timing; }
+  CU_TRY(cudaEventRecord(s->ev_t[slot][2], cs));
+  if (n_rec == 0) { CU_TRY(cudaEventRecord(s->ev_t[slot][3], cs)); goto timing; }
   {
     // ---- record offsets
-    if ((rc = s->d_recoff.ensure(4ull * (n_rec + 1)))) return rc;
-    uint32_t* d_recoff = s->d_recoff.as<uint32_t>();
+    if ((rc = s->d_recoff[slot].ensure(4ull * (n_rec + 1)))) return rc;
+    uint32_t* d_recoff = s->d_recoff[slot].as<uint32_t>();
     seg_emit_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, d_seg_start, d_seg_count, d_seg_base, d_recoff, n_rec, tail_off);
     s->st.kernel_launches++;
     uint32_t n = n_rec;
@@ -813,39 +835,39 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
         for (size_t k = 0; k < rf.strs.size(); k++) { D.refs[k] = -2; for (size_t r = 0; r < f->ref_names.size(); r++) if (f->ref_names[r] == rf.strs[k]) { D.refs[k] = (int32_t)r; break; } }
         if (rf.column == BAMSCAN_COL_END) RR.needs_end = 1;
       }
-      if ((rc = s->d_keep.ensure(8ull * n_rec + 64))) return rc;
-      if ((rc = s->d_recoff2.ensure(4ull * (n_rec + 1)))) return rc;
-      uint32_t* d_keep = s->d_keep.as<uint32_t>(); uint32_t* d_pos = d_keep + n_rec;
+      if ((rc = s->d_keep[slot].ensure(8ull * n_rec + 64))) return rc;
+      if ((rc = s->d_recoff2[slot].ensure(4ull * (n_rec + 1)))) return rc;
+      uint32_t* d_keep = s->d_keep[slot].as<uint32_t>(); uint32_t* d_pos = d_keep + n_rec;
       if (RR.mode == 2) { rule_first_target_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(U, d_recoff, n_rec, RR.ref, d_flags); s->st.kernel_launches++; }
       rule_keep_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(U, d_recoff, n_rec, RR, d_keep, d_flags);
       rule_scan_kernel<<<1, 1024, 0, cs>>>(d_keep, d_pos, n_rec, d_flags);
-      rule_compact_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(d_recoff, d_pos, n_rec, s->d_recoff2.as<uint32_t>());
+      rule_compact_kernel<<<(n_rec + 255) / 256, 256, 0, cs>>>(d_recoff, d_pos, n_rec, s->d_recoff2[slot].as<uint32_t>());
       s->st.kernel_launches += 3;
       publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
-      CU_TRY(cudaEventRecord(s->ev_flags, cs));
-      CU_TRY(cudaEventSynchronize(s->ev_flags));
+      CU_TRY(cudaEventRecord(s->ev_flags[slot], cs));
+      CU_TRY(cudaEventSynchronize(s->ev_flags[slot]));
       CU_TRY(cudaGetLastError());
       n = s->h_flags[7];
       if (RR.mode == 2) { if (s->h_flags[5] != 0xffffffffu) s->tail_seen = true; if (s->h_flags[6] != 0xffffffffu) s->range_stop = true; }
-      d_recoff = s->d_recoff2.as<uint32_t>();
-      if (n == 0) { CU_TRY(cudaEventRecord(s->ev_t[3], cs)); goto timing; }
+      d_recoff = s->d_recoff2[slot].as<uint32_t>();
+      if (n == 0) { CU_TRY(cudaEventRecord(s->ev_t[slot][3], cs)); goto timing; }
     }
     // ---- hand the rows to decode_slice(): one batch per slice of <= SLICE_BYTES inflated
     const uint32_t n_slices = (uint32_t)std::max<uint64_t>(1, (c.ubytes + SLICE_BYTES - 1) / SLICE_BYTES);
-    s->cur.U = U; s->cur.recoff = d_recoff; s->cur.n = n; s->cur.pos = 0;
+    s->cur.U = U; s->cur.recoff = d_recoff; s->cur.n = n; s->cur.pos = 0; s->cur.cs = cs;
     s->cur.rows_per_slice = (n + n_slices - 1) / n_slices;
     s->cur.long_records = (f->debug_flags & 2) || (uint64_t)(data_hi - HEADROOM) / std::max<uint32_t>(n_rec, 1) > 2048;
     s->cur.ubytes = c.ubytes / n_slices + (HEADROOM / 4);
-    CU_TRY(cudaEventRecord(s->ev_t[3], cs));
+    CU_TRY(cudaEventRecord(s->ev_t[slot][3], cs));
   }
 timing:
-  CU_TRY(cudaEventRecord(s->ev_t[4], cs));
-  CU_TRY(cudaEventSynchronize(s->ev_t[4]));
+  CU_TRY(cudaEventRecord(s->ev_t[slot][4], cs));
+  CU_TRY(cudaEventSynchronize(s->ev_t[slot][4]));
   {
     float a = 0, b = 0, d = 0;
-    cudaEventElapsedTime(&a, s->ev_t[0], s->ev_t[1]);
-    cudaEventElapsedTime(&b, s->ev_t[1], s->ev_t[2]);
-    cudaEventElapsedTime(&d, s->ev_t[2], s->ev_t[3]);
+    cudaEventElapsedTime(&a, s->ev_t[slot][0], s->ev_t[slot][1]);
+    cudaEventElapsedTime(&b, s->ev_t[slot][1], s->ev_t[slot][2]);
+    cudaEventElapsedTime(&d, s->ev_t[slot][2], s->ev_t[slot][3]);
     s->st.ms_inflate += a; s->st.ms_boundary += b; s->st.ms_decode += d;
     if (trace2) fprintf(stderr, "[bamscan chunk] phase %d: %.2f ms wall in this call ; gpu inflate %.2f boundary %.2f emit+rules %.2f ms\n", phase, wall_ms() - tw0, a, b, d);
   }
@@ -862,10 +884,13 @@ static int issue_chunk_h2d(BamScanStream* s, size_t k) {
   return BAMSCAN_OK;
 }
 
-// Once every row of the current chunk is decoded, queue the next chunk's inflate + boundary kernels right away: the caller
-// is about to block on an older batch's D2H, and the GPU should not sit idle meanwhile.
+// Queues the next chunk's inflate + boundary kernels on the other chunk stream.  Called as soon as the current chunk's
+// boundaries (and so the carried tail) are known, i.e. BEFORE its rows are decoded: the two overlap on the GPU.
 static int launch_next_chunk_early(BamScanStream* s) {
-  if (s->cur.pos < s->cur.n || !s->range_open || s->finished || s->launched_chunk >= 0) return BAMSCAN_OK;
+  if (!s->range_open || s->finished || s->launched_chunk >= 0) return BAMSCAN_OK;
+  // host export is bound by the D2H link, not by the kernels: there the decode kernels keep the GPU to themselves (the batch
+  // reaches the link sooner) and the next inflate is queued once every row of this chunk is decoded
+  if (!s->device_resident && !s->device_export && s->cur.pos < s->cur.n) return BAMSCAN_OK;
   if (s->chunk_idx >= s->chunks.size()) return BAMSCAN_OK;          // extension chunks are planned when their turn comes
   const size_t k = s->chunk_idx;
   int rc = issue_chunk_h2d(s, k);
@@ -887,9 +912,9 @@ static int advance(BamScanStream* s, bool* produced) {
       if (!rc) rc = launch_next_chunk_early(s);
       return rc ? rc : 1;
     }
-    if (s->finished) return 0;
+    if (s->finished) { int frc = flush_slice(s); return frc ? frc : 0; }
     if (!s->range_open) {
-      if (s->range_idx >= s->part->ranges.size()) { s->finished = true; return 0; }
+      if (s->range_idx >= s->part->ranges.size()) { s->finished = true; int frc = flush_slice(s); return frc ? frc : 0; }
       const ScanRange& r = s->part->ranges[s->range_idx];
       if (r.region_mode < 0) { set_error("BAM region query failed: a region names a reference sequence that is not in the BAM header"); return BAMSCAN_ERR_INVALID; }
       s->tail_seen = false; s->range_stop = false;
@@ -925,11 +950,13 @@ static int advance(BamScanStream* s, bool* produced) {
     rc = run_chunk(s, s->chunks[k], r, slot, k == 0, produced, &new_carry, &owned_done, launched ? 2 : 0);
     s->launched_chunk = -1;
     if (rc) return rc;
-    if (s->cur.pos < s->cur.n && (rc = decode_slice(s, produced))) return rc;   // first slice now, the others on the next calls
     s->carry_len = new_carry;
     s->chunk_idx++;
     if (owned_done && s->chunks[k].extension) { s->carry_len = 0; s->range_open = false; s->range_idx++; }   // the tail record is complete
     else if (s->range_stop) { s->carry_len = 0; s->range_open = false; s->range_idx++; }                      // unmapped tail: another reference began
+    // first slice now (its kernels get the whole GPU: decode_slice does not wait for them), then the next chunk's inflate on the
+    // other stream -- a persistent kernel that fills the SMs as the decode CTAs drain and overlaps the remaining slices
+    if (s->cur.pos < s->cur.n && (rc = decode_slice(s, produced))) return rc;
     if ((rc = launch_next_chunk_early(s))) return rc;
     return 1;
   }
