@@ -888,9 +888,11 @@ static int issue_chunk_h2d(BamScanStream* s, size_t k) {
 // boundaries (and so the carried tail) are known, i.e. BEFORE its rows are decoded: the two overlap on the GPU.
 static int launch_next_chunk_early(BamScanStream* s) {
   if (!s->range_open || s->finished || s->launched_chunk >= 0) return BAMSCAN_OK;
-  // host export is bound by the D2H link, not by the kernels: there the decode kernels keep the GPU to themselves (the batch
-  // reaches the link sooner) and the next inflate is queued once every row of this chunk is decoded
-  if (!s->device_resident && !s->device_export && s->cur.pos < s->cur.n) return BAMSCAN_OK;
+  // By default the next inflate is queued once every row of this chunk is decoded.  debug_flags bit 5 queues it right behind
+  // the chunk's FIRST decode slice, so that inflate and the remaining decode kernels share the SMs.  Measured (100 M reads,
+  // device resident): the decode stage (66 ms) leaves the critical path but the co-running kernels take issue slots from the
+  // latency-bound inflate kernel (15.9 -> 17.5 ms per launch): 456 -> 450 ms per scan.  Not worth a 10 % slower dominant kernel.
+  if (!(s->f->debug_flags & 32) && s->cur.pos < s->cur.n) return BAMSCAN_OK;
   if (s->chunk_idx >= s->chunks.size()) return BAMSCAN_OK;          // extension chunks are planned when their turn comes
   const size_t k = s->chunk_idx;
   int rc = issue_chunk_h2d(s, k);

@@ -4,7 +4,7 @@ together with the hash of the kernel sources it was taken on (bench.py reports `
 while the hash still matches the tree -- never a literal).
 
 Run on the GPU box AFTER the plain command has exited 0:   python tools/prof_inflate.py 4500000 && python tools/ncu_traffic.py 4500000
-(4.5 M reads = 23 650 members: one full lane-group wave of 22 496 + the rest).
+(4.5 M reads = 23 650 members; bench.py scales the per-launch figure by members when its launches differ).
 """
 import csv, hashlib, io, json, os, subprocess, sys
 from pathlib import Path
@@ -33,9 +33,9 @@ for label, flags, regex in (("inflate_lg_kernel", "8", "regex:inflate_lg"), ("in
                              "duration_ms_under_ncu": dur * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}[du],
                              "registers": get("launch__registers_per_thread")[0], "ipc": get("sm__inst_executed.avg.per_cycle_elapsed")[0],
                              "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active")[0]}
-# the bench's dominant kernel on full waves is the lane-group kernel
-out["dram_bytes_per_launch"] = out["kernels"]["inflate_lg_kernel"]["dram_bytes_per_launch"]
-out["kernel"] = "inflate_lg_kernel (one full wave of 22496 members)"
+# the product path uses the CTA-per-member kernel for every launch (the lane-group kernel is captured beside it as the A/B baseline)
+out["dram_bytes_per_launch"] = out["kernels"]["inflate_cta_kernel"]["dram_bytes_per_launch"]
+out["kernel"] = "inflate_cta_kernel (one launch over %d reads' members)" % int(reads)
 (ROOT / "profiles").mkdir(exist_ok=True)
 (ROOT / "profiles" / "r2_inflate_traffic.json").write_text(json.dumps(out, indent=1))
 (ROOT / "gpurun_out" / "r2_inflate_traffic.json").write_text(json.dumps(out, indent=1))
