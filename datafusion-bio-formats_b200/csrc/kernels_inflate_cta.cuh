@@ -30,7 +30,10 @@ namespace icta {
 
 constexpr uint32_t INF_RETRY = 15;          // status: redo this member with the warp-per-member kernel
 constexpr uint32_t FRONT_DONE = 0xffffffffu;
-constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is given
+#ifndef BAMSCAN_ICTA_MIN_SUB_BITS
+#define BAMSCAN_ICTA_MIN_SUB_BITS 64
+#endif
+constexpr uint32_t MIN_SUB_BITS = BAMSCAN_ICTA_MIN_SUB_BITS;      // shortest sub-stream a lane is given
 #ifndef BAMSCAN_ICTA_RESOLVE_SLOTS
 #define BAMSCAN_ICTA_RESOLVE_SLOTS 1
 #endif
@@ -39,7 +42,14 @@ constexpr uint32_t MIN_SUB_BITS = 256;      // shortest sub-stream a lane is giv
 #endif
 constexpr int RESOLVE_SLOTS = BAMSCAN_ICTA_RESOLVE_SLOTS;   // matches per lane the resolver keeps in flight
 constexpr int RESOLVE_WARPS = BAMSCAN_ICTA_RESOLVE_WARPS;   // warps of the resolver
-constexpr uint32_t WARMUP_BITS = 640;       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
+#ifndef BAMSCAN_ICTA_WARMUP_BITS
+#define BAMSCAN_ICTA_WARMUP_BITS 640
+#endif
+constexpr uint32_t WARMUP_BITS = BAMSCAN_ICTA_WARMUP_BITS;
+#ifndef BAMSCAN_ICTA_WARMUP_MIN_BITS
+#define BAMSCAN_ICTA_WARMUP_MIN_BITS 192
+#endif
+constexpr uint32_t WARMUP_MIN_BITS = BAMSCAN_ICTA_WARMUP_MIN_BITS;   // (short sub-streams of a small block: the warm-up may span several predecessors)       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
 
 // global constant tables of the CRC stage, filled once per device by crc_tables_init_kernel:
 //   [0, 1024)     four 256-entry tables of the operator "multiply by x^(32*NT)" (strided slicing-by-4)
@@ -779,7 +789,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         const uint32_t my_stop = min(my_p + S, span_end);
         // round 0 starts every lane but the first `ov` bits EARLY and only warms the chain up until the lane's own cut is
         // reached: by then it is almost always the true chain (self-synchronisation), so most spans need no second round
-        const uint32_t ov = min(WARMUP_BITS, S);
+        const uint32_t ov = min(WARMUP_BITS, max(S, WARMUP_MIN_BITS));
         uint32_t my_s = (tid == 0 || my_p - span_beg <= ov) ? span_beg : my_p - ov;
         bool need = active;
         uint32_t my_e = 0, my_t = T_CROSS, my_n = 0, F = 0;
