@@ -47,7 +47,7 @@ class _Options(C.Structure):
                 ("infer_tag_types", C.c_int32), ("infer_tag_sample_size", C.c_int32),
                 ("n_tag_type_hints", C.c_int32), ("tag_type_hints", C.POINTER(C.c_char_p)),
                 ("device_id", C.c_int32), ("batch_rows", C.c_int32), ("chunk_inflated_bytes", C.c_uint64),
-                ("segment_bytes", C.c_uint32), ("skip_crc", C.c_int32), ("debug_flags", C.c_int32)]
+                ("segment_bytes", C.c_uint32), ("skip_crc", C.c_int32), ("debug_flags", C.c_int32), ("decode_all_tag_fields", C.c_int32)]
 
 
 class _Filter(C.Structure):
@@ -387,7 +387,7 @@ class BamTableProvider:
     def __init__(self, file_path, object_storage_options=None, coordinate_system_zero_based=True, tag_fields=None,
                  binary_cigar=False, infer_tag_types=True, infer_tag_sample_size=100, tag_type_hints=None, *,
                  index_path=None, device_id=0, batch_rows=0, chunk_inflated_bytes=0, segment_bytes=0, skip_crc=False,
-                 debug_flags=0):
+                 debug_flags=0, decode_all_tag_fields=False):
         if object_storage_options is not None:
             raise BamScanError(-5, "remote object storage is out of scope for this build (local files only)")
         L = load_library()
@@ -412,6 +412,7 @@ class BamTableProvider:
         o.segment_bytes = segment_bytes
         o.skip_crc = int(skip_crc)
         o.debug_flags = debug_flags
+        o.decode_all_tag_fields = int(decode_all_tag_fields)
         self._h = C.c_void_p()
         _check(L.bamscan_open(str(file_path).encode(), index_path.encode() if index_path is not None else None, C.byref(o), C.byref(self._h)))
         self.file_path = str(file_path)

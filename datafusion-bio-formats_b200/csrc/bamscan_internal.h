@@ -76,6 +76,7 @@ struct BamFile {
   uint32_t seg_bytes = 16384;
   bool skip_crc = false;
   int32_t debug_flags = 0;
+  bool decode_all_tags = false;           // BamScanOptions.decode_all_tag_fields
   std::unique_ptr<BaiIndex> bai;
 };
 

@@ -384,6 +384,12 @@ static int stream_init(BamScanStream* s) {
   }
   int n_tag_cols = 0;
   for (int32_t c : s->dec_cols) if (c >= 12) n_tag_cols++;
+  if (f->decode_all_tags && n_tag_cols) {
+    // reference quirk (sam_tag_io.rs:42-52): any projected tag makes the reader decode EVERY tag_fields entry; the extra columns
+    // are decoded (and their coercions checked) but never exported: no projection position maps to them
+    for (int32_t c = 12; c < (int32_t)f->fields.size(); c++)
+      if (std::find(s->dec_cols.begin(), s->dec_cols.end(), c) == s->dec_cols.end()) { s->dec_cols.push_back(c); n_tag_cols++; }
+  }
   if (n_tag_cols > MAX_TAGS) { set_error("more than %d projected tag columns are not supported by this build", MAX_TAGS); return BAMSCAN_ERR_UNSUPPORTED; }
   return BAMSCAN_OK;
 }
@@ -1103,7 +1109,7 @@ static int bamscan_open_impl(const char* path, const char* index_path_or_null, c
   f.batch_rows = opt.batch_rows;
   if (opt.chunk_inflated_bytes) f.chunk_bytes = std::min<uint64_t>(opt.chunk_inflated_bytes, 768ull << 20);   // an explicit size is also the slice size
   if (opt.segment_bytes) f.seg_bytes = std::max<uint32_t>(256, opt.segment_bytes);
-  f.skip_crc = opt.skip_crc != 0; f.debug_flags = opt.debug_flags;
+  f.skip_crc = opt.skip_crc != 0; f.debug_flags = opt.debug_flags; f.decode_all_tags = opt.decode_all_tag_fields != 0;
   int rc = load_file(&f);
   if (rc == BAMSCAN_ERR_IO || rc == BAMSCAN_ERR_CUDA) { release_file(&f); return rc; }
   // a file whose header cannot be read still yields a provider with empty metadata (table_provider.rs:423-426);

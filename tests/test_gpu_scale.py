@@ -91,3 +91,31 @@ def test_float_tags_into_utf8_columns(tmp_path):
         assert got[name].combine_chunks().equals(want[name].combine_chunks()), f"{name}: {got[name].to_pylist()} != {want[name].to_pylist()}"
     assert got["XF"].to_pylist()[0] == "1.5" and got["Ya"].to_pylist()[5] == "0.0000001" and got["Yc"].to_pylist()[5] == "0.1"
     p.close()
+
+
+def test_decode_all_tag_fields_switch(tmp_path):
+    """sam_tag_io.rs:42-52: once any tag column is projected the reference decodes EVERY tag_fields entry, so a value that
+    does not fit an unprojected tag column's type fails the scan.  Default here: only projected tags are decoded (the scan
+    succeeds); decode_all_tag_fields=True reproduces the reference (and the oracle): the scan fails."""
+    import bamscan
+    from oracle.bam_oracle import OracleBam
+    path = tmp_path / "edge.bam"
+    make_edge_bam(path, missing_qual=True)
+    tags, hints = ["NM", "XU"], ["XU:i"]          # XU is an 'I' of 4e9: does not fit Int32
+    proj = [0, 12]                                 # name + NM; XU is in tag_fields but not projected
+    o = OracleBam(str(path), tag_fields=tags, infer_tag_types=False, tag_type_hints=hints)
+    with pytest.raises(Exception):
+        o.scan(proj)
+    p = bamscan.BamTableProvider(str(path), None, True, tags, False, False, 100, hints, index_path="")
+    got = p.scan(proj, [], None).collect()
+    assert got.num_rows == 6 and got.column_names == ["name", "NM"]
+    p.close()
+    p = bamscan.BamTableProvider(str(path), None, True, tags, False, False, 100, hints, index_path="", decode_all_tag_fields=True)
+    with pytest.raises(bamscan.BamScanError):
+        p.scan(proj, [], None).collect()
+    p.close()
+    # a projection without any tag column decodes no tag at all, in the reference too
+    p = bamscan.BamTableProvider(str(path), None, True, tags, False, False, 100, hints, index_path="", decode_all_tag_fields=True)
+    assert p.scan([0, 2], [], None).collect().num_rows == 6
+    assert OracleBam(str(path), tag_fields=tags, infer_tag_types=False, tag_type_hints=hints).scan([0, 2]).num_rows == 6
+    p.close()
