@@ -26,7 +26,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE.parent / "libbamscan.so"
 
 EXPORTED_SYMBOLS = [
-    "bamscan_open", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
+    "bamscan_open", "bamscan_open_fastq", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
     "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_plan_num_ranges",
     "bamscan_plan_range_info", "bamscan_plan_partition_regions", "bamscan_extract_regions", "bamscan_balance_partitions",
     "bamscan_execute", "bamscan_next", "bamscan_execute_device", "bamscan_next_device",
@@ -103,6 +103,7 @@ def load_library():
     L.bamscan_last_error.restype = C.c_char_p
     L.bamscan_version.restype = C.c_char_p
     L.bamscan_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(_Options), C.POINTER(C.c_void_p)]
+    L.bamscan_open_fastq.argtypes = [C.c_char_p, C.POINTER(_Options), C.POINTER(C.c_void_p)]
     L.bamscan_close.argtypes = [C.c_void_p]
     L.bamscan_schema.argtypes = [C.c_void_p, C.c_void_p]
     L.bamscan_classify_filters.argtypes = [C.c_void_p, C.POINTER(_Filter), C.c_int32, C.POINTER(C.c_uint8)]
@@ -458,6 +459,34 @@ class BamTableProvider:
         _check(L.bamscan_plan(self._h, proj, n_proj, pack.arr, pack.n, -1 if limit is None else int(limit),
                               int(target_partitions), mode, C.byref(ph)))
         return BamExec(self, ph)
+
+
+class FastqTableProvider(BamTableProvider):
+    """== FastqTableProvider (bio-format-fastq/src/table_provider.rs:46-75) for BGZF-compressed FASTQ: `new(file_path,
+    object_storage_options)`; schema name / description / sequence / quality_scores (Utf8, description nullable).  `scan` with
+    target_partitions > 1 uses BGZF block ranges (physical_exec.rs:140-175); everything else is BamTableProvider's."""
+
+    def __init__(self, file_path, object_storage_options=None, *, device_id=0, batch_rows=0, chunk_inflated_bytes=0,
+                 skip_crc=False, debug_flags=0):
+        if object_storage_options is not None:
+            raise BamScanError(-5, "remote object storage is out of scope for this build (local files only)")
+        L = load_library()
+        o = _Options()
+        o.struct_size = C.sizeof(_Options)
+        o.device_id = device_id
+        o.batch_rows = batch_rows
+        o.chunk_inflated_bytes = chunk_inflated_bytes
+        o.skip_crc = int(skip_crc)
+        o.debug_flags = debug_flags
+        self._h = C.c_void_p()
+        _check(L.bamscan_open_fastq(str(file_path).encode(), C.byref(o), C.byref(self._h)))
+        self.file_path = str(file_path)
+        self._schema = None
+
+    def scan(self, projection=None, filters=None, limit=None, *, target_partitions=1, partition_mode=None) -> BamExec:
+        if partition_mode is None:
+            partition_mode = "block_range" if target_partitions > 1 else "reference"
+        return super().scan(projection, None, limit, target_partitions=target_partitions, partition_mode=partition_mode)
 
 
 def check_partition_seams(stats_list):

@@ -51,6 +51,7 @@ struct BaiIndex { std::vector<BaiRef> refs; bool has_no_coor = false; uint64_t n
 
 // == BamTableProvider (table_provider.rs:314-335)
 struct BamFile {
+  int format = 0;            // 0: BAM; 1: BGZF-compressed FASTQ (kernels_fastq.cuh): same engine, four Utf8 columns, no header / index
   std::string path, index_path;
   uint8_t* data = nullptr;   // whole file: read-only mapping (O_RDONLY / PROT_READ, not page-locked); small files: a plain copy
   uint64_t size = 0;

@@ -32,6 +32,7 @@
 #include "kernels_filter.cuh"
 #include "kernels_inflate.cuh"
 #include "kernels_inflate_cta.cuh"
+#include "kernels_fastq.cuh"
 
 namespace bamscan {
 
@@ -524,7 +525,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
   if ((rc = flush_slice(s))) return rc;
   const uint8_t* U = s->cur.U;
   const uint32_t n = std::min<uint32_t>(s->cur.rows_per_slice, s->cur.n - s->cur.pos);
-  const uint32_t* d_recoff = s->cur.recoff + s->cur.pos;
+  const uint32_t* d_recoff = s->cur.recoff + (size_t)s->cur.pos * (f->format == 1 ? 4 : 1);
   s->cur.pos += n;
   CU_TRY(cudaEventRecord(s->ev_dt[0], cs));
   {
@@ -540,7 +541,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       ColLayout& L = cols[i]; L.schema_idx = s->dec_cols[i]; L.kind = f->fields[L.schema_idx].kind;
       const int c_id = L.schema_idx;
       bool is_var = L.kind == HK_Utf8 || L.kind == HK_Binary || L.kind >= HK_ListInt8;
-      L.has_validity = c_id >= 12 || c_id == 1 || c_id == 2 || c_id == 3 || c_id == 7 || c_id == 8;
+      L.has_validity = f->format == 1 ? c_id == 1 : (c_id >= 12 || c_id == 1 || c_id == 2 || c_id == 3 || c_id == 7 || c_id == 8);
       if (L.has_validity) L.validity_off = AB.take(bm_bytes);
       if (is_var) L.offsets_off = AB.take(off_bytes); else L.values_off = AB.take(val_bytes);
       if (c_id >= 12 && is_var) { src_off[i] = scratch; scratch += align_up(val_bytes, 256); }
@@ -568,7 +569,8 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       uint32_t* v = L.has_validity ? reinterpret_cast<uint32_t*>(A + L.validity_off) : nullptr;
       int32_t* offs = reinterpret_cast<int32_t*>(A + L.offsets_off);
       uint32_t* vals = reinterpret_cast<uint32_t*>(A + L.values_off);
-      switch (L.schema_idx) {
+      static const int fq_slot[4] = {0, 1, 9, 10};      // FASTQ: name, description (nullable Utf8 like chrom), sequence, quality_scores
+      switch (f->format == 1 ? fq_slot[L.schema_idx] : L.schema_idx) {
         case 0: DP.l_name = offs; break;
         case 1: DP.l_chrom = offs; DP.v_chrom = v; break;
         case 2: DP.start = vals; DP.v_start = v; break;
@@ -597,7 +599,12 @@ static int decode_slice(BamScanStream* s, bool* produced) {
     }
     DP.n_tags = n_tags;
     CU_TRY(cudaMemsetAsync(A + err_off, 0, 64, cs));
-    if (s->cur.long_records) {
+    FastqCols FC;
+    if (f->format == 1) {
+      FC = FastqCols{U, d_recoff, n, DP.l_name, DP.l_chrom, DP.l_seq, DP.l_qual, DP.v_chrom, nullptr, nullptr, nullptr, nullptr, DP.err};
+      fq_lengths_kernel<<<(n + 255) / 256, 256, 0, cs>>>(FC);
+    }
+    else if (s->cur.long_records) {
       CU_TRY(cudaMemsetAsync(A, 0, regionA, cs));                                        // validity words are OR-ed in
       decode_fixed_warp_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, cs>>>(DP);     // long records: a warp per row, lanes co-operate inside the record
     }
@@ -650,12 +657,18 @@ static int decode_slice(BamScanStream* s, bool* produced) {
         uint8_t* d = A + L.data_off;
         switch (L.schema_idx) {
           case 0: DP.d_name = d; break; case 1: DP.d_chrom = d; break; case 5: DP.d_cigar = d; break; case 7: DP.d_mchrom = d; break;
+          case 2: if (f->format == 1) DP.d_seq = d; break; case 3: if (f->format == 1) DP.d_qual = d; break;
           case 9: DP.d_seq = d; break; case 10: DP.d_qual = d; break;
           default: DP.tags[tag_slot[i]].data = d;
         }
       }
+      if (f->format == 1) {
+        FC.l_name = DP.l_name; FC.l_desc = DP.l_chrom; FC.l_seq = DP.l_seq; FC.l_qual = DP.l_qual; FC.err = DP.err;      // (rebased with the arena)
+        FC.d_name = DP.d_name; FC.d_desc = DP.d_chrom; FC.d_seq = DP.d_seq; FC.d_qual = DP.d_qual;
+        fq_copy_kernel<8><<<(uint32_t)(((uint64_t)n * 8 + 255) / 256), 256, 0, cs>>>(FC);
+      }
       // short reads: 8 lanes per record (4 records per warp); long reads (and debug_flags bit 1): a warp per record
-      if (s->cur.long_records)
+      else if (s->cur.long_records)
         decode_var_kernel<32><<<std::min<uint32_t>((n + VAR_WARPS - 1) / VAR_WARPS, 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
       else
         decode_var_kernel<8><<<std::min<uint32_t>((n + VAR_WARPS * 4 - 1) / (VAR_WARPS * 4), 148u * 8u * 4u), VAR_WARPS * 32, 0, cs>>>(DP);
@@ -779,6 +792,25 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     CU_TRY(cudaStreamWaitEvent(cs, s->ev_carry, 0));                  // the previous chunk's tail was copied out on the other stream
     CU_TRY(cudaMemcpyAsync(U + HEADROOM - carry, s->d_carry.p, carry, cudaMemcpyDeviceToDevice, cs));
   }
+  if (f->format == 1) {
+    // FASTQ: line starts of the chunk -> d_recoff (kernels_fastq.cuh); the flags come out as the seg_* kernels report them
+    const uint32_t lo = BP.data_lo, span = data_hi - lo;
+    const uint32_t n_tiles = std::max<uint32_t>(1, (span + FQ_TILE - 1) / FQ_TILE);
+    if ((rc = s->d_seg[slot].ensure(8ull * n_tiles + 64))) return rc;
+    uint32_t* d_tile_count = s->d_seg[slot].as<uint32_t>(); uint32_t* d_tile_base = d_tile_count + n_tiles;
+    const uint32_t line_cap = span / 8 + 4096;                                          // lines[] capacity: FASTQ lines average far more than 8 bytes; beyond that the scan fails loudly
+    if ((rc = s->d_recoff[slot].ensure(4ull * line_cap))) return rc;
+    fq_count_kernel<<<n_tiles, 256, 0, cs>>>(U, lo, data_hi, d_tile_count);
+    fq_scan_kernel<<<1, 1024, 0, cs>>>(d_tile_count, d_tile_base, n_tiles, d_flags + 15);
+    s->st.kernel_launches += 2;
+    fq_lines_kernel<<<n_tiles, 256, 0, cs>>>(U, lo, data_hi, d_tile_base, s->d_recoff[slot].as<uint32_t>(), line_cap);
+    FastqFrame FF{U, lo, data_hi, BP.own_hi, (uint32_t)(s->need_spec ? 1 : 0), (uint32_t)(c.b1 == f->blocks.size() ? 1 : 0), line_cap};
+    fq_frame_kernel<<<1, 32, 0, cs>>>(FF, d_flags + 15, s->d_recoff[slot].as<uint32_t>(), d_flags);
+    s->st.kernel_launches += 2;
+    publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
+    CU_TRY(cudaEventRecord(s->ev_flags[slot], cs));
+    if (phase == 1) return BAMSCAN_OK;
+  } else {
   WalkOut W{d_seg_start, d_seg_exit, d_seg_count, d_seg_tail, d_flags};
   seg_candidates_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, cs>>>(BP, d_seg_start, (f->debug_flags & 1) ? 1 : 0);
   seg_walk_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
@@ -789,6 +821,7 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   publish_kernel<<<1, 32, 0, cs>>>(d_flags, s->d_hflags, 16);
   CU_TRY(cudaEventRecord(s->ev_flags[slot], cs));
     if (phase == 1) return BAMSCAN_OK;
+  }
   }
   CU_TRY(cudaEventSynchronize(s->ev_flags[slot]));
   CU_TRY(cudaGetLastError());
@@ -804,10 +837,12 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     set_error("BAM read error: BGZF member %u (file offset %llu): inflate failed: %s", blk, (unsigned long long)f->blocks[blk].coff, code < 10 ? names[code] : "?");
     return BAMSCAN_ERR_CRC;
   }
+  if (hf[1] && f->format == 1) { set_error("FASTQ read error: more lines in one chunk than supported (lines shorter than 8 bytes on average)"); return BAMSCAN_ERR_UNSUPPORTED; }
   if (hf[1]) { set_error("BAM read error: invalid record block_size at inflated offset %llu", (unsigned long long)(c.u0 + ((hf[1] & ~1u) - HEADROOM))); return BAMSCAN_ERR_FORMAT; }
   s->st.boundary_repairs += hf[4]; s->st.boundary_seam_mismatches += hf[10];
   const uint32_t n_rec = hf[3];
-  if (n_rec > 0 || hf[2] != 0xffffffffu) s->need_spec = false;
+  if (f->format == 1) { if (n_rec > 0) s->need_spec = false; }
+  else if (n_rec > 0 || hf[2] != 0xffffffffu) s->need_spec = false;
   uint32_t tail_off = hf[2] == 0xffffffffu ? data_hi : hf[2];
   if (tail_off > data_hi) tail_off = data_hi;
   *owned_done = tail_off >= BP.own_hi;
@@ -822,10 +857,14 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   if (n_rec == 0) { CU_TRY(cudaEventRecord(s->ev_t[slot][3], cs)); goto timing; }
   {
     // ---- record offsets
-    if ((rc = s->d_recoff[slot].ensure(4ull * (n_rec + 1)))) return rc;
-    uint32_t* d_recoff = s->d_recoff[slot].as<uint32_t>();
-    seg_emit_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, d_seg_start, d_seg_count, d_seg_base, d_recoff, n_rec, tail_off);
-    s->st.kernel_launches++;
+    uint32_t* d_recoff;
+    if (f->format == 1) d_recoff = s->d_recoff[slot].as<uint32_t>() + hf[14];       // lines[] from the first record's line on: 4 per row
+    else {
+      if ((rc = s->d_recoff[slot].ensure(4ull * (n_rec + 1)))) return rc;
+      d_recoff = s->d_recoff[slot].as<uint32_t>();
+      seg_emit_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, d_seg_start, d_seg_count, d_seg_base, d_recoff, n_rec, tail_off);
+      s->st.kernel_launches++;
+    }
     uint32_t n = n_rec;
     if (range.region_mode > 0) {
       // ---- row rule of the indexed scan + residual filters -> compacted record list
@@ -937,7 +976,7 @@ static int advance(BamScanStream* s, bool* produced) {
       uint32_t last = s->chunks.back().b1;
       if (s->carry_len == 0 || last >= f->blocks.size()) {
         if (s->carry_len) {
-          set_error("BAM read error: unexpected EOF inside a record (%u trailing bytes)", s->carry_len);
+          set_error("%s read error: unexpected EOF inside a record (%u trailing bytes)", f->format == 1 ? "FASTQ" : "BAM", s->carry_len);
           return BAMSCAN_ERR_FORMAT;
         }
         s->range_open = false; s->range_idx++;
@@ -1040,6 +1079,9 @@ static int decode_error_to_rc(uint32_t code, uint32_t row) {
     case DEC_ERR_UNSUPPORTED_F2S: set_error("record %u: float tag into a Utf8 column is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
     case DEC_ERR_QUAL: set_error("record %u: quality score in 95..222 (char::from(q + 33) is a two-byte UTF-8 sequence) is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
     case DEC_ERR_NAME: set_error("record %u: non-ASCII read name is not supported by this build", row); return BAMSCAN_ERR_UNSUPPORTED;
+    case FQ_ERR_NAME_PREFIX: set_error("FASTQ read error: record %u of the batch does not start with '@'", row); return BAMSCAN_ERR_FORMAT;
+    case FQ_ERR_PLUS: set_error("FASTQ read error: record %u of the batch: third line does not start with '+'", row); return BAMSCAN_ERR_FORMAT;
+    case FQ_ERR_UTF8: set_error("FASTQ record %u of the batch: non-ASCII byte (not supported by this build)", row); return BAMSCAN_ERR_UNSUPPORTED;
   }
   set_error("decode error %u at record %u", code, row);
   return BAMSCAN_ERR_FORMAT;
@@ -1074,7 +1116,7 @@ extern "C" {
 const char* bamscan_last_error(void) { return last_error_cstr(); }
 const char* bamscan_version(void) { return "bamscan-b200 0.1 (sm_100a)"; }
 
-static int bamscan_open_impl(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
+static int bamscan_open_impl(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out, int format = 0);
 
 // No C++ exception may cross the C ABI (a corrupt file can ask for absurd allocations): they become BAMSCAN_ERR_FORMAT.
 #define BAMSCAN_GUARD(call)                                                                                          \
@@ -1087,7 +1129,7 @@ int bamscan_open(const char* path, const char* index_path_or_null, const BamScan
   BAMSCAN_GUARD(bamscan_open_impl(path, index_path_or_null, options, out))
 }
 
-static int bamscan_open_impl(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out) {
+static int bamscan_open_impl(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out, int format) {
   if (!path || !out) { set_error("bamscan_open: null argument"); return BAMSCAN_ERR_INVALID; }
   BamScanOptions opt;
   memset(&opt, 0, sizeof opt);
@@ -1102,7 +1144,7 @@ static int bamscan_open_impl(const char* path, const char* index_path_or_null, c
   }
   std::unique_ptr<BamScanHandle> h(new BamScanHandle());
   BamFile& f = h->file;
-  f.path = path; f.device = opt.device_id;
+  f.path = path; f.device = opt.device_id; f.format = format;
   f.zero_based = opt.coordinate_system_zero_based != 0; f.binary_cigar = opt.binary_cigar != 0;
   f.has_tag_fields = opt.has_tag_fields != 0;
   for (int i = 0; i < opt.n_tag_fields && opt.tag_fields; i++) f.tag_fields.push_back(opt.tag_fields[i]);
@@ -1114,6 +1156,13 @@ static int bamscan_open_impl(const char* path, const char* index_path_or_null, c
   if (rc == BAMSCAN_ERR_IO || rc == BAMSCAN_ERR_CUDA) { release_file(&f); return rc; }
   // a file whose header cannot be read still yields a provider with empty metadata (table_provider.rs:423-426);
   // scans on it fail later
+  if (format == 1) {
+    // == determine_schema of bio-format-fastq/src/table_provider.rs:22-32
+    if (rc) { release_file(&f); return rc; }
+    f.fields = {FieldDef{"name", HK_Utf8, false, {}}, FieldDef{"description", HK_Utf8, true, {}}, FieldDef{"sequence", HK_Utf8, false, {}}, FieldDef{"quality_scores", HK_Utf8, false, {}}};
+    *out = h.release();
+    return BAMSCAN_OK;
+  }
   if ((rc = build_schema(&f, &opt))) { release_file(&f); return rc; }
   if (index_path_or_null) f.index_path = index_path_or_null; else f.index_path = discover_index(f.path);   // "" = no index
   if (!f.index_path.empty()) {
@@ -1122,6 +1171,10 @@ static int bamscan_open_impl(const char* path, const char* index_path_or_null, c
   }
   *out = h.release();
   return BAMSCAN_OK;
+}
+
+int bamscan_open_fastq(const char* path, const BamScanOptions* options, BamScanHandle** out) {
+  BAMSCAN_GUARD(bamscan_open_impl(path, nullptr, options, out, 1))
 }
 
 void bamscan_close(BamScanHandle* h) {
@@ -1139,6 +1192,7 @@ int bamscan_schema(BamScanHandle* h, struct ArrowSchema* out) {
 
 int bamscan_classify_filters(BamScanHandle* h, const BamScanFilter* filters, int32_t n_filters, uint8_t* out_pushdown) {
   if (!h || (n_filters && (!filters || !out_pushdown))) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  if (h->file.format == 1) { for (int i = 0; i < n_filters; i++) out_pushdown[i] = 0; return BAMSCAN_OK; }   // FastqTableProvider pushes no filter down
   return classify_filters(h->file, filters, n_filters, out_pushdown);
 }
 

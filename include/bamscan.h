@@ -121,6 +121,16 @@ int bamscan_check_partition_seams(const BamScanStats* stats, int32_t n_partition
 int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
 void bamscan_close(BamScanHandle* h);
 
+/* == FastqTableProvider::new (bio-format-fastq/src/table_provider.rs:63-75) for a BGZF-compressed FASTQ file.
+ * The handle is used with the same calls as a BAM handle: bamscan_schema gives determine_schema (table_provider.rs:22-32:
+ * name, description (nullable), sequence, quality_scores, all Utf8); bamscan_plan with BAMSCAN_PARTITION_BLOCK_RANGE cuts the
+ * BGZF block table as get_bgzf_partition_bounds does (physical_exec.rs:140-175; a partition > 0 finds its first record by
+ * the '@' ... '+' rule of synchronize_bgzf_reader, :184-219, and the seam check proves it); bamscan_execute / bamscan_next
+ * (and the device variants) stream the batches of physical_exec.rs:393-468.  No filter is pushed down (classify: all
+ * unsupported), there is no index, the options that concern BAM columns are ignored.  Plain gzip and uncompressed FASTQ are
+ * refused (BAMSCAN_ERR_FORMAT): this build reads BGZF. */
+int bamscan_open_fastq(const char* path, const BamScanOptions* options, BamScanHandle** out);
+
 /* == TableProvider::schema (table_provider.rs:933-935): the full, unprojected schema with all metadata. */
 int bamscan_schema(BamScanHandle* h, struct ArrowSchema* out);
 

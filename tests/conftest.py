@@ -94,3 +94,43 @@ def make_edge_bam(path, missing_qual=False):
     path.write_bytes(_bgzf(hdr + b"".join(recs)))
 
 
+
+
+def write_bgzf(path: Path, data: bytes, block=0xff00, level=6):
+    """`data` as a BGZF file (members of <= `block` inflated bytes + the EOF marker)."""
+    with open(path, "wb") as f:
+        for i in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if i is None else data[i:i + block]
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
+            body = c.compress(chunk) + c.flush()
+            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(body) + 25))
+            f.write(body + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
+def make_fastq_text(n_reads: int, seed: int, read_len=101, crlf=False, final_newline=True) -> bytes:
+    """Synthetic FASTQ: Illumina-like names, a mix of records with / without description (space- and tab-separated),
+    quality lines that often START with '@' or '+' (the characters a naive record synchroniser trips over)."""
+    import random
+    rng = random.Random(seed)
+    eol = "\r\n" if crlf else "\n"
+    out = []
+    for i in range(n_reads):
+        n = read_len if rng.random() < 0.8 else rng.randint(1, 2 * read_len)
+        seq = "".join(rng.choice("ACGTN") for _ in range(n))
+        first = rng.choice("@+II?") if n else ""
+        qual = (first + "".join(chr(33 + rng.randint(2, 40)) for _ in range(n - 1))) if n else ""
+        kind = rng.random()
+        name = f"SIM{seed}.{i}"
+        if kind < 0.5:
+            d = f"@{name} HSQ:{rng.randint(1, 9)}:{i}/1"
+        elif kind < 0.6:
+            d = f"@{name}\tcomment@with+signs {i}"
+        elif kind < 0.65:
+            d = f"@{name} "                      # delimiter but empty description -> NULL
+        else:
+            d = f"@{name}"
+        out.append(d + eol + seq + eol + "+" + eol + qual + eol)
+    text = "".join(out)
+    if not final_newline and text.endswith(eol):
+        text = text[:-len(eol)]
+    return text.encode()

@@ -228,6 +228,52 @@ static int resolve_static_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint
   return 0;
 }
 
+// Host model of a LIST-FREE resolver: the matches are dealt by head-bitmap WORD (32 output bytes): thread t owns the words
+// t, t + T, ... and resolves the matches whose heads lie in its current word one after the other, then moves to its next
+// word.  Lock-step rounds as in resolve_static_model.
+static int resolve_word_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint32_t olimit, int W, Stats& S) {
+  const uint32_t wbeg = obase >> 5, wend = (olimit + 31) >> 5;
+  std::vector<uint32_t> heads(hb + wbeg, hb + wend);
+  std::vector<uint8_t> fin(olimit + 64, 1);
+  for (uint32_t w = wbeg; w < wend; w++) { uint32_t bits = hb[w]; hb[w] = 0; while (bits) { uint32_t o = w * 32 + __builtin_ctz(bits); bits &= bits - 1; uint32_t len = (((win[o + 1] << 8) | (win[o + 2] << 16)) >> 15) + 3; for (uint32_t k = 0; k < len; k++) fin[o + k] = 0; } }
+  const int T = 32 * W;
+  struct Lane { uint32_t w, bits, o, dist, len, done; bool pend; };
+  std::vector<Lane> L(T);
+  const uint32_t nw = wend - wbeg;
+  auto next_match = [&](Lane& l) {   // take the next head of the current word, or move on to the next owned word
+    for (;;) {
+      if (l.bits) { l.o = (wbeg + l.w) * 32 + __builtin_ctz(l.bits); l.bits &= l.bits - 1; uint32_t v = win[l.o] | (win[l.o + 1] << 8) | (win[l.o + 2] << 16); l.dist = (v & 0x7fff) + 1; l.len = (v >> 15) + 3; l.done = 0; l.pend = true; return; }
+      l.w += T; if (l.w >= nw) { l.pend = false; l.w = nw; return; } l.bits = heads[l.w];
+    }
+  };
+  for (int t = 0; t < T; t++) { L[t].w = t; L[t].pend = false; if ((uint32_t)t < nw) { L[t].bits = heads[t]; next_match(L[t]); } else L[t].w = nw; }
+  long rounds = 0, polls = 0;
+  for (;;) {
+    bool any = false; for (auto& l : L) any |= l.pend;
+    if (!any) break;
+    rounds++;
+    std::vector<std::pair<int, uint32_t>> todo;
+    for (int w = 0; w < W; w++) {
+      bool wp = false;
+      for (int l = 0; l < 32; l++) {
+        Lane& a = L[w * 32 + l]; if (!a.pend) continue; wp = true;
+        uint32_t cur = a.o + a.done, sa = cur - a.dist, want = std::min(a.len - a.done, g_piece);
+        if (a.dist < want && a.dist >= 8) want = a.dist;
+        uint32_t outn = std::min(want, a.dist), k = 0; while (k < outn && fin[sa + k]) k++;
+        uint32_t n = k >= outn ? want : (a.dist >= want ? k : 0);
+        if (n) todo.push_back({w * 32 + l, n});
+      }
+      if (wp) polls++;
+    }
+    if (todo.empty()) return 52;
+    for (auto& td : todo) { Lane& a = L[td.first]; uint32_t cur = a.o + a.done, sa = cur - a.dist, j = 0; uint8_t v[64]; for (uint32_t k = 0; k < td.second; k++) { v[k] = win[sa + j]; if (++j == a.dist) j = 0; } for (uint32_t k = 0; k < td.second; k++) { win[cur + k] = v[k]; fin[cur + k] = 1; } a.done += td.second; if (a.done == a.len) { a.pend = false; } }
+    for (auto& l : L) if (!l.pend && l.w < nw) next_match(l);
+    if (rounds > 10000000) return 52;
+  }
+  S.resolve_iters += polls; S.resolve_batches += rounds;
+  return 0;
+}
+
 // One member through the modelled CTA.  Returns 0 ok, else an error code (string in *why).
 static uint32_t overlap = 448;
 static int g_rmode = 0;
@@ -362,7 +408,7 @@ static int inflate_member_sim(const uint8_t* payload, uint32_t clen, uint32_t is
     }
   }
   if (outpos != olimit) { *why = "isize mismatch"; return 7; }
-  if (int rr = g_rmode == 6 ? resolve_static_model(win.data(), bm.data(), obase, olimit, NT / 32, S) : g_rmode ? resolve_inorder_model(win.data(), bm.data(), obase, olimit, g_rmode, S) : resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
+  if (int rr = g_rmode == 7 ? resolve_word_model(win.data(), bm.data(), obase, olimit, NT / 32, S) : g_rmode == 6 ? resolve_static_model(win.data(), bm.data(), obase, olimit, NT / 32, S) : g_rmode ? resolve_inorder_model(win.data(), bm.data(), obase, olimit, g_rmode, S) : resolve_member_model(win.data(), bm.data(), obase, olimit, NT / 32, S)) { *why = "resolver"; return rr; }
   for (auto v : bm) if (v) { *why = "head bits left"; return 53; }
   out.assign(win.begin() + obase, win.begin() + obase + isize);
   return 0;
