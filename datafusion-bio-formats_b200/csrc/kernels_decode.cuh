@@ -512,7 +512,7 @@ constexpr int VAR_WARPS = 8;
 // 10 % of the HBM roofline.  Eight lanes per record cut that to ~120.  Group-wide shuffles use the width argument; a loop's
 // trip count is the maximum over the warp's groups (records of one file are alike, so little is lost).
 template <int G>
-__global__ void __launch_bounds__(VAR_WARPS * 32, 6)
+__global__ void __launch_bounds__(VAR_WARPS * 32, 8)
 decode_var_kernel(const DecodeParams P) {
   __shared__ uint16_t seq_lut[256];
   {
