@@ -513,7 +513,7 @@ static int flush_slice(BamScanStream* s) {
   s->slice_pending = false;
   CU_TRY(cudaEventSynchronize(s->ev_dt[1]));
   { float d = 0; cudaEventElapsedTime(&d, s->ev_dt[0], s->ev_dt[1]); s->st.ms_decode += d; }
-  if (s->device_resident && s->h_flags[64]) { set_error("decode error %u at row %u", s->h_flags[64], s->h_flags[65]); return BAMSCAN_ERR_FORMAT; }
+  if (s->device_resident && s->h_flags[512]) { set_error("decode error %u at row %u", s->h_flags[512], s->h_flags[513]); return BAMSCAN_ERR_FORMAT; }
   return BAMSCAN_OK;
 }
 
@@ -620,7 +620,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       multi_scan_tiles_kernel<<<SC.n_cols, 1024, 0, cs>>>(s->d_tiles.as<uint64_t>(), n_tiles, s->d_totals.as<uint64_t>());
       multi_scan_apply_kernel<<<dim3(n_tiles, SC.n_cols), SCAN_TPB, 0, cs>>>(SC, s->d_tiles.as<uint64_t>(), n_tiles);
       s->st.kernel_launches += 3;
-      publish_kernel<<<1, 64, 0, cs>>>(s->d_totals.as<uint32_t>(), s->d_hflags + 16, 2 * SC.n_cols);
+      publish_kernel<<<1, 128, 0, cs>>>(s->d_totals.as<uint32_t>(), s->d_hflags + 16, 2 * SC.n_cols);      // [16, 16 + 2 * MAX_SCAN_COLS) of the mapped flags page; the decode error words live at [512, 516)
       CU_TRY(cudaEventRecord(s->ev_dflags, cs));
       CU_TRY(cudaEventSynchronize(s->ev_dflags));
       CU_TRY(cudaGetLastError());
@@ -682,7 +682,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
     }
     if (s->device_resident) {
       // keep everything in HBM: only the decode error word travels
-      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 64, 2);     // (checked by flush_slice)
+      publish_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<const uint32_t*>(A + err_off), s->d_hflags + 512, 2);     // (checked by flush_slice)
     } else if (s->device_export) {
       // device hand-off: the batch gets its own exactly-sized device allocation (a device-to-device copy on the side
       // stream, ~3 TB/s); only the decode error word travels to the host
@@ -696,7 +696,7 @@ static int decode_slice(BamScanStream* s, bool* produced) {
       CU_TRY(cudaEventCreateWithFlags(&P.owner->dev_ready, cudaEventDisableTiming));
       CU_TRY(cudaStreamWaitEvent(s->s_d2h, s->ev_compute, 0));
       CU_TRY(cudaMemcpyAsync(P.owner->dev, A, arena_bytes, cudaMemcpyDeviceToDevice, s->s_d2h));
-      CU_TRY(cudaMemcpyAsync(s->h_flags + 66, A + err_off, 8, cudaMemcpyDeviceToHost, s->s_d2h));
+      CU_TRY(cudaMemcpyAsync(s->h_flags + 514, A + err_off, 8, cudaMemcpyDeviceToHost, s->s_d2h));
       CU_TRY(cudaEventRecord(P.owner->dev_ready, s->s_d2h));
       CU_TRY(cudaEventRecord(P.done, s->s_d2h));
       s->arena_flip ^= 1;
@@ -1094,7 +1094,7 @@ static int finalize_pending(BamScanStream* s) {
   if (!P.valid) return BAMSCAN_OK;
   CU_TRY(cudaEventSynchronize(P.done));
   P.valid = false;
-  const uint32_t* err = s->device_export ? s->h_flags + 66 : reinterpret_cast<const uint32_t*>(P.owner->arena.p + P.err_off);
+  const uint32_t* err = s->device_export ? s->h_flags + 514 : reinterpret_cast<const uint32_t*>(P.owner->arena.p + P.err_off);
   if (err[0]) { int rc = decode_error_to_rc(err[0], err[1]); owner_unref(P.owner); P.owner = nullptr; return rc; }
   s->ready.clear(); s->ready_pos = 0;
   uint64_t step = s->f->batch_rows > 0 ? (uint64_t)s->f->batch_rows : P.rows;

@@ -25,7 +25,7 @@
 
 namespace bamscan {
 
-constexpr int MAX_TAGS = 16;
+constexpr int MAX_TAGS = 32;        // projected tag columns per scan (DecodeParams travels as a kernel argument: 48 B per tag)
 
 enum ColKind : int32_t {
   K_Int32 = 1, K_UInt32 = 2, K_Float32 = 3, K_Utf8 = 4, K_Binary = 5,

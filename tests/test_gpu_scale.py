@@ -12,7 +12,7 @@ import os
 import pyarrow as pa
 import pytest
 
-from conftest import gen_bam, make_edge_bam
+from conftest import GOLDEN, gen_bam, make_edge_bam
 
 pytestmark = pytest.mark.gpu
 
@@ -118,4 +118,21 @@ def test_decode_all_tag_fields_switch(tmp_path):
     p = bamscan.BamTableProvider(str(path), None, True, tags, False, False, 100, hints, index_path="", decode_all_tag_fields=True)
     assert p.scan([0, 2], [], None).collect().num_rows == 6
     assert OracleBam(str(path), tag_fields=tags, infer_tag_types=False, tag_type_hints=hints).scan([0, 2]).num_rows == 6
+    p.close()
+
+
+def test_twenty_tag_columns():
+    """Round 1 stopped at 16 projected tag columns; the limit is 32 now (present and absent tags, all column kinds)."""
+    import bamscan
+    from oracle.bam_oracle import OracleBam, schema_equal
+    path = GOLDEN / "10x_pbmc_tags.bam"
+    tags = ["RE", "ts", "CB", "NH", "xf", "NM", "MD", "AS", "RG", "CR", "CY", "UB", "UR", "UY", "GX", "GN", "fx", "HI", "nM", "TX", "AN", "pa"]
+    o = OracleBam(str(path), tag_fields=tags)
+    want = pa.Table.from_batches([o.scan()])
+    p = bamscan.BamTableProvider(str(path), None, True, tags, False, True, 100, None, index_path="")
+    assert schema_equal(p.schema(), o.schema)
+    got = p.scan(None, [], None).collect()
+    assert got.num_rows == want.num_rows and len(got.schema) == 12 + len(tags)
+    for name in want.schema.names:
+        assert got[name].combine_chunks().equals(want[name].combine_chunks()), name
     p.close()
