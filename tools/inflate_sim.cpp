@@ -4,7 +4,11 @@
 // lanes of a CTA executed in a loop, using the very same per-lane code (csrc/inflate_cta_core.h), and compares every
 // BGZF member of a file with zlib.  Test/verification tool only: nothing in the product links it.
 //
-//   inflate_sim file.bam [--lanes 256] [--max-members N] [--span-bytes B] [--stats]
+//   inflate_sim file.bam [--lanes 256] [--max-members N] [--span-bytes B] [--overlap BITS] [--stats]
+//                        [--resolve MODE] [--piece BYTES] [--rlanes N] [--gate G] [--group-sync]
+// --resolve: 0 the round-2 v3 resolver (eight polling warps, groups of 32), 1 / 2 one warp in order with the frontier rule
+// (groups / rolling), 3 rolling + exact readiness, 4 static lane-strided + exact readiness, 6 the COMMITTED resolver (all warps,
+// static, exact readiness; --gate models the measured-and-dropped gate), 7 list-free dealing by bitmap word (292 rounds: dropped).
 #include <zlib.h>
 
 #include <algorithm>
