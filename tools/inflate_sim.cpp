@@ -169,8 +169,7 @@ static int resolve_inorder_model(uint8_t* win, uint32_t* hb, uint32_t obase, uin
       if (n[i]) nok++;
     }
     if (!nok) return 52;
-    S.lane_decodes += nok;
-    std::vector<std::array<uint8_t,64>> v(g_lanes);
+        std::vector<std::array<uint8_t,64>> v(g_lanes);
     for (int i = 0; i < g_lanes; i++) if (n[i]) { Lane& l = L[i]; uint32_t cur = l.o + l.done, sa = cur - l.dist, j = 0; for (uint32_t k = 0; k < n[i]; k++) { v[i][k] = win[sa + j]; if (++j == l.dist) j = 0; } }
     for (int i = 0; i < g_lanes; i++) if (n[i]) { Lane& l = L[i]; uint32_t cur = l.o + l.done; for (uint32_t k = 0; k < n[i]; k++) { win[cur + k] = v[i][k]; fin[cur + k] = 1; } l.done += n[i]; l.pend = l.done < l.len; }
   }
@@ -218,7 +217,6 @@ static int resolve_static_model(uint8_t* win, uint32_t* hb, uint32_t obase, uint
         uint32_t n = k >= outn ? want : (a.dist >= want ? k : 0);
         if (n) { todo.push_back({w * 32 + l, n}); warp_real[w] = 2; }
       }
-      if (warp_real[w] == 2) S.spans++;   // (reused as: productive iterations)
     }
     if (todo.empty() && cheap > 100000000) return 52;
     for (auto& td : todo) { Lane& a = L[td.first]; uint32_t cur = a.o + a.done, sa = cur - a.dist, j = 0; uint8_t v[64]; for (uint32_t k = 0; k < td.second; k++) { v[k] = win[sa + j]; if (++j == a.dist) j = 0; } for (uint32_t k = 0; k < td.second; k++) { win[cur + k] = v[k]; fin[cur + k] = 1; } a.done += td.second; if (a.done == a.len) { a.pend = false; grp_left[a.r / 32]--; } }
