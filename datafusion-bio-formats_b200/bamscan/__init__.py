@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "bamscan_execute", "bamscan_next", "bamscan_execute_device", "bamscan_next_device",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
     "bamscan_probe_pcie", "bamscan_check_partition_seams", "bamscan_last_error", "bamscan_version",
+    "bamscan_writer_open", "bamscan_writer_write", "bamscan_writer_finish", "bamscan_writer_stats", "bamscan_writer_free",
 ]
 
 
@@ -83,6 +84,20 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class _WriteOptions(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("coordinate_system_zero_based", C.c_int32), ("n_tag_fields", C.c_int32),
+                ("tag_fields", C.POINTER(C.c_char_p)), ("device_id", C.c_int32), ("compression", C.c_int32)]
+
+
+class WriteStats(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("batches", C.c_uint64), ("members", C.c_uint64), ("arrow_bytes", C.c_uint64),
+                ("bam_bytes", C.c_uint64), ("compressed_bytes", C.c_uint64), ("ms_encode", C.c_double), ("ms_deflate", C.c_double),
+                ("ms_total", C.c_double), ("kernel_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _OPS = {"=": 0, "==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "between": 6, "not_between": 7, "in": 8, "not_in": 9,
         "other": 100}
 CORE_COLUMNS = ["name", "chrom", "start", "end", "flags", "cigar", "mapping_quality", "mate_chrom", "mate_start",
@@ -126,6 +141,12 @@ def load_library():
     L.bamscan_bench_inflate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64)]
     L.bamscan_probe_pcie.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bamscan_writer_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_void_p,
+                                      C.POINTER(_WriteOptions), C.POINTER(C.c_void_p)]
+    L.bamscan_writer_write.argtypes = [C.c_void_p, C.c_void_p]
+    L.bamscan_writer_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.bamscan_writer_stats.argtypes = [C.c_void_p, C.POINTER(WriteStats)]
+    L.bamscan_writer_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -417,6 +438,7 @@ class BamTableProvider:
         self._h = C.c_void_p()
         _check(L.bamscan_open(str(file_path).encode(), index_path.encode() if index_path is not None else None, C.byref(o), C.byref(self._h)))
         self.file_path = str(file_path)
+        self.device_id = device_id
         self._schema = None
 
     def close(self):
@@ -459,6 +481,128 @@ class BamTableProvider:
         _check(L.bamscan_plan(self._h, proj, n_proj, pack.arr, pack.n, -1 if limit is None else int(limit),
                               int(target_partitions), mode, C.byref(ph)))
         return BamExec(self, ph)
+
+
+    def insert_into(self, batches, insert_op="overwrite", *, sort_on_write=False, compression=0):
+        """== TableProvider::insert_into (table_provider.rs:1117-1177) + BamWriteExec::execute: `INSERT OVERWRITE` of `batches`
+        (an iterable of pyarrow.RecordBatch with this provider's schema) into this provider's file.  Returns the row count (the
+        reference's one-row `count` batch).  sort_on_write is DataFusion's SortExec in front of the writer, not part of it: the
+        rows are written in arrival order and only the header's SO field follows the flag, as in the reference."""
+        if insert_op != "overwrite":
+            raise NotImplementedError("BAM insert_into only supports OVERWRITE mode")
+        schema = self.schema()
+        md = {k.decode(): v.decode() for k, v in (schema.metadata or {}).items()}
+        zero_based = md.get("bio.coordinate_system_zero_based", "true").lower() != "false"
+        tags = [f.name for f in schema if f.metadata and b"bio.bam.tag.tag" in f.metadata]
+        overrides = {"bio.bam.sort_order": "coordinate" if sort_on_write else "unsorted"}
+        ex = BamWriteExec(self.file_path, schema, tags, zero_based, overrides, device_id=getattr(self, "device_id", 0), compression=compression)
+        return ex.execute(batches)
+
+
+# ---- SURVEY 8 f4: the write path -------------------------------------------------------------------------------------
+_SQ_TAGS = {"AH", "AN", "AS", "DS", "M5", "SP", "TP", "UR"}
+_RG_TAGS = {"BC", "CN", "DT", "FO", "KS", "PG", "PI", "PM", "PU"}
+_PG_TAGS = {"PP", "DS"}
+
+
+def build_bam_header(schema: pa.Schema, tag_fields=None, overrides=None):
+    """== build_bam_header (bio-format-bam/src/header_builder.rs:43-186) followed by noodles' SAM header writer: the header
+    text and the reference dictionary reconstructed from the bio.bam.* schema metadata (defaults: VN 1.6, no @SQ).  In the
+    Rust host this function stays the reference's own; it is restated here because the tests drive the ABI from python.
+    Extra per-line fields sit in a HashMap in the reference (arbitrary order); here they are written in sorted key order."""
+    import json
+    md = {(k.decode() if isinstance(k, bytes) else k): (v.decode() if isinstance(v, bytes) else v) for k, v in (schema.metadata or {}).items()}
+    md.update(overrides or {})
+
+    def arr(key):
+        try:
+            return json.loads(md[key]) if key in md else []
+        except Exception:
+            return []
+
+    ver = md.get("bio.bam.file_format_version", "1.6").split(".")
+    ver = f"{int(ver[0])}.{int(ver[1])}" if len(ver) == 2 and all(p.isdigit() for p in ver) else "1.6"
+    hd = ["VN:" + ver] + [f"{t}:{md[k]}" for k, t in (("bio.bam.sort_order", "SO"), ("bio.bam.group_order", "GO"), ("bio.bam.subsort_order", "SS")) if k in md]
+    lines, names, lens = ["@HD\t" + "\t".join(hd)], [], []
+
+    def extra(d, allowed):
+        return [f"{k}:{v}" for k, v in sorted((d.get("other_fields") or {}).items()) if k in allowed]
+
+    for sq in arr("bio.bam.reference_sequences"):
+        if int(sq["length"]) == 0:
+            raise BamScanError(-6, "Reference sequence length cannot be zero")
+        lines.append("\t".join(["@SQ", f"SN:{sq['name']}", f"LN:{int(sq['length'])}"] + extra(sq, _SQ_TAGS)))
+        names.append(sq["name"]); lens.append(int(sq["length"]))
+    for rg in arr("bio.bam.read_groups"):
+        f = [f"{t}:{rg[k]}" for k, t in (("sample", "SM"), ("platform", "PL"), ("library", "LB"), ("description", "DS")) if rg.get(k) is not None]
+        lines.append("\t".join(["@RG", f"ID:{rg['id']}"] + f + extra(rg, _RG_TAGS)))
+    for pg in arr("bio.bam.program_info"):
+        f = [f"{t}:{pg[k]}" for k, t in (("name", "PN"), ("version", "VN"), ("command_line", "CL")) if pg.get(k) is not None]
+        lines.append("\t".join(["@PG", f"ID:{pg['id']}"] + f + extra(pg, _PG_TAGS)))
+    lines += [f"@CO\t{c}" for c in arr("bio.bam.comments")]
+    return "\n".join(lines) + "\n", names, lens
+
+
+class BamWriteExec:
+    """== BamWriteExec (bio-format-bam/src/write_exec.rs:43-110): new(input, output_path, compression, tag_fields,
+    coordinate_system_zero_based, schema_metadata_overrides, sort_on_write); `execute` consumes the batches and returns the
+    count.  Only BGZF BAM output (a `.sam` path is the reference's plain-text writer: out of scope)."""
+
+    def __init__(self, output_path, input_schema: pa.Schema, tag_fields=None, coordinate_system_zero_based=True,
+                 schema_metadata_overrides=None, *, device_id=0, compression=0):
+        if str(output_path).lower().endswith(".sam"):
+            raise BamScanError(-5, "plain SAM output is out of scope for this build (BGZF BAM only)")
+        self.output_path = str(output_path)
+        self.schema = input_schema
+        self.tag_fields = list(tag_fields or [])
+        self.zero_based = bool(coordinate_system_zero_based)
+        self.overrides = dict(schema_metadata_overrides or {})
+        self.device_id = device_id
+        self.compression = compression
+        self.stats = None
+
+    def execute(self, batches) -> int:
+        L = load_library()
+        text, names, lens = build_bam_header(self.schema, self.tag_fields, self.overrides)
+        o = _WriteOptions()
+        o.struct_size = C.sizeof(_WriteOptions)
+        o.coordinate_system_zero_based = int(self.zero_based)
+        tag_arr, _keep = _strs(self.tag_fields)
+        o.n_tag_fields = len(self.tag_fields)
+        if tag_arr is not None:
+            o.tag_fields = tag_arr
+        o.device_id = self.device_id
+        o.compression = self.compression
+        name_arr, _keep2 = _strs(names)
+        len_arr = (C.c_int32 * max(1, len(lens)))(*lens)
+        cs = _ArrowSchemaStruct()
+        pa.struct(list(self.schema))._export_to_c(C.addressof(cs))
+        h = C.c_void_p()
+        try:
+            _check(L.bamscan_writer_open(self.output_path.encode(), text.encode(), len(names), name_arr, len_arr, C.addressof(cs), C.byref(o), C.byref(h)))
+        finally:
+            if cs.release:
+                C.CFUNCTYPE(None, C.c_void_p)(cs.release)(C.addressof(cs))
+        try:
+            for b in batches:
+                if b.schema.names != self.schema.names:
+                    raise BamScanError(-7, "batch columns differ from the writer's input schema")
+                ca = _ArrowArrayStruct()
+                sa = b.to_struct_array()
+                sa._export_to_c(C.addressof(ca))
+                try:
+                    _check(L.bamscan_writer_write(h, C.addressof(ca)))
+                finally:
+                    if ca.release:
+                        C.CFUNCTYPE(None, C.c_void_p)(ca.release)(C.addressof(ca))
+            n = C.c_uint64()
+            _check(L.bamscan_writer_finish(h, C.byref(n)))
+            st = WriteStats()
+            _check(L.bamscan_writer_stats(h, C.byref(st)))
+            self.stats = st.as_dict()
+            return int(n.value)
+        finally:
+            L.bamscan_writer_free(h)
 
 
 class FastqTableProvider(BamTableProvider):

@@ -219,6 +219,49 @@ int bamscan_bench_inflate(BamScanPlan* plan, int32_t partition, int32_t repeats,
 /* Pinned-memory PCIe probe (the end-to-end ceiling): best of 3 for H2D, D2H and both at once, GB/s. */
 int bamscan_probe_pcie(int32_t device_id, uint64_t bytes, double* h2d_gbps, double* d2h_gbps, double* bidir_gbps);
 
+
+/* ---- the BAM WRITE path (`INSERT OVERWRITE INTO bam_table SELECT ...`) --------------------------------
+ * == BamTableProvider::insert_into -> BamWriteExec::execute -> write_bam_stream
+ *    (datafusion/bio-format-bam/src/table_provider.rs:1117-1177, write_exec.rs:195-350), with
+ *    batch_to_alignment_records (bio-format-core/src/sam_record_serializer.rs:15-212), build_tag_data
+ *    (bio-format-core/src/sam_tag_io.rs:109-147) and the noodles BAM record encoder + BGZF writer on the device:
+ *    Arrow batches (host memory, Arrow C Data Interface) -> H2D -> BAM records encoded by CUDA kernels -> BGZF members of
+ *    0xff00 inflated bytes compressed by a CTA-per-member DEFLATE kernel (LZ77 + dynamic Huffman, CRC-32 fused) -> D2H ->
+ *    file.  The SAM header text and the reference dictionary come from the caller: the Rust host keeps build_bam_header
+ *    (header_builder.rs:43-186) and serialises its result; the python mirror restates it.
+ *    `input_schema` names the columns (the reference looks every column up BY NAME: name, chrom, start, flags, cigar (Utf8 or
+ *    Binary), mapping_quality, mate_chrom, mate_start, sequence, quality_scores, template_length) and carries the tag
+ *    columns' field metadata (bio.bam.tag.tag / bio.bam.tag.type decide the aux type letter, sam_tag_io.rs:127-141).
+ *    Tag columns may be Int32, UInt32, Float32, Utf8 or List<Int8..UInt32 | Float32> (the types the scan produces); other
+ *    Arrow types are refused with BAMSCAN_ERR_UNSUPPORTED, as are records with more than 65535 CIGAR ops (CG-tag overflow).
+ *    Rows are written in arrival order (sort_on_write is a DataFusion SortExec in front of the writer, not part of it).
+ *    Data errors of the reference ("does not fit into 16-bit SAM flags", CIGAR parse errors, tag range / type mismatches,
+ *    sequence / quality length mismatch) come back as BAMSCAN_ERR_FORMAT / BAMSCAN_ERR_SCHEMA with the row in the message. */
+typedef struct BamWriter BamWriter;
+typedef struct BamWriteOptions {
+  uint32_t struct_size;
+  int32_t coordinate_system_zero_based;   /* write_exec.rs:208 */
+  int32_t n_tag_fields;
+  const char* const* tag_fields;          /* write_exec.rs:207; aux fields are written in this order */
+  int32_t device_id;
+  int32_t compression;                    /* 0 (default): LZ77 + dynamic Huffman; 1: stored DEFLATE blocks (tests) */
+} BamWriteOptions;
+typedef struct BamWriteStats {
+  uint64_t rows, batches, members;
+  uint64_t arrow_bytes, bam_bytes, compressed_bytes;   /* H2D Arrow bytes, uncompressed BAM stream bytes, file bytes */
+  double ms_encode, ms_deflate, ms_total;               /* CUDA-event device times */
+  uint64_t kernel_launches;
+} BamWriteStats;
+int bamscan_writer_open(const char* output_path, const char* sam_header_text, int32_t n_ref, const char* const* ref_names,
+                        const int32_t* ref_lengths, const struct ArrowSchema* input_schema, const BamWriteOptions* options,
+                        BamWriter** out);
+/* One RecordBatch as a struct array matching input_schema (not released by the callee). */
+int bamscan_writer_write(BamWriter* w, const struct ArrowArray* batch);
+/* Flushes the last (partial) member and the BGZF EOF marker, closes the file; *rows_written = the reference's `count`. */
+int bamscan_writer_finish(BamWriter* w, uint64_t* rows_written);
+int bamscan_writer_stats(const BamWriter* w, BamWriteStats* out);
+void bamscan_writer_free(BamWriter* w);
+
 const char* bamscan_last_error(void);   /* thread-local message of the last failing call on this thread */
 const char* bamscan_version(void);
 
