@@ -99,6 +99,8 @@ def test_synthetic_multi_batch_and_slices(mode, reads, syn_dir, tmp_path):
     batch = o.scan(None)
     n = batch.num_rows
     cuts = [0, 1, 17, n // 3, n // 3, (2 * n) // 3 + 5, n]                    # an empty batch and sliced batches (array offset != 0)
+    if mode == "short":
+        cuts = [0, 1, 17, 17 + 8192, n // 3, n // 3, (2 * n) // 3 + 5, n]      # a batch of exactly two scan tiles (4096 rows each)
     parts = [batch.slice(a, b - a) for a, b in zip(cuts, cuts[1:])]
     out = tmp_path / "o.bam"
     rows, st = gpu_write(out, parts, o.schema, tags)
