@@ -240,9 +240,13 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
         if (can) { h = (w4 * 2654435761u) >> (32u - HASH_BITS); cand = S.htab[h]; }
         __syncwarp();
         if (can) S.htab[h] = (uint16_t)p;
+        if (skip >= 32u) { skip -= 32u; continue; }                             // the whole step lies inside the previous token
+        // matches are first measured up to 32 bytes only: a match that long reaches the end of the step, so it is the step's LAST
+        // token whenever it is chosen, and only that one token is then extended to 258 bytes -- by the whole warp, 128 bytes per
+        // round -- instead of every lane walking its own long match (runs of equal qualities cost 65 divergent rounds per lane)
         uint32_t L = 1, D = 0;
         if (can) {
-          const uint32_t maxlen = min(258u, rend - p);
+          const uint32_t maxlen = min(32u, rend - p);
           uint32_t best = 0;
           if (cand < p && p - cand <= 32768u) {
             uint32_t n = 0;
@@ -259,7 +263,7 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
           if (best >= 4u) L = best;
         }
         // greedy parse of the 32 positions: lane i jumps to lane i + L_i; the lanes on the path from `skip` are the tokens
-        const uint32_t endl = (uint32_t)lane + L;
+        uint32_t endl = (uint32_t)lane + L;
         uint32_t nxt = min(endl, 32u), reach = 1u << lane;
         #pragma unroll
         for (int r = 0; r < 5; r++) {
@@ -267,9 +271,31 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
           if (nxt < 32u) { reach |= rn; nxt = nn; }
         }
         const uint32_t inmask = __ballot_sync(FULL, in);
-        if (skip >= 32u) { skip -= 32u; continue; }
         const uint32_t sel = __shfl_sync(FULL, reach, skip) & inmask;
         if (!sel) { skip = 0; continue; }
+        {
+          // the last token: if it stopped at the 32-byte cap, the warp extends it (lane j compares bytes 32 + 4 j + 128 r ...)
+          const int last = 31 - __clz(sel);
+          const uint32_t lL = __shfl_sync(FULL, L, last), lD = __shfl_sync(FULL, D, last), lp = pos + (uint32_t)last;
+          if (lL == 32u) {
+            const uint32_t lmax = min(258u, rend - lp);
+            uint32_t ext = 32;
+            for (uint32_t b = 32; b < lmax; b += 128) {
+              const uint32_t o = b + 4u * (uint32_t)lane;
+              uint32_t x = 0xffffffffu;
+              if (o < lmax) x = ld4(S.buf, lp - lD + o) ^ ld4(S.buf, lp + o);
+              const uint32_t bal = __ballot_sync(FULL, x != 0u);                   // (lanes past lmax count as mismatches)
+              if (bal) {
+                const int fl = __ffs((int)bal) - 1;
+                const uint32_t fx = __shfl_sync(FULL, x, fl), fo = b + 4u * (uint32_t)fl;
+                ext = fo < lmax ? min(lmax, fo + ((uint32_t)(__ffs((int)fx) - 1) >> 3)) : lmax;
+                break;
+              }
+              ext = min(lmax, b + 128u);
+            }
+            if (lane == last) { L = ext; endl = (uint32_t)lane + L; }
+          }
+        }
         if ((sel >> lane) & 1u) {
           const uint32_t idx = ntok + __popc(sel & ((1u << lane) - 1u));
           if (L >= 4u) {

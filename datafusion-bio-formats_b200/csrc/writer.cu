@@ -9,11 +9,17 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -35,7 +41,14 @@ namespace bamscan {
 
 constexpr uint64_t SLICE_BYTES = 512ull << 20;       // uncompressed BAM bytes encoded + compressed per device pass
 constexpr uint32_t SLICE_ROWS = 1u << 20;
-constexpr size_t OUT_CHUNK = 64ull << 20;             // pinned D2H staging
+constexpr size_t OUT_CHUNK = 16ull << 20;             // pinned D2H staging buffers (OUT_BUFS of them, drained by the file threads)
+constexpr int OUT_BUFS = 3, FILE_THREADS = 4;
+constexpr size_t IN_CHUNK = 8ull << 20;              // pinned H2D staging buffers (the caller's Arrow buffers are pageable)
+constexpr int IN_BUFS = 2, IN_THREADS = 4;
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool g_wtrace = getenv("BAMSCAN_WRITER_TRACE") != nullptr;
+#define WTRACE(...) do { if (g_wtrace) fprintf(stderr, __VA_ARGS__); } while (0)
 
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
@@ -72,7 +85,20 @@ struct BamWriter {
   DevBuf ref_blob, ref_off, ref_ids, in, stream_buf, rec_len, ref_pairs, cig_bin, rec_off, tile_sums, slots, sizes, offsets, packed, tok, small;
   int n_ref = 0;
   uint64_t pending = 0;                  // bytes of the uncompressed stream waiting at the front of stream_buf (header, tails)
-  uint8_t* h_out = nullptr;              // pinned
+  uint8_t* h_out[OUT_BUFS] = {};         // pinned; filled by D2H, written to the file by file_thread
+  uint8_t* h_in[IN_BUFS] = {};           // pinned; the caller's buffers are copied here by IN_THREADS host threads, then H2D
+  cudaEvent_t in_free[IN_BUFS] = {};
+  uint64_t in_seq = 0;
+  // file threads: pwrite(2) of the pieces of a staging buffer runs beside the GPU work of the next slice
+  struct FileJob { int slot; size_t at, bytes; uint64_t file_off; };
+  std::thread file_thread[FILE_THREADS];
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<FileJob> file_q;
+  int out_busy[OUT_BUFS] = {};           // outstanding pieces per buffer
+  uint64_t file_off = 0;
+  cudaEvent_t ev2[2] = {};
+  bool file_stop = false, file_failed = false;
   uint64_t* h_small = nullptr;           // pinned: tile sums, totals, error words
   int n_sms = 148;
   BamWriteStats st = {};
@@ -200,7 +226,10 @@ static int writer_open_impl(const char* output_path, const char* sam_header_text
   w->n_sms = prop.multiProcessorCount;
   WCU_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
   for (auto& e : w->ev) WCU_TRY(cudaEventCreate(&e));
-  WCU_TRY(cudaHostAlloc((void**)&w->h_out, OUT_CHUNK, cudaHostAllocDefault));
+  for (auto& e : w->ev2) WCU_TRY(cudaEventCreate(&e));
+  for (auto& b : w->h_out) WCU_TRY(cudaHostAlloc((void**)&b, OUT_CHUNK, cudaHostAllocDefault));
+  for (auto& b : w->h_in) WCU_TRY(cudaHostAlloc((void**)&b, IN_CHUNK, cudaHostAllocDefault));
+  for (auto& e : w->in_free) WCU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   WCU_TRY(cudaHostAlloc((void**)&w->h_small, 1 << 16, cudaHostAllocDefault));
   {
     auto mulmod = [](uint32_t a, uint32_t b) { uint32_t p = 0; for (int i = 0; i < 32; i++) { if (b & 0x80000000u) p ^= a; a = (a >> 1) ^ ((a & 1u) ? 0xEDB88320u : 0u); b <<= 1; } return p; };
@@ -237,17 +266,60 @@ static int writer_open_impl(const char* output_path, const char* sam_header_text
   w->pending = hdr.size();
   w->fd = ::open(output_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
   if (w->fd < 0) { set_error("Failed to create output file: %s", output_path); return BAMSCAN_ERR_IO; }
+  {
+    BamWriter* wp = w.get();
+    for (auto& th : wp->file_thread) th = std::thread([wp] {
+      for (;;) {
+        BamWriter::FileJob job;
+        {
+          std::unique_lock<std::mutex> lk(wp->mu);
+          wp->cv.wait(lk, [wp] { return wp->file_stop || !wp->file_q.empty(); });
+          if (wp->file_q.empty()) return;
+          job = wp->file_q.front(); wp->file_q.pop_front();
+        }
+        size_t done = 0;
+        while (done < job.bytes && !wp->file_failed) {
+          const ssize_t k = ::pwrite(wp->fd, wp->h_out[job.slot] + job.at + done, job.bytes - done, (off_t)(job.file_off + done));
+          if (k <= 0) { wp->file_failed = true; break; }
+          done += (size_t)k;
+        }
+        { std::lock_guard<std::mutex> lk(wp->mu); wp->out_busy[job.slot]--; }
+        wp->cv.notify_all();
+      }
+    });
+  }
   *out = w.release();
   return BAMSCAN_OK;
 }
 
-// H2D of one buffer slice; returns the device address of its first byte
+// H2D of one buffer slice; returns the device address of its first byte.  Large slices go through the pinned ring: IN_THREADS
+// host threads copy a chunk into a pinned buffer, one cudaMemcpyAsync sends it on (pageable H2D would be staged by the
+// driver on one thread at a fraction of the link rate).
 static int stage(BamWriter* w, size_t* cursor, const void* src, size_t bytes, uint8_t** dev) {
   const size_t at = (*cursor + 15) & ~size_t(15);
   *dev = static_cast<uint8_t*>(w->in.p) + at;
-  if (bytes) WCU_TRY(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, w->stream));
   *cursor = at + bytes;
   w->st.arrow_bytes += bytes;
+  const uint8_t* s = static_cast<const uint8_t*>(src);
+  for (size_t done = 0; done < bytes;) {
+    const size_t nb = std::min(IN_CHUNK, bytes - done);
+    const int slot = (int)(w->in_seq % IN_BUFS);
+    if (w->in_seq >= (uint64_t)IN_BUFS) WCU_TRY(cudaEventSynchronize(w->in_free[slot]));
+    uint8_t* h = w->h_in[slot];
+    if (nb >= (4u << 20)) {
+      std::thread th[IN_THREADS];
+      const size_t per = (nb + IN_THREADS - 1) / IN_THREADS;
+      for (int t = 0; t < IN_THREADS; t++) {
+        const size_t b = std::min(nb, per * t), e = std::min(nb, b + per);
+        th[t] = std::thread([=] { if (e > b) memcpy(h + b, s + done + b, e - b); });
+      }
+      for (auto& t : th) t.join();
+    } else memcpy(h, s + done, nb);
+    WCU_TRY(cudaMemcpyAsync(*dev + done, h, nb, cudaMemcpyHostToDevice, w->stream));
+    WCU_TRY(cudaEventRecord(w->in_free[slot], w->stream));
+    w->in_seq++;
+    done += nb;
+  }
   return BAMSCAN_OK;
 }
 
@@ -311,6 +383,7 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
     } else need += (size_t)n * 4 + (size_t)n / 8 + 64;
   }
   int rc;
+  const double t_w0 = now_ms();
   if ((rc = w->in.reserve(need))) return rc;
   enc::EncArgs A;
   memset(&A, 0, sizeof A);
@@ -355,6 +428,7 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
   A.ref_blob = static_cast<const uint8_t*>(w->ref_blob.p); A.ref_off = static_cast<const int32_t*>(w->ref_off.p);
   A.ref_ids = static_cast<const int32_t*>(w->ref_ids.p); A.n_ref = w->n_ref;
   A.cigar_binary = w->cigar_binary; A.zero_based = w->zero_based;
+  WTRACE("[writer] batch of %lld rows: staged %.1f MB in %.1f ms\n", (long long)n, cur / 1e6, now_ms() - t_w0);
   // ---- slices of rows: sizes -> offsets -> records -> members ----
   if ((rc = w->small.reserve(4096))) return rc;
   uint32_t* d_err = static_cast<uint32_t*>(w->small.p);
@@ -416,7 +490,9 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
       float ms = 0; cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]); w->st.ms_encode += ms; w->st.ms_total += ms;
     }
     w->st.rows += rows; w->st.bam_bytes += total;
+    const double t_f0 = now_ms();
     if ((rc = writer_flush_members(w, w->pending + total, false))) return rc;
+    WTRACE("[writer] slice of %u rows: encode done at +%.1f ms, members flushed in %.1f ms\n", rows, t_f0 - t_w0, now_ms() - t_f0);
     r0 += rows;
   }
   return BAMSCAN_OK;
@@ -441,31 +517,46 @@ static int writer_flush_members(BamWriter* w, uint64_t total, bool final_flush) 
                                                                            static_cast<uint8_t*>(w->slots.p), static_cast<uint32_t*>(w->sizes.p),
                                                                            static_cast<uint32_t*>(w->tok.p), d_ticket, w->compression == 1);
   dfl::bgzf_offsets_kernel<<<1, 1024, 0, w->stream>>>(static_cast<uint32_t*>(w->sizes.p), (uint32_t)n_members, static_cast<unsigned long long*>(w->offsets.p), d_total);
+  WCU_TRY(cudaEventRecord(w->ev[3], w->stream));
   WCU_TRY(cudaMemcpyAsync(w->h_small + 5000, d_total, 8, cudaMemcpyDeviceToHost, w->stream));
   WCU_TRY(cudaStreamSynchronize(w->stream));
   WCU_TRY(cudaGetLastError());
   const uint64_t packed_bytes = w->h_small[5000];
+  const double t_d = now_ms();
   if ((rc = w->packed.reserve(packed_bytes + 16))) return rc;
+  WCU_TRY(cudaEventRecord(w->ev2[0], w->stream));
   dfl::bgzf_gather_kernel<<<(uint32_t)n_members, 256, 0, w->stream>>>(static_cast<const uint8_t*>(w->slots.p), static_cast<uint32_t*>(w->sizes.p),
                                                                      static_cast<unsigned long long*>(w->offsets.p), static_cast<uint8_t*>(w->packed.p));
-  WCU_TRY(cudaEventRecord(w->ev[3], w->stream));
+  WCU_TRY(cudaEventRecord(w->ev2[1], w->stream));
   w->st.kernel_launches += 3;
   // the tail moves to the front (source and destination cannot overlap: the tail is shorter than one member)
   const uint64_t tail = total - consumed;
   if (tail) WCU_TRY(cudaMemcpyAsync(w->stream_buf.p, static_cast<uint8_t*>(w->stream_buf.p) + consumed, tail, cudaMemcpyDeviceToDevice, w->stream));
   for (uint64_t at = 0; at < packed_bytes; at += OUT_CHUNK) {
     const size_t nb = (size_t)std::min<uint64_t>(OUT_CHUNK, packed_bytes - at);
-    WCU_TRY(cudaMemcpyAsync(w->h_out, static_cast<uint8_t*>(w->packed.p) + at, nb, cudaMemcpyDeviceToHost, w->stream));
-    WCU_TRY(cudaStreamSynchronize(w->stream));
-    size_t done = 0;
-    while (done < nb) {
-      const ssize_t k = ::write(w->fd, w->h_out + done, nb - done);
-      if (k <= 0) { set_error("Failed to write BAM record: write(%s) failed", w->path.c_str()); return BAMSCAN_ERR_IO; }
-      done += (size_t)k;
+    int slot = -1;
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { for (int b = 0; b < OUT_BUFS; b++) if (!w->out_busy[b]) { slot = b; return true; } return w->file_failed; });
+      if (w->file_failed || slot < 0) { set_error("Failed to write BAM record: write(%s) failed", w->path.c_str()); return BAMSCAN_ERR_IO; }
+      w->out_busy[slot] = FILE_THREADS;
     }
+    WCU_TRY(cudaMemcpyAsync(w->h_out[slot], static_cast<uint8_t*>(w->packed.p) + at, nb, cudaMemcpyDeviceToHost, w->stream));
+    WCU_TRY(cudaStreamSynchronize(w->stream));
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      const size_t per = (nb + FILE_THREADS - 1) / FILE_THREADS;
+      for (int t = 0; t < FILE_THREADS; t++) {
+        const size_t b = std::min(nb, per * t), e = std::min(nb, b + per);
+        w->file_q.push_back(BamWriter::FileJob{slot, b, e - b, w->file_off + b});
+      }
+      w->file_off += nb;
+    }
+    w->cv.notify_all();
   }
   WCU_TRY(cudaStreamSynchronize(w->stream));
-  { float ms = 0; cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]); w->st.ms_deflate += ms; w->st.ms_total += ms; }
+  WTRACE("[writer] %llu members, %.1f MB packed: gather + D2H + queueing %.1f ms\n", (unsigned long long)n_members, packed_bytes / 1e6, now_ms() - t_d);
+  { float ms = 0, ms2 = 0; cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]); cudaEventElapsedTime(&ms2, w->ev2[0], w->ev2[1]); w->st.ms_deflate += ms + ms2; w->st.ms_total += ms + ms2; }
   w->st.members += n_members; w->st.compressed_bytes += packed_bytes;
   w->pending = tail;
   return BAMSCAN_OK;
@@ -473,16 +564,23 @@ static int writer_flush_members(BamWriter* w, uint64_t total, bool final_flush) 
 
 static int writer_finish_impl(BamWriter* w, uint64_t* rows_written) {
   if (!w) { set_error("bamscan_writer_finish: null argument"); return BAMSCAN_ERR_INVALID; }
+  const double t_fin = now_ms();
   if (!w->finished) {
     WCU_TRY(cudaSetDevice(w->device));
     int rc;
     if ((rc = w->small.reserve(4096))) return rc;
     if ((rc = writer_flush_members(w, w->pending, true))) return rc;
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { if (!w->file_q.empty()) return false; for (int b = 0; b < OUT_BUFS; b++) if (w->out_busy[b]) return false; return true; });
+      if (w->file_failed) { set_error("Failed to finish BAM stream: write(%s) failed", w->path.c_str()); return BAMSCAN_ERR_IO; }
+    }
     static const uint8_t eof_marker[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (::write(w->fd, eof_marker, 28) != 28) { set_error("Failed to finish BAM stream: write(%s) failed", w->path.c_str()); return BAMSCAN_ERR_IO; }
+    if (::pwrite(w->fd, eof_marker, 28, (off_t)w->file_off) != 28) { set_error("Failed to finish BAM stream: write(%s) failed", w->path.c_str()); return BAMSCAN_ERR_IO; }
     w->st.compressed_bytes += 28;
     ::close(w->fd); w->fd = -1;
     w->finished = true;
+    WTRACE("[writer] finish: %.1f ms\n", now_ms() - t_fin);
   }
   if (rows_written) *rows_written = w->st.rows;
   return BAMSCAN_OK;
@@ -513,11 +611,17 @@ void bamscan_writer_free(BamWriter* w) {
   if (!w) return;
   cudaSetDevice(w->device);
   if (w->stream) cudaStreamSynchronize(w->stream);
+  { std::lock_guard<std::mutex> lk(w->mu); w->file_stop = true; }
+  w->cv.notify_all();
+  for (auto& th : w->file_thread) if (th.joinable()) th.join();
+  for (auto& e : w->ev2) if (e) cudaEventDestroy(e);
   if (w->fd >= 0) ::close(w->fd);
   for (DevBuf* b : {&w->ref_blob, &w->ref_off, &w->ref_ids, &w->in, &w->stream_buf, &w->rec_len, &w->ref_pairs, &w->cig_bin, &w->rec_off, &w->tile_sums,
                     &w->slots, &w->sizes, &w->offsets, &w->packed, &w->tok, &w->small})
     b->release();
-  if (w->h_out) cudaFreeHost(w->h_out);
+  for (auto b : w->h_out) if (b) cudaFreeHost(b);
+  for (auto b : w->h_in) if (b) cudaFreeHost(b);
+  for (auto& e : w->in_free) if (e) cudaEventDestroy(e);
   if (w->h_small) cudaFreeHost(w->h_small);
   for (auto& e : w->ev) if (e) cudaEventDestroy(e);
   if (w->stream) cudaStreamDestroy(w->stream);

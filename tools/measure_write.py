@@ -31,6 +31,7 @@ def main():
     res = {}
     for rep in range(3):
         ex = bamscan.BamWriteExec(str(out), p.schema(), tags, True, {"bio.bam.sort_order": "unsorted"})
+        print(f"-- rep {rep}", file=sys.stderr, flush=True)
         t0 = time.perf_counter()
         n = ex.execute(batches)
         dt = time.perf_counter() - t0
