@@ -335,7 +335,8 @@ def main():
     tags = TAGS if not long_reads else ["NM", "MD", "MM", "ML"]
     t_open = time.time()
     provider = bamscan.BamTableProvider(str(path), None, True, tags, False, True, 100, None, device_id=local,
-                                        index_path=None if args.config == 4 else "")
+                                        index_path=None if args.config == 4 else "",
+                                        debug_flags=int(os.environ.get("BAMSCAN_DEBUG_FLAGS", "0")))   # (A/B runs of the profiles; default 0 = product path)
     projection = None if args.projection == "full" else [1, 2, 3, 6, 4]
     filters = [("chrom", "=", ["chr1"]), ("start", "between", [50_000_000, 150_000_000])] if args.config == 4 else []
     if args.config == 4:

@@ -815,6 +815,15 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   seg_candidates_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, cs>>>(BP, d_seg_start, (f->debug_flags & 1) ? 1 : 0);
   seg_walk_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
   seg_check_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
+  if (!(f->debug_flags & 64)) {
+    // parallel repair rounds (no-ops when every seam agreed); debug_flags bit 6 leaves everything to the sequential repair
+    for (int round = 0; round < 3; round++) {
+      seg_fix_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W, round);
+      seg_reset_kernel<<<1, 1, 0, cs>>>(W);
+      seg_check_kernel<<<(n_seg + 127) / 128, 128, 0, cs>>>(BP, W);
+    }
+    s->st.kernel_launches += 9;
+  }
   seg_repair_kernel<<<1, 1, 0, cs>>>(BP, W);
   seg_scan_kernel<<<1, 1024, 0, cs>>>(d_seg_count, d_seg_start, d_seg_exit, d_seg_tail, d_seg_base, n_seg, d_flags);
   s->st.kernel_launches += 5;

@@ -181,11 +181,43 @@ seg_check_kernel(BoundaryParams P, WalkOut W) {
   if (bad) { atomicAdd(&W.flags[0], 1u); atomicMin(&W.flags[11], s); }   // [11] = first segment whose seam disagrees
 }
 
+// Parallel repair rounds (in front of the sequential one).  One thread per segment whose seam disagrees -- and whose own walk ran
+// past its segment -- re-anchors the segment its chain lands in: the starts in between are dropped, the landing segment is
+// re-walked from the landing offset.  This is only right when the fixing segment itself lies on the true chain, which a thread
+// cannot know; but segment 0 is exact, so after round r the first r links of the chain are final, a wrong "fix" made by a
+// false start is undone in a later round by the true predecessor, and independent errors (the common case in long-read files,
+// where a 10 kb record covers whole segments and a false candidate shows up every few thousand segments) are all gone after
+// two or three rounds.  Exactness does not rest on these rounds: seg_check runs again behind them and seg_repair_kernel
+// re-chains sequentially whatever still disagrees.
+__global__ void __launch_bounds__(128)
+seg_fix_kernel(BoundaryParams P, WalkOut W, int round) {
+  if (W.flags[0] == 0) return;
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0 && round == 0) W.flags[10] = W.flags[0];   // seams the first check rejected (stats)
+  if (s >= P.n_seg || W.seg_start[s] == SEG_NONE || W.seg_tail[s]) return;
+  const uint32_t e = W.seg_exit[s];
+  uint32_t t = (e - P.seg0) / P.seg_bytes;
+  if (t >= P.n_seg) t = P.n_seg - 1;
+  if (t <= s) return;
+  for (uint32_t u = s + 1; u < t; u++)
+    if (W.seg_start[u] != SEG_NONE) { W.seg_start[u] = SEG_NONE; W.seg_count[u] = 0; W.seg_exit[u] = SEG_NONE; W.seg_tail[u] = 0; }
+  if (W.seg_start[t] != e) {
+    atomicAdd(&W.flags[4], 1u);
+    W.seg_start[t] = e;
+    WalkResult r = walk_segment(P, t, e);
+    W.seg_count[t] = r.n; W.seg_exit[t] = r.exit; W.seg_tail[t] = r.tail;
+  }
+}
+__global__ void seg_reset_kernel(WalkOut W) {
+  if (W.flags[0] == 0) return;
+  W.flags[0] = 0; W.flags[2] = 0xffffffffu; W.flags[11] = 0xffffffffu;
+}
+
 // Sequential repair (rare): follows the chain from the first start, reusing per-segment walks whose start
 // agrees and re-walking those that do not.  Launched with one thread; returns at once when every seam agreed.
 __global__ void seg_repair_kernel(BoundaryParams P, WalkOut W) {
   if (W.flags[0] == 0) return;
-  W.flags[10] = W.flags[0];   // reported in the stats
+  if (W.flags[10] == 0) W.flags[10] = W.flags[0];   // reported in the stats (the parallel rounds record the first check's count)
   // every seam before the first disagreeing one was verified, so that segment's own start is on the true chain
   uint32_t s = W.flags[11] < P.n_seg ? W.flags[11] : 0;
   while (s < P.n_seg && W.seg_start[s] == SEG_NONE) s++;

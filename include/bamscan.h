@@ -67,7 +67,7 @@ typedef struct BamScanOptions {
   uint64_t chunk_inflated_bytes;          /* device chunk size cap (inflated bytes), max 768 MiB; 0 = one inflate wave per chunk (~1.5 GiB on a B200), decoded in slices of <= 768 MiB: one batch per slice */
   uint32_t segment_bytes;                 /* record-boundary segment size; 0 = default 16 KiB */
   int32_t skip_crc;                       /* 0 (default): verify CRC32 of every BGZF member on the device; 1: skip */
-  int32_t debug_flags;                    /* tests only. bit0: poison boundary candidates (exercises the repair path); bit1: force the long-record decode kernels (a warp per record); bit2 / bit3 / bit4: force the warp-per-member / the lane-group / the CTA-per-member inflate kernel (default: the CTA-per-member kernel); bit5: queue the next chunk's inflate behind the current chunk's first decode slice (the two overlap on the GPU; measured +1 % scan rate, -10 % inflate rate) */
+  int32_t debug_flags;                    /* tests only. bit0: poison boundary candidates (exercises the repair path); bit1: force the long-record decode kernels (a warp per record); bit2 / bit3 / bit4: force the warp-per-member / the lane-group / the CTA-per-member inflate kernel (default: the CTA-per-member kernel); bit5: queue the next chunk's inflate behind the current chunk's first decode slice (the two overlap on the GPU; measured +1 % scan rate, -10 % inflate rate); bit6: skip the parallel boundary-repair rounds (every disagreeing seam goes to the sequential repair) */
   int32_t decode_all_tag_fields;          /* 1: reference behaviour (sam_tag_io.rs:42-52): once ANY tag column is projected every tag_fields entry is decoded, so a value that does not fit an UNPROJECTED tag column's type fails the scan; 0 (default): only projected tag columns are decoded */
 } BamScanOptions;
 

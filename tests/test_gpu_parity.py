@@ -183,10 +183,12 @@ def test_block_range_partitions_concatenate_to_full_scan(syn_dir, nparts, mode):
     _assert_tables_equal(got, o.scan(), f"{mode} x{nparts}")
 
 
-def test_boundary_repair_path(syn_dir):
+@pytest.mark.parametrize("sequential_only", [0, 64])
+def test_boundary_repair_path(syn_dir, sequential_only):
+    """bit 6 leaves every disagreeing seam to the sequential repair; without it the parallel rounds (seg_fix_kernel) go first."""
     path = gen_bam(syn_dir, "short", 20000, seed=3)
     o = _oracle(path)
-    p = _provider(path, segment_bytes=2048, debug_flags=1)   # every third segment gets a wrong start
+    p = _provider(path, segment_bytes=2048, debug_flags=1 | sequential_only)   # every third segment gets a wrong start
     plan = p.scan([0, 2, 5], [], None)
     got = plan.collect()
     assert plan.last_stats["boundary_repairs"] > 0
