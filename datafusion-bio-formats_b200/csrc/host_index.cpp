@@ -322,8 +322,23 @@ int plan_indexed(BamFile* f, Plan* plan, const BamScanFilter* filters, int32_t n
     }
     plan->residual.push_back(rf);
   }
-  const uint32_t first_block = 0;
-  (void)first_block;
+  // An upper bound on `start` that the pushed record filters enforce on every row (start BETWEEN / = / < / <=).  balance_partitions
+  // leaves the last sub-region of a split contig open-ended (partition_balancer.rs: `end = None`), so the reference -- and this
+  // build before -- reads that partition's chunks up to the end of the contig and throws the rows away again in the filter.
+  // The file is coordinate sorted: chunks that only hold records starting behind the bound cannot contribute a row, so they are
+  // not read (same argument as the upper-bound prune of bai_query; fewer bytes, identical rows).
+  bool has_start_sup = false; uint64_t start_sup = 0;
+  for (int i = 0; i < n_filters; i++) {
+    const BamScanFilter& q = filters[i];
+    if (q.column != BAMSCAN_COL_START || !q.num_values || !filter_is_record_pushable(*f, q)) continue;
+    uint64_t v = 0; bool have = false;
+    if (q.op == BAMSCAN_OP_BETWEEN && q.n_values >= 2) have = as_u64(q.num_values[1], &v);
+    else if ((q.op == BAMSCAN_OP_EQ || q.op == BAMSCAN_OP_LE) && q.n_values >= 1) have = as_u64(q.num_values[0], &v);
+    else if (q.op == BAMSCAN_OP_LT && q.n_values >= 1) { have = as_u64(q.num_values[0], &v); if (have) v = v ? v - 1 : 0; }
+    if (!have) continue;
+    v += f->zero_based ? 1 : 0;                       // 1-based closed, like GenomicRegion
+    start_sup = has_start_sup ? std::min(start_sup, v) : v; has_start_sup = true;
+  }
   for (const Assignment& a : assignments) {
     Partition part;
     part.regions = a.regions; part.estimated_bytes = a.total_estimated_bytes;
@@ -367,7 +382,10 @@ int plan_indexed(BamFile* f, Plan* plan, const BamScanFilter* filters, int32_t n
       rule.region_start = g.has_start ? g.start : 0; rule.region_end = g.has_end ? g.end : 0;
       if (!R) continue;
       if (g.has_start && g.has_end && g.start > g.end) continue;
-      std::vector<BaiChunk> chunks = bai_query(*R, g.has_start ? std::max<uint64_t>(g.start, 1) : 1, g.has_end, g.end);
+      const bool q_has_end = g.has_end || has_start_sup;
+      const uint64_t q_end = g.has_end ? (has_start_sup ? std::min(g.end, start_sup) : g.end) : start_sup;
+      if (g.has_start && q_has_end && g.start > q_end) continue;
+      std::vector<BaiChunk> chunks = bai_query(*R, g.has_start ? std::max<uint64_t>(g.start, 1) : 1, q_has_end, q_end);
       for (auto& c : chunks) { int rc = add_range(*f, c.beg, c.end, rule, &part); if (rc) return rc; }
     }
     plan->partitions.push_back(part);
