@@ -15,8 +15,9 @@ roofline: the inflate stage (dominant), algorithmic bytes = compressed bytes rea
 N > 1   : STRONG scaling of the ONE file (BASELINE config 2, "by BGZF block range"): the plan has N block-range partitions,
           rank r scans partition r on its own GPU (ranks > 0 find their first record by speculation); no collective on the
           data path.  `replicas` keeps the round-1 number (every rank scans a whole copy) beside it.
---verify: (outside every timed region) the default product path over a <= 10 M-read file of the same generator is compared
-          with the oracle, every row of every column (oracle/verify.py); the result goes into the line's "verify" key.
+verify  : at N = 1, config 2 (or with --verify; --no-verify skips it), outside every timed region, the default product path
+          over a <= 10 M-read file of the same generator is compared with the oracle, every row of every column
+          (oracle/verify.py); the result goes into the line's "verify" key.
 --config: 2 (default) full projection | 3 fixed-width projection | 4 BAI region query chr1:50M-150M | 5 long reads
 """
 import argparse
@@ -274,7 +275,8 @@ def main():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--projection", default="full", choices=["full", "fixed"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
-    ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="(default at N = 1, config 2) compare the product path with the oracle outside the timed regions")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-replicas", action="store_true")
     args = ap.parse_args()
     if args.config == 3:
@@ -485,17 +487,59 @@ def main():
                                 "one_thread": {"value": cst["rows"] / dt, "unit": "reads/s", "cores": 1, "sample": f"first {cst['rows']} reads, one sequential loop",
                                                "inflated_gbps": cst["inflated_bytes"] / dt / 1e9},
                                 "inflate_only": inflate_only_cpu(path)}
-    if args.verify:
-        from oracle.bam_oracle import OracleBam
-        from oracle.verify import verify_full_scan
-        vreads = min(args.reads, int(os.environ.get("BAMSCAN_VERIFY_READS", 10_000_000)))
-        vpath, _vinfo = ensure_bam(vreads, args.seed, True)
-        vp = bamscan.BamTableProvider(str(vpath), None, True, TAGS, False, True, 100, None, device_id=local, index_path="")
-        vo = OracleBam(str(vpath), tag_fields=TAGS)
-        rep = verify_full_scan(vo, str(vpath) + ".bai", vp.scan(None, [], None).execute(0), n_parts=max(8, vreads // 1_000_000), threads=os.cpu_count())
-        rep.pop("checksums", None)
-        rep["result"] = "bit-exact: per-column checksums over every row + RecordBatch equality on 3 windows"
+    if (args.verify or (world == 1 and args.config == 2)) and not args.no_verify:
+        # parity at the benchmarked shape, outside every timed region: the DEFAULT product path (no chunk cap, no forced kernels,
+        # >= 2 full inflate launches) over a <= 10 M-read file of the same generator against the oracle on all host threads
+        t_v = time.time()
+        try:
+            from oracle.bam_oracle import OracleBam
+            from oracle.verify import verify_full_scan
+            vreads = min(args.reads, int(os.environ.get("BAMSCAN_VERIFY_READS", 10_000_000)))
+            vpath, _vinfo = ensure_bam(vreads, args.seed, True)
+            vp = bamscan.BamTableProvider(str(vpath), None, True, TAGS, False, True, 100, None, device_id=local, index_path="")
+            vo = OracleBam(str(vpath), tag_fields=TAGS)
+            rep = verify_full_scan(vo, str(vpath) + ".bai", vp.scan(None, [], None).execute(0), n_parts=max(8, vreads // 1_000_000), threads=os.cpu_count())
+            rep.pop("checksums", None)
+            rep["result"] = "bit-exact: per-column checksums over every row + RecordBatch equality on 3 windows"
+        except Exception as e:      # a parity failure must show up IN the line, not instead of it
+            rep = {"result": f"FAILED: {type(e).__name__}: {e}"[:500]}
+        rep["seconds"] = round(time.time() - t_v, 1)
         line["verify"] = rep
+    if world == 1 and args.config == 2 and not args.no_verify:
+        # SURVEY 8 f4 beside it (outside every timed region of the scan): the first ~4 M rows of the verify file go back out through
+        # bamscan_writer_* (Arrow -> BAM records -> BGZF members compressed on the GPU), and the GPU scan reads the file back
+        try:
+            import pyarrow as pa
+            wreads = min(args.reads, int(os.environ.get("BAMSCAN_VERIFY_READS", 10_000_000)))
+            wpath, winfo = ensure_bam(wreads, args.seed, True)
+            wp = bamscan.BamTableProvider(str(wpath), None, True, TAGS, False, True, 100, None, device_id=local, index_path="")
+            batches, nrows = [], 0
+            for b in wp.scan(None, [], None).execute(0):
+                batches.append(b); nrows += b.num_rows
+                if nrows >= 4_000_000:
+                    break
+            out = wpath.parent / "bench_written.bam"
+            best = None
+            for _ in range(2):
+                ex = bamscan.BamWriteExec(str(out), wp.schema(), TAGS, True, {"bio.bam.sort_order": "unsorted"}, device_id=local)
+                t0 = time.perf_counter()
+                n = ex.execute(batches)
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, ex.stats)
+            dt, wst = best
+            rp = bamscan.BamTableProvider(str(out), None, True, TAGS, False, True, 100, None, device_id=local, index_path="")
+            back = pa.Table.from_batches(list(rp.scan(None, [], None).execute(0)))
+            want = pa.Table.from_batches(batches)
+            same = back.num_rows == want.num_rows and all(back.column(i).combine_chunks().equals(want.column(i).combine_chunks()) for i in range(want.num_columns))
+            line["write_path"] = {"rows": n, "e2e_reads_per_s": n / dt, "device_reads_per_s": n / (wst["ms_total"] / 1e3), "encode_ms": wst["ms_encode"], "deflate_ms": wst["ms_deflate"],
+                                  "arrow_bytes_h2d": wst["arrow_bytes"], "bam_stream_bytes": wst["bam_bytes"], "file_bytes": wst["compressed_bytes"], "members": wst["members"],
+                                  "compression_ratio": wst["bam_bytes"] / max(1, wst["compressed_bytes"]), "kernel_launches": wst["kernel_launches"],
+                                  "read_back": "equal to the batches written (GPU scan of the written file, every column)" if same else "DIFFERS",
+                                  "note": "bamscan_writer_* (INSERT OVERWRITE): enc_size / enc_records / bgzf_deflate kernels; best of 2; file on tmpfs"}
+            out.unlink(missing_ok=True)
+        except Exception as e:
+            line["write_path"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
