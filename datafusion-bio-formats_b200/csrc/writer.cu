@@ -42,7 +42,7 @@ namespace bamscan {
 constexpr uint64_t SLICE_BYTES = 512ull << 20;       // uncompressed BAM bytes encoded + compressed per device pass
 constexpr uint32_t SLICE_ROWS = 1u << 20;
 constexpr size_t OUT_CHUNK = 16ull << 20;             // pinned D2H staging buffers (OUT_BUFS of them, drained by the file threads)
-constexpr int OUT_BUFS = 3, FILE_THREADS = 4;
+constexpr int OUT_BUFS = 12, FILE_THREADS = 4;   // 192 MB: one slice of compressed members never waits for the file threads
 constexpr size_t IN_CHUNK = 8ull << 20;              // pinned H2D staging buffers (the caller's Arrow buffers are pageable)
 constexpr int IN_BUFS = 2, IN_THREADS = 4;
 
@@ -66,11 +66,36 @@ struct DevBuf {
 
 struct WTag { int col; int32_t kind; uint8_t tag[2], sam_type, subtype; };
 
+// Device buffers, pinned staging, stream and events of a writer.  One set per device is kept between writers (cudaMalloc /
+// cudaHostAlloc / cudaFree of a few GB cost more than writing a few million records).
+struct WriterRes {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {}, ev2[2] = {}, in_free[IN_BUFS] = {};
+  DevBuf ref_blob, ref_off, ref_ids, in, stream_buf, rec_len, ref_pairs, cig_bin, rec_off, tile_sums, slots, sizes, offsets, packed, tok, small;
+  uint8_t* h_out[OUT_BUFS] = {};         // pinned; filled by D2H, written to the file by the file threads
+  uint8_t* h_in[IN_BUFS] = {};           // pinned; the caller's buffers are copied here by IN_THREADS host threads, then H2D
+  uint64_t* h_small = nullptr;           // pinned: tile sums, totals, error words
+  bool ready = false;
+  void destroy() {
+    for (DevBuf* b : {&ref_blob, &ref_off, &ref_ids, &in, &stream_buf, &rec_len, &ref_pairs, &cig_bin, &rec_off, &tile_sums, &slots, &sizes, &offsets, &packed, &tok, &small}) b->release();
+    for (auto& b : h_out) { if (b) cudaFreeHost(b); b = nullptr; }
+    for (auto& b : h_in) { if (b) cudaFreeHost(b); b = nullptr; }
+    if (h_small) { cudaFreeHost(h_small); h_small = nullptr; }
+    for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : ev2) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : in_free) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    ready = false;
+  }
+};
+static std::mutex g_res_mu;
+static WriterRes g_res_pool[64];
+
 }  // namespace bamscan
 
 using namespace bamscan;
 
-struct BamWriter {
+struct BamWriter : bamscan::WriterRes {
   int fd = -1;
   std::string path;
   int device = 0;
@@ -79,15 +104,8 @@ struct BamWriter {
   int col[11] = {};                      // name chrom start flags cigar mapq mate_chrom mate_start seq qual tlen
   std::vector<WTag> tags;
   int n_cols = 0;
-  // device state
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {};
-  DevBuf ref_blob, ref_off, ref_ids, in, stream_buf, rec_len, ref_pairs, cig_bin, rec_off, tile_sums, slots, sizes, offsets, packed, tok, small;
   int n_ref = 0;
   uint64_t pending = 0;                  // bytes of the uncompressed stream waiting at the front of stream_buf (header, tails)
-  uint8_t* h_out[OUT_BUFS] = {};         // pinned; filled by D2H, written to the file by file_thread
-  uint8_t* h_in[IN_BUFS] = {};           // pinned; the caller's buffers are copied here by IN_THREADS host threads, then H2D
-  cudaEvent_t in_free[IN_BUFS] = {};
   uint64_t in_seq = 0;
   // file threads: pwrite(2) of the pieces of a staging buffer runs beside the GPU work of the next slice
   struct FileJob { int slot; size_t at, bytes; uint64_t file_off; };
@@ -97,9 +115,7 @@ struct BamWriter {
   std::deque<FileJob> file_q;
   int out_busy[OUT_BUFS] = {};           // outstanding pieces per buffer
   uint64_t file_off = 0;
-  cudaEvent_t ev2[2] = {};
   bool file_stop = false, file_failed = false;
-  uint64_t* h_small = nullptr;           // pinned: tile sums, totals, error words
   int n_sms = 148;
   BamWriteStats st = {};
 };
@@ -167,7 +183,7 @@ static int writer_open_impl(const char* output_path, const char* sam_header_text
   opt.coordinate_system_zero_based = 1;
   if (options) memcpy(&opt, options, std::min<size_t>(sizeof opt, options->struct_size ? options->struct_size : sizeof opt));
   if (!schema->format || strcmp(schema->format, "+s") != 0) { set_error("bamscan_writer_open: input_schema must be a struct"); return BAMSCAN_ERR_INVALID; }
-  std::unique_ptr<BamWriter> w(new BamWriter());
+  std::unique_ptr<BamWriter, void (*)(BamWriter*)> w(new BamWriter(), [](BamWriter* p) { bamscan_writer_free(p); });   // (error paths give the pooled resources back)
   w->path = output_path; w->device = opt.device_id; w->zero_based = opt.coordinate_system_zero_based != 0; w->compression = opt.compression;
   w->n_cols = (int)schema->n_children;
   // columns by name (sam_record_serializer.rs:27-37: every core column is required; `end` is not read)
@@ -224,13 +240,21 @@ static int writer_open_impl(const char* output_path, const char* sam_header_text
   cudaDeviceProp prop;
   WCU_TRY(cudaGetDeviceProperties(&prop, opt.device_id));
   w->n_sms = prop.multiProcessorCount;
-  WCU_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
-  for (auto& e : w->ev) WCU_TRY(cudaEventCreate(&e));
-  for (auto& e : w->ev2) WCU_TRY(cudaEventCreate(&e));
-  for (auto& b : w->h_out) WCU_TRY(cudaHostAlloc((void**)&b, OUT_CHUNK, cudaHostAllocDefault));
-  for (auto& b : w->h_in) WCU_TRY(cudaHostAlloc((void**)&b, IN_CHUNK, cudaHostAllocDefault));
-  for (auto& e : w->in_free) WCU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  WCU_TRY(cudaHostAlloc((void**)&w->h_small, 1 << 16, cudaHostAllocDefault));
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    WriterRes& pooled = g_res_pool[opt.device_id & 63];
+    if (pooled.ready) { static_cast<WriterRes&>(*w) = pooled; pooled = WriterRes(); }
+  }
+  if (!w->ready) {
+    WCU_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    for (auto& e : w->ev) WCU_TRY(cudaEventCreate(&e));
+    for (auto& e : w->ev2) WCU_TRY(cudaEventCreate(&e));
+    for (auto& b : w->h_out) WCU_TRY(cudaHostAlloc((void**)&b, OUT_CHUNK, cudaHostAllocDefault));
+    for (auto& b : w->h_in) WCU_TRY(cudaHostAlloc((void**)&b, IN_CHUNK, cudaHostAllocDefault));
+    for (auto& e : w->in_free) WCU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    WCU_TRY(cudaHostAlloc((void**)&w->h_small, 1 << 16, cudaHostAllocDefault));
+    w->ready = true;
+  }
   {
     auto mulmod = [](uint32_t a, uint32_t b) { uint32_t p = 0; for (int i = 0; i < 32; i++) { if (b & 0x80000000u) p ^= a; a = (a >> 1) ^ ((a & 1u) ? 0xEDB88320u : 0u); b <<= 1; } return p; };
     uint32_t tab[18];
@@ -614,17 +638,13 @@ void bamscan_writer_free(BamWriter* w) {
   { std::lock_guard<std::mutex> lk(w->mu); w->file_stop = true; }
   w->cv.notify_all();
   for (auto& th : w->file_thread) if (th.joinable()) th.join();
-  for (auto& e : w->ev2) if (e) cudaEventDestroy(e);
   if (w->fd >= 0) ::close(w->fd);
-  for (DevBuf* b : {&w->ref_blob, &w->ref_off, &w->ref_ids, &w->in, &w->stream_buf, &w->rec_len, &w->ref_pairs, &w->cig_bin, &w->rec_off, &w->tile_sums,
-                    &w->slots, &w->sizes, &w->offsets, &w->packed, &w->tok, &w->small})
-    b->release();
-  for (auto b : w->h_out) if (b) cudaFreeHost(b);
-  for (auto b : w->h_in) if (b) cudaFreeHost(b);
-  for (auto& e : w->in_free) if (e) cudaEventDestroy(e);
-  if (w->h_small) cudaFreeHost(w->h_small);
-  for (auto& e : w->ev) if (e) cudaEventDestroy(e);
-  if (w->stream) cudaStreamDestroy(w->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    WriterRes& pooled = g_res_pool[w->device & 63];
+    if (w->ready && !pooled.ready) { pooled = static_cast<WriterRes&>(*w); static_cast<WriterRes&>(*w) = WriterRes(); }
+  }
+  w->destroy();
   delete w;
 }
 
