@@ -262,6 +262,12 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
           }
           if (best >= 4u) L = best;
         }
+        // lazy evaluation for free (every lane already knows its own match): a match gives way to a literal when the next
+        // position starts a longer one (zlib's deflate_slow rule)
+        {
+          const uint32_t Ln = __shfl_down_sync(FULL, L, 1);
+          if (lane < 31 && L >= 4u && Ln > L) L = 1;
+        }
         // greedy parse of the 32 positions: lane i jumps to lane i + L_i; the lanes on the path from `skip` are the tokens
         uint32_t endl = (uint32_t)lane + L;
         uint32_t nxt = min(endl, 32u), reach = 1u << lane;
