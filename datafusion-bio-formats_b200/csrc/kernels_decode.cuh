@@ -506,13 +506,19 @@ __device__ __forceinline__ uint32_t utf8_put(uint8_t* out, uint32_t cp) {
 }
 
 constexpr int VAR_WARPS = 8;
+#ifndef BAMSCAN_DV_PREFETCH
+#define BAMSCAN_DV_PREFETCH 0          // 1: every column offset of the record is loaded up front (A/B: profiles/r2_decode_var.md)
+#endif
+#ifndef BAMSCAN_DV_MINBLOCKS
+#define BAMSCAN_DV_MINBLOCKS 8
+#endif
 
 // One warp instruction serves 32 / G records.  With a warp per 340-byte record (round 1) most steps moved a handful of bytes
 // (name 20, chrom 4, CIGAR text 4, MD 3, RG 6) with 32 lanes issued: ~700 warp instructions per record, issue bound at
 // 10 % of the HBM roofline.  Eight lanes per record cut that to ~120.  Group-wide shuffles use the width argument; a loop's
 // trip count is the maximum over the warp's groups (records of one file are alike, so little is lost).
 template <int G>
-__global__ void __launch_bounds__(VAR_WARPS * 32, 8)
+__global__ void __launch_bounds__(VAR_WARPS * 32, BAMSCAN_DV_MINBLOCKS)
 decode_var_kernel(const DecodeParams P) {
   __shared__ uint16_t seq_lut[256];
   {
@@ -538,16 +544,26 @@ decode_var_kernel(const DecodeParams P) {
   const int32_t nref = (int32_t)ld_u32(U, o + 24);
   const uint32_t o_name = o + 36, o_cig = o_name + l_name, o_seq = o_cig + 4u * n_cig;
   const uint32_t o_qual = o_seq + (l_seq + 1u) / 2u;
+#if BAMSCAN_DV_PREFETCH
+  // the per-column output offsets do not depend on the record: loading them here takes one memory round trip off every
+  // column's "offset -> bytes -> store" chain (the compiler cannot hoist them itself past the stores below)
+  const uint32_t f_name = (P.d_name && on) ? (uint32_t)__ldg(P.l_name + r) : 0u, f_chrom = (P.d_chrom && on) ? (uint32_t)__ldg(P.l_chrom + r) : 0u;
+  const uint32_t f_mchrom = (P.d_mchrom && on) ? (uint32_t)__ldg(P.l_mchrom + r) : 0u, f_cigar = (P.d_cigar && on) ? (uint32_t)__ldg(P.l_cigar + r) : 0u;
+  const uint32_t f_seq = (P.d_seq && on) ? (uint32_t)__ldg(P.l_seq + r) : 0u, f_qual = (P.d_qual && on) ? (uint32_t)__ldg(P.l_qual + r) : 0u;
+#define DV_OFF(col, arr) f_##col
+#else
+#define DV_OFF(col, arr) (uint32_t)P.arr[r]
+#endif
 
   if (P.d_name && on) {
-    uint8_t* dst = P.d_name + P.l_name[r];
+    uint8_t* dst = P.d_name + DV_OFF(name, l_name);
     uint32_t n = l_name ? l_name - 1u : 0u;
     if (grp_map4<G>(dst, U + o_name, n, gl, 0u)) set_err(P.err, DEC_ERR_NAME, r);
   }
-  if (P.d_chrom && on && ref >= 0) grp_copy<G>(P.d_chrom + P.l_chrom[r], P.ref_names + P.ref_name_off[ref], P.ref_name_off[ref + 1] - P.ref_name_off[ref], gl);
-  if (P.d_mchrom && on && nref >= 0) grp_copy<G>(P.d_mchrom + P.l_mchrom[r], P.ref_names + P.ref_name_off[nref], P.ref_name_off[nref + 1] - P.ref_name_off[nref], gl);
+  if (P.d_chrom && on && ref >= 0) grp_copy<G>(P.d_chrom + DV_OFF(chrom, l_chrom), P.ref_names + P.ref_name_off[ref], P.ref_name_off[ref + 1] - P.ref_name_off[ref], gl);
+  if (P.d_mchrom && on && nref >= 0) grp_copy<G>(P.d_mchrom + DV_OFF(mchrom, l_mchrom), P.ref_names + P.ref_name_off[nref], P.ref_name_off[nref + 1] - P.ref_name_off[nref], gl);
   if (P.d_cigar) {
-    uint8_t* dst = P.d_cigar + (on ? P.l_cigar[r] : 0);
+    uint8_t* dst = P.d_cigar + (on ? DV_OFF(cigar, l_cigar) : 0u);
     if (P.binary_cigar) { if (on) grp_copy<G>(dst, U + o_cig, 4u * n_cig, gl); }
     else {
       uint32_t base = 0;
@@ -570,7 +586,7 @@ decode_var_kernel(const DecodeParams P) {
     }
   }
   if (P.d_seq && on) {
-    uint8_t* dst = P.d_seq + P.l_seq[r];
+    uint8_t* dst = P.d_seq + DV_OFF(seq, l_seq);
     // 4 output characters (one aligned word) per lane and step: 2 or 3 input bytes through the two-base LUT
     const uint32_t head = min(l_seq, (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
     const uint8_t* ps = U + o_seq;
@@ -599,7 +615,7 @@ decode_var_kernel(const DecodeParams P) {
     if (c0 + (uint32_t)gl < l_seq) { const uint32_t c = c0 + gl; uint16_t two = seq_lut[ps[c >> 1]]; dst[c] = (uint8_t)((c & 1u) ? (two >> 8) : two); }
   }
   if (P.d_qual && on) {
-    uint8_t* dst = P.d_qual + P.l_qual[r];
+    uint8_t* dst = P.d_qual + DV_OFF(qual, l_qual);
     if (grp_map4<G>(dst, U + o_qual, l_seq, gl, 0x21212121u)) set_err(P.err, DEC_ERR_QUAL, r);
   }
   for (int t = 0; t < P.n_tags; t++) {
