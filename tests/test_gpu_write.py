@@ -197,3 +197,23 @@ def test_incompressible_and_tiny_members(tmp_path):
     out0 = tmp_path / "none.bam"
     gpu_write(out0, [], schema, [])
     check_file(out0, [], schema, [])
+
+
+def test_degenerate_alphabets_and_long_runs(tmp_path):
+    """Constant columns: matches of the maximum length 258, a distance code with one used symbol, literal alphabets of a few
+    symbols (the forced second symbol keeps both Huffman codes complete); zlib must accept every member."""
+    o = OracleBam(str(GOLDEN / "multi_chrom.bam"), tag_fields=[])
+    schema = o.schema
+    rows = [dict(name="r", chrom="chr1", start=7, end=None, flags=0, cigar="1000M", mapping_quality=60, mate_chrom="=", mate_start=7, sequence="A" * 1000,
+                 quality_scores="I" * 1000, template_length=0) for _ in range(2000)]
+    b = pa.RecordBatch.from_pylist(rows, schema=schema)
+    out = tmp_path / "runs.bam"
+    _n, st = gpu_write(out, [b], schema, [])
+    size = check_file(out, [b], schema, [])
+    assert size < st["bam_bytes"] / 30                                      # (one 258-byte match costs ~2.5 bytes; zlib reaches more with its longer look-ahead)
+    # two symbols only: alternating qualities, one base
+    rows2 = [dict(r, quality_scores="!~" * 500, name="q") for r in rows[:300]]
+    b2 = pa.RecordBatch.from_pylist(rows2, schema=schema)
+    out2 = tmp_path / "alt.bam"
+    gpu_write(out2, [b2], schema, [])
+    check_file(out2, [b2], schema, [])
