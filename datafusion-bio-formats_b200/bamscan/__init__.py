@@ -483,7 +483,21 @@ class BamTableProvider:
         return BamExec(self, ph)
 
 
-    def insert_into(self, batches, insert_op="overwrite", *, sort_on_write=False, compression=0):
+    @classmethod
+    def new_for_write(cls, output_path, schema: pa.Schema, tag_fields=None, coordinate_system_zero_based=True, sort_on_write=False, *, device_id=0):
+        """== BamTableProvider::new_for_write (table_provider.rs:639-664): a provider for a file that does not exist yet; only
+        schema() and insert_into() are meaningful on it."""
+        self = cls.__new__(cls)
+        self._h = None
+        self.file_path = str(output_path)
+        self.device_id = device_id
+        self._schema = schema
+        self._write_tag_fields = list(tag_fields) if tag_fields is not None else None
+        self._write_zero_based = bool(coordinate_system_zero_based)
+        self._sort_on_write = bool(sort_on_write)
+        return self
+
+    def insert_into(self, batches, insert_op="overwrite", *, sort_on_write=None, compression=0):
         """== TableProvider::insert_into (table_provider.rs:1117-1177) + BamWriteExec::execute: `INSERT OVERWRITE` of `batches`
         (an iterable of pyarrow.RecordBatch with this provider's schema) into this provider's file.  Returns the row count (the
         reference's one-row `count` batch).  sort_on_write is DataFusion's SortExec in front of the writer, not part of it: the
@@ -492,8 +506,13 @@ class BamTableProvider:
             raise NotImplementedError("BAM insert_into only supports OVERWRITE mode")
         schema = self.schema()
         md = {k.decode(): v.decode() for k, v in (schema.metadata or {}).items()}
-        zero_based = md.get("bio.coordinate_system_zero_based", "true").lower() != "false"
+        zero_based = md.get("bio.coordinate_system_zero_based", "true").lower() != "false"      # table_provider.rs:1133-1136 (the schema decides)
         tags = [f.name for f in schema if f.metadata and b"bio.bam.tag.tag" in f.metadata]
+        for t in getattr(self, "_write_tag_fields", None) or []:                                 # explicitly requested tags are honoured too (:1146-1154)
+            if t not in tags:
+                tags.append(t)
+        if sort_on_write is None:
+            sort_on_write = getattr(self, "_sort_on_write", False)
         overrides = {"bio.bam.sort_order": "coordinate" if sort_on_write else "unsorted"}
         ex = BamWriteExec(self.file_path, schema, tags, zero_based, overrides, device_id=getattr(self, "device_id", 0), compression=compression)
         return ex.execute(batches)

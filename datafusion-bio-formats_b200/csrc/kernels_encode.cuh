@@ -215,6 +215,30 @@ enc_size_kernel(const EncArgs a, uint32_t* __restrict__ rec_len, int32_t* __rest
 __device__ __forceinline__ void st_u32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 __device__ __forceinline__ void st_u16(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
 
+// unaligned 32-bit little-endian load from global memory: two aligned loads + funnel shift (reads up to 3 bytes before / behind)
+__device__ __forceinline__ uint32_t ldw(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+// dst[i] = op(src[i]) for i < n by a group of G lanes, with destination-aligned 32-bit stores (head / tail bytes singly); `op`
+// maps four bytes at a time.  Records are byte packed, so a plain byte loop costs one store instruction and one 32-byte
+// sector write per byte (ncu: 9.5 x store-sector amplification in the first version of this kernel).
+template <int G, class OP>
+__device__ __forceinline__ void grp_xform4(uint8_t* dst, const uint8_t* src, uint32_t n, int gl, OP op) {
+  const uint32_t head = min(n, (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+  if ((uint32_t)gl < head) dst[gl] = (uint8_t)op((uint32_t)src[gl]);
+  const uint32_t nw = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const uint8_t* s = src + head;
+  for (uint32_t j = gl; j < nw; j += G) dw[j] = op(ldw(s + 4u * j));
+  const uint32_t t0 = head + (nw << 2);
+  if (t0 + (uint32_t)gl < n) dst[t0 + gl] = (uint8_t)op((uint32_t)src[t0 + gl]);
+}
+struct OpCopy { __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return v; } };
+struct OpQual { __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return __vsubus4(v, 0x21212121u); } };   // byte-wise saturating - 33
+
 template <int G>
 __global__ void __launch_bounds__(256)
 enc_records_kernel(const EncArgs a, const unsigned long long* __restrict__ rec_off, const int32_t* __restrict__ ref_ids,
@@ -274,11 +298,25 @@ enc_records_kernel(const EncArgs a, const unsigned long long* __restrict__ rec_o
       const unsigned long long p1 = is_valid(a.mate_start.valid, r) ? (unsigned long long)a.mate_start.values[r] + (a.zero_based ? 1u : 0u) : 0ull;
       w[7] = p1 >= 1 ? (uint32_t)(p1 - 1) : 0xffffffffu; }
     w[8] = a.tlen.values[a.tlen.base + row];
-    #pragma unroll
-    for (int j = 0; j < 9; j++) if (j % G == gl) st_u32(rec + 4 * j, w[j]);
+    {
+      // 36 bytes at an arbitrary byte offset: the aligned words inside them are funnel shifts of two neighbouring header words,
+      // the 0..3 bytes in front of the first and behind the last aligned word go singly
+      const uint32_t al = (uint32_t)(reinterpret_cast<uintptr_t>(rec) & 3u);
+      if (al == 0) {
+        #pragma unroll
+        for (int j = 0; j < 9; j++) if (j % G == gl) reinterpret_cast<uint32_t*>(rec)[j] = w[j];
+      } else {
+        const uint32_t hb = 4u - al;                         // bytes of w[0] in front of the first aligned word
+        if ((uint32_t)gl < hb) rec[gl] = (uint8_t)(w[0] >> (8u * gl));
+        uint32_t* aw = reinterpret_cast<uint32_t*>(rec + hb);
+        #pragma unroll
+        for (int j = 0; j < 8; j++) if (j % G == gl) aw[j] = __funnelshift_r(w[j], w[j + 1], hb * 8u);
+        if ((uint32_t)gl < al) rec[hb + 32u + gl] = (uint8_t)(w[8] >> (8u * (hb + gl)));
+      }
+    }
     // ---- name + NUL ----
     uint8_t* np = rec + 36;
-    if (name_p) { for (uint32_t k = gl; k < name_n; k += G) np[k] = name_p[k]; }
+    if (name_p) grp_xform4<G>(np, name_p, name_n, gl, OpCopy());
     else if (gl == 0) np[0] = '*';
     if (gl == 0) np[l_name] = 0;
   }
@@ -310,12 +348,26 @@ enc_records_kernel(const EncArgs a, const unsigned long long* __restrict__ rec_o
   // ---- bases (two per byte, high nibble first) + qualities ----
   uint8_t* const sp = cp + 4 * n_ops;
   const uint32_t nb = (l_seq + 1u) >> 1;
-  for (uint32_t k = gl; k < nb; k += G) {
-    const uint32_t hi = base_code[seq_p[2 * k]], lo = (2 * k + 1 < l_seq) ? base_code[seq_p[2 * k + 1]] : 0u;
-    sp[k] = (uint8_t)((hi << 4) | lo);
+  {
+    // packed byte k holds bases 2k (high nibble) and 2k + 1; one aligned output word = 8 bases = two unaligned source words
+    auto pack1 = [&](uint32_t k) { const uint32_t hi = base_code[seq_p[2 * k]], lo = (2 * k + 1 < l_seq) ? base_code[seq_p[2 * k + 1]] : 0u; return (uint8_t)((hi << 4) | lo); };
+    const uint32_t full = l_seq >> 1;                        // packed bytes made of two real bases
+    const uint32_t head = min(full, (uint32_t)((4u - (reinterpret_cast<uintptr_t>(sp) & 3u)) & 3u));
+    if ((uint32_t)gl < head) sp[gl] = pack1(gl);
+    const uint32_t nw = (full - head) >> 2;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(sp + head);
+    const uint8_t* s8 = seq_p + 2u * head;
+    for (uint32_t j = gl; j < nw; j += G) {
+      const uint32_t x = ldw(s8 + 8u * j), y = ldw(s8 + 8u * j + 4u);
+      const uint32_t b0 = (base_code[x & 0xffu] << 4) | base_code[(x >> 8) & 0xffu], b1 = (base_code[(x >> 16) & 0xffu] << 4) | base_code[x >> 24];
+      const uint32_t b2 = (base_code[y & 0xffu] << 4) | base_code[(y >> 8) & 0xffu], b3 = (base_code[(y >> 16) & 0xffu] << 4) | base_code[y >> 24];
+      dw[j] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    const uint32_t t0 = head + (nw << 2);
+    if (t0 + (uint32_t)gl < nb) sp[t0 + gl] = pack1(t0 + gl);  // <= 3 full bytes + the odd last base
   }
   uint8_t* const qp = sp + nb;
-  if (qual_p) { for (uint32_t k = gl; k < l_seq; k += G) { const uint32_t q = qual_p[k]; qp[k] = (uint8_t)(q > 33u ? q - 33u : 0u); } }
+  if (qual_p) grp_xform4<G>(qp, qual_p, l_seq, gl, OpQual());
   else { for (uint32_t k = gl; k < l_seq; k += G) qp[k] = 0xff; }
   // ---- aux fields, tag_fields order ----
   uint8_t* ap = qp + l_seq;
@@ -338,7 +390,8 @@ enc_records_kernel(const EncArgs a, const unsigned long long* __restrict__ rec_o
       if (st == 'A') { if (gl == 0) { ap[2] = 'A'; ap[3] = s[0]; } }
       else {
         if (gl == 0) { ap[2] = st == 'H' ? 'H' : 'Z'; ap[3 + n] = 0; }
-        for (uint32_t k = gl; k < n; k += G) { uint8_t c = s[k]; if (st == 'H' && c >= 'a' && c <= 'f') c -= 32; ap[3 + k] = c; }
+        if (st == 'H') { for (uint32_t k = gl; k < n; k += G) { uint8_t c = s[k]; if (c >= 'a' && c <= 'f') c -= 32; ap[3 + k] = c; } }
+        else grp_xform4<G>(ap + 3, s, n, gl, OpCopy());
       }
     } else {
       const uint32_t b = (uint32_t)T.off[r], n = (uint32_t)T.off[r + 1] - b;

@@ -394,6 +394,20 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
   if (n == 0) return BAMSCAN_OK;
   WCU_TRY(cudaSetDevice(w->device));
   auto hc = [&](int idx) { return HostCol{batch->children[idx], batch->offset + batch->children[idx]->offset}; };
+  // shape checks before any buffer is touched (the arrays carry no type: the schema given at open decides how they are read)
+  auto shape_ok = [&](int idx, int64_t want_buffers, bool list) {
+    const ArrowArray* a = batch->children[idx];
+    if (!a || !a->buffers || a->n_buffers < want_buffers || a->length + a->offset < n + batch->offset) return false;
+    for (int64_t b = 1; b < want_buffers; b++) if (!a->buffers[b] && !(b == 2)) return false;     // (an all-empty Utf8 column may have no data buffer)
+    if (list && (a->n_children < 1 || !a->children || !a->children[0] || !a->children[0]->buffers || a->children[0]->n_buffers < 2)) return false;
+    return true;
+  };
+  for (int k = 0; k < 11; k++) {
+    const bool utf8 = k == 0 || k == 1 || k == 4 || k == 6 || k == 8 || k == 9;
+    if (!shape_ok(w->col[k], utf8 ? 3 : 2, false)) { set_error("bamscan_writer_write: column %d of the batch does not have the layout of the writer's input schema", w->col[k]); return BAMSCAN_ERR_INVALID; }
+  }
+  for (auto& g : w->tags)
+    if (!shape_ok(g.col, g.kind == HK_Utf8 ? 3 : 2, g.kind >= HK_ListInt8)) { set_error("bamscan_writer_write: tag column %d of the batch does not have the layout of the writer's input schema", g.col); return BAMSCAN_ERR_INVALID; }
   // ---- H2D of every buffer the encoder reads ----
   size_t need = 4096;
   for (int k : {0, 1, 4, 6, 8, 9}) need += utf8_bytes(hc(w->col[k]), n);

@@ -141,6 +141,13 @@ def test_insert_into_overwrites_the_providers_file(tmp_path):
     p2 = bamscan.BamTableProvider(str(dst), None, True, ["NM"], index_path="")
     back = list(p2.scan(None, [], None).execute(0))
     assert pa.Table.from_batches(back).equals(pa.Table.from_batches(keep))
+    # new_for_write (table_provider.rs:639-664): a provider for a file that does not exist yet; sort_on_write only labels the header
+    fresh = tmp_path / "fresh.bam"
+    pw = bamscan.BamTableProvider.new_for_write(str(fresh), p.schema(), ["NM"], True, sort_on_write=True)
+    assert pw.insert_into(keep) == n
+    p3 = bamscan.BamTableProvider(str(fresh), None, True, ["NM"], index_path="")
+    assert pa.Table.from_batches(list(p3.scan(None, [], None).execute(0))).equals(pa.Table.from_batches(keep))
+    assert p3.schema().metadata[b"bio.bam.sort_order"] == b"coordinate"
     assert p2.schema().metadata[b"bio.bam.sort_order"] == b"unsorted"        # write_test.rs::test_sort_on_write_false_sets_unsorted
 
 
