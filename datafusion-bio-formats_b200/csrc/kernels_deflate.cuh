@@ -4,14 +4,19 @@
 // (datafusion/bio-format-bam/src/writer.rs:62-113).  The compressed bytes are not the reference's (any conformant DEFLATE
 // stream of the same data is equivalent; the reference's own tests are write -> read round trips); the inflated stream is.
 //
-// bgzf_deflate_kernel: one CTA (256 threads, two CTAs per SM, persistent grid + atomic ticket) per member.
+// bgzf_deflate_kernel: one CTA (384 threads, two CTAs per SM, persistent grid + atomic ticket) per member.
 //   0  the member's <= 65 280 inflated bytes come into shared memory with 16-byte loads; CRC-32: every thread takes one
 //      contiguous piece (table look-ups from shared memory), the pieces are shifted by x^(8 * bytes behind them) and folded;
-//   A  LZ77: the member is cut into 8 regions, one per warp; a warp takes 32 consecutive positions per step: every lane
-//      hashes its 4 bytes into a CTA-wide table of most recent positions (16-bit), extends the candidate (and the run
-//      candidate p - 1) word by word, and the warp picks the greedy non-overlapping parse of the 32 positions by pointer
-//      jumping over the lanes (5 shuffle rounds).  Tokens go to an L2-resident scratch slot, symbol counts to per-warp
-//      histograms in shared memory.  Matches do not cross a region's end, so every region's token list stands alone;
+//   A  LZ77: the member is cut into 12 regions, one per warp; a warp takes 32 consecutive positions per step: every lane
+//      hashes its 4 bytes into the REGION'S OWN slice of the hash table (most recent position per slot, 16 bit; the slice is
+//      pre-seeded with the last 1 KB in front of the region), extends the candidate (and the run candidate p - 1) word by word
+//      up to 32 bytes, gives way to a literal when the next position starts a longer match (lazy evaluation: every lane already
+//      knows its match), and the warp picks the greedy non-overlapping parse of the 32 positions by pointer jumping over the
+//      lanes (5 shuffle rounds); the step's last token is extended to 258 bytes by the whole warp.  Tokens go to an L2-resident
+//      scratch slot, symbol counts to per-warp histograms (packed 16-bit counters) in shared memory.  Matches do not cross a
+//      region's end, so every region's token list stands alone.  (A table shared by all warps was the first version: positions
+//      that other regions insert concurrently -- useless to a region in front of them -- evict the entries a region needs;
+//      region-local slices took the file from 1.29 x to 1.10 x the size of zlib level 6, profiles/r2_write.md);
 //   B  dynamic Huffman codes (RFC 1951 3.2.7): symbols ranked by count in parallel, the two-queue merge by one thread per
 //      tree (litlen / distance side by side), depths in parallel, lengths limited to 15 by moving leaves up from the deepest
 //      level (Kraft sum kept exact), canonical codes in parallel.  The code lengths are sent with a flat 4-bit code-length
@@ -28,10 +33,21 @@
 namespace bamscan {
 namespace dfl {
 
-constexpr int NT = 256, WARPS = NT / 32;
+#ifndef BAMSCAN_DFL_NT
+#define BAMSCAN_DFL_NT 384
+#endif
+constexpr int NT = BAMSCAN_DFL_NT, WARPS = NT / 32;   // threads per CTA (one LZ77 region per warp); A/B: profiles/r2_write.md
 constexpr uint32_t BLOCK = 0xff00;           // inflated bytes per member (noodles-bgzf MAX_BUF_SIZE)
 constexpr uint32_t SLOT = 65536;             // bytes per member slot in the output staging area
 constexpr uint32_t HASH_BITS = 13;
+#ifndef BAMSCAN_DFL_LOCAL_HASH
+#define BAMSCAN_DFL_LOCAL_HASH 1
+#endif
+constexpr uint32_t LOCAL_SLOTS = (1u << HASH_BITS) / WARPS;
+#ifndef BAMSCAN_DFL_PRESEED
+#define BAMSCAN_DFL_PRESEED 1024
+#endif
+constexpr uint32_t PRESEED = BAMSCAN_DFL_PRESEED;                  // per-region slice of the hash table (A/B switch above)
 constexpr uint32_t D0 = 288;                 // distance symbols live at [D0, D0 + 30) of the combined tables
 constexpr uint32_t NSYM = 320;
 constexpr uint32_t FULL = 0xffffffffu;
@@ -41,7 +57,7 @@ __constant__ uint32_t c_xpow8[18];           // x^(8 * 2^j) mod P, reflected (wr
 struct Smem {
   uint32_t buf[SLOT / 4 + 8];                // input bytes (zero padded), later the member image
   uint16_t htab[1u << HASH_BITS];
-  uint32_t hist[WARPS][NSYM];
+  uint32_t hist[WARPS][NSYM / 2];            // per-warp symbol counts, two 16-bit counters per word (a region holds < 65536 tokens)
   uint32_t cnt[NSYM];                        // true symbol counts of the member
   uint32_t freq[NSYM];                       // counts the trees are built from (>= 2 symbols per tree forced)
   uint16_t code[NSYM];                       // bit-reversed canonical codes
@@ -58,6 +74,8 @@ struct Smem {
   uint32_t ticket, total_bits;
 };
 
+__device__ __forceinline__ void hist_add(uint32_t* H, uint32_t s) { atomicAdd(H + (s >> 1), 1u << (16u * (s & 1u))); }
+__device__ __forceinline__ uint32_t hist_get(const uint32_t* H, uint32_t s) { return (H[s >> 1] >> (16u * (s & 1u))) & 0xffffu; }
 __device__ __forceinline__ uint32_t ld4(const uint32_t* buf, uint32_t p) { return __funnelshift_r(buf[p >> 2], buf[(p >> 2) + 1], (p & 3u) * 8u); }
 __device__ __forceinline__ uint32_t crc_mul(uint32_t a, uint32_t b) {
   uint32_t p = 0;
@@ -167,11 +185,11 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* const tok_base = tok_scratch + (size_t)blockIdx.x * SLOT;
-  {
-    uint32_t c = (uint32_t)tid;
+  for (int i = tid; i < 256; i += NT) {
+    uint32_t c = (uint32_t)i;
     #pragma unroll
     for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
-    S.crc_tab[tid] = c;
+    S.crc_tab[i] = c;
   }
   for (;;) {
     __syncthreads();
@@ -189,7 +207,7 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
       const uint32_t n16 = (isize + 15u) >> 4;
       for (uint32_t i = tid; i < (SLOT / 16) + 2; i += NT) dst[i] = i < n16 ? src[i] : make_uint4(0, 0, 0, 0);   // (the stream buffer is padded to 16 bytes)
       for (uint32_t i = tid; i < (1u << HASH_BITS); i += NT) S.htab[i] = 0xffff;
-      for (uint32_t i = tid; i < WARPS * NSYM; i += NT) (&S.hist[0][0])[i] = 0;
+      for (uint32_t i = tid; i < WARPS * (NSYM / 2); i += NT) (&S.hist[0][0])[i] = 0;
     }
     __syncthreads();
     if ((isize & 15u) && tid == 0) {                                        // bytes behind isize inside the last 16-byte load: zero them
@@ -231,13 +249,28 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
       uint32_t* const tok = tok_base + rbeg;
       uint32_t* const H = S.hist[warp];
       uint32_t ntok = 0, skip = 0;
+#if BAMSCAN_DFL_LOCAL_HASH
+      // the region's table starts with the last PRESEED bytes in front of the region (the previous region's tail), so that its
+      // first records find their predecessors too
+      for (uint32_t q0 = rbeg > PRESEED ? rbeg - PRESEED : 0u; q0 < rbeg; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        if (q + 4u <= rbeg) S.htab[(uint32_t)warp * LOCAL_SLOTS + __umulhi(ld4(S.buf, q) * 2654435761u, LOCAL_SLOTS)] = (uint16_t)q;
+        __syncwarp();
+      }
+#endif
       for (uint32_t pos = rbeg; pos < rend; pos += 32) {
         const uint32_t p = pos + lane;
         const bool in = p < rend;
         const bool can = in && p + 4u <= rend;
         const uint32_t w4 = ld4(S.buf, min(p, SLOT));
         uint32_t h = 0, cand = 0xffffu;
+#if BAMSCAN_DFL_LOCAL_HASH
+        // one table slice per region: every candidate is an earlier position of the SAME region (the shared table also offers
+        // other regions' positions, but concurrently inserted later ones evict the useful entries)
+        if (can) { h = (uint32_t)warp * LOCAL_SLOTS + __umulhi(w4 * 2654435761u, LOCAL_SLOTS); cand = S.htab[h]; }
+#else
         if (can) { h = (w4 * 2654435761u) >> (32u - HASH_BITS); cand = S.htab[h]; }
+#endif
         __syncwarp();
         if (can) S.htab[h] = (uint16_t)p;
         if (skip >= 32u) { skip -= 32u; continue; }                             // the whole step lies inside the previous token
@@ -307,11 +340,11 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
           if (L >= 4u) {
             tok[idx] = 0x80000000u | ((L - 3u) << 16) | (D - 1u);
             uint32_t sy, eb, ev;
-            len_symbol(L, sy, eb, ev); atomicAdd(H + sy, 1u);
-            dist_symbol(D, sy, eb, ev); atomicAdd(H + D0 + sy, 1u);
+            len_symbol(L, sy, eb, ev); hist_add(H, sy);
+            dist_symbol(D, sy, eb, ev); hist_add(H, D0 + sy);
           } else {
             const uint32_t b = w4 & 0xffu;
-            tok[idx] = b; atomicAdd(H + b, 1u);
+            tok[idx] = b; hist_add(H, b);
           }
         }
         ntok += __popc(sel);
@@ -324,7 +357,7 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
       for (uint32_t s = tid; s < NSYM; s += NT) {
         uint32_t c = 0;
         #pragma unroll
-        for (int w = 0; w < WARPS; w++) c += S.hist[w][s];
+        for (int w = 0; w < WARPS; w++) c += hist_get(S.hist[w], s);
         if (s == 256u) c = 1;
         S.cnt[s] = c;
         uint32_t f = c;
@@ -339,7 +372,7 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
       // widths: per warp (emit offsets) and in total
       {
         uint32_t bits = 0;
-        for (uint32_t s = lane; s < NSYM; s += 32) bits += S.hist[warp][s] * ((uint32_t)S.len[s] + extra_bits_of(s));
+        for (uint32_t s = lane; s < NSYM; s += 32) bits += hist_get(S.hist[warp], s) * ((uint32_t)S.len[s] + extra_bits_of(s));
         #pragma unroll
         for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(FULL, bits, o);
         if (lane == 0) S.warp_bits[warp] = bits;

@@ -4,9 +4,10 @@
 // build_tag_data + arrow_to_sam_tag_value (bio-format-core/src/sam_tag_io.rs:109-147, 206-520) and the noodles-bam 0.92.0 record
 // encoder behind `writer.write_alignment_record` (bio-format-bam/src/writer.rs:150-166).  Record layout: SAMv1 4.2.
 //
+//   enc_cigar_kernel    a GROUP of 8 lanes per row: CIGAR op count, reference span, validation (text or binary CIGAR).
 //   enc_size_kernel     one THREAD per row: validates the row, resolves chrom / mate_chrom against the header's reference
-//                       dictionary (binary search over the sorted names), counts CIGAR ops + reference span, sizes the aux
-//                       fields -> record length, reference ids, n_cigar_op | bin.
+//                       dictionary (binary search over the sorted names), sizes the aux fields -> record length, reference
+//                       ids, n_cigar_op | bin.
 //   (exclusive scan of the lengths: writer.cu)
 //   enc_records_kernel  a GROUP of G lanes per row (G = 8: four rows per warp): writes the record at its offset in the
 //                       uncompressed BAM stream: 36 fixed bytes, name, CIGAR (text parsed group-parallel: an op character's
@@ -85,6 +86,29 @@ __device__ __forceinline__ int op_code(uint8_t c) {
   switch (c) { case 'M': return 0; case 'I': return 1; case 'D': return 2; case 'N': return 3; case 'S': return 4; case 'H': return 5; case 'P': return 6; case '=': return 7; case 'X': return 8; default: return -1; }
 }
 
+// unaligned 32-bit little-endian load from global memory: two aligned loads + funnel shift (reads up to 3 bytes before / behind)
+__device__ __forceinline__ uint32_t ldw(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+// The decimal number made of the run of digits that ends in front of s[k] (at most 12 digits are looked at; more than that is
+// >= 2^28 anyway).  The 12 bytes come with three independent loads: a digit-by-digit backward walk is a chain of dependent
+// global loads (one memory round trip per digit, 600+ steps per long-read CIGAR).
+__device__ __forceinline__ unsigned long long digits_before(const uint8_t* s, uint32_t k) {
+  const uint32_t w0 = ldw(s + (long long)k - 4), w1 = ldw(s + (long long)k - 8), w2 = ldw(s + (long long)k - 12);
+  unsigned long long len = 0, mul = 1;
+  #pragma unroll
+  for (uint32_t j = 0; j < 12; j++) {
+    const uint32_t w = j < 4 ? w0 : j < 8 ? w1 : w2;
+    const uint32_t d = (w >> (8u * (3u - (j & 3u)))) & 0xffu;
+    if (j >= k || d < '0' || d > '9') break;
+    len += (unsigned long long)(d - '0') * mul; mul *= 10;
+  }
+  return len;
+}
+
 // Bytes one aux field occupies in the record (0: NULL / dropped); *e receives a validation error.
 __device__ __forceinline__ uint32_t tag_bytes(const TagCol& t, uint32_t row, uint32_t* e) {
   const int64_t r = t.base + row;
@@ -115,8 +139,57 @@ __device__ __forceinline__ uint32_t tag_bytes(const TagCol& t, uint32_t row, uin
   return 3u + 1u + 4u + n * elem_size(t.subtype);
 }
 
+// CIGAR scan, a group of G lanes per row: op count, reference span (saturating at 2^32 - 1: only `bin` uses it) and validation.
+// An op character must follow a digit, its length is the run of digits in front of it, the text must end in an op.  (One thread
+// per row walking a 5 000-character long-read CIGAR byte by byte made the size pass 40 x slower than the record writer.)
+template <int G>
 __global__ void __launch_bounds__(256)
-enc_size_kernel(const EncArgs a, uint32_t* __restrict__ rec_len, int32_t* __restrict__ ref_ids, uint32_t* __restrict__ cig_bin, uint32_t* __restrict__ err) {
+enc_cigar_kernel(const EncArgs a, uint32_t* __restrict__ cig_ops, uint32_t* __restrict__ cig_span, uint32_t* __restrict__ err) {
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / G) + (uint32_t)(lane / G);
+  const bool live = i < a.n_rows;
+  const uint32_t row = a.row0 + (live ? i : 0u);
+  const int64_t r = a.cigar.base + row;
+  const uint8_t* s = a.cigar.data + a.cigar.off[r];
+  const uint32_t n = (live && is_valid(a.cigar.valid, r)) ? (uint32_t)(a.cigar.off[r + 1] - a.cigar.off[r]) : 0u;
+  uint32_t ops = 0, e = ENC_OK; unsigned long long span = 0;
+  if (a.cigar_binary) {
+    if (n & 3u) e = ENC_ERR_CIGAR_BIN;
+    for (uint32_t k = gl; k < (n >> 2); k += G) {
+      const uint32_t w = (uint32_t)s[4 * k] | ((uint32_t)s[4 * k + 1] << 8) | ((uint32_t)s[4 * k + 2] << 16) | ((uint32_t)s[4 * k + 3] << 24);
+      const uint32_t op = w & 15u;
+      if (op > 8u) e = ENC_ERR_CIGAR_BIN;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += w >> 4;
+      ops++;
+    }
+  } else if (!(n == 0 || (n == 1 && s[0] == '*'))) {
+    for (uint32_t k = gl; k < n; k += G) {
+      const uint8_t c = s[k];
+      if (c >= '0' && c <= '9') continue;
+      const int op = op_code(c);
+      if (op < 0 || k == 0 || s[k - 1] < '0' || s[k - 1] > '9') e = ENC_ERR_CIGAR;
+      const unsigned long long len = digits_before(s, k);
+      if (len >= (1ull << 28)) e = ENC_ERR_CIGAR_LEN;
+      else if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += len;
+      ops++;
+    }
+    if (gl == 0 && s[n - 1] >= '0' && s[n - 1] <= '9') e = ENC_ERR_CIGAR;
+  }
+  #pragma unroll
+  for (int o = G / 2; o; o >>= 1) {
+    ops += __shfl_xor_sync(FULLMASK, ops, o, G);
+    span += __shfl_xor_sync(FULLMASK, span, o, G);
+    e = max(e, __shfl_xor_sync(FULLMASK, e, o, G));
+  }
+  if (!live || gl) return;
+  if (ops > 65535u) e = ENC_ERR_CIGAR_OPS;
+  cig_ops[i] = ops; cig_span[i] = (uint32_t)min(span, 0xffffffffull);
+  if (e) report(err, e, row);
+}
+
+__global__ void __launch_bounds__(256)
+enc_size_kernel(const EncArgs a, const uint32_t* __restrict__ cig_ops, const uint32_t* __restrict__ cig_span, uint32_t* __restrict__ rec_len,
+                int32_t* __restrict__ ref_ids, uint32_t* __restrict__ cig_bin, uint32_t* __restrict__ err) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_rows) return;
   const uint32_t row = a.row0 + i;
@@ -140,37 +213,8 @@ enc_size_kernel(const EncArgs a, uint32_t* __restrict__ rec_len, int32_t* __rest
       mref = (n == 1 && s[0] == '=') ? ref : lookup_ref(a, s, n);
     }
   }
-  // CIGAR: op count + reference span
-  uint32_t n_ops = 0; unsigned long long span = 0;
-  {
-    const int64_t r = a.cigar.base + row;
-    const uint8_t* s = a.cigar.data + a.cigar.off[r];
-    const uint32_t n = is_valid(a.cigar.valid, r) ? (uint32_t)(a.cigar.off[r + 1] - a.cigar.off[r]) : 0u;
-    if (a.cigar_binary) {
-      if (n & 3u) e = ENC_ERR_CIGAR_BIN;
-      n_ops = n >> 2;
-      for (uint32_t k = 0; k < n_ops; k++) {
-        const uint32_t w = (uint32_t)s[4 * k] | ((uint32_t)s[4 * k + 1] << 8) | ((uint32_t)s[4 * k + 2] << 16) | ((uint32_t)s[4 * k + 3] << 24);
-        const uint32_t op = w & 15u;
-        if (op > 8u) e = ENC_ERR_CIGAR_BIN;
-        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += w >> 4;
-      }
-    } else if (!(n == 0 || (n == 1 && s[0] == '*'))) {
-      unsigned long long len = 0; bool have = false;
-      for (uint32_t k = 0; k < n; k++) {
-        const uint8_t c = s[k];
-        if (c >= '0' && c <= '9') { len = len * 10 + (c - '0'); have = true; if (len >= (1ull << 28)) { e = ENC_ERR_CIGAR_LEN; len = 0; } }
-        else {
-          const int op = op_code(c);
-          if (op < 0 || !have) e = ENC_ERR_CIGAR;
-          if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += len;
-          n_ops++; len = 0; have = false;
-        }
-      }
-      if (have) e = ENC_ERR_CIGAR;
-    }
-    if (n_ops > 65535u) e = ENC_ERR_CIGAR_OPS;
-  }
+  // CIGAR: op count + reference span come from enc_cigar_kernel
+  const uint32_t n_ops = cig_ops[i]; const unsigned long long span = cig_span[i];
   // sequence / qualities ("*" and "" are absent)
   uint32_t l_seq = 0;
   {
@@ -215,13 +259,6 @@ enc_size_kernel(const EncArgs a, uint32_t* __restrict__ rec_len, int32_t* __rest
 __device__ __forceinline__ void st_u32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 __device__ __forceinline__ void st_u16(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
 
-// unaligned 32-bit little-endian load from global memory: two aligned loads + funnel shift (reads up to 3 bytes before / behind)
-__device__ __forceinline__ uint32_t ldw(const uint8_t* p) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
-}
 // dst[i] = op(src[i]) for i < n by a group of G lanes, with destination-aligned 32-bit stores (head / tail bytes singly); `op`
 // maps four bytes at a time.  Records are byte packed, so a plain byte loop costs one store instruction and one 32-byte
 // sector write per byte (ncu: 9.5 x store-sector amplification in the first version of this kernel).
@@ -336,8 +373,7 @@ enc_records_kernel(const EncArgs a, const unsigned long long* __restrict__ rec_o
       const bool is_op = !(c >= '0' && c <= '9');
       const uint32_t bal = (__ballot_sync(FULLMASK, is_op) & gmask) >> gbase;
       if (is_op) {
-        uint32_t len = 0, mul = 1;
-        for (uint32_t b = k; b > 0; b--) { const uint8_t d = cig_p[b - 1]; if (d < '0' || d > '9' || mul > 100000000u) break; len += (d - '0') * mul; mul *= 10; }
+        const uint32_t len = (uint32_t)digits_before(cig_p, k);
         const uint32_t idx = ops_before + __popc(bal & ((1u << gl) - 1u));
         if (idx < n_ops) st_u32(cp + 4 * idx, (len << 4) | (uint32_t)max(op_code(c), 0));
       }

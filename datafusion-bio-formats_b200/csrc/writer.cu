@@ -71,13 +71,13 @@ struct WTag { int col; int32_t kind; uint8_t tag[2], sam_type, subtype; };
 struct WriterRes {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {}, ev2[2] = {}, in_free[IN_BUFS] = {};
-  DevBuf ref_blob, ref_off, ref_ids, in, stream_buf, rec_len, ref_pairs, cig_bin, rec_off, tile_sums, slots, sizes, offsets, packed, tok, small;
+  DevBuf ref_blob, ref_off, ref_ids, in, stream_buf, rec_len, ref_pairs, cig_bin, cig_tmp, rec_off, tile_sums, slots, sizes, offsets, packed, tok, small;
   uint8_t* h_out[OUT_BUFS] = {};         // pinned; filled by D2H, written to the file by the file threads
   uint8_t* h_in[IN_BUFS] = {};           // pinned; the caller's buffers are copied here by IN_THREADS host threads, then H2D
   uint64_t* h_small = nullptr;           // pinned: tile sums, totals, error words
   bool ready = false;
   void destroy() {
-    for (DevBuf* b : {&ref_blob, &ref_off, &ref_ids, &in, &stream_buf, &rec_len, &ref_pairs, &cig_bin, &rec_off, &tile_sums, &slots, &sizes, &offsets, &packed, &tok, &small}) b->release();
+    for (DevBuf* b : {&ref_blob, &ref_off, &ref_ids, &in, &stream_buf, &rec_len, &ref_pairs, &cig_bin, &cig_tmp, &rec_off, &tile_sums, &slots, &sizes, &offsets, &packed, &tok, &small}) b->release();
     for (auto& b : h_out) { if (b) cudaFreeHost(b); b = nullptr; }
     for (auto& b : h_in) { if (b) cudaFreeHost(b); b = nullptr; }
     if (h_small) { cudaFreeHost(h_small); h_small = nullptr; }
@@ -105,6 +105,7 @@ struct BamWriter : bamscan::WriterRes {
   std::vector<WTag> tags;
   int n_cols = 0;
   int n_ref = 0;
+  uint32_t slice_rows = SLICE_ROWS;      // rows per device pass (shrinks for long reads)
   uint64_t pending = 0;                  // bytes of the uncompressed stream waiting at the front of stream_buf (header, tails)
   uint64_t in_seq = 0;
   // file threads: pwrite(2) of the pieces of a staging buffer runs beside the GPU work of the next slice
@@ -471,17 +472,20 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
   if ((rc = w->small.reserve(4096))) return rc;
   uint32_t* d_err = static_cast<uint32_t*>(w->small.p);
   int64_t r0 = 0;
-  uint32_t want_rows = SLICE_ROWS;
+  uint32_t want_rows = w->slice_rows;
   while (r0 < n) {
     uint32_t rows = (uint32_t)std::min<int64_t>(want_rows, n - r0);
     if ((rc = w->rec_len.reserve((size_t)rows * 4)) || (rc = w->ref_pairs.reserve((size_t)rows * 8)) || (rc = w->cig_bin.reserve((size_t)rows * 4)) ||
-        (rc = w->rec_off.reserve(((size_t)rows + 1) * 8)) || (rc = w->tile_sums.reserve(((size_t)rows / 4096 + 2) * 16)))
+        (rc = w->rec_off.reserve(((size_t)rows + 1) * 8)) || (rc = w->cig_tmp.reserve((size_t)rows * 8)) || (rc = w->tile_sums.reserve(((size_t)rows / 4096 + 2) * 16)))
       return rc;
     A.row0 = (uint32_t)r0; A.n_rows = rows;
     WCU_TRY(cudaEventRecord(w->ev[0], w->stream));
     WCU_TRY(cudaMemsetAsync(d_err, 0, 16, w->stream));
-    enc::enc_size_kernel<<<(rows + 255) / 256, 256, 0, w->stream>>>(A, static_cast<uint32_t*>(w->rec_len.p), static_cast<int32_t*>(w->ref_pairs.p),
+    uint32_t* d_cig_ops = static_cast<uint32_t*>(w->cig_tmp.p); uint32_t* d_cig_span = d_cig_ops + rows;
+    enc::enc_cigar_kernel<8><<<(((rows + 3) / 4) * 32 + 255) / 256, 256, 0, w->stream>>>(A, d_cig_ops, d_cig_span, d_err);
+    enc::enc_size_kernel<<<(rows + 255) / 256, 256, 0, w->stream>>>(A, d_cig_ops, d_cig_span, static_cast<uint32_t*>(w->rec_len.p), static_cast<int32_t*>(w->ref_pairs.p),
                                                                    static_cast<uint32_t*>(w->cig_bin.p), d_err);
+    w->st.kernel_launches += 1;
     const uint32_t n_tiles = (rows + 4095) / 4096;
     unsigned long long* d_tiles = static_cast<unsigned long long*>(w->tile_sums.p);
     dfl::len_tile_sums_kernel<<<n_tiles, 256, 0, w->stream>>>(static_cast<uint32_t*>(w->rec_len.p), rows, d_tiles);
@@ -501,6 +505,7 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
     for (uint32_t t = 0; t < n_tiles; t++) { const uint64_t s = w->h_small[t]; w->h_small[t] = total; total += s; }
     if (total > SLICE_BYTES && rows > 1) {                   // long reads: fewer rows per pass
       want_rows = std::max<uint32_t>(1, (uint32_t)((double)rows * (double)SLICE_BYTES / (double)total * 0.9));
+      w->slice_rows = want_rows;                               // (the next batch starts from this estimate)
       continue;
     }
     if (w->pending + total + 65536 > w->stream_buf.cap) {    // one record larger than a slice: grow, keeping the pending bytes
@@ -515,9 +520,14 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
                                                            static_cast<unsigned long long*>(w->rec_off.p));
     w->h_small[6000] = w->pending + total;                    // (rows % 4096 == 0: no tile of the kernel above owns element `rows`)
     WCU_TRY(cudaMemcpyAsync(static_cast<unsigned long long*>(w->rec_off.p) + rows, w->h_small + 6000, 8, cudaMemcpyHostToDevice, w->stream));
-    const uint32_t warps = (rows + 3) / 4;
-    enc::enc_records_kernel<8><<<(warps * 32 + 255) / 256, 256, 0, w->stream>>>(A, static_cast<unsigned long long*>(w->rec_off.p), static_cast<int32_t*>(w->ref_pairs.p),
-                                                                                 static_cast<uint32_t*>(w->cig_bin.p), static_cast<uint8_t*>(w->stream_buf.p), d_err);
+    if (total / rows > 2048) {                                 // long reads: a warp per row
+      enc::enc_records_kernel<32><<<(rows * 32 + 255) / 256, 256, 0, w->stream>>>(A, static_cast<unsigned long long*>(w->rec_off.p), static_cast<int32_t*>(w->ref_pairs.p),
+                                                                                   static_cast<uint32_t*>(w->cig_bin.p), static_cast<uint8_t*>(w->stream_buf.p), d_err);
+    } else {
+      const uint32_t warps = (rows + 3) / 4;
+      enc::enc_records_kernel<8><<<(warps * 32 + 255) / 256, 256, 0, w->stream>>>(A, static_cast<unsigned long long*>(w->rec_off.p), static_cast<int32_t*>(w->ref_pairs.p),
+                                                                                   static_cast<uint32_t*>(w->cig_bin.p), static_cast<uint8_t*>(w->stream_buf.p), d_err);
+    }
     w->st.kernel_launches += 2;
     WCU_TRY(cudaEventRecord(w->ev[1], w->stream));
     WCU_TRY(cudaMemcpyAsync(w->h_small + 4096, d_err, 16, cudaMemcpyDeviceToHost, w->stream));
