@@ -167,3 +167,28 @@ def test_header_defaults_and_bgzf_blocks(tmp_path):
     stream, sizes = W.inflate_bgzf(out.read_bytes())
     assert all(x == 0xff00 for x in sizes[:-2]) and 0 < sizes[-2] <= 0xff00 and sizes[-1] == 0    # full blocks, a tail, the EOF marker
     assert OracleBam(str(out), tag_fields=[]).scan(None).num_rows == 3000
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_python_mirror_builds_the_same_header_as_the_oracle(name):
+    """bamscan.build_bam_header (the host mirror of header_builder.rs the tests drive the C ABI with) against the oracle's
+    restatement, on the schema of every fixture and with the insert_into overrides; defaults for an empty schema."""
+    import bamscan
+    o = OracleBam(str(GOLDEN / name), tag_fields=["NM"])
+    for ov in (None, {"bio.bam.sort_order": "unsorted"}, {"bio.bam.sort_order": "coordinate", "bio.bam.file_format_version": "1.5"}):
+        assert bamscan.build_bam_header(o.schema, ["NM"], ov) == W.build_bam_header(o.schema, ov)
+    bare = pa.schema(list(o.schema))
+    assert bamscan.build_bam_header(bare) == ("@HD\tVN:1.6\n", [], []) == W.build_bam_header(bare)
+    bad = pa.schema(list(o.schema), metadata={"bio.bam.file_format_version": "x.y", "bio.bam.reference_sequences": "not json"})
+    assert bamscan.build_bam_header(bad) == W.build_bam_header(bad) == ("@HD\tVN:1.6\n", [], [])
+
+
+def test_edge_header_lines_survive_both_builders(tmp_path):
+    import bamscan
+    src = tmp_path / "edge.bam"
+    make_edge_bam(src)
+    o = OracleBam(str(src), tag_fields=[])
+    text, names, lens = bamscan.build_bam_header(o.schema)
+    assert (text, names, lens) == W.build_bam_header(o.schema)
+    assert names == ["chrA", "chrB"] and lens == [1000, 2000]
+    assert "@PG\tID:p\tPN:prog\tVN:1\tCL:cmd \"q\"" in text and text.startswith("@HD\tVN:1.6\tSO:unsorted\n")
