@@ -49,7 +49,10 @@ constexpr uint32_t WARMUP_BITS = BAMSCAN_ICTA_WARMUP_BITS;
 #ifndef BAMSCAN_ICTA_WARMUP_MIN_BITS
 #define BAMSCAN_ICTA_WARMUP_MIN_BITS 192
 #endif
-constexpr uint32_t WARMUP_MIN_BITS = BAMSCAN_ICTA_WARMUP_MIN_BITS;   // (short sub-streams of a small block: the warm-up may span several predecessors)       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
+constexpr uint32_t WARMUP_MIN_BITS = BAMSCAN_ICTA_WARMUP_MIN_BITS;
+#ifndef BAMSCAN_ICTA_NSUB
+#define BAMSCAN_ICTA_NSUB 0          // sub-streams per span; 0 = one per thread.  (A CTA of 384 threads with 256 sub-streams keeps the
+#endif                               //  decode passes as they are and gives header / tables / resolve / CRC four more warps.)   // (short sub-streams of a small block: the warm-up may span several predecessors)       // round 0 of the count pass starts this many bits in front of a lane's cut (99.9 % of false starts are on the true chain by then)
 
 // global constant tables of the CRC stage, filled once per device by crc_tables_init_kernel:
 //   [0, 1024)     four 256-entry tables of the operator "multiply by x^(32*NT)" (strided slicing-by-4)
@@ -782,10 +785,12 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
         const uint32_t span_beg = buf_bit(abs_bit);
         const bool to_end = has_tail();
         const uint32_t span_end = to_end ? buf_bit(end_bit) : (uint32_t)(((int64_t)loaded - 32) * 8);
-        uint32_t S = (span_end - span_beg + NT - 1) / NT;
+        constexpr uint32_t NSUB = BAMSCAN_ICTA_NSUB ? BAMSCAN_ICTA_NSUB : NT;
+        static_assert(NSUB <= NT && NSUB % 32 == 0, "sub-streams are lanes");
+        uint32_t S = (span_end - span_beg + NSUB - 1) / NSUB;
         if (S < MIN_SUB_BITS) S = MIN_SUB_BITS;
         const uint32_t my_p = span_beg + (uint32_t)tid * S;
-        const bool active = my_p < span_end;
+        const bool active = (uint32_t)tid < NSUB && my_p < span_end;
         const uint32_t my_stop = min(my_p + S, span_end);
         // round 0 starts every lane but the first `ov` bits EARLY and only warms the chain up until the lane's own cut is
         // reached: by then it is almost always the true chain (self-synchronisation), so most spans need no second round
@@ -806,7 +811,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
               laneE[tid] = my_e;
             }
           }
-          if (tid == 0) C->first_term[round & 1] = NT - 1;
+          if (tid == 0) C->first_term[round & 1] = NSUB - 1;
           __syncthreads();
           {
             const uint32_t m = __ballot_sync(FULL, !active || my_t != T_CROSS);
@@ -825,7 +830,7 @@ inflate_cta_kernel(const uint8_t* __restrict__ comp, const BlockDesc* __restrict
           }
           if (prof && tid == 0) prof[blockIdx.x * 16 + 12] += 1;
           if (!__syncthreads_or(need ? 1 : 0)) break;
-          if (round > NT + 2) { err = INF_ERR_INPUT; break; }
+          if (round > (int)NSUB + 2) { err = INF_ERR_INPUT; break; }
         }
         ICTA_PROF(4);
         if (err) break;
