@@ -45,3 +45,34 @@ def test_scan_refuses_without_gpu():
     with pytest.raises(bamscan.BamScanError) as e:
         list(plan.execute(0))
     assert e.value.code == -4 and "no CPU path" in str(e.value)
+
+
+def test_writer_validates_the_schema_and_refuses_without_gpu(tmp_path):
+    """The write path checks the input schema on the host like the reference's column look-ups
+    (sam_record_serializer.rs:27-37, 248-279) and, like the scan, has no CPU path behind it."""
+    import pyarrow as pa
+    import bamscan
+    from oracle.bam_oracle import OracleBam
+    o = OracleBam(str(GOLDEN / "multi_chrom.bam"), tag_fields=["NM"])
+    out = tmp_path / "o.bam"
+    no_flags = pa.schema([f for f in o.schema if f.name != "flags"], metadata=o.schema.metadata)
+    with pytest.raises(bamscan.BamScanError, match="Required column 'flags' not found") as e:
+        bamscan.BamWriteExec(str(out), no_flags, ["NM"]).execute([])
+    assert e.value.code == -7
+    wrong = pa.schema([pa.field("start", pa.int64()) if f.name == "start" else f for f in o.schema], metadata=o.schema.metadata)
+    with pytest.raises(bamscan.BamScanError, match="Column 'start' must be UInt32"):
+        bamscan.BamWriteExec(str(out), wrong, ["NM"]).execute([])
+    bad_tag = pa.schema(list(o.schema)[:12] + [pa.field("NM", pa.int32(), True, {"bio.bam.tag.tag": "NM", "bio.bam.tag.type": "Z"})])
+    with pytest.raises(bamscan.BamScanError, match="Tag value type mismatch"):
+        bamscan.BamWriteExec(str(out), bad_tag, ["NM"]).execute([])
+    with pytest.raises(bamscan.BamScanError, match="plain SAM output is out of scope"):
+        bamscan.BamWriteExec(str(tmp_path / "o.sam"), o.schema, ["NM"])
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return
+    except ImportError:
+        pass
+    with pytest.raises(bamscan.BamScanError, match="no CPU path") as e:
+        bamscan.BamWriteExec(str(out), o.schema, ["NM"]).execute([])
+    assert e.value.code == -4 and not out.exists()
