@@ -42,9 +42,15 @@ namespace bamscan {
 constexpr uint64_t SLICE_BYTES = 512ull << 20;       // uncompressed BAM bytes encoded + compressed per device pass
 constexpr uint32_t SLICE_ROWS = 1u << 20;
 constexpr size_t OUT_CHUNK = 16ull << 20;             // pinned D2H staging buffers (OUT_BUFS of them, drained by the file threads)
-constexpr int OUT_BUFS = 12, FILE_THREADS = 4;   // 192 MB: one slice of compressed members never waits for the file threads
+#ifndef BAMSCAN_W_FILE_THREADS
+#define BAMSCAN_W_FILE_THREADS 4
+#endif
+#ifndef BAMSCAN_W_IN_THREADS
+#define BAMSCAN_W_IN_THREADS 4
+#endif
+constexpr int OUT_BUFS = 12, FILE_THREADS = BAMSCAN_W_FILE_THREADS;   // 192 MB: one slice of compressed members never waits for the file threads
 constexpr size_t IN_CHUNK = 8ull << 20;              // pinned H2D staging buffers (the caller's Arrow buffers are pageable)
-constexpr int IN_BUFS = 2, IN_THREADS = 4;
+constexpr int IN_BUFS = 2, IN_THREADS = BAMSCAN_W_IN_THREADS;
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_wtrace = getenv("BAMSCAN_WRITER_TRACE") != nullptr;
