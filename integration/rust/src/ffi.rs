@@ -86,4 +86,35 @@ unsafe extern "C" {
     pub fn bamscan_next(s: *mut BamScanStream, out: *mut FFI_ArrowArray) -> c_int;
     pub fn bamscan_stream_free(s: *mut BamScanStream);
     pub fn bamscan_last_error() -> *const c_char;
+
+    // write path (INSERT OVERWRITE): include/bamscan.h, "SURVEY 8 f4"
+    pub fn bamscan_writer_open(
+        output_path: *const c_char,
+        sam_header_text: *const c_char,
+        n_ref: i32,
+        ref_names: *const *const c_char,
+        ref_lengths: *const i32,
+        input_schema: *const FFI_ArrowSchema,
+        options: *const BamWriteOptions,
+        out: *mut *mut BamWriter,
+    ) -> c_int;
+    pub fn bamscan_writer_write(w: *mut BamWriter, batch: *const FFI_ArrowArray) -> c_int;
+    pub fn bamscan_writer_finish(w: *mut BamWriter, rows_written: *mut u64) -> c_int;
+    pub fn bamscan_writer_free(w: *mut BamWriter);
+}
+
+#[repr(C)]
+pub struct BamWriter {
+    _p: [u8; 0],
+}
+
+/// == BamWriteOptions of include/bamscan.h (zero-initialise, set struct_size)
+#[repr(C)]
+pub struct BamWriteOptions {
+    pub struct_size: u32,
+    pub coordinate_system_zero_based: i32,
+    pub n_tag_fields: i32,
+    pub tag_fields: *const *const c_char,
+    pub device_id: i32,
+    pub compression: i32,
 }
