@@ -26,7 +26,7 @@ constexpr uint32_t FULLMASK = 0xffffffffu;
 enum EncErr : uint32_t {
   ENC_OK = 0, ENC_ERR_FLAGS = 1 /* > 16 bits */, ENC_ERR_CIGAR = 2 /* text does not parse */, ENC_ERR_CIGAR_LEN = 3 /* op length >= 2^28 */,
   ENC_ERR_CIGAR_OPS = 4 /* > 65535 ops (unsupported) */, ENC_ERR_QUAL_LEN = 5, ENC_ERR_NAME_LEN = 6, ENC_ERR_TAG_RANGE = 7, ENC_ERR_TAG_HEX = 8,
-  ENC_ERR_TAG_CHAR = 9, ENC_ERR_CIGAR_BIN = 10 /* binary CIGAR: length % 4 or op > 8 */, ENC_ERR_REC_LEN = 11
+  ENC_ERR_TAG_CHAR = 9, ENC_ERR_CIGAR_BIN = 10 /* binary CIGAR: length % 4 or op > 8 */, ENC_ERR_REC_LEN = 11, ENC_ERR_POS = 12 /* position - 1 > i32::MAX */
 };
 
 // tag column kinds (== HK_* of bamscan_internal.h)
@@ -226,12 +226,17 @@ enc_size_kernel(const EncArgs a, const uint32_t* __restrict__ cig_ops, const uin
     const bool q_absent = qn == 0 || (qn == 1 && a.qual.data[a.qual.off[q]] == '*');
     if (!q_absent && qn != l_seq) e = ENC_ERR_QUAL_LEN;
   }
+  {
+    const int64_t m = a.mate_start.base + row;      // the encoder's i32::try_from(position - 1)
+    if (is_valid(a.mate_start.valid, m) && (unsigned long long)a.mate_start.values[m] + (a.zero_based ? 1u : 0u) > 0x80000000ull) e = ENC_ERR_POS;
+  }
   // bin (RecordBuf::alignment_end is start + span - 1, unconditionally; Position 0 does not exist -> the unmapped bin)
   uint32_t bin = 4680;
   {
     const int64_t r = a.start.base + row;
     if (is_valid(a.start.valid, r)) {
       const unsigned long long p1 = (unsigned long long)a.start.values[r] + (a.zero_based ? 1u : 0u);
+      if (p1 > 0x80000000ull) e = ENC_ERR_POS;
       if (p1 >= 1) {
         const unsigned long long end1 = p1 + span - 1;
         if (end1 >= 1) {

@@ -142,6 +142,7 @@ static const char* enc_err_text(uint32_t code) {
     case enc::ENC_ERR_TAG_CHAR: return "Character tags must be a single ASCII byte";
     case enc::ENC_ERR_CIGAR_BIN: return "Failed to decode binary CIGAR";
     case enc::ENC_ERR_REC_LEN: return "record larger than 2 GiB";
+    case enc::ENC_ERR_POS: return "position does not fit the 32-bit BAM field";
     default: return "encode error";
   }
 }

@@ -254,6 +254,8 @@ def encode_record(row: dict, ref_map: dict, tags, zero_based: bool) -> bytes:
         if v is None:
             return None
         p = v + 1 if zero_based else v
+        if p - 1 > 0x7fffffff:
+            raise WriteError("position does not fit the 32-bit BAM field")      # the encoder's i32::try_from(position - 1)
         return p if p >= 1 else None              # Position::try_from(0) fails -> None
 
     start = pos1(row["start"])

@@ -180,6 +180,9 @@ def test_data_errors_surface(tmp_path):
         gpu_write(tmp_path / "e5.bam", [], bad, ["Xz"])
     with pytest.raises(bamscan.BamScanError, match="Required column 'flags'"):
         gpu_write(tmp_path / "e6.bam", [], pa.schema([f for f in batch.schema if f.name != "flags"]), [])
+    ms = cols["mate_start"].to_pylist(); ms[11] = 2**31
+    with pytest.raises(bamscan.BamScanError, match="row 11.*position does not fit"):
+        gpu_write(tmp_path / "e7.bam", [with_col("mate_start", ms)], o.schema, [])
 
 
 def test_incompressible_and_tiny_members(tmp_path):
@@ -224,3 +227,57 @@ def test_degenerate_alphabets_and_long_runs(tmp_path):
     out2 = tmp_path / "alt.bam"
     gpu_write(out2, [b2], schema, [])
     check_file(out2, [b2], schema, [])
+
+
+def test_random_rows_against_the_oracle(tmp_path):
+    """Seeded random rows over the corners of the column rules: NULL / "*" / empty names, chromosomes outside the header, "=" mates of
+    unplaced reads, NULL positions, position 0 in both coordinate systems, "*" / empty CIGAR + sequence + qualities, odd lengths,
+    lower-case and unknown bases, qualities below '!', every tag kind with NULLs and empty values."""
+    import random
+    rng = random.Random(20261019)
+    o = OracleBam(str(GOLDEN / "multi_chrom.bam"), tag_fields=[])
+    refs = [d["name"] for d in __import__("json").loads(o.schema.metadata[b"bio.bam.reference_sequences"])]
+
+    def tf(name, typ, spec):
+        return pa.field(name, typ, True, {"bio.bam.tag.tag": name, "bio.bam.tag.type": spec})
+    tag_fields = [tf("NM", pa.int32(), "i"), tf("XC", pa.uint32(), "C"), tf("Xs", pa.int32(), "s"), tf("Xf", pa.float32(), "f"), tf("MD", pa.string(), "Z"),
+                  tf("XH", pa.string(), "H"), tf("XA", pa.string(), "A"), tf("ML", pa.list_(pa.uint8()), "B:C"), tf("Xi", pa.list_(pa.int32()), "B:i"),
+                  tf("XF", pa.list_(pa.float32()), "B:f"), tf("XS", pa.list_(pa.uint16()), "B")]
+    schema = pa.schema(list(o.schema)[:12] + tag_fields, metadata=o.schema.metadata)
+    names = [f.name for f in tag_fields]
+
+    def maybe(p, v):
+        return None if rng.random() < p else v
+
+    def cigar_and_len():
+        r = rng.random()
+        if r < 0.1:
+            return rng.choice(["*", ""]), rng.randint(0, 40)
+        ops, qlen = [], 0
+        for _ in range(rng.randint(1, 12)):
+            n, op = rng.choice([1, 2, 9, 10, 99, 100, 12345, 268435455]), rng.choice("MIDNSHP=X")
+            ops.append(f"{n}{op}")
+        return "".join(ops), rng.randint(0, 60)
+
+    rows = []
+    for i in range(3000):
+        cig, L = cigar_and_len()
+        seq = rng.choice(["*", "", None]) if rng.random() < 0.08 else "".join(rng.choice("ACGTNacgtn=MRSVWYHKDBxz.") for _ in range(L))
+        has_seq = seq not in ("*", "", None)
+        qual = rng.choice(["*", ""]) if (not has_seq or rng.random() < 0.15) else "".join(chr(rng.choice([32, 33, 34, 73, 126])) for _ in range(len(seq)))
+        chrom = maybe(0.15, rng.choice(refs + ["chrNope"]))
+        rows.append(dict(
+            name=rng.choice([None, "*", "", "r" * rng.randint(1, 254), f"read{i}"]), chrom=chrom, start=maybe(0.15, rng.choice([0, 1, 16383, 16384, 5_000_000, 2**29])),
+            end=None, flags=rng.choice([0, 4, 99, 65535]), cigar=cig, mapping_quality=rng.choice([0, 60, 255, 256, 300]),
+            mate_chrom=maybe(0.3, rng.choice(refs + ["=", "chrNope"])), mate_start=maybe(0.3, rng.choice([0, 7, 2**31 - 2])), sequence=seq, quality_scores=qual,
+            template_length=rng.choice([0, -1, 2**31 - 1, -2**31]),
+            NM=maybe(0.3, rng.choice([0, -2**31, 2**31 - 1])), XC=maybe(0.3, rng.randint(0, 255)), Xs=maybe(0.3, rng.randint(-32768, 32767)),
+            Xf=maybe(0.3, rng.choice([0.0, -1.5, 3.4028234663852886e38, 1e-45])), MD=maybe(0.3, rng.choice(["", "10A5", "x" * 300])),
+            XH=maybe(0.3, rng.choice(["", "1a2B", "FF" * 40])), XA=maybe(0.3, rng.choice("AZ~!")), ML=maybe(0.3, [rng.randint(0, 255) for _ in range(rng.randint(0, 70))]),
+            Xi=maybe(0.3, [rng.choice([0, -2**31, 2**31 - 1]) for _ in range(rng.randint(0, 9))]), XF=maybe(0.3, [rng.choice([0.5, -2.0]) for _ in range(rng.randint(0, 5))]),
+            XS=maybe(0.3, [rng.randint(0, 65535) for _ in range(rng.randint(0, 33))])))
+    batch = pa.RecordBatch.from_pylist(rows, schema=schema)
+    for zero_based in (True, False):
+        out = tmp_path / f"rnd{int(zero_based)}.bam"
+        gpu_write(out, [batch.slice(0, 1111), batch.slice(1111)], schema, names, zero_based)
+        check_file(out, [batch], schema, names, zero_based)
