@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "bamscan_execute", "bamscan_next", "bamscan_execute_device", "bamscan_next_device",
     "bamscan_stream_free", "bamscan_run_device_resident", "bamscan_stream_stats", "bamscan_bench_inflate",
     "bamscan_probe_pcie", "bamscan_check_partition_seams", "bamscan_last_error", "bamscan_version",
-    "bamscan_writer_open", "bamscan_writer_write", "bamscan_writer_finish", "bamscan_writer_stats", "bamscan_writer_free",
+    "bamscan_writer_open", "bamscan_writer_write", "bamscan_writer_write_device", "bamscan_writer_finish", "bamscan_writer_stats", "bamscan_writer_free",
 ]
 
 
@@ -144,6 +144,7 @@ def load_library():
     L.bamscan_writer_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_void_p,
                                       C.POINTER(_WriteOptions), C.POINTER(C.c_void_p)]
     L.bamscan_writer_write.argtypes = [C.c_void_p, C.c_void_p]
+    L.bamscan_writer_write_device.argtypes = [C.c_void_p, C.c_void_p]
     L.bamscan_writer_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.bamscan_writer_stats.argtypes = [C.c_void_p, C.POINTER(WriteStats)]
     L.bamscan_writer_free.argtypes = [C.c_void_p]
@@ -604,6 +605,11 @@ class BamWriteExec:
                 C.CFUNCTYPE(None, C.c_void_p)(cs.release)(C.addressof(cs))
         try:
             for b in batches:
+                if isinstance(b, DeviceBatch):               # stays in HBM: bamscan_writer_write_device
+                    if b.schema.names != self.schema.names:
+                        raise BamScanError(-7, "batch columns differ from the writer's input schema")
+                    _check(L.bamscan_writer_write_device(h, C.byref(b._dev)))
+                    continue
                 if b.schema.names != self.schema.names:
                     raise BamScanError(-7, "batch columns differ from the writer's input schema")
                 ca = _ArrowArrayStruct()

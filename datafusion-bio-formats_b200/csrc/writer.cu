@@ -112,6 +112,7 @@ struct BamWriter : bamscan::WriterRes {
   int n_cols = 0;
   int n_ref = 0;
   uint32_t slice_rows = SLICE_ROWS;      // rows per device pass (shrinks for long reads)
+  bool src_on_device = false;            // bamscan_writer_write_device: the batch's buffers are device pointers
   uint64_t pending = 0;                  // bytes of the uncompressed stream waiting at the front of stream_buf (header, tails)
   uint64_t in_seq = 0;
   // file threads: pwrite(2) of the pieces of a staging buffer runs beside the GPU work of the next slice
@@ -328,6 +329,7 @@ static int writer_open_impl(const char* output_path, const char* sam_header_text
 // host threads copy a chunk into a pinned buffer, one cudaMemcpyAsync sends it on (pageable H2D would be staged by the
 // driver on one thread at a fraction of the link rate).
 static int stage(BamWriter* w, size_t* cursor, const void* src, size_t bytes, uint8_t** dev) {
+  if (w->src_on_device) { *dev = const_cast<uint8_t*>(static_cast<const uint8_t*>(src)); return BAMSCAN_OK; }   // the batch already lives in HBM
   const size_t at = (*cursor + 15) & ~size_t(15);
   *dev = static_cast<uint8_t*>(w->in.p) + at;
   *cursor = at + bytes;
@@ -357,15 +359,23 @@ static int stage(BamWriter* w, size_t* cursor, const void* src, size_t bytes, ui
 
 struct HostCol { const ArrowArray* a; int64_t off; };     // off = struct offset + child offset
 
-static size_t utf8_bytes(const HostCol& c, int64_t n) {
-  const int32_t* o = static_cast<const int32_t*>(c.a->buffers[1]);
-  return (size_t)(o[c.off + n] - o[c.off]) + (size_t)(n + 1) * 4 + (size_t)(n / 8 + 2) + 64;
+// first and last entry of an offsets buffer (a device batch: two 4-byte reads from HBM)
+static bool off_ends(const BamWriter* w, const void* offsets, int64_t i0, int64_t i1, int32_t* first, int32_t* last) {
+  const int32_t* o = static_cast<const int32_t*>(offsets);
+  if (!w->src_on_device) { *first = o[i0]; *last = o[i1]; return true; }
+  return cudaMemcpy(first, o + i0, 4, cudaMemcpyDeviceToHost) == cudaSuccess && cudaMemcpy(last, o + i1, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+static size_t utf8_bytes(const BamWriter* w, const HostCol& c, int64_t n) {
+  int32_t a = 0, b = 0;
+  off_ends(w, c.a->buffers[1], c.off, c.off + n, &a, &b);
+  return (size_t)(b - a) + (size_t)(n + 1) * 4 + (size_t)(n / 8 + 2) + 64;
 }
 
 static int stage_validity(BamWriter* w, size_t* cur, const HostCol& c, int64_t n, const uint8_t** out) {
   *out = nullptr;
   const uint8_t* v = static_cast<const uint8_t*>(c.a->buffers[0]);
   if (!v || c.a->null_count == 0) return BAMSCAN_OK;
+  if (w->src_on_device) { *out = v; return BAMSCAN_OK; }
   const int64_t b0 = c.off >> 3, b1 = (c.off + n + 7) >> 3;
   uint8_t* d; int rc = stage(w, cur, v + b0, (size_t)(b1 - b0), &d);
   if (rc) return rc;
@@ -378,7 +388,8 @@ static int stage_utf8(BamWriter* w, size_t* cur, const HostCol& c, int64_t n, en
   uint8_t* d; int rc;
   if ((rc = stage(w, cur, o + c.off, (size_t)(n + 1) * 4, &d))) return rc;
   out->off = reinterpret_cast<const int32_t*>(d) - c.off;
-  const int32_t first = o[c.off], last = o[c.off + n];
+  int32_t first = 0, last = 0;
+  if (!off_ends(w, o, c.off, c.off + n, &first, &last)) { set_error("bamscan_writer_write_device: cannot read the offsets of a device batch"); return BAMSCAN_ERR_CUDA; }
   if ((rc = stage(w, cur, data ? data + first : nullptr, data ? (size_t)(last - first) : 0, &d))) return rc;
   out->data = d - first;
   out->base = c.off;
@@ -418,11 +429,12 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
     if (!shape_ok(g.col, g.kind == HK_Utf8 ? 3 : 2, g.kind >= HK_ListInt8)) { set_error("bamscan_writer_write: tag column %d of the batch does not have the layout of the writer's input schema", g.col); return BAMSCAN_ERR_INVALID; }
   // ---- H2D of every buffer the encoder reads ----
   size_t need = 4096;
-  for (int k : {0, 1, 4, 6, 8, 9}) need += utf8_bytes(hc(w->col[k]), n);
+  if (!w->src_on_device) for (int k : {0, 1, 4, 6, 8, 9}) need += utf8_bytes(w, hc(w->col[k]), n);
   need += 5 * ((size_t)n * 4 + (size_t)n / 8 + 64);
   for (auto& g : w->tags) {
+    if (w->src_on_device) break;
     const HostCol c = hc(g.col);
-    if (g.kind == HK_Utf8) need += utf8_bytes(c, n);
+    if (g.kind == HK_Utf8) need += utf8_bytes(w, c, n);
     else if (g.kind >= HK_ListInt8) {
       const int32_t* o = static_cast<const int32_t*>(c.a->buffers[1]);
       need += (size_t)(o[c.off + n] - o[c.off]) * 4 + (size_t)(n + 1) * 4 + (size_t)n / 8 + 64;
@@ -459,7 +471,8 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
       const ArrowArray* ch = c.a->children[0];
       if (ch->null_count > 0) { set_error("SAM array tags cannot contain null elements"); return BAMSCAN_ERR_SCHEMA; }
       const size_t es = (g.kind == HK_ListInt8 || g.kind == HK_ListUInt8) ? 1 : (g.kind == HK_ListInt16 || g.kind == HK_ListUInt16) ? 2 : 4;
-      const int32_t first = o[c.off], last = o[c.off + n];
+      int32_t first = 0, last = 0;
+      if (!off_ends(w, o, c.off, c.off + n, &first, &last)) { set_error("bamscan_writer_write_device: cannot read the offsets of a device batch"); return BAMSCAN_ERR_CUDA; }
       const uint8_t* cv = static_cast<const uint8_t*>(ch->buffers[1]);
       if ((rc = stage(w, &cur, cv ? cv + (size_t)(ch->offset + first) * es : nullptr, cv ? (size_t)(last - first) * es : 0, &d))) return rc;
       T.values = d - (size_t)first * es;                   // element index = list offset (child offset already applied)
@@ -656,6 +669,18 @@ int bamscan_writer_open(const char* output_path, const char* sam_header_text, in
   WRITER_GUARD(writer_open_impl(output_path, sam_header_text, n_ref, ref_names, ref_lengths, input_schema, options, out))
 }
 int bamscan_writer_write(BamWriter* w, const struct ArrowArray* batch) { WRITER_GUARD(writer_write_impl(w, batch)) }
+static int writer_write_device_impl(BamWriter* w, const struct ArrowDeviceArray* batch) {
+  if (!w || !batch) { set_error("bamscan_writer_write_device: null argument"); return BAMSCAN_ERR_INVALID; }
+  if (batch->device_type != ARROW_DEVICE_CUDA || batch->device_id != w->device) { set_error("bamscan_writer_write_device: the batch lives on device %lld (type %d), the writer on CUDA device %d", (long long)batch->device_id, (int)batch->device_type, w->device); return BAMSCAN_ERR_INVALID; }
+  if (cudaSetDevice(w->device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", w->device); return BAMSCAN_ERR_CUDA; }
+  if (batch->sync_event && cudaStreamWaitEvent(w->stream, *static_cast<cudaEvent_t*>(batch->sync_event), 0) != cudaSuccess) { set_error("cudaStreamWaitEvent on the batch's sync_event failed"); return BAMSCAN_ERR_CUDA; }
+  if (batch->sync_event && cudaEventSynchronize(*static_cast<cudaEvent_t*>(batch->sync_event)) != cudaSuccess) { set_error("waiting for the batch's sync_event failed"); return BAMSCAN_ERR_CUDA; }   // (offset ends are read with plain cudaMemcpy)
+  w->src_on_device = true;
+  const int rc = writer_write_impl(w, &batch->array);
+  w->src_on_device = false;
+  return rc;
+}
+int bamscan_writer_write_device(BamWriter* w, const struct ArrowDeviceArray* batch) { WRITER_GUARD(writer_write_device_impl(w, batch)) }
 int bamscan_writer_finish(BamWriter* w, uint64_t* rows_written) { WRITER_GUARD(writer_finish_impl(w, rows_written)) }
 int bamscan_writer_stats(const BamWriter* w, BamWriteStats* out) {
   if (!w || !out) { set_error("bamscan_writer_stats: null argument"); return BAMSCAN_ERR_INVALID; }

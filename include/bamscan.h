@@ -257,6 +257,10 @@ int bamscan_writer_open(const char* output_path, const char* sam_header_text, in
                         BamWriter** out);
 /* One RecordBatch as a struct array matching input_schema (not released by the callee). */
 int bamscan_writer_write(BamWriter* w, const struct ArrowArray* batch);
+/* The same for a batch that lives in HBM on the writer's device (Arrow C Device Data Interface, e.g. what bamscan_next_device
+ * hands out, or a GPU consumer's filtered copy of it): no H2D, the encoder reads the batch's buffers in place; waits for
+ * batch->sync_event.  Not released by the callee. */
+int bamscan_writer_write_device(BamWriter* w, const struct ArrowDeviceArray* batch);
 /* Flushes the last (partial) member and the BGZF EOF marker, closes the file; *rows_written = the reference's `count`. */
 int bamscan_writer_finish(BamWriter* w, uint64_t* rows_written);
 int bamscan_writer_stats(const BamWriter* w, BamWriteStats* out);

@@ -281,3 +281,20 @@ def test_random_rows_against_the_oracle(tmp_path):
         out = tmp_path / f"rnd{int(zero_based)}.bam"
         gpu_write(out, [batch.slice(0, 1111), batch.slice(1111)], schema, names, zero_based)
         check_file(out, [batch], schema, names, zero_based)
+
+
+@pytest.mark.parametrize("mode,reads,tags", [("short", 30000, ["NM", "MD", "AS", "RG"]), ("long", 300, ["NM", "MD", "MM", "ML"])])
+def test_device_batches_are_written_in_place(mode, reads, tags, syn_dir, tmp_path):
+    """SURVEY 8 f2 + f4: batches that stay in HBM (bamscan_execute_device / bamscan_next_device) go straight into
+    bamscan_writer_write_device -- no D2H, no H2D -- and the file equals the oracle's."""
+    import bamscan
+    path = gen_bam(syn_dir, mode, reads, seed=11)
+    o = OracleBam(str(path), tag_fields=tags)
+    want = o.scan(None)
+    p = bamscan.BamTableProvider(str(path), None, True, tags, index_path="", chunk_inflated_bytes=4 << 20)    # several device batches
+    plan = p.scan(None, [], None)
+    out = tmp_path / "dev.bam"
+    ex = bamscan.BamWriteExec(str(out), p.schema(), tags, True)
+    n = ex.execute(plan.execute_device(0))
+    assert n == want.num_rows and ex.stats["arrow_bytes"] == 0 and ex.stats["batches"] > 1
+    check_file(out, [want], o.schema, tags)

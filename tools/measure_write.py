@@ -41,6 +41,15 @@ def main():
                "deflate_gbps_uncompressed": st["bam_bytes"] / (st["ms_deflate"] / 1e3) / 1e9, "encode_gbps": (st["bam_bytes"] + st["arrow_bytes"]) / (st["ms_encode"] / 1e3) / 1e9,
                "members": st["members"], "kernel_launches": st["kernel_launches"]}
     assert res["rows"] == rows
+    if len(sys.argv) > 3 and sys.argv[3] == "device":
+        # device-resident transcode: the scan's batches stay in HBM (bamscan_next_device) and are written in place
+        for rep in range(3):
+            ex = bamscan.BamWriteExec(str(out), p.schema(), tags, True, {"bio.bam.sort_order": "unsorted"})
+            t0 = time.perf_counter()
+            n = ex.execute(p.scan(None, [], None).execute_device(0))
+            dt = time.perf_counter() - t0
+            res["transcode_device"] = {"rows": n, "e2e_s": dt, "reads_per_s": n / dt, "write_device_ms": ex.stats["ms_total"],
+                                       "note": "scan (H2D of the compressed file, inflate, decode) -> device batches -> encode + deflate -> D2H of the compressed members -> file"}
     res["zlib6_file_bytes"] = info["compressed_bytes"]
     res["size_vs_zlib6"] = res["file_bytes"] / info["compressed_bytes"]
     res["ratio"] = res["bam_bytes"] / res["file_bytes"]
