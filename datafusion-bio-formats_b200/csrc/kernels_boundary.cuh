@@ -254,7 +254,13 @@ seg_scan_kernel(const uint32_t* __restrict__ seg_count, const uint32_t* __restri
   for (uint32_t base = 0; base < n_seg; base += 1024) {
     uint32_t i = base + tid;
     uint32_t v = i < n_seg ? seg_count[i] : 0u;
-    if (v) atomicMin(&flags[13], seg_start[i]);                        // offset of the first owned record of the chunk
+    {
+      // offset of the first owned record of the chunk: one atomic per warp that holds one (a 1.5 GB chunk has 90 k segments with
+      // records; one same-address atomic each made this kernel the slowest of the stage)
+      const uint32_t mine = v ? seg_start[i] : 0xffffffffu;
+      const uint32_t wmin = __reduce_min_sync(0xffffffffu, mine);
+      if (lane == 0 && wmin != 0xffffffffu && wmin < flags[13]) atomicMin(&flags[13], wmin);
+    }
     if (i < n_seg && seg_start[i] != SEG_NONE && seg_tail[i] == 2) atomicExch(&flags[1], seg_exit[i] | 1u);   // corrupt block_size on the live chain
     uint32_t x = v;
     #pragma unroll
