@@ -191,6 +191,15 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
     for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
     S.crc_tab[i] = c;
   }
+  // x^(8 * bytes behind this thread's CRC piece) for a full member, once per CTA (every member but the file's last is full)
+  uint32_t pow_full;
+  {
+    const uint32_t seg = (((BLOCK + NT - 1) / NT) + 3u) & ~3u;
+    const uint32_t b1 = min(BLOCK, min(BLOCK, (uint32_t)tid * seg) + seg);
+    uint32_t rem = BLOCK - b1, p = 0x80000000u;                               // x^0
+    for (int j = 0; rem; j++, rem >>= 1) if (rem & 1u) p = crc_mul(p, c_xpow8[j]);
+    pow_full = p;
+  }
   for (;;) {
     __syncthreads();
     if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
@@ -228,8 +237,8 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
         for (int q = 0; q < 4; q++) st = S.crc_tab[st & 0xffu] ^ (st >> 8);
       }
       for (; k < b1; k++) st = S.crc_tab[(st ^ bytes[k]) & 0xffu] ^ (st >> 8);
-      uint32_t rem = isize - b1;                                            // bytes behind this piece
-      for (int j = 0; rem; j++, rem >>= 1) if (rem & 1u) st = crc_mul(st, c_xpow8[j]);
+      if (isize == BLOCK) st = crc_mul(st, pow_full);
+      else { uint32_t rem = isize - b1; for (int j = 0; rem; j++, rem >>= 1) if (rem & 1u) st = crc_mul(st, c_xpow8[j]); }   // bytes behind this piece
       if (b0 == b1 && tid != 0) st = 0;
       #pragma unroll
       for (int o = 16; o; o >>= 1) st ^= __shfl_xor_sync(FULL, st, o);
