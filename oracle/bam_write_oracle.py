@@ -11,8 +11,10 @@ noodles-bgzf 0.49.0 writer; git fork @42a3c016, not vendored), the published for
 layout, reg2bin, 4-bit bases, 0xFF for missing qualities), 1.3 (header lines), 4.1 (BGZF, 0xff00-byte blocks + EOF marker).
 
 PARITY PINNING: the reference holds no golden BAM bytes for this path; its tests (bio-format-bam/tests/write_test.rs) are
-write -> read round trips.  This oracle is pinned the same way: tests/test_write_oracle.py writes the reference's fixtures and
-the write_test.rs vectors with it and reads them back with the (pinned) read oracle.  Details only noodles decides and no
+write -> read round trips.  This oracle is pinned the same way -- tests/test_write_oracle.py writes the reference's fixtures and
+the write_test.rs vectors with it and reads them back with the (pinned) read oracle -- and, beyond that, against the BYTES of the
+reference's fixtures (written by htslib): re-encoding their rows reproduces every record's core fields, and whole records (aux
+included) wherever the requested type letters are the file's own.  Details only noodles decides and no
 reference test fixes are listed in DESIGN.md 3.6 ("unpinned": bin of zero-span reads, base case folding, HashMap order of
 extra header fields).
 """
