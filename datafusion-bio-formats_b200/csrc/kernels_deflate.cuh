@@ -67,6 +67,7 @@ struct Smem {
   uint16_t parent[2][576];
   uint8_t depth[2][576];
   uint32_t n_used[2];
+  uint16_t first[2][16];                     // first canonical code per length (advanced while the codes are handed out)
   uint32_t crc_tab[256];
   uint32_t crc_part[WARPS];
   uint32_t warp_bits[WARPS];
@@ -107,24 +108,32 @@ __device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, unsigned l
   if (s + n > 64u) atomicOr(buf + w + 2, (uint32_t)(v >> (64u - s)));
 }
 
-// Code lengths (<= 15) of one tree from S.freq[base .. base + n); `who` = first thread of the warp that owns the tree.
-__device__ __forceinline__ void build_tree(Smem& S, int T, uint32_t base, uint32_t n, int tid) {
-  // (a) rank the used symbols by (count, symbol)
-  if (tid == 0) S.n_used[T] = 0;
+// Code lengths (<= 15) and canonical codes of BOTH trees from S.freq, side by side: tree 0 = literal/length symbols [0, 286),
+// tree 1 = distance symbols [D0, D0 + 30).  The serial steps of the two trees run on two threads of different warps at the
+// same time; the canonical codes are assigned by one warp per tree, 32 symbols per step (`match_any` ranks).
+__device__ __forceinline__ void build_trees(Smem& S, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  // (a) rank the used symbols by (count, symbol): thread s < 286 takes litlen symbol s, thread 286 + d distance symbol d
+  if (tid < 2) S.n_used[tid] = 0;
   __syncthreads();
-  for (uint32_t s = tid; s < n; s += NT) {
+  static_assert(NT >= 316, "one thread per symbol of both alphabets");
+  if (tid < 316) {
+    const int T = tid < 286 ? 0 : 1;
+    const uint32_t base = T ? D0 : 0u, n = T ? 30u : 286u, s = T ? (uint32_t)tid - 286u : (uint32_t)tid;
     const uint32_t f = S.freq[base + s];
     S.len[base + s] = 0;
-    if (!f) continue;
-    uint32_t r = 0;
-    for (uint32_t u = 0; u < n; u++) { const uint32_t g = S.freq[base + u]; r += (g && (g < f || (g == f && u < s))) ? 1u : 0u; }
-    S.sorted[T][r] = (uint16_t)s; S.weight[T][r] = f;
-    atomicAdd(&S.n_used[T], 1u);
+    if (f) {
+      uint32_t r = 0;
+      for (uint32_t u = 0; u < n; u++) { const uint32_t g = S.freq[base + u]; r += (g && (g < f || (g == f && u < s))) ? 1u : 0u; }
+      S.sorted[T][r] = (uint16_t)s; S.weight[T][r] = f;
+      atomicAdd(&S.n_used[T], 1u);
+    }
   }
   __syncthreads();
-  const uint32_t m = S.n_used[T];
-  // (b) two-queue merge, one thread; then the depth of every internal node from the root down
-  if (tid == T * 32) {
+  // (b) two-queue merge, one thread per tree; then the depth of every internal node from the root down
+  if (tid == 0 || tid == 32) {
+    const int T = tid >> 5;
+    const uint32_t m = S.n_used[T];
     uint32_t i = 0, j = m;                         // next unused leaf / internal node
     for (uint32_t k = 0; k + 1 < m; k++) {
       const uint32_t node = m + k;
@@ -142,10 +151,17 @@ __device__ __forceinline__ void build_tree(Smem& S, int T, uint32_t base, uint32
     for (uint32_t k = root; k-- > m;) S.depth[T][k] = (uint8_t)min(60u, (uint32_t)S.depth[T][S.parent[T][k]] + 1u);
   }
   __syncthreads();
-  for (uint32_t i = tid; i < m; i += NT) S.depth[T][i] = (uint8_t)min(60u, (uint32_t)S.depth[T][S.parent[T][i]] + 1u);
+  if (tid < 316) {
+    const int T = tid < 286 ? 0 : 1;
+    const uint32_t i = T ? (uint32_t)tid - 286u : (uint32_t)tid;
+    if (i < S.n_used[T]) S.depth[T][i] = (uint8_t)min(60u, (uint32_t)S.depth[T][S.parent[T][i]] + 1u);
+  }
   __syncthreads();
-  // (c) limit to 15 bits: counts per length, overflow folded into 15, Kraft sum repaired by splitting a shallower leaf
-  if (tid == T * 32) {
+  // (c) limit to 15 bits: counts per length, overflow folded into 15, Kraft sum repaired by splitting a shallower leaf;
+  //     S.first[T][l] = first canonical code of length l
+  if (tid == 0 || tid == 32) {
+    const int T = tid >> 5;
+    const uint32_t base = T ? D0 : 0u, m = S.n_used[T];
     uint32_t bl[64];
     for (int l = 0; l < 64; l++) bl[l] = 0;
     for (uint32_t i = 0; i < m; i++) bl[S.depth[T][i]]++;
@@ -160,20 +176,26 @@ __device__ __forceinline__ void build_tree(Smem& S, int T, uint32_t base, uint32
     // leaves are sorted by count ascending: the rarest take the longest codes
     uint32_t i = 0;
     for (int l = 15; l >= 1; l--) for (uint32_t c = 0; c < bl[l]; c++, i++) S.len[base + S.sorted[T][i]] = (uint8_t)l;
+    uint32_t code = 0;
+    S.first[T][0] = 0;
+    for (int l = 1; l <= 15; l++) { code = (code + (l > 1 ? bl[l - 1] : 0u)) << 1; S.first[T][l] = (uint16_t)code; }
   }
   __syncthreads();
-  // (d) canonical codes, bit-reversed for the LSB-first bit stream
-  for (uint32_t s = tid; s < n; s += NT) {
-    const uint32_t L = S.len[base + s];
-    if (!L) { S.code[base + s] = 0; continue; }
-    uint32_t code = 0, below = 0;
-    uint32_t cntl[16];
-    #pragma unroll
-    for (int l = 0; l < 16; l++) cntl[l] = 0;
-    for (uint32_t u = 0; u < n; u++) { const uint32_t lu = S.len[base + u]; cntl[lu]++; below += (lu == L && u < s) ? 1u : 0u; }
-    for (uint32_t l = 1; l <= L; l++) code = (code + (l > 1 ? cntl[l - 1] : 0u)) << 1;
-    code += below;
-    S.code[base + s] = (uint16_t)(__brev(code) >> (32u - L));
+  // (d) canonical codes (symbols of one length in symbol order), bit-reversed for the LSB-first bit stream: warp T, 32 symbols a step
+  if (warp < 2) {
+    const int T = warp;
+    const uint32_t base = T ? D0 : 0u, n = T ? 30u : 286u;
+    for (uint32_t s0 = 0; s0 < n; s0 += 32) {
+      const uint32_t s = s0 + (uint32_t)lane;
+      const uint32_t L = s < n ? S.len[base + s] : 0u;
+      const uint32_t grp = __match_any_sync(FULL, L);
+      const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+      const uint32_t code = (uint32_t)S.first[T][L] + rank;
+      __syncwarp();
+      if (L && rank == 0) S.first[T][L] = (uint16_t)(S.first[T][L] + __popc(grp));     // the group's first lane moves the counter on
+      __syncwarp();
+      if (s < n) S.code[base + s] = L ? (uint16_t)(__brev(code) >> (32u - L)) : (uint16_t)0;
+    }
   }
   __syncthreads();
 }
@@ -376,8 +398,7 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
         S.freq[s] = f;
       }
       __syncthreads();
-      build_tree(S, 0, 0, 286, tid);
-      build_tree(S, 1, D0, 30, tid);
+      build_trees(S, tid);
       // widths: per warp (emit offsets) and in total
       {
         uint32_t bits = 0;
