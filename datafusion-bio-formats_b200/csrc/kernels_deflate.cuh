@@ -43,7 +43,11 @@ constexpr uint32_t HASH_BITS = 13;
 #ifndef BAMSCAN_DFL_LOCAL_HASH
 #define BAMSCAN_DFL_LOCAL_HASH 1
 #endif
-constexpr uint32_t LOCAL_SLOTS = (1u << HASH_BITS) / WARPS;
+#ifndef BAMSCAN_DFL_HTAB
+#define BAMSCAN_DFL_HTAB 12288
+#endif
+constexpr uint32_t HTAB_ENTRIES = BAMSCAN_DFL_HTAB;                         // 16-bit entries of the hash table (all regions together)
+constexpr uint32_t LOCAL_SLOTS = HTAB_ENTRIES / WARPS;
 #ifndef BAMSCAN_DFL_PRESEED
 #define BAMSCAN_DFL_PRESEED 1024
 #endif
@@ -56,7 +60,7 @@ __constant__ uint32_t c_xpow8[18];           // x^(8 * 2^j) mod P, reflected (wr
 
 struct Smem {
   uint32_t buf[SLOT / 4 + 8];                // input bytes (zero padded), later the member image
-  uint16_t htab[1u << HASH_BITS];
+  uint16_t htab[HTAB_ENTRIES];
   uint32_t hist[WARPS][NSYM / 2];            // per-warp symbol counts, two 16-bit counters per word (a region holds < 65536 tokens)
   uint32_t cnt[NSYM];                        // true symbol counts of the member
   uint32_t freq[NSYM];                       // counts the trees are built from (>= 2 symbols per tree forced)
@@ -237,7 +241,7 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
       uint4* dst = reinterpret_cast<uint4*>(S.buf);
       const uint32_t n16 = (isize + 15u) >> 4;
       for (uint32_t i = tid; i < (SLOT / 16) + 2; i += NT) dst[i] = i < n16 ? src[i] : make_uint4(0, 0, 0, 0);   // (the stream buffer is padded to 16 bytes)
-      for (uint32_t i = tid; i < (1u << HASH_BITS); i += NT) S.htab[i] = 0xffff;
+      for (uint32_t i = tid; i < HTAB_ENTRIES; i += NT) S.htab[i] = 0xffff;
       for (uint32_t i = tid; i < WARPS * (NSYM / 2); i += NT) (&S.hist[0][0])[i] = 0;
     }
     __syncthreads();
