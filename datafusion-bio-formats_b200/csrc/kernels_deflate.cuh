@@ -44,7 +44,7 @@ constexpr uint32_t HASH_BITS = 13;
 #define BAMSCAN_DFL_LOCAL_HASH 1
 #endif
 #ifndef BAMSCAN_DFL_HTAB
-#define BAMSCAN_DFL_HTAB 12288
+#define BAMSCAN_DFL_HTAB 16896
 #endif
 constexpr uint32_t HTAB_ENTRIES = BAMSCAN_DFL_HTAB;                         // 16-bit entries of the hash table (all regions together)
 constexpr uint32_t LOCAL_SLOTS = HTAB_ENTRIES / WARPS;
@@ -60,16 +60,19 @@ __constant__ uint32_t c_xpow8[18];           // x^(8 * 2^j) mod P, reflected (wr
 
 struct Smem {
   uint32_t buf[SLOT / 4 + 8];                // input bytes (zero padded), later the member image
-  uint16_t htab[HTAB_ENTRIES];
+  union {                                    // the hash table is dead when the trees are built: their scratch lives in its place
+    uint16_t htab[HTAB_ENTRIES];
+    struct {
+      uint16_t sorted[2][288];               // used symbols by (count, symbol) ascending
+      uint32_t weight[2][576];               // leaves [0, m), internal nodes [m, 2m - 1)
+      uint16_t parent[2][576];
+      uint8_t depth[2][576];
+    } t;
+  };
   uint32_t hist[WARPS][NSYM / 2];            // per-warp symbol counts, two 16-bit counters per word (a region holds < 65536 tokens)
-  uint32_t cnt[NSYM];                        // true symbol counts of the member
   uint32_t freq[NSYM];                       // counts the trees are built from (>= 2 symbols per tree forced)
   uint16_t code[NSYM];                       // bit-reversed canonical codes
   uint8_t len[NSYM];
-  uint16_t sorted[2][288];                   // used symbols by (count, symbol) ascending
-  uint32_t weight[2][576];                   // leaves [0, m), internal nodes [m, 2m - 1)
-  uint16_t parent[2][576];
-  uint8_t depth[2][576];
   uint32_t n_used[2];
   uint16_t first[2][16];                     // first canonical code per length (advanced while the codes are handed out)
   uint32_t crc_tab[256];
@@ -121,6 +124,7 @@ __device__ __forceinline__ void build_trees(Smem& S, int tid) {
   if (tid < 2) S.n_used[tid] = 0;
   __syncthreads();
   static_assert(NT >= 316, "one thread per symbol of both alphabets");
+  static_assert(sizeof(S.t) <= sizeof(S.htab), "tree scratch fits the hash table");
   if (tid < 316) {
     const int T = tid < 286 ? 0 : 1;
     const uint32_t base = T ? D0 : 0u, n = T ? 30u : 286u, s = T ? (uint32_t)tid - 286u : (uint32_t)tid;
@@ -129,7 +133,7 @@ __device__ __forceinline__ void build_trees(Smem& S, int tid) {
     if (f) {
       uint32_t r = 0;
       for (uint32_t u = 0; u < n; u++) { const uint32_t g = S.freq[base + u]; r += (g && (g < f || (g == f && u < s))) ? 1u : 0u; }
-      S.sorted[T][r] = (uint16_t)s; S.weight[T][r] = f;
+      S.t.sorted[T][r] = (uint16_t)s; S.t.weight[T][r] = f;
       atomicAdd(&S.n_used[T], 1u);
     }
   }
@@ -145,20 +149,20 @@ __device__ __forceinline__ void build_trees(Smem& S, int tid) {
       #pragma unroll
       for (int c = 0; c < 2; c++) {
         uint32_t pick;
-        if (i < m && (j >= node || S.weight[T][i] <= S.weight[T][j])) pick = i++; else pick = j++;
-        w += S.weight[T][pick]; S.parent[T][pick] = (uint16_t)node;
+        if (i < m && (j >= node || S.t.weight[T][i] <= S.t.weight[T][j])) pick = i++; else pick = j++;
+        w += S.t.weight[T][pick]; S.t.parent[T][pick] = (uint16_t)node;
       }
-      S.weight[T][node] = w;
+      S.t.weight[T][node] = w;
     }
     const uint32_t root = 2 * m - 2;
-    S.depth[T][root] = 0;
-    for (uint32_t k = root; k-- > m;) S.depth[T][k] = (uint8_t)min(60u, (uint32_t)S.depth[T][S.parent[T][k]] + 1u);
+    S.t.depth[T][root] = 0;
+    for (uint32_t k = root; k-- > m;) S.t.depth[T][k] = (uint8_t)min(60u, (uint32_t)S.t.depth[T][S.t.parent[T][k]] + 1u);
   }
   __syncthreads();
   if (tid < 316) {
     const int T = tid < 286 ? 0 : 1;
     const uint32_t i = T ? (uint32_t)tid - 286u : (uint32_t)tid;
-    if (i < S.n_used[T]) S.depth[T][i] = (uint8_t)min(60u, (uint32_t)S.depth[T][S.parent[T][i]] + 1u);
+    if (i < S.n_used[T]) S.t.depth[T][i] = (uint8_t)min(60u, (uint32_t)S.t.depth[T][S.t.parent[T][i]] + 1u);
   }
   __syncthreads();
   // (c) limit to 15 bits: counts per length, overflow folded into 15, Kraft sum repaired by splitting a shallower leaf;
@@ -168,7 +172,7 @@ __device__ __forceinline__ void build_trees(Smem& S, int tid) {
     const uint32_t base = T ? D0 : 0u, m = S.n_used[T];
     uint32_t bl[64];
     for (int l = 0; l < 64; l++) bl[l] = 0;
-    for (uint32_t i = 0; i < m; i++) bl[S.depth[T][i]]++;
+    for (uint32_t i = 0; i < m; i++) bl[S.t.depth[T][i]]++;
     for (int l = 16; l < 64; l++) { bl[15] += bl[l]; bl[l] = 0; }
     unsigned long long kraft = 0;
     for (int l = 1; l <= 15; l++) kraft += (unsigned long long)bl[l] << (15 - l);
@@ -179,7 +183,7 @@ __device__ __forceinline__ void build_trees(Smem& S, int tid) {
     }
     // leaves are sorted by count ascending: the rarest take the longest codes
     uint32_t i = 0;
-    for (int l = 15; l >= 1; l--) for (uint32_t c = 0; c < bl[l]; c++, i++) S.len[base + S.sorted[T][i]] = (uint8_t)l;
+    for (int l = 15; l >= 1; l--) for (uint32_t c = 0; c < bl[l]; c++, i++) S.len[base + S.t.sorted[T][i]] = (uint8_t)l;
     uint32_t code = 0;
     S.first[T][0] = 0;
     for (int l = 1; l <= 15; l++) { code = (code + (l > 1 ? bl[l - 1] : 0u)) << 1; S.first[T][l] = (uint16_t)code; }
@@ -394,7 +398,6 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
         #pragma unroll
         for (int w = 0; w < WARPS; w++) c += hist_get(S.hist[w], s);
         if (s == 256u) c = 1;
-        S.cnt[s] = c;
         uint32_t f = c;
         if ((s == 0u || s == D0 || s == D0 + 1u) && f == 0u) f = 1;        // >= 2 used symbols per tree: complete codes
         if (s >= 286u && s < D0) f = 0;
