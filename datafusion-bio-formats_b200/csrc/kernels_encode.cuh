@@ -30,6 +30,7 @@ enum EncErr : uint32_t {
 };
 
 // tag column kinds (== HK_* of bamscan_internal.h)
+enum : int32_t { WK_Int8 = 20, WK_UInt8 = 21, WK_Int16 = 22, WK_UInt16 = 23, WK_Int64 = 24, WK_UInt64 = 25, WK_Float64 = 26 };   // scalar tag columns a query may hand over (extract_signed_int / extract_unsigned_int, sam_tag_io.rs:390-438)
 enum : int32_t { WK_Int32 = 1, WK_UInt32 = 2, WK_Float32 = 3, WK_Utf8 = 4, WK_ListInt8 = 10, WK_ListUInt8 = 11, WK_ListInt16 = 12,
                  WK_ListUInt16 = 13, WK_ListInt32 = 14, WK_ListUInt32 = 15, WK_ListFloat32 = 16 };
 
@@ -109,20 +110,43 @@ __device__ __forceinline__ unsigned long long digits_before(const uint8_t* s, ui
   return len;
 }
 
+__device__ __forceinline__ bool is_int_kind(int32_t k) { return k == WK_Int32 || k == WK_UInt32 || (k >= WK_Int8 && k <= WK_UInt64); }
+// the integer at row r of a scalar tag column; *big = a UInt64 beyond i64 (fits no SAM type)
+__device__ __forceinline__ long long load_int(const TagCol& t, int64_t r, bool* big) {
+  *big = false;
+  switch (t.kind) {
+    case WK_Int8: return reinterpret_cast<const int8_t*>(t.values)[r];
+    case WK_UInt8: return reinterpret_cast<const uint8_t*>(t.values)[r];
+    case WK_Int16: return reinterpret_cast<const int16_t*>(t.values)[r];
+    case WK_UInt16: return reinterpret_cast<const uint16_t*>(t.values)[r];
+    case WK_Int32: return reinterpret_cast<const int32_t*>(t.values)[r];
+    case WK_UInt32: return reinterpret_cast<const uint32_t*>(t.values)[r];
+    case WK_Int64: return reinterpret_cast<const long long*>(t.values)[r];
+    default: { const unsigned long long u = reinterpret_cast<const unsigned long long*>(t.values)[r]; *big = u > 0x7fffffffffffffffull; return (long long)u; }
+  }
+}
+// Float64 -> f32 with the reference's check (finite and within f32's range, sam_tag_io.rs:292-303)
+__device__ __forceinline__ bool f64_to_f32(double d, float* out) {
+  if (!isfinite(d) || d < -3.4028234663852886e38 || d > 3.4028234663852886e38) return false;
+  *out = (float)d;
+  return true;
+}
+
 // Bytes one aux field occupies in the record (0: NULL / dropped); *e receives a validation error.
 __device__ __forceinline__ uint32_t tag_bytes(const TagCol& t, uint32_t row, uint32_t* e) {
   const int64_t r = t.base + row;
   if (!is_valid(t.valid, r)) return 0;
   const uint8_t st = t.sam_type;
   const bool is_int_type = st == 'c' || st == 'C' || st == 's' || st == 'S' || st == 'i' || st == 'I';
-  if (t.kind == WK_Int32 || t.kind == WK_UInt32) {
-    const uint32_t raw = reinterpret_cast<const uint32_t*>(t.values)[r];
-    const long long v = t.kind == WK_Int32 ? (long long)(int32_t)raw : (long long)raw;
-    if (is_int_type) { if (!int_fits(v, st)) *e = ENC_ERR_TAG_RANGE; return 3u + elem_size(st); }
-    if (st == 'A') { if (v < 0 || v > 255) *e = ENC_ERR_TAG_CHAR; return 4; }
+  if (is_int_kind(t.kind)) {
+    bool big;
+    const long long v = load_int(t, r, &big);
+    if (is_int_type) { if (big || !int_fits(v, st)) *e = ENC_ERR_TAG_RANGE; return 3u + elem_size(st); }
+    if (st == 'A') { if (big || v < 0 || v > 255) *e = ENC_ERR_TAG_CHAR; return 4; }
     *e = ENC_ERR_TAG_RANGE; return 0;                     // (host refuses these combinations before any launch)
   }
   if (t.kind == WK_Float32) return 7;
+  if (t.kind == WK_Float64) { float f; if (!f64_to_f32(reinterpret_cast<const double*>(t.values)[r], &f)) *e = ENC_ERR_TAG_RANGE; return 7; }
   if (t.kind == WK_Utf8) {
     const uint32_t b = (uint32_t)t.off[r], n = (uint32_t)t.off[r + 1] - b;
     const uint8_t* s = reinterpret_cast<const uint8_t*>(t.values) + b;
@@ -420,11 +444,15 @@ enc_records_kernel(const EncArgs a, const unsigned long long* __restrict__ rec_o
     const int64_t r = T.base + row;
     const uint8_t st = T.sam_type;
     if (gl == 0) { ap[0] = T.tag[0]; ap[1] = T.tag[1]; }
-    if (T.kind == WK_Int32 || T.kind == WK_UInt32) {
-      const uint32_t v = reinterpret_cast<const uint32_t*>(T.values)[r];
+    if (is_int_kind(T.kind)) {
+      bool big;
+      const uint32_t v = (uint32_t)load_int(T, r, &big);
       if (gl == 0) { ap[2] = st; const uint32_t es = st == 'A' ? 1u : elem_size(st); ap[3] = (uint8_t)v; if (es > 1) ap[4] = (uint8_t)(v >> 8); if (es > 2) { ap[5] = (uint8_t)(v >> 16); ap[6] = (uint8_t)(v >> 24); } }
     } else if (T.kind == WK_Float32) {
       if (gl == 0) { ap[2] = 'f'; st_u32(ap + 3, reinterpret_cast<const uint32_t*>(T.values)[r]); }
+    } else if (T.kind == WK_Float64) {
+      float f = 0.f; f64_to_f32(reinterpret_cast<const double*>(T.values)[r], &f);
+      if (gl == 0) { ap[2] = 'f'; st_u32(ap + 3, __float_as_uint(f)); }
     } else if (T.kind == WK_Utf8) {
       const uint32_t b = (uint32_t)T.off[r], n = (uint32_t)T.off[r + 1] - b;
       const uint8_t* s = reinterpret_cast<const uint8_t*>(T.values) + b;

@@ -169,6 +169,13 @@ static int32_t kind_of_format(const ArrowSchema* c) {
   if (f == "f") return HK_Float32;
   if (f == "u") return HK_Utf8;
   if (f == "z") return HK_Binary;
+  if (f == "c") return enc::WK_Int8;          // scalar tag columns only (the scan itself never produces these)
+  if (f == "C") return enc::WK_UInt8;
+  if (f == "s") return enc::WK_Int16;
+  if (f == "S") return enc::WK_UInt16;
+  if (f == "l") return enc::WK_Int64;
+  if (f == "L") return enc::WK_UInt64;
+  if (f == "g") return enc::WK_Float64;
   if (f == "+l" && c->n_children == 1 && c->children[0]->format) {
     const std::string e = c->children[0]->format;
     if (e == "c") return HK_ListInt8;
@@ -220,12 +227,13 @@ static int writer_open_impl(const char* output_path, const char* sam_header_text
     if (spec.size() == 1) g.sam_type = (uint8_t)spec[0];
     else if (spec.size() == 3 && spec[0] == 'B' && spec[1] == ':' && strchr("cCsSiIf", spec[2])) { g.sam_type = 'B'; g.subtype = (uint8_t)spec[2]; }
     else { set_error("Invalid SAM tag type metadata: '%s'", spec.c_str()); return BAMSCAN_ERR_SCHEMA; }
-    if (!g.kind) { set_error("tag column '%s': Arrow type '%s' is not supported by this build (Int32, UInt32, Float32, Utf8, List of 8/16/32-bit integers or Float32)", tn, schema->children[idx]->format); return BAMSCAN_ERR_UNSUPPORTED; }
-    const bool is_int = g.kind == HK_Int32 || g.kind == HK_UInt32, is_list = g.kind >= HK_ListInt8;
+    if (!g.kind) { set_error("tag column '%s': Arrow type '%s' is not supported by this build (integers of 8 to 64 bits, Float32 / Float64, Utf8, List of 8/16/32-bit integers or Float32)", tn, schema->children[idx]->format); return BAMSCAN_ERR_UNSUPPORTED; }
+    const bool is_int = g.kind == HK_Int32 || g.kind == HK_UInt32 || (g.kind >= enc::WK_Int8 && g.kind <= enc::WK_UInt64);
+    const bool is_list = g.kind >= HK_ListInt8 && g.kind <= HK_ListFloat32;
     const char st = (char)g.sam_type;
     bool ok;
     if (strchr("cCsSiI", st)) ok = is_int;
-    else if (st == 'f') ok = g.kind == HK_Float32;
+    else if (st == 'f') ok = g.kind == HK_Float32 || g.kind == enc::WK_Float64;
     else if (st == 'Z' || st == 'H') ok = g.kind == HK_Utf8;
     else if (st == 'A') ok = g.kind == HK_Utf8 || is_int;
     else if (st == 'B') {
@@ -395,11 +403,11 @@ static int stage_utf8(BamWriter* w, size_t* cur, const HostCol& c, int64_t n, en
   out->base = c.off;
   return stage_validity(w, cur, c, n, &out->valid);
 }
-static int stage_prim(BamWriter* w, size_t* cur, const HostCol& c, int64_t n, enc::PrimCol* out) {
-  const uint32_t* v = static_cast<const uint32_t*>(c.a->buffers[1]);
+static int stage_prim(BamWriter* w, size_t* cur, const HostCol& c, int64_t n, enc::PrimCol* out, size_t es = 4) {
+  const uint8_t* v = static_cast<const uint8_t*>(c.a->buffers[1]);
   uint8_t* d; int rc;
-  if ((rc = stage(w, cur, v + c.off, (size_t)n * 4, &d))) return rc;
-  out->values = reinterpret_cast<const uint32_t*>(d) - c.off;
+  if ((rc = stage(w, cur, v + (size_t)c.off * es, (size_t)n * es, &d))) return rc;
+  out->values = reinterpret_cast<const uint32_t*>(d - (size_t)c.off * es);
   out->base = c.off;
   return stage_validity(w, cur, c, n, &out->valid);
 }
@@ -426,7 +434,7 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
     if (!shape_ok(w->col[k], utf8 ? 3 : 2, false)) { set_error("bamscan_writer_write: column %d of the batch does not have the layout of the writer's input schema", w->col[k]); return BAMSCAN_ERR_INVALID; }
   }
   for (auto& g : w->tags)
-    if (!shape_ok(g.col, g.kind == HK_Utf8 ? 3 : 2, g.kind >= HK_ListInt8)) { set_error("bamscan_writer_write: tag column %d of the batch does not have the layout of the writer's input schema", g.col); return BAMSCAN_ERR_INVALID; }
+    if (!shape_ok(g.col, g.kind == HK_Utf8 ? 3 : 2, g.kind >= HK_ListInt8 && g.kind <= HK_ListFloat32)) { set_error("bamscan_writer_write: tag column %d of the batch does not have the layout of the writer's input schema", g.col); return BAMSCAN_ERR_INVALID; }
   // ---- H2D of every buffer the encoder reads ----
   size_t need = 4096;
   if (!w->src_on_device) for (int k : {0, 1, 4, 6, 8, 9}) need += utf8_bytes(w, hc(w->col[k]), n);
@@ -435,10 +443,10 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
     if (w->src_on_device) break;
     const HostCol c = hc(g.col);
     if (g.kind == HK_Utf8) need += utf8_bytes(w, c, n);
-    else if (g.kind >= HK_ListInt8) {
+    else if (g.kind >= HK_ListInt8 && g.kind <= HK_ListFloat32) {
       const int32_t* o = static_cast<const int32_t*>(c.a->buffers[1]);
       need += (size_t)(o[c.off + n] - o[c.off]) * 4 + (size_t)(n + 1) * 4 + (size_t)n / 8 + 64;
-    } else need += (size_t)n * 4 + (size_t)n / 8 + 64;
+    } else need += (size_t)n * 8 + (size_t)n / 8 + 64;
   }
   int rc;
   const double t_w0 = now_ms();
@@ -463,7 +471,7 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
       enc::Utf8Col u;
       if ((rc = stage_utf8(w, &cur, c, n, &u))) return rc;
       T.values = u.data; T.off = u.off; T.valid = u.valid;
-    } else if (g.kind >= HK_ListInt8) {
+    } else if (g.kind >= HK_ListInt8 && g.kind <= HK_ListFloat32) {
       const int32_t* o = static_cast<const int32_t*>(c.a->buffers[1]);
       uint8_t* d;
       if ((rc = stage(w, &cur, o + c.off, (size_t)(n + 1) * 4, &d))) return rc;
@@ -480,7 +488,9 @@ static int writer_write_impl(BamWriter* w, const ArrowArray* batch) {
       if ((rc = stage_validity(w, &cur, c, n, &T.valid))) return rc;
     } else {
       enc::PrimCol p;
-      if ((rc = stage_prim(w, &cur, c, n, &p))) return rc;
+      const size_t es = (g.kind == enc::WK_Int8 || g.kind == enc::WK_UInt8) ? 1 : (g.kind == enc::WK_Int16 || g.kind == enc::WK_UInt16) ? 2
+                        : (g.kind == enc::WK_Int64 || g.kind == enc::WK_UInt64 || g.kind == enc::WK_Float64) ? 8 : 4;
+      if ((rc = stage_prim(w, &cur, c, n, &p, es))) return rc;
       T.values = p.values; T.valid = p.valid;
     }
   }

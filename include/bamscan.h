@@ -232,8 +232,9 @@ int bamscan_probe_pcie(int32_t device_id, uint64_t bytes, double* h2d_gbps, doub
  *    `input_schema` names the columns (the reference looks every column up BY NAME: name, chrom, start, flags, cigar (Utf8 or
  *    Binary), mapping_quality, mate_chrom, mate_start, sequence, quality_scores, template_length) and carries the tag
  *    columns' field metadata (bio.bam.tag.tag / bio.bam.tag.type decide the aux type letter, sam_tag_io.rs:127-141).
- *    Tag columns may be Int32, UInt32, Float32, Utf8 or List<Int8..UInt32 | Float32> (the types the scan produces); other
- *    Arrow types are refused with BAMSCAN_ERR_UNSUPPORTED, as are records with more than 65535 CIGAR ops (CG-tag overflow).
+ *    Tag columns may be integers of 8 to 64 bits, Float32 / Float64, Utf8 or List<Int8..UInt32 | Float32> (what the scan produces
+ *    and what a query can make of it); other Arrow types are refused with BAMSCAN_ERR_UNSUPPORTED, as are records with more than
+ *    65535 CIGAR ops (CG-tag overflow).
  *    Rows are written in arrival order (sort_on_write is a DataFusion SortExec in front of the writer, not part of it).
  *    Data errors of the reference ("does not fit into 16-bit SAM flags", CIGAR parse errors, tag range / type mismatches,
  *    sequence / quality length mismatch) come back as BAMSCAN_ERR_FORMAT / BAMSCAN_ERR_SCHEMA with the row in the message. */

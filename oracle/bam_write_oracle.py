@@ -173,6 +173,9 @@ def encode_tag(tag: str, value, arrow_type: pa.DataType, spec: str) -> bytes:
     if t == "f":
         if not pa.types.is_floating(arrow_type):
             raise WriteError(f"Tag value type mismatch for float: {arrow_type}")
+        import math
+        if arrow_type == pa.float64() and (not math.isfinite(value) or abs(value) > 3.4028234663852886e38):
+            raise WriteError(f"Float value {value} does not fit SAM type 'f'")
         return tb + b"f" + struct.pack("<f", value)
     if t == "Z":
         if not pa.types.is_string(arrow_type):

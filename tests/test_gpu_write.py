@@ -72,7 +72,10 @@ def test_edge_bam_and_every_tag_type(tmp_path):
     fields = [tf("Xc", pa.int32(), "c"), tf("XC", pa.int32(), "C"), tf("Xs", pa.int32(), "s"), tf("XS", pa.int32(), "S"), tf("Xi", pa.int32(), "i"),
               tf("XI", pa.uint32(), "I"), tf("Xf", pa.float32(), "f"), tf("XZ", pa.string(), "Z"), tf("XH", pa.string(), "H"), tf("XA", pa.string(), "A"),
               tf("XB", pa.list_(pa.uint8()), "B:C"), tf("Xb", pa.list_(pa.int16()), "B:s"), tf("XF", pa.list_(pa.float32()), "B:f"),
-              tf("Xa", pa.uint32(), "A"), tf("Xl", pa.list_(pa.int32()), "B"), tf("XL", pa.list_(pa.uint32()), "B:I")]
+              tf("Xa", pa.uint32(), "A"), tf("Xl", pa.list_(pa.int32()), "B"), tf("XL", pa.list_(pa.uint32()), "B:I"),
+              # column types only a query can produce (CAST, arithmetic): every integer width and Float64 (sam_tag_io.rs:390-438, 292-303)
+              tf("Y1", pa.int8(), "c"), tf("Y2", pa.uint8(), "C"), tf("Y3", pa.int16(), "s"), tf("Y4", pa.uint16(), "S"), tf("Y5", pa.int64(), "i"),
+              tf("Y6", pa.uint64(), "I"), tf("Y7", pa.float64(), "f"), tf("Y8", pa.int64(), "A"), tf("Y9", pa.int64(), "C")]
     schema = pa.schema(list(o.schema)[:12] + fields, metadata=o.schema.metadata)
     base = batch.select(range(12)).to_pylist()
     rows = []
@@ -80,7 +83,8 @@ def test_edge_bam_and_every_tag_type(tmp_path):
         r = dict(r)
         if i % 2 == 0:
             r.update(Xc=-5 - i, XC=200, Xs=-3000, XS=60000, Xi=-70000, XI=4000000000, Xf=1.5, XZ="hello", XH="1a2b", XA="q", XB=[1, 2, 255], Xb=[-1, 300],
-                     XF=[0.5, -2.0], Xa=65, Xl=[-5, 70000], XL=[0, 4294967295])
+                     XF=[0.5, -2.0], Xa=65, Xl=[-5, 70000], XL=[0, 4294967295],
+                     Y1=-128, Y2=255, Y3=-32768, Y4=65535, Y5=-2**31, Y6=2**32 - 1, Y7=-1.5e-3, Y8=126, Y9=7)
         else:
             r.update(XZ="", XB=[], XF=[1e-7])
         rows.append(r)
@@ -175,6 +179,15 @@ def test_data_errors_surface(tmp_path):
     with pytest.raises(bamscan.BamScanError, match="row 49") as e:
         gpu_write(tmp_path / "e4.bam", [b2], s2, ["Xc"])
     assert e.value.code == -7
+    for typ, val, spec in ((pa.int64(), 2**31, "i"), (pa.uint64(), 2**63 + 5, "I"), (pa.float64(), 1e39, "f"), (pa.float64(), float("nan"), "f")):
+        tfw = pa.field("Yw", typ, True, {"bio.bam.tag.tag": "Yw", "bio.bam.tag.type": spec})
+        sw = pa.schema(list(batch.schema) + [tfw], metadata=o.schema.metadata)
+        bw = pa.RecordBatch.from_arrays(list(batch.columns) + [pa.array([None] * 20 + [val] + [None] * 29, type=typ)], schema=sw)
+        with pytest.raises(bamscan.BamScanError, match="row 20") as e:
+            gpu_write(tmp_path / "e8.bam", [bw], sw, ["Yw"])
+        assert e.value.code == -7
+        with pytest.raises(W.WriteError):
+            W.encode_batch(bw, ["chr1"], ["Yw"], True)
     bad = pa.schema(list(batch.schema) + [pa.field("Xz", pa.int32(), True, {"bio.bam.tag.tag": "Xz", "bio.bam.tag.type": "Z"})])
     with pytest.raises(bamscan.BamScanError, match="type mismatch"):
         gpu_write(tmp_path / "e5.bam", [], bad, ["Xz"])
