@@ -75,6 +75,7 @@ struct BamFile {
   int32_t batch_rows = 0;
   uint64_t chunk_bytes = 0;              // 0 = one inflate wave per chunk (engine.cu::plan_chunks); else the caller's cap (<= 768 MiB)
   uint32_t seg_bytes = 16384;
+  bool seg_bytes_set = false;             // BamScanOptions.segment_bytes given: no adaptive segment size
   bool skip_crc = false;
   int32_t debug_flags = 0;
   bool decode_all_tags = false;           // BamScanOptions.decode_all_tag_fields

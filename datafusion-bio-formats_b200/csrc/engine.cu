@@ -211,6 +211,7 @@ struct BamScanPlan { Plan* plan = nullptr; BamScanHandle* handle = nullptr; };
 struct BamScanStream {
   Plan* plan = nullptr; BamFile* f = nullptr; const Partition* part = nullptr; BamScanHandle* handle = nullptr;
   bool resources_ready = false;
+  uint32_t mean_record_bytes = 0;        // of the last chunk whose records were counted (segment size of the next ones)
   bool device_resident = false;
   bool device_export = false;            // batches stay in HBM and are handed out through the Arrow C Device Data Interface
   // Chunk k runs entirely on s_chunk[k & 1] (inflate, record boundaries, rows, decode): the next chunk's inflate is queued on
@@ -743,7 +744,10 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
   if ((rc = s->d_status[slot].ensure(4 * std::max<uint32_t>(nb, 1)))) return rc;
   if ((rc = s->d_flags[slot].ensure(256))) return rc;
   if ((rc = s->d_carry.ensure(HEADROOM))) return rc;
-  const uint32_t seg_bytes = f->seg_bytes;
+  // Long records (the previous chunk's mean above 2 KiB): 64 KiB segments.  seg_candidates tests every byte offset of a segment up
+  // to its first record start, i.e. about half a record per segment (and all of it when a 10 kb record covers the segment): with
+  // 16 KiB segments that scan was 9.5 % of the long-read scan.
+  const uint32_t seg_bytes = (!f->seg_bytes_set && s->mean_record_bytes > 2048) ? 65536u : f->seg_bytes;
   const uint32_t n_seg = std::max<uint32_t>(1, (uint32_t)((c.ubytes + seg_bytes - 1) / seg_bytes));
   // seg arrays: start, exit, count, base (u32 each) + tail (u8)
   if ((rc = s->d_seg[slot].ensure((size_t)n_seg * 17 + 64))) return rc;
@@ -910,7 +914,8 @@ static int run_chunk(BamScanStream* s, const ChunkPlan& c, const ScanRange& rang
     const uint32_t n_slices = (uint32_t)std::max<uint64_t>(1, (c.ubytes + SLICE_BYTES - 1) / SLICE_BYTES);
     s->cur.U = U; s->cur.recoff = d_recoff; s->cur.n = n; s->cur.pos = 0; s->cur.cs = cs;
     s->cur.rows_per_slice = (n + n_slices - 1) / n_slices;
-    s->cur.long_records = (f->debug_flags & 2) || (uint64_t)(data_hi - HEADROOM) / std::max<uint32_t>(n_rec, 1) > 2048;
+    s->mean_record_bytes = (uint32_t)std::min<uint64_t>(0xffffffffull, (uint64_t)(data_hi - HEADROOM) / std::max<uint32_t>(n_rec, 1));
+    s->cur.long_records = (f->debug_flags & 2) || s->mean_record_bytes > 2048;
     s->cur.ubytes = c.ubytes / n_slices + (HEADROOM / 4);
     CU_TRY(cudaEventRecord(s->ev_t[slot][3], cs));
   }
@@ -1159,7 +1164,7 @@ static int bamscan_open_impl(const char* path, const char* index_path_or_null, c
   for (int i = 0; i < opt.n_tag_fields && opt.tag_fields; i++) f.tag_fields.push_back(opt.tag_fields[i]);
   f.batch_rows = opt.batch_rows;
   if (opt.chunk_inflated_bytes) f.chunk_bytes = std::min<uint64_t>(opt.chunk_inflated_bytes, 768ull << 20);   // an explicit size is also the slice size
-  if (opt.segment_bytes) f.seg_bytes = std::max<uint32_t>(256, opt.segment_bytes);
+  if (opt.segment_bytes) { f.seg_bytes = std::max<uint32_t>(256, opt.segment_bytes); f.seg_bytes_set = true; }
   f.skip_crc = opt.skip_crc != 0; f.debug_flags = opt.debug_flags; f.decode_all_tags = opt.decode_all_tag_fields != 0;
   int rc = load_file(&f);
   if (rc == BAMSCAN_ERR_IO || rc == BAMSCAN_ERR_CUDA) { release_file(&f); return rc; }
