@@ -143,3 +143,28 @@ def test_corrupt_bai_is_an_error_not_a_crash(tmp_path):
     except bamscan.BamScanError as e:
         assert "BAI" in str(e)                           # ... or a clean error; never a crash
     p.close()
+
+
+def test_open_ended_sub_regions_are_bounded_by_the_start_filter(syn_dir):
+    """balance_partitions leaves the last sub-region of a split contig open-ended (partition_balancer.rs: end = None); with a pushed
+    `start` upper bound the planner must not read that partition to the end of the contig: no partition's block ranges may reach
+    beyond what the one-partition plan (whose region carries the bound) reads.  Without the filter bound they do."""
+    import bamscan
+    path = gen_bam(syn_dir, "short", 200000, seed=9, bai=True)
+    p = bamscan.BamTableProvider(str(path))
+    lo, hi = 20_000_000, 60_000_000
+    flt = [("chrom", "=", ["chr1"]), ("start", "between", [lo, hi])]
+    one = p.scan(None, flt, None, target_partitions=1)
+    limit = max(r["coff_end"] for r in one.partition_ranges(0))
+    for tp in (2, 4, 8):
+        plan = p.scan(None, flt, None, target_partitions=tp)
+        n = plan.output_partition_count()
+        assert n > 1
+        ends = [max((r["coff_end"] for r in plan.partition_ranges(i)), default=0) for i in range(n)]
+        assert max(ends) <= limit, (tp, ends, limit)
+        regions = [g for i in range(n) for g in plan.partition_regions(i)]
+        assert any(g["end"] is None and not g["unmapped_tail"] for g in regions)   # the open-ended last piece is still what is ASSIGNED
+    # only a lower bound: the last partition legitimately runs to the end of the contig
+    open_plan = p.scan(None, [("chrom", "=", ["chr1"]), ("start", ">=", [lo])], None, target_partitions=4)
+    ends = [max((r["coff_end"] for r in open_plan.partition_ranges(i)), default=0) for i in range(open_plan.output_partition_count())]
+    assert max(ends) > limit
