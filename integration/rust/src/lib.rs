@@ -9,6 +9,7 @@
 //! reference's argument list so that call sites (`BamTableProvider::new(...)`) only change the type name.
 
 pub mod ffi;
+pub mod write;
 
 use arrow::array::{Array, StructArray};
 use arrow::datatypes::{DataType, Schema, SchemaRef};
