@@ -343,6 +343,16 @@ static int stage(BamWriter* w, size_t* cursor, const void* src, size_t bytes, ui
   *cursor = at + bytes;
   w->st.arrow_bytes += bytes;
   const uint8_t* s = static_cast<const uint8_t*>(src);
+  if (bytes >= (1u << 20)) {
+    // a source that is already page-locked (e.g. the arenas the scan hands its batches out in) goes by DMA as it stands; the
+    // stream is synchronised before bamscan_writer_write returns, so the caller's buffer outlives the copy
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+      WCU_TRY(cudaMemcpyAsync(*dev, s, bytes, cudaMemcpyHostToDevice, w->stream));
+      return BAMSCAN_OK;
+    }
+    cudaGetLastError();
+  }
   for (size_t done = 0; done < bytes;) {
     const size_t nb = std::min(IN_CHUNK, bytes - done);
     const int slot = (int)(w->in_seq % IN_BUFS);
