@@ -47,7 +47,12 @@ constexpr uint32_t HASH_BITS = 13;
 #define BAMSCAN_DFL_HTAB 16896
 #endif
 constexpr uint32_t HTAB_ENTRIES = BAMSCAN_DFL_HTAB;                         // 16-bit entries of the hash table (all regions together)
-constexpr uint32_t LOCAL_SLOTS = HTAB_ENTRIES / WARPS;
+#ifndef BAMSCAN_DFL_WAYS
+#define BAMSCAN_DFL_WAYS 2
+#endif
+constexpr uint32_t WAYS = BAMSCAN_DFL_WAYS;                                // candidates per hash bucket (the most recent positions);
+                                                                           // host model tools/deflate_sim.cpp: 2 / 4 / 8 ways in the same memory = -2.2 / -4.0 / -5.1 % bytes
+constexpr uint32_t LOCAL_SLOTS = HTAB_ENTRIES / WARPS / WAYS;             // buckets per region
 #ifndef BAMSCAN_DFL_PRESEED
 #define BAMSCAN_DFL_PRESEED 1024
 #endif
@@ -293,7 +298,12 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
       // first records find their predecessors too
       for (uint32_t q0 = rbeg > PRESEED ? rbeg - PRESEED : 0u; q0 < rbeg; q0 += 32) {
         const uint32_t q = q0 + lane;
-        if (q + 4u <= rbeg) S.htab[(uint32_t)warp * LOCAL_SLOTS + __umulhi(ld4(S.buf, q) * 2654435761u, LOCAL_SLOTS)] = (uint16_t)q;
+        if (q + 4u <= rbeg) {
+          uint16_t* B = S.htab + ((uint32_t)warp * LOCAL_SLOTS + __umulhi(ld4(S.buf, q) * 2654435761u, LOCAL_SLOTS)) * WAYS;
+          #pragma unroll
+          for (int k = WAYS - 1; k > 0; k--) B[k] = B[k - 1];
+          B[0] = (uint16_t)q;
+        }
         __syncwarp();
       }
 #endif
@@ -303,15 +313,33 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
         const bool can = in && p + 4u <= rend;
         const uint32_t w4 = ld4(S.buf, min(p, SLOT));
         uint32_t h = 0, cand = 0xffffu;
-#if BAMSCAN_DFL_LOCAL_HASH
+#if BAMSCAN_DFL_LOCAL_HASH && BAMSCAN_DFL_WAYS > 1
+        uint32_t cands[WAYS];
+        #pragma unroll
+        for (int k = 0; k < (int)WAYS; k++) cands[k] = 0xffffu;
+        if (can) {
+          h = ((uint32_t)warp * LOCAL_SLOTS + __umulhi(w4 * 2654435761u, LOCAL_SLOTS)) * WAYS;
+          #pragma unroll
+          for (int k = 0; k < (int)WAYS; k++) cands[k] = S.htab[h + k];
+        }
+        __syncwarp();
+        if (can) {                                      // the bucket ages by one: lanes of one step that share it race, any order is fine
+          #pragma unroll
+          for (int k = WAYS - 1; k > 0; k--) S.htab[h + k] = (uint16_t)cands[k - 1];
+          S.htab[h] = (uint16_t)p;
+        }
+        cand = cands[0];
+#elif BAMSCAN_DFL_LOCAL_HASH
         // one table slice per region: every candidate is an earlier position of the SAME region (the shared table also offers
         // other regions' positions, but concurrently inserted later ones evict the useful entries)
         if (can) { h = (uint32_t)warp * LOCAL_SLOTS + __umulhi(w4 * 2654435761u, LOCAL_SLOTS); cand = S.htab[h]; }
 #else
         if (can) { h = (w4 * 2654435761u) >> (32u - HASH_BITS); cand = S.htab[h]; }
 #endif
+#if !(BAMSCAN_DFL_LOCAL_HASH && BAMSCAN_DFL_WAYS > 1)
         __syncwarp();
         if (can) S.htab[h] = (uint16_t)p;
+#endif
         if (skip >= 32u) { skip -= 32u; continue; }                             // the whole step lies inside the previous token
         // matches are first measured up to 32 bytes only: a match that long reaches the end of the step, so it is the step's LAST
         // token whenever it is chosen, and only that one token is then extended to 258 bytes -- by the whole warp, 128 bytes per
@@ -326,6 +354,18 @@ bgzf_deflate_kernel(const uint8_t* __restrict__ stream, unsigned long long strea
             n = min(n, maxlen);
             if (n >= 4u) { best = n; D = p - cand; }
           }
+#if BAMSCAN_DFL_LOCAL_HASH && BAMSCAN_DFL_WAYS > 1
+          #pragma unroll
+          for (int k = 1; k < (int)WAYS; k++) {                                    // the older entries of the bucket
+            const uint32_t c2 = cands[k];
+            if (best < maxlen && c2 < p && p - c2 <= 32768u && ld4(S.buf, c2) == w4) {
+              uint32_t n = 4;
+              while (n < maxlen) { const uint32_t x = ld4(S.buf, c2 + n) ^ ld4(S.buf, p + n); if (x) { n += (uint32_t)(__ffs((int)x) - 1) >> 3; break; } n += 4; }
+              n = min(n, maxlen);
+              if (n > best) { best = n; D = p - c2; }
+            }
+          }
+#endif
           if (p > 0u && ld4(S.buf, p - 1u) == w4 && best < maxlen) {            // run candidate (sources inside this step are not in the table yet)
             uint32_t n = 4;
             while (n < maxlen) { const uint32_t x = ld4(S.buf, p - 1u + n) ^ ld4(S.buf, p + n); if (x) { n += (uint32_t)(__ffs((int)x) - 1) >> 3; break; } n += 4; }
