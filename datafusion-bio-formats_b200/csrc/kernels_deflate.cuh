@@ -8,8 +8,8 @@
 //   0  the member's <= 65 280 inflated bytes come into shared memory with 16-byte loads; CRC-32: every thread takes one
 //      contiguous piece (table look-ups from shared memory), the pieces are shifted by x^(8 * bytes behind them) and folded;
 //   A  LZ77: the member is cut into 12 regions, one per warp; a warp takes 32 consecutive positions per step: every lane
-//      hashes its 4 bytes into the REGION'S OWN slice of the hash table (most recent position per slot, 16 bit; the slice is
-//      pre-seeded with the last 1 KB in front of the region), extends the candidate (and the run candidate p - 1) word by word
+//      hashes its 4 bytes into the REGION'S OWN slice of the hash table (buckets of the two most recent positions, 16 bit; the
+//      slice is pre-seeded with the last 1 KB in front of the region), extends the candidates (and the run candidate p - 1) word by word
 //      up to 32 bytes, gives way to a literal when the next position starts a longer match (lazy evaluation: every lane already
 //      knows its match), and the warp picks the greedy non-overlapping parse of the 32 positions by pointer jumping over the
 //      lanes (5 shuffle rounds); the step's last token is extended to 258 bytes by the whole warp.  Tokens go to an L2-resident
