@@ -58,3 +58,25 @@ def test_bai_linear_offsets_are_record_starts(syn_dir):
     starts = set(int(v) for v in voff)
     assert nrec == 20000 and len(offs) > 100
     assert all(v in starts for v in offs)
+
+
+def test_deflate_sim_host_model_runs(syn_dir, tmp_path):
+    """tools/deflate_sim.cpp (host model of the write path's LZ77 stage, the tool the compressor's variants were sized with)
+    builds and prints its table: the committed parser stays within 1.25 x of zlib level 6 on the synthetic stream and the
+    two-way buckets are smaller than one-way ones."""
+    import re, struct, subprocess, zlib
+    from conftest import ROOT, gen_bam
+    exe = tmp_path / "deflate_sim"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), str(ROOT / "tools" / "deflate_sim.cpp"), "-lz"])
+    data = gen_bam(syn_dir, "short", 20000, seed=5).read_bytes()
+    off, out = 0, []
+    while off < len(data):
+        bs = struct.unpack_from("<H", data, off + 16)[0] + 1
+        out.append(zlib.decompress(data[off + 18: off + bs - 8], -15)); off += bs
+    raw = tmp_path / "s.raw"
+    raw.write_bytes(b"".join(out))
+    txt = subprocess.check_output([str(exe), str(raw), "40"]).decode()
+    rows = {m.group(1).strip(): float(m.group(2)) for m in re.finditer(r"^(.*?)\s+\d+ bytes\s+([0-9.]+) x zlib-6$", txt, re.M)}
+    base = next(v for k, v in rows.items() if k.startswith("committed"))
+    assert 0.95 < base < 1.25, txt
+    assert rows["4-way buckets (same memory)"] < base < rows["one candidate per slot (the kernel before the last change)"]

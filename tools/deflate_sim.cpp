@@ -110,17 +110,17 @@ int main(int argc, char** argv) {
   std::vector<uint8_t> data; { uint8_t buf[1 << 16]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + n); } fclose(f);
   const uint32_t members = std::min<uint32_t>(argc > 2 ? atoi(argv[2]) : 200, (uint32_t)(data.size() / 0xff00));
   const Variant vs[] = {
-    {"committed: 12 warps, 16896 slots, preseed 1024, lazy", 12, 16896, 1024, true, 1, 4, false},
-    {"no lazy", 12, 16896, 1024, false, 1, 4, false},
-    {"2-way buckets (same memory)", 12, 16896 / 2, 1024, true, 2, 4, false},
+    {"committed: 12 warps, 16896 entries in 2-way buckets, preseed 1024, lazy", 12, 16896 / 2, 1024, true, 2, 4, false},
+    {"one candidate per slot (the kernel before the last change)", 12, 16896, 1024, true, 1, 4, false},
+    {"one candidate, no lazy", 12, 16896, 1024, false, 1, 4, false},
     {"2-way buckets (double memory)", 12, 16896, 1024, true, 2, 4, false},
     {"4-way buckets (same memory)", 12, 16896 / 4, 1024, true, 4, 4, false},
-    {"min match 3 (hash of 3 bytes)", 12, 16896, 1024, true, 1, 3, false},
-    {"lazy over two positions", 12, 16896, 1024, true, 1, 4, true},
-    {"8 warps", 8, 16896, 1024, true, 1, 4, false},
-    {"16 warps", 16, 16896, 1024, true, 1, 4, false},
-    {"preseed 4096", 12, 16896, 4096, true, 1, 4, false},
-    {"32768 slots", 12, 32768, 1024, true, 1, 4, false},
+    {"one candidate, min match 3 (hash of 3 bytes)", 12, 16896, 1024, true, 1, 3, false},
+    {"one candidate, lazy over two positions", 12, 16896, 1024, true, 1, 4, true},
+    {"one candidate, 8 warps", 8, 16896, 1024, true, 1, 4, false},
+    {"one candidate, 16 warps", 16, 16896, 1024, true, 1, 4, false},
+    {"one candidate, preseed 4096", 12, 16896, 4096, true, 1, 4, false},
+    {"one candidate, 32768 slots", 12, 32768, 1024, true, 1, 4, false},
     {"3-way buckets (same memory)", 12, 16896 / 3, 1024, true, 3, 4, false},
     {"8-way buckets (same memory)", 12, 16896 / 8, 1024, true, 8, 4, false},
     {"4-way buckets, 8 warps", 8, 16896 / 4, 1024, true, 4, 4, false},
@@ -133,7 +133,7 @@ int main(int argc, char** argv) {
   for (const Variant& V : vs) {
     uint64_t bits = 0;
     for (uint32_t m = 0; m < members; m++) bits += (member_bits(data.data() + (size_t)m * 0xff00, 0xff00, V) + 7) / 8 * 8;
-    printf("%-58s %10llu bytes  %.4f x zlib-6\n", V.name, (unsigned long long)(bits / 8), (double)(bits / 8) / z6);
+    printf("%-72s %10llu bytes  %.4f x zlib-6\n", V.name, (unsigned long long)(bits / 8), (double)(bits / 8) / z6);
   }
   return 0;
 }
