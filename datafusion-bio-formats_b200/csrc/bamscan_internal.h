@@ -43,11 +43,21 @@ struct BgzfBlock {
 struct BaiChunk { uint64_t beg, end; };
 struct BaiRef {
   std::map<uint32_t, std::vector<BaiChunk>> bins;
-  std::vector<uint64_t> intervals;
+  std::vector<uint64_t> intervals;            // BAI: linear index (16 KiB windows)
+  std::map<uint32_t, uint64_t> loffset;       // CSI: per-bin smallest virtual offset (replaces the linear index)
   bool has_meta = false;
   uint64_t meta_beg = 0, meta_end = 0, n_mapped = 0, n_unmapped = 0;
 };
-struct BaiIndex { std::vector<BaiRef> refs; bool has_no_coor = false; uint64_t n_no_coor = 0; };
+// One structure for both binning indices: BAI is the fixed scheme min_shift = 14, depth = 5 (SAMv1 5.1.1); CSI carries its own
+// (CSIv1 1-2).  Bin ids of level l start at (8^l - 1) / 7; the metadata pseudo-bin is first_bin(depth + 1) + 1 (37450 for BAI).
+struct BaiIndex {
+  std::vector<BaiRef> refs; bool has_no_coor = false; uint64_t n_no_coor = 0;
+  bool csi = false; int min_shift = 14, depth = 5;
+  uint32_t level_first(int l) const { return (uint32_t)(((1ull << (3 * l)) - 1) / 7); }
+  uint32_t leaf_first() const { return level_first(depth); }
+  uint32_t meta_bin() const { return level_first(depth + 1) + 1; }
+  uint64_t max_pos() const { return 1ull << (min_shift + 3 * depth); }
+};
 
 // == BamTableProvider (table_provider.rs:314-335)
 struct BamFile {
@@ -121,7 +131,7 @@ int load_file(BamFile* f);                       // reads the file into pinned m
 int infer_tag_types(const BamFile& f, const std::vector<std::string>& tags, int sample_size,
                     std::map<std::string, std::pair<char, int32_t>>* out);   // table_provider.rs:145-202
 std::string discover_index(const std::string& path);   // index_utils.rs:43-76
-int load_bai(const std::string& path, BaiIndex* out);
+int load_bai(const std::string& path, BaiIndex* out);     // BAI, or CSI when the file is BGZF / starts with "CSI\1"
 
 // host_schema.cpp
 int build_schema(BamFile* f, const BamScanOptions* opt);   // determine_schema (table_provider.rs:42-140)

@@ -1,5 +1,5 @@
 // host_file.cpp -- BGZF ingest on the host: file load into page-locked memory, BSIZE-chain walk, BAM header,
-// tag-type inference sample, index discovery and BAI parse.
+// tag-type inference sample, index discovery and BAI / CSI parse.
 //
 // Replaces (reference, datafusion/):
 //   bio-format-bam/src/storage.rs:161-169        open_local_bam_sync (BGZF reader + read_header)
@@ -198,7 +198,7 @@ int infer_tag_types(const BamFile& f, const std::vector<std::string>& tags, int 
 
 static bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
 
-// index_utils.rs:43-76: <path>.bai, <stem>.bai, <path>.csi
+// index_utils.rs:43-76: <path>.bai, <stem>.bai, then <path>.csi
 std::string discover_index(const std::string& path) {
   std::string c1 = path + ".bai";
   if (file_exists(c1)) return c1;
@@ -207,7 +207,78 @@ std::string discover_index(const std::string& path) {
     std::string c2 = path.substr(0, dot) + ".bai";
     if (file_exists(c2)) return c2;
   }
-  return std::string();   // CSI is discovered by the reference too; this build reads BAI only
+  std::string c3 = path + ".csi";   // discover_bam_index: BAI first, then CSI (index_utils.rs:68-76)
+  if (file_exists(c3)) return c3;
+  return std::string();
+}
+
+// A CSI file is BGZF: inflate every gzip member (host zlib, planning work) into one buffer.
+static bool gunzip_members(const std::vector<uint8_t>& in, std::vector<uint8_t>* out) {
+  size_t p = 0;
+  while (p < in.size()) {
+    z_stream s; memset(&s, 0, sizeof s);
+    if (inflateInit2(&s, 15 + 16) != Z_OK) return false;
+    s.next_in = const_cast<Bytef*>(in.data() + p); s.avail_in = (uInt)std::min<size_t>(in.size() - p, 1u << 30);
+    int rc = Z_OK;
+    while (rc == Z_OK) {
+      uint8_t tmp[65536]; s.next_out = tmp; s.avail_out = sizeof tmp;
+      rc = inflate(&s, Z_NO_FLUSH);
+      if (rc != Z_OK && rc != Z_STREAM_END) { inflateEnd(&s); return false; }
+      out->insert(out->end(), tmp, tmp + (sizeof tmp - s.avail_out));
+      if (out->size() > (1ull << 32)) { inflateEnd(&s); return false; }   // an index of more than 4 GiB is not an index
+    }
+    p += s.total_in; inflateEnd(&s);
+  }
+  return true;
+}
+
+// CSIv1 (SAM/BAM specification group, "Coordinate Sorted Index"): magic, min_shift, depth, l_aux, aux, n_ref,
+// per reference n_bin x { bin, loffset, n_chunk, chunks }, optional n_no_coor.  noodles-csi reads the same layout; the reference
+// discovers `<path>.csi` (index_utils.rs:54-56, 68-76) and then hands it to `bam::bai::fs::read`, which refuses the magic, so an
+// indexed scan over a CSI is an error there; this build reads it (same planner, bin scheme from the file).
+static int parse_csi(const std::string& path, const std::vector<uint8_t>& d, BaiIndex* out) {
+  size_t p = 0;
+  auto need = [&](uint64_t k) { return k <= d.size() - p; };
+  if (d.size() < 16 || memcmp(d.data(), "CSI\1", 4) != 0) { set_error("%s: missing CSI magic", path.c_str()); return BAMSCAN_ERR_FORMAT; }
+  const int32_t min_shift = (int32_t)rd32(d.data() + 4), depth = (int32_t)rd32(d.data() + 8);
+  const uint32_t l_aux = rd32(d.data() + 12); p = 16;
+  // bin ids are 32-bit: first_bin(depth + 1) + 1 must fit => depth <= 9; positions stay below 2^44 here
+  if (min_shift < 1 || depth < 1 || depth > 9 || min_shift + 3 * depth > 44) { set_error("%s: CSI min_shift %d / depth %d not supported", path.c_str(), min_shift, depth); return BAMSCAN_ERR_UNSUPPORTED; }
+  out->csi = true; out->min_shift = min_shift; out->depth = depth;
+  if (!need((uint64_t)l_aux + 4)) goto trunc;
+  p += l_aux;
+  {
+    const uint32_t n_ref = rd32(d.data() + p); p += 4;
+    if ((uint64_t)n_ref * 4ull > d.size() - p) { set_error("%s: CSI n_ref %u exceeds the file size", path.c_str(), n_ref); return BAMSCAN_ERR_FORMAT; }
+    const uint32_t meta = out->meta_bin();
+    out->refs.resize(n_ref);
+    for (uint32_t r = 0; r < n_ref; r++) {
+      if (!need(4)) goto trunc;
+      const uint32_t n_bin = rd32(d.data() + p); p += 4;
+      BaiRef& R = out->refs[r];
+      for (uint32_t b = 0; b < n_bin; b++) {
+        if (!need(16)) goto trunc;
+        const uint32_t bin = rd32(d.data() + p); uint64_t loff; memcpy(&loff, d.data() + p + 4, 8);
+        const uint32_t n_chunk = rd32(d.data() + p + 12); p += 16;
+        if (!need(16ull * n_chunk)) goto trunc;
+        if (bin == meta && n_chunk == 2) {
+          R.has_meta = true;
+          memcpy(&R.meta_beg, d.data() + p, 8); memcpy(&R.meta_end, d.data() + p + 8, 8);
+          memcpy(&R.n_mapped, d.data() + p + 16, 8); memcpy(&R.n_unmapped, d.data() + p + 24, 8);
+        } else {
+          auto& v = R.bins[bin];
+          for (uint32_t c = 0; c < n_chunk; c++) { BaiChunk ch; memcpy(&ch.beg, d.data() + p + 16 * c, 8); memcpy(&ch.end, d.data() + p + 16 * c + 8, 8); v.push_back(ch); }
+          R.loffset[bin] = loff;
+        }
+        p += 16ull * n_chunk;
+      }
+    }
+    if (need(8)) { memcpy(&out->n_no_coor, d.data() + p, 8); out->has_no_coor = true; }
+  }
+  return BAMSCAN_OK;
+trunc:
+  set_error("%s: truncated CSI", path.c_str());
+  return BAMSCAN_ERR_FORMAT;
 }
 
 int load_bai(const std::string& path, BaiIndex* out) {
@@ -217,6 +288,12 @@ int load_bai(const std::string& path, BaiIndex* out) {
   uint8_t tmp[65536]; size_t n;
   while ((n = fread(tmp, 1, sizeof tmp, fp)) > 0) d.insert(d.end(), tmp, tmp + n);
   fclose(fp);
+  if (d.size() >= 4 && d[0] == 0x1f && d[1] == 0x8b) {   // BGZF container: a CSI
+    std::vector<uint8_t> u;
+    if (!gunzip_members(d, &u)) { set_error("%s: cannot inflate the index", path.c_str()); return BAMSCAN_ERR_FORMAT; }
+    return parse_csi(path, u, out);
+  }
+  if (d.size() >= 4 && memcmp(d.data(), "CSI\1", 4) == 0) return parse_csi(path, d, out);
   size_t p = 0;
   auto need = [&](size_t k) { return p + k <= d.size(); };
   if (!need(8) || memcmp(d.data(), "BAI\1", 4) != 0) { set_error("%s: missing BAI magic", path.c_str()); return BAMSCAN_ERR_FORMAT; }

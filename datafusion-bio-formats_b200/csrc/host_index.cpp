@@ -194,7 +194,7 @@ static std::vector<SizeEstimate> estimate_sizes_from_bai(const BamFile& f, const
   for (size_t i = 0; i < regions.size(); i++) {
     SizeEstimate e;
     e.region = regions[i]; e.source_index = (int32_t)i;
-    e.leaf_bin_span = 16384;
+    e.leaf_bin_span = 1ull << idx.min_shift;   // 16384 for a BAI
     int ref = -1;
     for (size_t k = 0; k < f.meta_ref_names.size(); k++) if (f.meta_ref_names[k] == regions[i].chrom) ref = (int)k;   // last duplicate wins (HashMap collect)
     e.estimated_bytes = 1;
@@ -204,7 +204,8 @@ static std::vector<SizeEstimate> estimate_sizes_from_bai(const BamFile& f, const
       for (auto& kv : R.bins) for (auto& c : kv.second) { mn = std::min(mn, c.beg >> 16); mx = std::max(mx, c.end >> 16); }
       e.estimated_bytes = mx > mn ? mx - mn : 0;
       e.unmapped_count = R.has_meta ? R.n_unmapped : 0;
-      for (auto& kv : R.bins) if (kv.first >= 4681 && kv.first <= 37448) e.nonempty_bin_positions.push_back((uint64_t)(kv.first - 4681) * 16384 + 1);
+      const uint32_t leaf0 = idx.leaf_first(), leaf1 = idx.level_first(idx.depth + 1);   // 4681 .. 37448 for a BAI
+      for (auto& kv : R.bins) if (kv.first >= leaf0 && kv.first < leaf1) e.nonempty_bin_positions.push_back((uint64_t)(kv.first - leaf0) * e.leaf_bin_span + 1);
       std::sort(e.nonempty_bin_positions.begin(), e.nonempty_bin_positions.end());
     }
     if (ref >= 0 && (size_t)ref < f.meta_ref_lens.size() && f.meta_ref_lens[(size_t)ref] > 0) e.contig_length = f.meta_ref_lens[(size_t)ref];
@@ -215,35 +216,47 @@ static std::vector<SizeEstimate> estimate_sizes_from_bai(const BamFile& f, const
 
 // ---------------------------------------------------------------------------------------------
 // BAI query: bins overlapping [beg, end) (0-based half open), linear-index minimum offset, merged chunks
-static void reg2bins(uint64_t beg, uint64_t end, std::vector<uint32_t>* bins) {
-  if (end > (1ull << 29)) end = 1ull << 29;
+static void reg2bins(const BaiIndex& I, uint64_t beg, uint64_t end, std::vector<uint32_t>* bins) {
+  if (end > I.max_pos()) end = I.max_pos();
   if (beg >= end) return;
   --end;
-  bins->push_back(0);
-  for (uint32_t k = 1 + (uint32_t)(beg >> 26); k <= 1 + (uint32_t)(end >> 26); ++k) bins->push_back(k);
-  for (uint32_t k = 9 + (uint32_t)(beg >> 23); k <= 9 + (uint32_t)(end >> 23); ++k) bins->push_back(k);
-  for (uint32_t k = 73 + (uint32_t)(beg >> 20); k <= 73 + (uint32_t)(end >> 20); ++k) bins->push_back(k);
-  for (uint32_t k = 585 + (uint32_t)(beg >> 17); k <= 585 + (uint32_t)(end >> 17); ++k) bins->push_back(k);
-  for (uint32_t k = 4681 + (uint32_t)(beg >> 14); k <= 4681 + (uint32_t)(end >> 14); ++k) bins->push_back(k);
+  // level l: bins of 2^(min_shift + 3 (depth - l)) bases, ids from (8^l - 1) / 7 (SAMv1 5.3 for BAI; CSIv1 reg2bins)
+  for (int l = 0; l <= I.depth; l++) {
+    const int sh = I.min_shift + 3 * (I.depth - l);
+    const uint32_t t = I.level_first(l);
+    for (uint64_t k = beg >> sh; k <= (end >> sh); ++k) bins->push_back(t + (uint32_t)k);
+  }
 }
 
-static std::vector<BaiChunk> bai_query(const BaiRef& R, uint64_t start1, bool has_end, uint64_t end1) {
-  const uint64_t beg0 = start1 ? start1 - 1 : 0, end0 = has_end ? end1 : (1ull << 29);
+static std::vector<BaiChunk> bai_query(const BaiIndex& I, const BaiRef& R, uint64_t start1, bool has_end, uint64_t end1) {
+  const uint64_t beg0 = start1 ? start1 - 1 : 0, end0 = has_end ? end1 : I.max_pos();
   std::vector<uint32_t> bins;
-  reg2bins(beg0, end0, &bins);
+  reg2bins(I, beg0, end0, &bins);
   std::vector<BaiChunk> chunks;
   for (uint32_t b : bins) { auto it = R.bins.find(b); if (it != R.bins.end()) chunks.insert(chunks.end(), it->second.begin(), it->second.end()); }
   uint64_t min_off = 0;
-  size_t win = (size_t)(beg0 >> 14);
-  if (!R.intervals.empty()) min_off = win < R.intervals.size() ? R.intervals[win] : R.intervals.back();
+  if (I.csi) {
+    // noodles-csi BinnedIndex::min_offset: the loffset of the leaf bin holding the start, else of its nearest indexed ancestor
+    uint32_t bin = I.leaf_first() + (uint32_t)(std::min(beg0, I.max_pos() - 1) >> I.min_shift);
+    for (;;) {
+      auto it = R.loffset.find(bin);
+      if (it != R.loffset.end()) { min_off = it->second; break; }
+      if (bin == 0) break;
+      bin = (bin - 1) >> 3;
+    }
+  } else {
+    size_t win = (size_t)(beg0 >> 14);
+    if (!R.intervals.empty()) min_off = win < R.intervals.size() ? R.intervals[win] : R.intervals.back();
+  }
   // Upper bound (this build; noodles reads every chunk of the overlapping bins): a BAI indexes a coordinate-sorted file, so
   // every record that starts at or before the region end precedes the first record held by a LEAF bin (16 kb window,
   // records lying entirely inside it) of a later window.  Chunks of the coarse bins beyond that offset only hold records
   // that start after the region and would be dropped by the row rule (physical_exec.rs:1295-1314) anyway.
   uint64_t max_off = ~0ull;
   if (has_end) {
-    const uint32_t last_leaf = 4681u + (uint32_t)std::min<uint64_t>((end1 ? end1 - 1 : 0) >> 14, 32767);
-    for (auto it = R.bins.upper_bound(last_leaf); it != R.bins.end() && it->first <= 37448u; ++it)
+    const uint32_t leaf0 = I.leaf_first(), n_leaf = 1u << (3 * I.depth);
+    const uint32_t last_leaf = leaf0 + (uint32_t)std::min<uint64_t>((end1 ? end1 - 1 : 0) >> I.min_shift, n_leaf - 1);
+    for (auto it = R.bins.upper_bound(last_leaf); it != R.bins.end() && it->first < leaf0 + n_leaf; ++it)
       for (auto& c : it->second) max_off = std::min(max_off, c.beg);
   }
   std::vector<BaiChunk> kept;
@@ -385,7 +398,7 @@ int plan_indexed(BamFile* f, Plan* plan, const BamScanFilter* filters, int32_t n
       const bool q_has_end = g.has_end || has_start_sup;
       const uint64_t q_end = g.has_end ? (has_start_sup ? std::min(g.end, start_sup) : g.end) : start_sup;
       if (g.has_start && q_has_end && g.start > q_end) continue;
-      std::vector<BaiChunk> chunks = bai_query(*R, g.has_start ? std::max<uint64_t>(g.start, 1) : 1, q_has_end, q_end);
+      std::vector<BaiChunk> chunks = bai_query(*f->bai, *R, g.has_start ? std::max<uint64_t>(g.start, 1) : 1, q_has_end, q_end);
       for (auto& c : chunks) { int rc = add_range(*f, c.beg, c.end, rule, &part); if (rc) return rc; }
     }
     plan->partitions.push_back(part);

@@ -116,7 +116,8 @@ typedef struct BamScanStats {
 int bamscan_check_partition_seams(const BamScanStats* stats, int32_t n_partitions);
 
 /* == BamTableProvider::new (table_provider.rs:381-529): header read, tag-type inference, schema, index discovery.
- * index_path_or_null: NULL => discover `<path>.bai`, `<stem>.bai` (index_utils.rs:43-76; CSI is not read by this build);
+ * index_path_or_null: NULL => discover `<path>.bai`, `<stem>.bai`, then `<path>.csi` (index_utils.rs:43-76); a BAI or a CSI
+ *   (CSIv1, BGZF or plain, any min_shift / depth up to 9 levels) is read -- the reference discovers a CSI but parses it as a BAI;
  * "" => behave as if no index existed (sequential single-partition scans). */
 int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
 void bamscan_close(BamScanHandle* h);

@@ -134,3 +134,41 @@ def make_fastq_text(n_reads: int, seed: int, read_len=101, crlf=False, final_new
     if not final_newline and text.endswith(eol):
         text = text[:-len(eol)]
     return text.encode()
+
+
+# ---- BAI -> CSI (CSIv1) with the same bins, or re-binned one level deeper; used by the CSI planner / scan tests ----
+def bai_to_csi(bai_path, csi_path, depth=5, bgzf=True):
+    """Rewrite a BAI as a CSI with min_shift 14 and `depth` levels (5 = BAI's own scheme; 6 = every bin moved one level down,
+    what `samtools index -c -m 14` gives contigs above 512 Mb).  A bin's loffset is the linear-index entry of its first 16 KiB
+    window, as htslib computes it when it writes a CSI."""
+    import struct
+    d = Path(bai_path).read_bytes()
+    assert d[:4] == b"BAI\x01" and depth in (5, 6)
+    n_ref, = struct.unpack_from("<I", d, 4)
+    p = 8
+    first = lambda l: ((1 << (3 * l)) - 1) // 7
+    out = [b"CSI\x01", struct.pack("<iii", 14, depth, 0), struct.pack("<I", n_ref)]
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<I", d, p); p += 4
+        bins = []
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<II", d, p); p += 8
+            bins.append((b, d[p:p + 16 * n_chunk], n_chunk)); p += 16 * n_chunk
+        n_intv, = struct.unpack_from("<I", d, p); p += 4
+        intv = struct.unpack_from(f"<{n_intv}Q", d, p); p += 8 * n_intv
+        body = []
+        for b, chunks, n_chunk in bins:
+            if b == 37450:
+                nb, loff = first(depth + 1) + 1, 0
+            else:
+                level = max(l for l in range(6) if first(l) <= b)
+                k = b - first(level)
+                nb = first(level + depth - 5) + k
+                win = k << (3 * (5 - level))
+                loff = intv[win] if win < n_intv else (intv[-1] if n_intv else 0)
+            body.append(struct.pack("<IQi", nb, loff, n_chunk) + chunks)
+        out.append(struct.pack("<I", len(body)) + b"".join(body))
+    out.append(d[p:p + 8])                                              # n_no_coor, when the BAI has it
+    raw = b"".join(out)
+    Path(csi_path).write_bytes(_bgzf(raw) if bgzf else raw)
+    return Path(csi_path)

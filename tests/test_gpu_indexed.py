@@ -183,3 +183,21 @@ def test_config4_region_query_partitioned(syn_dir, gpus):
     got_t = pa.Table.from_batches(got_all, schema=manual.schema)
     assert got_t.num_rows == manual.num_rows > 500
     assert got_t.equals(manual)       # sub-regions are emitted in genomic order, so the concatenation is the file-order subset
+
+
+@pytest.mark.parametrize("depth", [5, 6])
+def test_csi_index_scans_the_same_rows_as_the_bai(tmp_path, depth):
+    """index_utils.rs:54-56, 68-76 discover `<path>.csi`; this build also reads it (CSIv1, any min_shift / depth): the rows of a
+    region query planned from a CSI equal the rows planned from the BAI (indexed_read_large_test.rs pins 1662 for chr1)."""
+    from conftest import bai_to_csi
+    path = GOLDEN / "multi_chrom_large.bam"
+    csi = bai_to_csi(str(path) + ".bai", tmp_path / "l.csi", depth=depth)
+    for filters, want in (([("chrom", "=", ["chr1"])], 1662), ([("chrom", "=", ["chr2"]), ("start", "between", [1000, 20000])], None), ([], 4277)):
+        tabs = []
+        for prov in (_provider(path, tag_fields=["NM"]), _provider(path, tag_fields=["NM"], index_path=str(csi))):
+            plan = prov.scan(None, filters, None, target_partitions=3)
+            assert all(r["region_mode"] != 0 for i in range(plan.output_partition_count()) for r in plan.partition_ranges(i))
+            tabs.append([b for i in range(plan.output_partition_count()) for b in run_partition(plan, i)])
+        assert_same(tabs[1], tabs[0], f"csi depth {depth} {filters}")
+        if want is not None:
+            assert sum(b.num_rows for b in tabs[1]) == want

@@ -249,3 +249,99 @@ def test_region_query_ranges_cover_only_needed_blocks(syn_dir):
     assert ranges and all(r["region_mode"] in (1, 2) and r["region_ref"] == 1 for r in ranges)
     touched = sum(r["block_end"] - r["block_begin"] for r in ranges if r["region_mode"] == 1)
     assert touched < total_blocks // 4                                   # the index pruned most of the file
+
+
+# ---------------------------------------------------------------- CSI (index_utils.rs:54-56, 68-76; CSIv1)
+def _plan_ranges(p, filters, tp):
+    plan = p.scan(None, filters, None, target_partitions=tp)
+    n = plan.output_partition_count()
+    return [[(r["region_mode"], r["region_ref"], r["block_begin"], r["block_end"]) for r in plan.partition_ranges(i)] for i in range(n)], \
+           [plan.partition_regions(i) for i in range(n)]
+
+
+CSI_QUERIES = [[], [("chrom", "=", ["chr1"])], [("chrom", "=", ["chr2"]), ("start", "between", [100_000_000, 120_000_000])],
+               [("chrom", "in", ["chr1", "chr3"]), ("start", ">", [30_000_000])], [("chrom", "=", ["chr2"]), ("start", "<", [5_000_000])]]
+
+
+@pytest.mark.parametrize("depth,bgzf", [(5, True), (5, False), (6, True)])
+def test_csi_plans_like_the_bai(syn_dir, tmp_path, depth, bgzf):
+    """A CSI holding the BAI's own bins (same scheme, or one level deeper) must plan the same partitions and regions; a range may
+    only start EARLIER than the BAI's (loffset of an ancestor bin instead of the 16 KiB linear-index window), never later."""
+    from conftest import bai_to_csi
+    path = gen_bam(syn_dir, "short", 20000, seed=4, bai=True)
+    csi = bai_to_csi(str(path) + ".bai", tmp_path / "x.csi", depth=depth, bgzf=bgzf)
+    import bamscan
+    pb = _provider(path)
+    pc = bamscan.BamTableProvider(str(path), None, True, None, False, True, 100, None, index_path=str(csi))
+    for filters in CSI_QUERIES:
+        for tp in (1, 4):
+            rb, gb = _plan_ranges(pb, filters, tp)
+            rc, gc = _plan_ranges(pc, filters, tp)
+            assert gb == gc, (filters, tp)                                   # estimates, balancer input and output are the same
+            assert len(rb) == len(rc)
+            for qb, qc in zip(rb, rc):
+                assert [(m, r) for m, r, _, _ in qb if m != 1] == [(m, r) for m, r, _, _ in qc if m != 1]
+                beg_b = min((b for m, _, b, _ in qb if m == 1), default=None); beg_c = min((b for m, _, b, _ in qc if m == 1), default=None)
+                end_b = max((e for m, _, _, e in qb if m == 1), default=None); end_c = max((e for m, _, _, e in qc if m == 1), default=None)
+                assert (beg_b is None) == (beg_c is None)
+                if beg_b is not None:
+                    assert beg_c <= beg_b and end_c == end_b, (filters, tp, qb, qc)
+
+
+def test_csi_is_discovered_after_bai(syn_dir, tmp_path):
+    """discover_bam_index: `<path>.bai`, `<stem>.bai`, then `<path>.csi`."""
+    import shutil
+    from conftest import bai_to_csi
+    src = gen_bam(syn_dir, "short", 20000, seed=4, bai=True)
+    bam = tmp_path / "only_csi.bam"
+    shutil.copy(src, bam)
+    assert _provider(bam).scan(None, [("chrom", "=", ["chr1"])], None, target_partitions=2).partition_ranges(0)[0]["region_mode"] == 0   # no index: full scan
+    bai_to_csi(str(src) + ".bai", str(bam) + ".csi")
+    plan = _provider(bam).scan(None, [("chrom", "=", ["chr1"])], None, target_partitions=2)
+    assert all(r["region_mode"] in (1, 2) for i in range(plan.output_partition_count()) for r in plan.partition_ranges(i))
+
+
+def test_csi_fixture_metadata_and_no_coor(tmp_path):
+    from conftest import bai_to_csi
+    import bamscan
+    csi = bai_to_csi(GOLDEN / "no_coor_only.bam.bai", tmp_path / "n.csi", depth=6)
+    p = bamscan.BamTableProvider(str(GOLDEN / "no_coor_only.bam"), None, True, None, False, True, 100, None, index_path=str(csi))
+    plan = p.scan(None, [], None, target_partitions=4)
+    assert plan.partition_regions(plan.output_partition_count() - 1) == [dict(ref=-1, start=None, end=None, unmapped_tail=True, estimated_bytes=2)]
+    csi = bai_to_csi(GOLDEN / "multi_chrom.bam.bai", tmp_path / "m.csi", depth=6)
+    p = bamscan.BamTableProvider(str(GOLDEN / "multi_chrom.bam"), None, True, None, False, True, 100, None, index_path=str(csi))
+    plan = p.scan(None, [], None, target_partitions=4)
+    regs = [g for i in range(plan.output_partition_count()) for g in plan.partition_regions(i)]
+    assert sum(1 for g in regs if g["unmapped_tail"]) == 3               # the metadata pseudo-bin (first_bin(depth + 1) + 1) was read
+
+
+def test_corrupt_csi_is_refused(tmp_path):
+    import bamscan
+    bad = tmp_path / "bad.csi"
+    bad.write_bytes(b"CSI\x01" + b"\x0e\0\0\0\x05\0\0\0\0\0\0\0" + b"\xff\xff\xff\x7f")           # n_ref the file cannot hold
+    with pytest.raises(Exception):
+        bamscan.BamTableProvider(str(GOLDEN / "multi_chrom.bam"), None, True, None, False, True, 100, None, index_path=str(bad))
+    bad.write_bytes(b"CSI\x01" + b"\x0e\0\0\0\x40\0\0\0\0\0\0\0\0\0\0\0")                        # depth 64
+    with pytest.raises(Exception):
+        bamscan.BamTableProvider(str(GOLDEN / "multi_chrom.bam"), None, True, None, False, True, 100, None, index_path=str(bad))
+
+
+@pytest.mark.parametrize("depth", [5, 6])
+def test_csi_planned_ranges_hold_the_pinned_rows(tmp_path, depth):
+    """CPU: the oracle run over the ranges a CSI plan exposes returns the rows the reference pins for the BAI
+    (indexed_read_large_test.rs:63,85,95: 1662 / 1694 / 921) -- the GPU twin is test_csi_index_scans_the_same_rows_as_the_bai."""
+    from conftest import bai_to_csi
+    from oracle.bam_oracle import OracleBam
+    import bamscan
+    path = GOLDEN / "multi_chrom_large.bam"
+    csi = bai_to_csi(str(path) + ".bai", tmp_path / "l.csi", depth=depth)
+    p = bamscan.BamTableProvider(str(path), None, True, None, False, True, 100, None, index_path=str(csi))
+    o = OracleBam(str(path))
+    for chrom, want in (("chr1", 1662), ("chr2", 1694), ("chrX", 921)):
+        plan = p.scan(None, [("chrom", "=", [chrom])], None, target_partitions=3)
+        rows = 0
+        for i in range(plan.output_partition_count()):
+            for r in plan.partition_ranges(i):
+                rows += o.scan(projection=[0], start_voffset=r["start_voffset"], stop_voffset=r["stop_voffset"],
+                               region=(r["region_mode"], r["region_ref"], r["region_start"], r["region_end"]), filters=[]).num_rows
+        assert rows == want, (chrom, depth)
