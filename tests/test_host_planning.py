@@ -168,3 +168,37 @@ def test_open_ended_sub_regions_are_bounded_by_the_start_filter(syn_dir):
     open_plan = p.scan(None, [("chrom", "=", ["chr1"]), ("start", ">=", [lo])], None, target_partitions=4)
     ends = [max((r["coff_end"] for r in open_plan.partition_ranges(i)), default=0) for i in range(open_plan.output_partition_count())]
     assert max(ends) > limit
+
+
+def test_corrupt_bam_files_open_or_fail_cleanly(tmp_path):
+    """bamscan_open walks the BSIZE chain and inflates the header on the host: truncations and byte flips anywhere in a file
+    (header block, block headers, payload) either open + plan or raise BamScanError -- never a crash of the host process."""
+    import random
+    import bamscan
+    rng, opened, refused = random.Random(3), 0, 0
+    srcs = [(GOLDEN / n).read_bytes() for n in ("multi_chrom.bam", "bam_with_tags.bam", "10x_pbmc_tags.bam")]
+    for it in range(300):
+        b = bytearray(srcs[it % 3])
+        mode = rng.randrange(4)
+        if mode == 0:
+            b = b[:rng.randrange(len(b))]
+        elif mode == 1:
+            for _ in range(rng.randrange(1, 8)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        elif mode == 2:
+            for _ in range(rng.randrange(1, 8)):
+                b[rng.randrange(600)] = rng.randrange(256)
+        else:
+            pos = rng.randrange(0, 40)
+            b[pos:pos + 2] = rng.randrange(65536).to_bytes(2, "little")
+        p = tmp_path / "f.bam"
+        p.write_bytes(bytes(b))
+        try:
+            pr = bamscan.BamTableProvider(str(p), None, True, None, False, True, 100, None, index_path="")
+            plan = pr.scan(None, [], None, target_partitions=4, partition_mode="block_range")
+            for i in range(plan.output_partition_count()):
+                plan.partition_ranges(i)
+            opened += 1
+        except bamscan.BamScanError:
+            refused += 1
+    assert opened > 0 and refused > 0

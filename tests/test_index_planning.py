@@ -345,3 +345,38 @@ def test_csi_planned_ranges_hold_the_pinned_rows(tmp_path, depth):
                 rows += o.scan(projection=[0], start_voffset=r["start_voffset"], stop_voffset=r["stop_voffset"],
                                region=(r["region_mode"], r["region_ref"], r["region_start"], r["region_end"]), filters=[]).num_rows
         assert rows == want, (chrom, depth)
+
+
+def test_corrupt_indices_never_crash_the_planner(tmp_path):
+    """Truncated / bit-flipped BAI and CSI files either plan or raise BamScanError (an index is untrusted input; a count the file
+    cannot hold must not become an allocation)."""
+    import random
+    from conftest import bai_to_csi
+    import bamscan
+    bam = GOLDEN / "multi_chrom_large.bam"
+    bai = (GOLDEN / "multi_chrom_large.bam.bai").read_bytes()
+    csi = bai_to_csi(GOLDEN / "multi_chrom_large.bam.bai", tmp_path / "a.csi", depth=6, bgzf=False).read_bytes()
+    rng, planned = random.Random(7), 0
+    for it in range(400):
+        b = bytearray(bai if it % 2 == 0 else csi)
+        mode = rng.randrange(3)
+        if mode == 0:
+            b = b[:rng.randrange(len(b))]
+        elif mode == 1:
+            for _ in range(rng.randrange(1, 6)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        else:
+            pos = rng.randrange(0, 200)
+            b[pos:pos + 4] = rng.randrange(2 ** 32).to_bytes(4, "little")
+        p = tmp_path / "f.idx"
+        p.write_bytes(bytes(b))
+        try:
+            pr = bamscan.BamTableProvider(str(bam), None, True, None, False, True, 100, None, index_path=str(p))
+            for f in ([], [("chrom", "=", ["chr1"]), ("start", "between", [1000, 50000])]):
+                plan = pr.scan(None, f, None, target_partitions=4)
+                for i in range(plan.output_partition_count()):
+                    plan.partition_ranges(i)
+            planned += 1
+        except bamscan.BamScanError:
+            pass
+    assert planned > 0
