@@ -216,24 +216,26 @@ static std::vector<SizeEstimate> estimate_sizes_from_bai(const BamFile& f, const
 
 // ---------------------------------------------------------------------------------------------
 // BAI query: bins overlapping [beg, end) (0-based half open), linear-index minimum offset, merged chunks
-static void reg2bins(const BaiIndex& I, uint64_t beg, uint64_t end, std::vector<uint32_t>* bins) {
+// Chunks of every indexed bin overlapping [beg, end) (0-based half open).  reg2bins (SAMv1 5.3; CSIv1) names the candidate
+// bins level by level -- level l holds bins of 2^(min_shift + 3 (depth - l)) bases with ids from (8^l - 1) / 7 --; instead of
+// listing all candidates (8^depth leaf bins for an open-ended region of a deep CSI) each level is one range walk over the
+// bins the index actually holds.
+static void overlapping_chunks(const BaiIndex& I, const BaiRef& R, uint64_t beg, uint64_t end, std::vector<BaiChunk>* chunks) {
   if (end > I.max_pos()) end = I.max_pos();
   if (beg >= end) return;
   --end;
-  // level l: bins of 2^(min_shift + 3 (depth - l)) bases, ids from (8^l - 1) / 7 (SAMv1 5.3 for BAI; CSIv1 reg2bins)
   for (int l = 0; l <= I.depth; l++) {
     const int sh = I.min_shift + 3 * (I.depth - l);
     const uint32_t t = I.level_first(l);
-    for (uint64_t k = beg >> sh; k <= (end >> sh); ++k) bins->push_back(t + (uint32_t)k);
+    const uint32_t lo = t + (uint32_t)(beg >> sh), hi = t + (uint32_t)(end >> sh);
+    for (auto it = R.bins.lower_bound(lo); it != R.bins.end() && it->first <= hi; ++it) chunks->insert(chunks->end(), it->second.begin(), it->second.end());
   }
 }
 
 static std::vector<BaiChunk> bai_query(const BaiIndex& I, const BaiRef& R, uint64_t start1, bool has_end, uint64_t end1) {
   const uint64_t beg0 = start1 ? start1 - 1 : 0, end0 = has_end ? end1 : I.max_pos();
-  std::vector<uint32_t> bins;
-  reg2bins(I, beg0, end0, &bins);
   std::vector<BaiChunk> chunks;
-  for (uint32_t b : bins) { auto it = R.bins.find(b); if (it != R.bins.end()) chunks.insert(chunks.end(), it->second.begin(), it->second.end()); }
+  overlapping_chunks(I, R, beg0, end0, &chunks);
   uint64_t min_off = 0;
   if (I.csi) {
     // noodles-csi BinnedIndex::min_offset: the loffset of the leaf bin holding the start, else of its nearest indexed ancestor

@@ -138,12 +138,12 @@ def make_fastq_text(n_reads: int, seed: int, read_len=101, crlf=False, final_new
 
 # ---- BAI -> CSI (CSIv1) with the same bins, or re-binned one level deeper; used by the CSI planner / scan tests ----
 def bai_to_csi(bai_path, csi_path, depth=5, bgzf=True):
-    """Rewrite a BAI as a CSI with min_shift 14 and `depth` levels (5 = BAI's own scheme; 6 = every bin moved one level down,
-    what `samtools index -c -m 14` gives contigs above 512 Mb).  A bin's loffset is the linear-index entry of its first 16 KiB
+    """Rewrite a BAI as a CSI with min_shift 14 and `depth` levels (5 = BAI's own scheme; 6 .. 9 = every bin moved depth - 5 levels
+    down, what `samtools index -c -m 14` gives contigs above 512 Mb).  A bin's loffset is the linear-index entry of its first 16 KiB
     window, as htslib computes it when it writes a CSI."""
     import struct
     d = Path(bai_path).read_bytes()
-    assert d[:4] == b"BAI\x01" and depth in (5, 6)
+    assert d[:4] == b"BAI\x01" and 5 <= depth <= 9
     n_ref, = struct.unpack_from("<I", d, 4)
     p = 8
     first = lambda l: ((1 << (3 * l)) - 1) // 7

@@ -263,7 +263,7 @@ CSI_QUERIES = [[], [("chrom", "=", ["chr1"])], [("chrom", "=", ["chr2"]), ("star
                [("chrom", "in", ["chr1", "chr3"]), ("start", ">", [30_000_000])], [("chrom", "=", ["chr2"]), ("start", "<", [5_000_000])]]
 
 
-@pytest.mark.parametrize("depth,bgzf", [(5, True), (5, False), (6, True)])
+@pytest.mark.parametrize("depth,bgzf", [(5, True), (5, False), (6, True), (9, True)])
 def test_csi_plans_like_the_bai(syn_dir, tmp_path, depth, bgzf):
     """A CSI holding the BAI's own bins (same scheme, or one level deeper) must plan the same partitions and regions; a range may
     only start EARLIER than the BAI's (loffset of an ancestor bin instead of the 16 KiB linear-index window), never later."""
