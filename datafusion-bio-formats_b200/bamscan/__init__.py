@@ -633,7 +633,9 @@ class BamWriteExec:
 class FastqTableProvider(BamTableProvider):
     """== FastqTableProvider (bio-format-fastq/src/table_provider.rs:46-75) for BGZF-compressed FASTQ: `new(file_path,
     object_storage_options)`; schema name / description / sequence / quality_scores (Utf8, description nullable).  `scan` with
-    target_partitions > 1 uses BGZF block ranges (physical_exec.rs:140-175); everything else is BamTableProvider's."""
+    target_partitions > 1 uses BGZF block ranges balanced by compressed bytes; partition_mode="reference" cuts by block count from
+    the companion .gzi exactly as get_bgzf_partition_bounds does (physical_exec.rs:140-175; no .gzi: one partition); everything
+    else is BamTableProvider's."""
 
     def __init__(self, file_path, object_storage_options=None, *, device_id=0, batch_rows=0, chunk_inflated_bytes=0,
                  skip_crc=False, debug_flags=0):

@@ -281,6 +281,24 @@ trunc:
   return BAMSCAN_ERR_FORMAT;
 }
 
+// GZI (bgzip -i; noodles-bgzf gzi::fs::read): u64 count, then count x (compressed offset, inflated offset), little endian.
+int load_gzi(const std::string& path, std::vector<std::pair<uint64_t, uint64_t>>* out) {
+  FILE* fp = fopen(path.c_str(), "rb");
+  if (!fp) return BAMSCAN_ERR_IO;
+  std::vector<uint8_t> d;
+  uint8_t tmp[65536]; size_t n;
+  while ((n = fread(tmp, 1, sizeof tmp, fp)) > 0) d.insert(d.end(), tmp, tmp + n);
+  fclose(fp);
+  uint64_t cnt = 0;
+  if (d.size() >= 8) memcpy(&cnt, d.data(), 8);
+  if (d.size() < 8 || cnt > (d.size() - 8) / 16 || d.size() != 8 + 16 * cnt) { set_error("%s: not a GZI index (size %zu, count %llu)", path.c_str(), d.size(), (unsigned long long)cnt); return BAMSCAN_ERR_FORMAT; }
+  out->resize((size_t)cnt);
+  for (uint64_t i = 0; i < cnt; i++) { memcpy(&(*out)[i].first, d.data() + 8 + 16 * i, 8); memcpy(&(*out)[i].second, d.data() + 16 + 16 * i, 8); }
+  for (uint64_t i = 1; i < cnt; i++)
+    if ((*out)[i].first <= (*out)[i - 1].first) { set_error("%s: GZI offsets are not increasing", path.c_str()); return BAMSCAN_ERR_FORMAT; }
+  return BAMSCAN_OK;
+}
+
 int load_bai(const std::string& path, BaiIndex* out) {
   FILE* fp = fopen(path.c_str(), "rb");
   if (!fp) { set_error("cannot open index %s", path.c_str()); return BAMSCAN_ERR_IO; }

@@ -112,6 +112,46 @@ int make_plan(BamFile* f, const int32_t* projection, int32_t n_projection, const
     return BAMSCAN_OK;
   }
 
+  // FASTQ, reference rule (bio-format-fastq/src/physical_exec.rs:94-116, 140-175): a BGZF file with a companion `<path>.gzi`
+  // is cut into min(target, blocks) runs of whole blocks by block COUNT (num_blocks / n, the first num_blocks % n runs one
+  // longer), where blocks = the GZI entries plus the implicit first member; without a GZI the scan is sequential.
+  if (f->format == 1 && target_partitions > 1) {
+    std::vector<std::pair<uint64_t, uint64_t>> gzi;
+    int rc = load_gzi(f->path + ".gzi", &gzi);
+    if (rc == BAMSCAN_OK) {
+      gzi.insert(gzi.begin(), std::make_pair(0ull, 0ull));
+      std::vector<uint32_t> idx(gzi.size());
+      for (size_t i = 0; i < gzi.size(); i++) {
+        size_t lo = 0, hi = n_blocks;
+        while (lo < hi) { size_t mid = (lo + hi) / 2; if (f->blocks[mid].coff < gzi[i].first) lo = mid + 1; else hi = mid; }
+        if (lo >= n_blocks || f->blocks[lo].coff != gzi[i].first || f->blocks[lo].uoff != gzi[i].second) {
+          set_error("%s.gzi: entry %zu (%llu, %llu) does not name a BGZF member of the file", f->path.c_str(), i, (unsigned long long)gzi[i].first, (unsigned long long)gzi[i].second);
+          return BAMSCAN_ERR_FORMAT;
+        }
+        idx[i] = (uint32_t)lo;
+      }
+      const size_t num_blocks = gzi.size(), num_partitions = std::min<size_t>((size_t)target_partitions, num_blocks);
+      size_t cur = 0;
+      for (size_t i = 0; i < num_partitions && cur < num_blocks; i++) {
+        const size_t next = cur + num_blocks / num_partitions + (i < num_blocks % num_partitions ? 1 : 0);
+        const uint32_t b = idx[cur], e = next >= num_blocks ? n_blocks : idx[next];
+        Partition part;
+        ScanRange r;
+        r.block_begin = b; r.block_end = e;
+        r.exact_start = (cur == 0);
+        r.first_uoff = f->blocks[b].uoff;
+        r.stop_uoff = e < n_blocks ? f->blocks[e].uoff : ~0ull;
+        if (b < e) part.ranges.push_back(r);
+        part.estimated_bytes = (e < n_blocks ? f->blocks[e].coff : f->size) - f->blocks[b].coff;
+        plan->partitions.push_back(part);
+        cur = next;
+      }
+      *out = plan.release();
+      return BAMSCAN_OK;
+    }
+    if (rc != BAMSCAN_ERR_IO) return rc;   // an unreadable GZI is "no index" (sequential), a corrupt one is an error
+  }
+
   // reference rule: index present -> region partitions (table_provider.rs:1001-1093)
   if (!f->index_path.empty()) {
     bool handled = false;

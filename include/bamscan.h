@@ -91,7 +91,9 @@ enum { BAMSCAN_PUSHDOWN_UNSUPPORTED = 0, BAMSCAN_PUSHDOWN_INEXACT = 1 };
 /* ---- partitioning ---- */
 enum {
   BAMSCAN_PARTITION_REFERENCE = 0,   /* the reference's rule: no index -> 1 partition; index -> <= target_partitions
-                                        balanced region partitions (table_provider.rs:1036-1114) */
+                                        balanced region partitions (table_provider.rs:1036-1114).  FASTQ handles: a
+                                        companion `<path>.gzi` -> min(target, blocks) runs of whole BGZF blocks cut by
+                                        block count (bio-format-fastq physical_exec.rs:94-116, 140-175), else 1 partition */
   BAMSCAN_PARTITION_BLOCK_RANGE = 1  /* target_partitions contiguous BGZF block ranges (multi-GPU full scans);
                                         concatenated in partition order the rows equal the 1-partition scan */
 };

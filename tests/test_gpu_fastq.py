@@ -54,14 +54,16 @@ def test_projection(proj):
     p.close()
 
 
+@pytest.mark.parametrize("mode", [None, "reference"])
 @pytest.mark.parametrize("partitions", [1, 2, 4, 8])
-def test_partitions_concatenate_to_sequential_scan(partitions):
+def test_partitions_concatenate_to_sequential_scan(partitions, mode):
     """parallel_read_test.rs:230-231: the rows of 1 and of N partitions are the same; here also in the same order, and every
-    partition's speculated first record is proven by the seam check."""
+    partition's speculated first record is proven by the seam check.  mode None: block ranges balanced by compressed bytes;
+    "reference": the reference's own cut, by block count from the companion .gzi (physical_exec.rs:140-175)."""
     import bamscan
     o = OracleFastq(FQ / "sample.fastq.bgz")
     p = bamscan.FastqTableProvider(str(FQ / "sample.fastq.bgz"))
-    plan = p.scan(None, None, None, target_partitions=partitions)
+    plan = p.scan(None, None, None, target_partitions=partitions, partition_mode=mode)
     n = plan.output_partition_count()
     parts, stats = [], []
     for i in range(n):

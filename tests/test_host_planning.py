@@ -1,6 +1,7 @@
 """CPU: host-side planning of the product (schema, tag typing, filter classification, partitions) against the oracle's
 restatement and the reference's pins.  No kernels run here."""
 import json
+from pathlib import Path
 
 import pyarrow as pa
 import pytest
@@ -202,3 +203,58 @@ def test_corrupt_bam_files_open_or_fail_cleanly(tmp_path):
         except bamscan.BamScanError:
             refused += 1
     assert opened > 0 and refused > 0
+
+
+def _gzi_bounds(gzi_path, thread_num):
+    """get_bgzf_partition_bounds (bio-format-fastq/src/physical_exec.rs:140-175), restated: (start_uncomp, end_comp) per partition."""
+    import struct
+    d = Path(gzi_path).read_bytes()
+    n, = struct.unpack_from("<Q", d, 0)
+    blocks = [(0, 0)] + [struct.unpack_from("<QQ", d, 8 + 16 * i) for i in range(n)]
+    nb, np_ = len(blocks), min(thread_num, len(blocks))
+    out, cur = [], 0
+    for i in range(np_):
+        if cur >= nb:
+            break
+        nxt = cur + nb // np_ + (1 if i < nb % np_ else 0)
+        out.append((blocks[cur][1], None if nxt >= nb else blocks[nxt][0]))
+        cur = nxt
+    return out
+
+
+@pytest.mark.parametrize("tp", [1, 2, 3, 4, 7, 10, 16])
+def test_fastq_reference_partitions_follow_the_gzi(tp):
+    """FASTQ + companion .gzi: the reference cuts the file into runs of whole BGZF blocks by block count
+    (detect_local_strategy, physical_exec.rs:94-116); the plan must expose exactly those bounds."""
+    import bamscan
+    path = GOLDEN / "fastq" / "sample.fastq.bgz"
+    p = bamscan.FastqTableProvider(str(path))
+    plan = p.scan(None, None, None, target_partitions=tp, partition_mode="reference")
+    want = _gzi_bounds(str(path) + ".gzi", tp)
+    assert plan.output_partition_count() == len(want)
+    for i, (start_u, end_c) in enumerate(want):
+        (r,) = plan.partition_ranges(i)
+        assert r["first_uoff"] == start_u
+        assert r["coff_begin"] == (0 if i == 0 else want[i - 1][1])
+        if end_c is not None:
+            assert r["coff_end"] == end_c
+    # contiguous cover of the block table
+    rs = [plan.partition_ranges(i)[0] for i in range(len(want))]
+    assert rs[0]["block_begin"] == 0 and all(a["block_end"] == b["block_begin"] for a, b in zip(rs, rs[1:]))
+
+
+def test_fastq_without_gzi_is_sequential_and_corrupt_gzi_is_refused(tmp_path):
+    import shutil
+    import bamscan
+    f = tmp_path / "s.fastq.bgz"
+    shutil.copy(GOLDEN / "fastq" / "sample.fastq.bgz", f)
+    plan = bamscan.FastqTableProvider(str(f)).scan(None, None, None, target_partitions=4, partition_mode="reference")
+    assert plan.output_partition_count() == 1                            # no GZI -> FastqPartitionStrategy::Sequential
+    gzi = bytearray((GOLDEN / "fastq" / "sample.fastq.bgz.gzi").read_bytes())
+    gzi[8] ^= 1                                                          # first entry no longer names a member
+    Path(str(f) + ".gzi").write_bytes(bytes(gzi))
+    with pytest.raises(bamscan.BamScanError):
+        bamscan.FastqTableProvider(str(f)).scan(None, None, None, target_partitions=4, partition_mode="reference")
+    Path(str(f) + ".gzi").write_bytes(bytes(gzi[:-3]))
+    with pytest.raises(bamscan.BamScanError):
+        bamscan.FastqTableProvider(str(f)).scan(None, None, None, target_partitions=4, partition_mode="reference")
