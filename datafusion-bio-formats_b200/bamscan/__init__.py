@@ -26,7 +26,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE.parent / "libbamscan.so"
 
 EXPORTED_SYMBOLS = [
-    "bamscan_open", "bamscan_open_fastq", "bamscan_close", "bamscan_schema", "bamscan_classify_filters", "bamscan_plan",
+    "bamscan_open", "bamscan_open_fastq", "bamscan_close", "bamscan_schema", "bamscan_describe_tags", "bamscan_classify_filters", "bamscan_plan",
     "bamscan_plan_num_partitions", "bamscan_plan_schema", "bamscan_plan_free", "bamscan_plan_num_ranges",
     "bamscan_plan_range_info", "bamscan_plan_partition_regions", "bamscan_extract_regions", "bamscan_balance_partitions",
     "bamscan_execute", "bamscan_next", "bamscan_execute_device", "bamscan_next_device",
@@ -121,6 +121,7 @@ def load_library():
     L.bamscan_open_fastq.argtypes = [C.c_char_p, C.POINTER(_Options), C.POINTER(C.c_void_p)]
     L.bamscan_close.argtypes = [C.c_void_p]
     L.bamscan_schema.argtypes = [C.c_void_p, C.c_void_p]
+    L.bamscan_describe_tags.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.bamscan_classify_filters.argtypes = [C.c_void_p, C.POINTER(_Filter), C.c_int32, C.POINTER(C.c_uint8)]
     L.bamscan_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(_Filter), C.c_int32, C.c_int64,
                                C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
@@ -462,6 +463,45 @@ class BamTableProvider:
 
     def table_type(self) -> str:
         return "Base"
+
+    @classmethod
+    def try_new_with_inferred_schema(cls, file_path, object_storage_options=None, coordinate_system_zero_based=True,
+                                     tag_fields=None, sample_size=None, binary_cigar=False, **kw):
+        """== BamTableProvider::try_new_with_inferred_schema (table_provider.rs:568-621): `new` with tag types always inferred
+        from the first `sample_size` (default 100) records and no hints."""
+        return cls(file_path, object_storage_options, coordinate_system_zero_based, tag_fields, binary_cigar, True,
+                   100 if sample_size is None else sample_size, None, **kw)
+
+    def describe(self, ctx=None, sample_size=None) -> pa.Table:
+        """== BamTableProvider::describe (table_provider.rs:703-927): one row per core column and per aux tag found in the first
+        `sample_size` (default 100) records: column_name, data_type, nullable, category ("core" / "tag"), sam_type, description.
+        `ctx` (the reference's SessionContext, which only wraps the batch in a DataFrame) is accepted and ignored."""
+        L = load_library()
+        need = C.c_uint64(0)
+        buf = C.create_string_buffer(1 << 16)
+        rc = L.bamscan_describe_tags(self._h, int(sample_size or 0), buf, len(buf), C.byref(need))
+        if rc != 0 and need.value > len(buf):
+            buf = C.create_string_buffer(need.value)
+            rc = L.bamscan_describe_tags(self._h, int(sample_size or 0), buf, len(buf), C.byref(need))
+        _check(rc)
+        binary = pa.types.is_binary(self.schema().field("cigar").type)
+        zero_based = (self.schema().metadata or {}).get(b"bio.coordinate_system_zero_based", b"true") == b"true"
+        rows = [("name", "Utf8", True, "Read name/query template name"), ("chrom", "Utf8", True, "Reference sequence name"),
+                ("start", "UInt32", True, "Leftmost mapping position (%s)" % ("0-based" if zero_based else "1-based")),
+                ("end", "UInt32", True, "Rightmost mapping position"), ("flags", "UInt32", False, "Bitwise flags"),
+                ("cigar", "Binary" if binary else "Utf8", False, "CIGAR (binary LE u32 ops)" if binary else "CIGAR string"),
+                ("mapping_quality", "UInt32", False, "Mapping quality (0-255)"), ("mate_chrom", "Utf8", True, "Mate reference sequence name"),
+                ("mate_start", "UInt32", True, "Mate position"), ("sequence", "Utf8", False, "Segment sequence"),
+                ("quality_scores", "Utf8", False, "Base quality scores"), ("template_length", "Int32", False, "Template length (TLEN)")]
+        cols = [[r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], ["core"] * 12, [None] * 12, [r[3] for r in rows]]
+        for line in buf.value.decode().splitlines():
+            tag, sam, typ, desc = line.split("\t", 3)
+            for c, v in zip(cols, (tag, typ, True, "tag", sam, desc)):
+                c.append(v)
+        schema = pa.schema([pa.field("column_name", pa.utf8(), False), pa.field("data_type", pa.utf8(), False),
+                            pa.field("nullable", pa.bool_(), False), pa.field("category", pa.utf8(), False),
+                            pa.field("sam_type", pa.utf8(), True), pa.field("description", pa.utf8(), False)])
+        return pa.Table.from_arrays([pa.array(c, f.type) for c, f in zip(cols, schema)], schema=schema)
 
     def supports_filters_pushdown(self, filters):
         pack = _FilterPack(filters, self.schema().names)

@@ -129,7 +129,7 @@ struct Plan {
 // host_file.cpp
 int load_file(BamFile* f);                       // reads the file into pinned memory, walks BGZF, parses header
 int infer_tag_types(const BamFile& f, const std::vector<std::string>& tags, int sample_size,
-                    std::map<std::string, std::pair<char, int32_t>>* out);   // table_provider.rs:145-202
+                    std::map<std::string, std::pair<char, int32_t>>* out, bool all = false);   // table_provider.rs:145-202
 std::string discover_index(const std::string& path);   // index_utils.rs:43-76
 int load_gzi(const std::string& path, std::vector<std::pair<uint64_t, uint64_t>>* out);   // bgzip -i index: (compressed, inflated) offset of every member after the first; BAMSCAN_ERR_IO when absent
 int load_bai(const std::string& path, BaiIndex* out);     // BAI, or CSI when the file is BGZF / starts with "CSI\1"

@@ -1204,6 +1204,35 @@ int bamscan_schema(BamScanHandle* h, struct ArrowSchema* out) {
   return export_schema(h->file.fields, h->file.schema_metadata, out);
 }
 
+static int bamscan_describe_tags_impl(BamScanHandle* h, int32_t sample_size, char* buf, uint64_t cap, uint64_t* needed) {
+  if (!h || !needed || (cap && !buf)) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
+  if (h->file.format != 0) { set_error("describe is a BamTableProvider call"); return BAMSCAN_ERR_INVALID; }
+  if (!h->file.header_ok) { set_error("BAM header could not be read: %s", h->file.path.c_str()); return BAMSCAN_ERR_FORMAT; }
+  std::map<std::string, std::pair<char, int32_t>> found;
+  infer_tag_types(h->file, {}, sample_size > 0 ? sample_size : 100, &found, true);
+  static const char* kind_names[] = {"?", "Int32", "UInt32", "Float32", "Utf8", "Binary"};
+  const auto& reg = known_tags();
+  std::string out;
+  for (auto& kv : found) {   // std::map: sorted by tag name, as describe() sorts them
+    const int32_t k = kv.second.second;
+    std::string ty;
+    if (k >= HK_ListInt8) {
+      static const char* el[] = {"Int8", "UInt8", "Int16", "UInt16", "Int32", "UInt32", "Float32"};
+      ty = std::string("List<") + el[k - HK_ListInt8] + ">";
+    } else ty = kind_names[k];
+    auto r = reg.find(kv.first);
+    const std::string desc = r != reg.end() ? r->second.description : std::string("Custom/unknown tag (") + kv.second.first + ")";
+    out += kv.first; out += '\t'; out += kv.second.first; out += '\t'; out += ty; out += '\t'; out += desc; out += '\n';
+  }
+  *needed = out.size() + 1;
+  if (cap < *needed) { set_error("buffer of %llu bytes is too small (%llu needed)", (unsigned long long)cap, (unsigned long long)*needed); return BAMSCAN_ERR_INVALID; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BAMSCAN_OK;
+}
+int bamscan_describe_tags(BamScanHandle* h, int32_t sample_size, char* buf, uint64_t cap, uint64_t* needed) {
+  BAMSCAN_GUARD(bamscan_describe_tags_impl(h, sample_size, buf, cap, needed))
+}
+
 int bamscan_classify_filters(BamScanHandle* h, const BamScanFilter* filters, int32_t n_filters, uint8_t* out_pushdown) {
   if (!h || (n_filters && (!filters || !out_pushdown))) { set_error("null argument"); return BAMSCAN_ERR_INVALID; }
   if (h->file.format == 1) { for (int i = 0; i < n_filters; i++) out_pushdown[i] = 0; return BAMSCAN_OK; }   // FastqTableProvider pushes no filter down

@@ -147,8 +147,9 @@ int load_file(BamFile* f) {
 }
 
 // table_provider.rs:145-202 + tag_registry.rs:772-792
+// `all` (BamTableProvider::describe, table_provider.rs:715-745): every tag met in the sample, first occurrence wins.
 int infer_tag_types(const BamFile& f, const std::vector<std::string>& tags, int sample_size,
-                    std::map<std::string, std::pair<char, int32_t>>* out) {
+                    std::map<std::string, std::pair<char, int32_t>>* out, bool all) {
   HostStream hs(f);
   // position on the first record
   while (hs.base_uoff + hs.buf.size() <= f.first_record_uoff) if (!hs.fill()) return BAMSCAN_OK;
@@ -184,6 +185,7 @@ int infer_tag_types(const BamFile& f, const std::vector<std::string>& tags, int 
       } else break;
       if (a + sz > bs) break;
       if (!seen.count(tag)) seen[tag] = v;
+      if (all && !out->count(tag)) (*out)[tag] = v;
       a += sz;
     }
     for (const auto& t : tags) {

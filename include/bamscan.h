@@ -122,6 +122,13 @@ int bamscan_check_partition_seams(const BamScanStats* stats, int32_t n_partition
  *   (CSIv1, BGZF or plain, any min_shift / depth up to 9 levels) is read -- the reference discovers a CSI but parses it as a BAI;
  * "" => behave as if no index existed (sequential single-partition scans). */
 int bamscan_open(const char* path, const char* index_path_or_null, const BamScanOptions* options, BamScanHandle** out);
+
+/* == BamTableProvider::describe (table_provider.rs:703-927), the part that reads the file: every aux tag present in the first
+ * `sample_size` records (<= 0: 100), first occurrence deciding its type (infer_type_from_noodles_value, tag_registry.rs:772-792),
+ * sorted by name, one line per tag "TAG\tsam_type\tarrow_type\tdescription\n" (description: the registry's, else
+ * "Custom/unknown tag (<sam_type>)"), NUL-terminated into buf.  *needed = bytes required; BAMSCAN_ERR_INVALID when cap is smaller
+ * (call again).  The twelve core rows of describe() are constants the binding adds (python: BamTableProvider.describe). */
+int bamscan_describe_tags(BamScanHandle* h, int32_t sample_size, char* buf, uint64_t cap, uint64_t* needed);
 void bamscan_close(BamScanHandle* h);
 
 /* == FastqTableProvider::new (bio-format-fastq/src/table_provider.rs:63-75) for a BGZF-compressed FASTQ file.

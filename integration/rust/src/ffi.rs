@@ -67,6 +67,8 @@ unsafe extern "C" {
     pub fn bamscan_open(path: *const c_char, index_path_or_null: *const c_char, options: *const BamScanOptions, out: *mut *mut BamScanHandle) -> c_int;
     pub fn bamscan_close(h: *mut BamScanHandle);
     pub fn bamscan_schema(h: *mut BamScanHandle, out: *mut FFI_ArrowSchema) -> c_int;
+    /// describe(): "TAG\tsam_type\tarrow_type\tdescription\n" per aux tag of the first `sample_size` records.
+    pub fn bamscan_describe_tags(h: *mut BamScanHandle, sample_size: i32, buf: *mut std::os::raw::c_char, cap: u64, needed: *mut u64) -> c_int;
     pub fn bamscan_classify_filters(h: *mut BamScanHandle, filters: *const BamScanFilter, n: i32, out_pushdown: *mut u8) -> c_int;
     pub fn bamscan_plan(
         h: *mut BamScanHandle,

@@ -258,3 +258,53 @@ def test_fastq_without_gzi_is_sequential_and_corrupt_gzi_is_refused(tmp_path):
     Path(str(f) + ".gzi").write_bytes(bytes(gzi[:-3]))
     with pytest.raises(bamscan.BamScanError):
         bamscan.FastqTableProvider(str(f)).scan(None, None, None, target_partitions=4, partition_mode="reference")
+
+
+def _arrow_name(t: pa.DataType) -> str:
+    names = {pa.utf8(): "Utf8", pa.int32(): "Int32", pa.uint32(): "UInt32", pa.float32(): "Float32", pa.int8(): "Int8", pa.uint8(): "UInt8",
+             pa.int16(): "Int16", pa.uint16(): "UInt16"}
+    return f"List<{_arrow_name(t.value_type)}>" if pa.types.is_list(t) else names[t]
+
+
+@pytest.mark.parametrize("name,sample", [("10x_pbmc_tags.bam", 50), ("nanopore_custom_tags.bam", None), ("bam_with_tags.bam", 3), ("multi_chrom_large.bam", 100)])
+def test_describe_lists_core_columns_and_every_sampled_tag(name, sample):
+    """BamTableProvider::describe (table_provider.rs:703-927; tag_tests.rs:730-792): 12 core rows, then every aux tag of the first
+    `sample_size` records sorted by name, typed by its first occurrence -- against the oracle's pure-python aux walk."""
+    from oracle.bam_oracle import OracleBam, kind_to_arrow, load_registry
+    p = _provider(GOLDEN / name)
+    t = p.describe(None, sample)
+    assert t.schema.names == ["column_name", "data_type", "nullable", "category", "sam_type", "description"]
+    assert [f.nullable for f in t.schema] == [False, False, False, False, True, False]
+    rows = t.to_pylist()
+    assert [r["column_name"] for r in rows[:12]] == p.schema().names[:12]
+    assert all(r["category"] == "core" and r["sam_type"] is None for r in rows[:12])
+    assert [(r["data_type"], r["nullable"]) for r in rows[:12]] == [(_arrow_name(f.type), f.nullable) for f in list(p.schema())[:12]]
+    assert rows[2]["description"] == "Leftmost mapping position (0-based)"
+    want = {}
+    o = OracleBam(str(GOLDEN / name))
+    for aux in o._iter_aux(sample or 100):
+        for tag, v in aux.items():
+            want.setdefault(tag, v)
+    reg = load_registry()
+    got = rows[12:]
+    assert [r["column_name"] for r in got] == sorted(want) and len(got) > 0
+    for r in got:
+        sam, kind = want[r["column_name"]]
+        assert (r["sam_type"], r["data_type"], r["nullable"], r["category"]) == (sam, _arrow_name(kind_to_arrow(kind)), True, "tag")
+        known = reg.get(r["column_name"])
+        assert r["description"] == (known[2] if known else f"Custom/unknown tag ({sam})")
+
+
+def test_describe_follows_provider_options_and_inferred_constructor():
+    import bamscan
+    p = _provider(GOLDEN / "multi_chrom.bam", zero_based=False, binary_cigar=True)
+    rows = p.describe().to_pylist()
+    assert rows[2]["description"] == "Leftmost mapping position (1-based)"
+    assert (rows[5]["data_type"], rows[5]["description"]) == ("Binary", "CIGAR (binary LE u32 ops)")
+    # try_new_with_inferred_schema (table_provider.rs:568-621) == new(.., infer_tag_types = true, sample_size, no hints)
+    a = bamscan.BamTableProvider.try_new_with_inferred_schema(str(GOLDEN / "10x_pbmc_tags.bam"), None, True, ["CB", "xf", "ZZ"], None, False)
+    b = _provider(GOLDEN / "10x_pbmc_tags.bam", tag_fields=["CB", "xf", "ZZ"])
+    assert a.schema().equals(b.schema(), check_metadata=True)
+    assert a.schema().field("xf").type == pa.int32()
+    with pytest.raises(bamscan.BamScanError):
+        bamscan.FastqTableProvider(str(GOLDEN / "fastq" / "sample.fastq.bgz")).describe()
