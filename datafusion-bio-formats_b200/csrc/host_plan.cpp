@@ -122,6 +122,7 @@ int make_plan(BamFile* f, const int32_t* projection, int32_t n_projection, const
       gzi.insert(gzi.begin(), std::make_pair(0ull, 0ull));
       std::vector<uint32_t> idx(gzi.size());
       for (size_t i = 0; i < gzi.size(); i++) {
+        if (gzi[i].first == f->size && gzi[i].second == f->total_inflated) { idx[i] = n_blocks; continue; }   // an entry for the end of the file: an empty run
         size_t lo = 0, hi = n_blocks;
         while (lo < hi) { size_t mid = (lo + hi) / 2; if (f->blocks[mid].coff < gzi[i].first) lo = mid + 1; else hi = mid; }
         if (lo >= n_blocks || f->blocks[lo].coff != gzi[i].first || f->blocks[lo].uoff != gzi[i].second) {
@@ -139,10 +140,10 @@ int make_plan(BamFile* f, const int32_t* projection, int32_t n_projection, const
         ScanRange r;
         r.block_begin = b; r.block_end = e;
         r.exact_start = (cur == 0);
-        r.first_uoff = f->blocks[b].uoff;
+        r.first_uoff = b < n_blocks ? f->blocks[b].uoff : f->total_inflated;
         r.stop_uoff = e < n_blocks ? f->blocks[e].uoff : ~0ull;
         if (b < e) part.ranges.push_back(r);
-        part.estimated_bytes = (e < n_blocks ? f->blocks[e].coff : f->size) - f->blocks[b].coff;
+        part.estimated_bytes = b < n_blocks ? (e < n_blocks ? f->blocks[e].coff : f->size) - f->blocks[b].coff : 0;
         plan->partitions.push_back(part);
         cur = next;
       }

@@ -308,3 +308,24 @@ def test_describe_follows_provider_options_and_inferred_constructor():
     assert a.schema().field("xf").type == pa.int32()
     with pytest.raises(bamscan.BamScanError):
         bamscan.FastqTableProvider(str(GOLDEN / "fastq" / "sample.fastq.bgz")).describe()
+
+
+def test_fastq_gzi_with_an_end_of_file_entry(tmp_path):
+    """A GZI that also lists the end of the file (no member there) plans an empty last run instead of failing."""
+    import shutil
+    import struct
+    import bamscan
+    f = tmp_path / "s.fastq.bgz"
+    shutil.copy(GOLDEN / "fastq" / "sample.fastq.bgz", f)
+    gzi = (GOLDEN / "fastq" / "sample.fastq.bgz.gzi").read_bytes()
+    n, = struct.unpack_from("<Q", gzi, 0)
+    data, off, inflated = f.read_bytes(), 0, 0
+    while off < len(data):                                               # BSIZE chain: total inflated size of the file
+        bs = struct.unpack_from("<H", data, off + 16)[0] + 1
+        inflated += struct.unpack_from("<I", data, off + bs - 4)[0]
+        off += bs
+    Path(str(f) + ".gzi").write_bytes(struct.pack("<Q", n + 1) + gzi[8:] + struct.pack("<QQ", len(data), inflated))
+    plan = bamscan.FastqTableProvider(str(f)).scan(None, None, None, target_partitions=n + 2, partition_mode="reference")
+    assert plan.output_partition_count() == n + 2
+    assert plan.partition_ranges(n + 1) == []                            # the run that starts at the end of the file
+    assert sum(len(plan.partition_ranges(i)) for i in range(n + 2)) == n + 1
