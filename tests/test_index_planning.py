@@ -425,3 +425,53 @@ def test_random_region_plans_lose_no_row(syn_dir, tmp_path, index):
         assert got == want, (filters, got, want)
         checked += want
     assert checked > 0
+
+
+def test_balance_partitions_tiles_every_contig_property():
+    """Property (hypothesis): whatever the estimates, the sub-regions of a contig tile it -- first piece starts at 1 (or is the
+    whole contig), each next piece starts one base after the previous end, only the last piece is open-ended -- so the row rule
+    `start in [region.start, region.end]` (physical_exec.rs:1295-1314) can neither duplicate nor lose a row across partitions;
+    the partition count never exceeds the target and the byte estimates are conserved (partition_balancer.rs:61-295)."""
+    from hypothesis import given, settings, strategies as st
+    import bamscan
+
+    contig = st.tuples(st.integers(0, 10 ** 10), st.one_of(st.none(), st.integers(1, 3 * 10 ** 8)), st.integers(0, 5),
+                       st.one_of(st.none(), st.lists(st.integers(0, 2000), min_size=1, max_size=40, unique=True)))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(contig, min_size=1, max_size=8), st.integers(1, 24))
+    def check(contigs, target):
+        ests = []
+        for i, (b, length, unm, bins) in enumerate(contigs):
+            pos = sorted(k * 16384 + 1 for k in bins) if bins else None
+            if pos and length:
+                pos = [x for x in pos if x <= length] or None
+            ests.append(est(f"c{i}", b, contig_len=length, unmapped=unm, bins=pos, span=16384 if pos else 0))
+        parts = bamscan.balance_partitions(ests, target)
+        assert len(parts) <= target
+        total = sum(e["bytes"] for e in ests)
+        n_tail_regions = sum(1 for p in parts for g in p["regions"] if g["unmapped_tail"])
+        assert sum(p["total_estimated_bytes"] for p in parts) == total + n_tail_regions      # a tail counts one byte (:267)
+        pieces, tails = {}, {}
+        for p in parts:
+            for g in p["regions"]:
+                (tails if g["unmapped_tail"] else pieces).setdefault(g["chrom"], []).append(g)
+        assert set(pieces) == {e["chrom"] for e in ests}
+        for e in ests:
+            ps = pieces[e["chrom"]]                                        # in partition order = genomic order
+            if len(ps) == 1:
+                assert ps[0]["start"] in (None, 1) and ps[0]["end"] is None
+            else:
+                assert ps[0]["start"] == 1 and ps[-1]["end"] is None
+                for a, b in zip(ps, ps[1:]):
+                    assert a["end"] is not None and a["end"] >= a["start"] and b["start"] == a["end"] + 1
+            n_tails = len(tails.get(e["chrom"], []))
+            # tails: none on the target == 1 and all-zero fast paths (:71-95), else one per reference with unmapped reads
+            if target == 1 or total == 0:
+                assert n_tails == 0
+            elif e["bytes"] > 0:
+                assert n_tails == (1 if e["unmapped_count"] > 0 else 0)
+            else:
+                assert n_tails <= 1
+
+    check()
