@@ -475,3 +475,35 @@ def test_balance_partitions_tiles_every_contig_property():
                 assert n_tails <= 1
 
     check()
+
+
+def test_extract_regions_is_a_superset_property():
+    """Property (hypothesis): the pushed-down region is sound -- every position whose `start` passes all the conjuncts lies inside
+    [region.start, region.end] (1-based, after the coordinate shift), and `unsatisfiable` is only claimed when no position passes
+    (genomic_filter.rs:51-329: the pushdown is Inexact, it may keep too much, never too little)."""
+    from hypothesis import given, settings, strategies as st
+
+    val = st.integers(0, 400)
+    conj = st.one_of(st.tuples(st.sampled_from([">", ">=", "<", "<=", "="]), st.tuples(val)),
+                     st.tuples(st.just("between"), st.tuples(val, val)))
+
+    def passes(pos, op, v):
+        return {">": lambda: pos > v[0], ">=": lambda: pos >= v[0], "<": lambda: pos < v[0], "<=": lambda: pos <= v[0],
+                "=": lambda: pos == v[0], "between": lambda: v[0] <= pos <= v[1]}[op]()
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.lists(conj, min_size=0, max_size=4), st.booleans())
+    def check(conjs, zero_based):
+        filters = [("chrom", "=", ["chr1"])] + [("start", op, list(v)) for op, v in conjs]
+        r = eg(filters, zero_based)
+        ok = [p for p in range(0 if zero_based else 1, 402) if all(passes(p, op, v) for op, v in conjs)]
+        if r["unsatisfiable"]:
+            assert not ok, (filters, ok[:3])
+            return
+        assert [g["chrom"] for g in r["regions"]] == ["chr1"]
+        lo, hi = r["regions"][0]["start"], r["regions"][0]["end"]
+        for p in ok:
+            one = p + 1 if zero_based else p
+            assert (lo is None or one >= lo) and (hi is None or one <= hi), (filters, p, lo, hi)
+
+    check()
