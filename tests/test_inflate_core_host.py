@@ -44,3 +44,35 @@ def test_host_model_equals_zlib_on_synthetic_files(inflate_sim, syn_dir, mode, r
     # a second sub-stream geometry (shorter spans, shorter warm-up) must decode the same bytes
     members2, bad2, _ = _run(inflate_sim, path, "--span-bytes", "2048", "--overlap", "256", "--max-members", "200")
     assert members2 > 0 and bad2 == 0
+
+
+def test_corrupt_payloads_under_address_sanitizer(tmp_path):
+    """compute-sanitizer is closed on the GPU pool; the shared per-lane code runs here under ASan + UBSan instead: byte flips inside
+    the DEFLATE payloads (half of them in the block-header bytes that describe the Huffman tables) must end as a clean refusal
+    or as zlib's own output -- no out-of-bounds access, no undefined shift, no disagreement with zlib."""
+    import random
+    import struct
+    exe = tmp_path / "inflate_sim_asan"
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", str(exe),
+                        str(ROOT / "tools" / "inflate_sim.cpp"), "-lz"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + r.stderr[-200:])
+    src = (GOLDEN / "multi_chrom.bam").read_bytes()
+    members, off = [], 0
+    while off < len(src):
+        bs = struct.unpack_from("<H", src, off + 16)[0] + 1
+        xlen = struct.unpack_from("<H", src, off + 10)[0]
+        if off + bs - 8 > off + 12 + xlen + 2:
+            members.append((off + 12 + xlen, off + bs - 8))
+        off += bs
+    rng = random.Random(5)
+    f = tmp_path / "f.bin"
+    for it in range(40):
+        b = bytearray(src)
+        for _ in range(rng.randrange(1, 6)):
+            lo, hi = rng.choice(members)
+            pos = lo + (rng.randrange(min(hi - lo, 80)) if rng.random() < 0.5 else rng.randrange(hi - lo))
+            b[pos] = rng.randrange(256)
+        f.write_bytes(bytes(b))
+        r = subprocess.run([str(exe), str(f)], capture_output=True, text=True)
+        assert r.returncode == 0 and "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, (it, r.returncode, r.stderr[:2000])
