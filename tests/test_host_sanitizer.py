@@ -90,3 +90,40 @@ def test_corrupt_inputs_never_trip_the_sanitizers(driver, tmp_path):
                 Path(str(f) + ".gzi").write_bytes(_mutate(rng, Path(str(fq) + ".gzi").read_bytes()))
             _run(driver, f, "-", "fastq")
         shutil.rmtree(d)
+
+
+def test_corrupt_inflated_contents_never_trip_the_sanitizers(driver, tmp_path):
+    """Same, one layer down: the INFLATED stream is damaged (l_text / n_ref / reference entries, record and aux bytes, truncation)
+    and re-packed into valid BGZF members (CRC-32 correct), so the damage reaches the header parser and the aux walk of the tag
+    inference instead of stopping at the member checksum."""
+    import struct
+    import zlib
+    from conftest import _bgzf
+
+    def inflate_all(b):
+        out, off = bytearray(), 0
+        while off < len(b):
+            bs = struct.unpack_from("<H", b, off + 16)[0] + 1
+            xlen = struct.unpack_from("<H", b, off + 10)[0]
+            out += zlib.decompress(b[off + 12 + xlen:off + bs - 8], -15)
+            off += bs
+        return bytes(out)
+
+    rng = random.Random(13)
+    srcs = [inflate_all((GOLDEN / n).read_bytes()) for n in ("multi_chrom.bam", "bam_with_tags.bam", "10x_pbmc_tags.bam", "nanopore_custom_tags.bam")]
+    f = tmp_path / "a.bam"
+    for it in range(45):
+        u = bytearray(rng.choice(srcs))
+        l_text = struct.unpack_from("<i", u, 4)[0]
+        mode = it % 3
+        if mode == 0:
+            for _ in range(rng.randrange(1, 4)):
+                u[rng.choice([4, 5, 6, 7, 8 + l_text, 9 + l_text, 12 + l_text, 13 + l_text, 8 + l_text + rng.randrange(64)])] = rng.randrange(256)
+        elif mode == 1:
+            base = 12 + l_text
+            for _ in range(rng.randrange(1, 12)):
+                u[rng.randrange(base, min(len(u), base + 60000))] = rng.randrange(256)
+        else:
+            u = u[:rng.randrange(8, len(u))]
+        f.write_bytes(_bgzf(bytes(u)))
+        _run(driver, f, "-")
