@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
     opt.struct_size = sizeof opt; opt.coordinate_system_zero_based = 1; opt.infer_tag_types = 1; opt.infer_tag_sample_size = 100; opt.has_tag_fields = 1;
     if (build_schema(&f, &opt) != BAMSCAN_OK) { release_file(&f); return 0; }
     if (f.header_ok) { std::map<std::string, std::pair<char, int32_t>> all; infer_tag_types(f, {}, 1000, &all, true); }
+    { struct ArrowSchema sc; memset(&sc, 0, sizeof sc); if (export_schema(f.fields, f.schema_metadata, &sc) == BAMSCAN_OK && sc.release) sc.release(&sc); }   // Arrow C Data Interface: export + release (LeakSanitizer watches)
     if (argc > 2 && strcmp(argv[2], "-") != 0) {
       f.index_path = *argv[2] ? std::string(argv[2]) : discover_index(f.path);
       if (!f.index_path.empty()) {
