@@ -77,7 +77,7 @@ def test_corrupt_inputs_never_trip_the_sanitizers(driver, tmp_path):
             _run(driver, bam, "")
         elif what == 2:                                                  # good BAM, corrupt CSI
             shutil.copy(src, bam)
-            c = bai_to_csi(str(src) + ".bai", d / "t.csi", depth=rng.choice([5, 6, 9]), bgzf=False).read_bytes()
+            c = bai_to_csi(str(src) + ".bai", d / "t.csi", depth=rng.choice([5, 6, 9]), bgzf=it % 8 == 2).read_bytes()   # plain or BGZF-wrapped
             (d / "f.bam.csi").write_bytes(_mutate(rng, c))
             _run(driver, bam, "")
         else:                                                            # FASTQ: corrupt file or corrupt GZI
