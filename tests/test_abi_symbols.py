@@ -76,3 +76,19 @@ def test_writer_validates_the_schema_and_refuses_without_gpu(tmp_path):
     with pytest.raises(bamscan.BamScanError, match="no CPU path") as e:
         bamscan.BamWriteExec(str(out), o.schema, ["NM"]).execute([])
     assert e.value.code == -4 and not out.exists()
+
+
+def test_cpp_mirror_header_compiles_and_plans(tmp_path):
+    """include/bamscan.hpp (the C++ face of BamTableProvider / BamExec over the C ABI: the reference's host language, Rust, is not
+    available here) compiles with -Wall against the library and reproduces the planning pins: schema, pushdown classes, EmptyExec
+    for an unsatisfiable conjunction, partition counts, describe rows, error codes."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "datafusion-bio-formats_b200"
+    exe = tmp_path / "cpp_mirror_check"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{root / 'include'}", "-o", str(exe), str(root / "tests" / "native" / "cpp_mirror_check.cpp"),
+                        str(lib / "libbamscan.so"), f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe), str(root / "tests" / "golden" / "multi_chrom.bam"), str(root / "tests" / "golden" / "10x_pbmc_tags.bam")], capture_output=True, text=True)
+    assert r.returncode == 0 and "cpp mirror ok" in r.stdout, r.stdout + r.stderr
