@@ -170,4 +170,31 @@ class BamTableProvider {
   BamScanHandle* h_ = nullptr;
 };
 
+// == FastqTableProvider (bio-format-fastq/src/table_provider.rs:46-75, 90-151) for BGZF-compressed FASTQ: new(file_path,
+// object_storage_options); scan() with BAMSCAN_PARTITION_REFERENCE follows the companion .gzi (physical_exec.rs:94-116, 140-175).
+class FastqTableProvider {
+ public:
+  explicit FastqTableProvider(const std::string& file_path, const std::optional<std::string>& object_storage_options = std::nullopt,
+                              int32_t device_id = 0, int32_t batch_rows = 0) {
+    if (object_storage_options) throw Error(BAMSCAN_ERR_UNSUPPORTED, "remote object storage is out of scope for this build (local files only)");
+    BamScanOptions o; std::memset(&o, 0, sizeof o);
+    o.struct_size = sizeof o; o.device_id = device_id; o.batch_rows = batch_rows;
+    check(bamscan_open_fastq(file_path.c_str(), &o, &h_));
+  }
+  FastqTableProvider(FastqTableProvider&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  FastqTableProvider(const FastqTableProvider&) = delete;
+  ~FastqTableProvider() { if (h_) bamscan_close(h_); }
+  void schema(ArrowSchema* out) const { check(bamscan_schema(h_, out)); }
+  const char* table_type() const { return "Base"; }
+  BamExec scan(const std::optional<std::vector<int32_t>>& projection, std::optional<int64_t> limit, int32_t target_partitions = 1,
+               int32_t partition_mode = BAMSCAN_PARTITION_REFERENCE) const {
+    BamScanPlan* p = nullptr;
+    check(bamscan_plan(h_, projection && !projection->empty() ? projection->data() : nullptr, projection ? (int32_t)projection->size() : -1,
+                       nullptr, 0, limit.value_or(-1), target_partitions, partition_mode, &p));
+    return BamExec(p);
+  }
+ private:
+  BamScanHandle* h_ = nullptr;
+};
+
 }  // namespace bamscan_cpp

@@ -1,5 +1,5 @@
 // cpp_mirror_check.cpp -- compile-and-run check of include/bamscan.hpp (planning calls only: no GPU needed).
-//   cpp_mirror_check <multi_chrom.bam> <10x_pbmc_tags.bam>
+//   cpp_mirror_check <multi_chrom.bam> <10x_pbmc_tags.bam> <sample.fastq.bgz (with its .gzi)>
 #include <cstdio>
 #include <cstdlib>
 
@@ -10,7 +10,7 @@ using namespace bamscan_cpp;
 #define REQUIRE(c) do { if (!(c)) { fprintf(stderr, "FAILED line %d: %s\n", __LINE__, #c); return 1; } } while (0)
 
 int main(int argc, char** argv) {
-  if (argc < 3) return 2;
+  if (argc < 4) return 2;
   BamTableProvider t(argv[1], std::nullopt, true, std::vector<std::string>{"NM", "MD"});
   ArrowSchema sc;
   t.schema(&sc);
@@ -39,6 +39,13 @@ int main(int argc, char** argv) {
   REQUIRE(threw);
   try { BamTableProvider remote(argv[1], std::string("{}")); threw = false; } catch (const Error& e) { threw = e.code == BAMSCAN_ERR_UNSUPPORTED; }
   REQUIRE(threw);
+  FastqTableProvider fq(argv[3]);
+  fq.schema(&sc);
+  REQUIRE(sc.n_children == 4 && std::string(sc.children[1]->name) == "description");
+  sc.release(&sc);
+  REQUIRE(fq.scan(std::nullopt, std::nullopt, 1).output_partition_count() == 1);
+  REQUIRE(fq.scan(std::nullopt, std::nullopt, 4).output_partition_count() == 4);          // the reference's cut by block count from the .gzi
+  REQUIRE(fq.scan(std::vector<int32_t>{0}, std::nullopt, 64).output_partition_count() == 10);   // min(target, blocks): 9 GZI entries + the first member
   printf("cpp mirror ok\n");
   return 0;
 }

@@ -90,5 +90,6 @@ def test_cpp_mirror_header_compiles_and_plans(tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{root / 'include'}", "-o", str(exe), str(root / "tests" / "native" / "cpp_mirror_check.cpp"),
                         str(lib / "libbamscan.so"), f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    r = subprocess.run([str(exe), str(root / "tests" / "golden" / "multi_chrom.bam"), str(root / "tests" / "golden" / "10x_pbmc_tags.bam")], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(root / "tests" / "golden" / "multi_chrom.bam"), str(root / "tests" / "golden" / "10x_pbmc_tags.bam"),
+                        str(root / "tests" / "golden" / "fastq" / "sample.fastq.bgz")], capture_output=True, text=True)
     assert r.returncode == 0 and "cpp mirror ok" in r.stdout, r.stdout + r.stderr
