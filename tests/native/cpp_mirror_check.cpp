@@ -46,6 +46,14 @@ int main(int argc, char** argv) {
   REQUIRE(fq.scan(std::nullopt, std::nullopt, 1).output_partition_count() == 1);
   REQUIRE(fq.scan(std::nullopt, std::nullopt, 4).output_partition_count() == 4);          // the reference's cut by block count from the .gzi
   REQUIRE(fq.scan(std::vector<int32_t>{0}, std::nullopt, 64).output_partition_count() == 10);   // min(target, blocks): 9 GZI entries + the first member
+  if (argc > 100) {   // compile-only here: execute / write need a GPU (tests/test_gpu_*.py drive them through the same C ABI)
+    RecordBatchStream st = plan.execute(0);
+    ArrowArray batch;
+    t.schema(&sc);
+    BamWriteExec w("/tmp/out.bam", "@HD\tVN:1.6\n", {"chr1"}, {1000}, &sc, {"NM"});
+    while (st.next(&batch)) { w.write(&batch); batch.release(&batch); }
+    printf("%llu rows, %llu members\n", (unsigned long long)w.finish(), (unsigned long long)w.stats().members);
+  }
   printf("cpp mirror ok\n");
   return 0;
 }
