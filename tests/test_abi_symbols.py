@@ -93,3 +93,14 @@ def test_cpp_mirror_header_compiles_and_plans(tmp_path):
     r = subprocess.run([str(exe), str(root / "tests" / "golden" / "multi_chrom.bam"), str(root / "tests" / "golden" / "10x_pbmc_tags.bam"),
                         str(root / "tests" / "golden" / "fastq" / "sample.fastq.bgz")], capture_output=True, text=True)
     assert r.returncode == 0 and "cpp mirror ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_c_abi_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/bamscan.h must parse as strict C99 (what cgo / bindgen / ctypes generators read)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "bamscan.h"\nint main(void) { return bamscan_version() == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root / 'include'}", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
